@@ -1,0 +1,843 @@
+// mlp_tc.cu -- FLNERF_MODE_BF16: the NeRF MLP (model.py:38-63) on the 5th-gen tensor cores.
+//
+//   * persistent, warp-specialised kernels: warp 0 = bulk-copy producer (UBLKCP into an mbarrier ring),
+//     warp 1 = single-thread tcgen05.mma issuer, warps 2..9 = epilogue (tcgen05.ld -> bias/ReLU/bf16 -> smem);
+//   * the activations of a 128-row tile never leave the SM between layers: the epilogue writes the next
+//     layer's A operand straight into shared memory in the SWIZZLE_128B K-major image the UMMA descriptor
+//     reads; every CTA carries TWO 128-row tiles so each 32 KB weight chunk fetched from L2 feeds 2x128 rows;
+//   * accumulators live in TMEM (2 tiles x 256 fp32 columns = all 512 columns);
+//   * weights are pre-packed once per optimiser step (flnerf_mlp_pack_weights) into the exact shared-memory
+//     image, so a chunk is ONE contiguous 32 KB bulk copy -- no tensor maps, no driver API;
+//   * for training the epilogue also bulk-stores every activation tile (and a ReLU bitmask) to HBM; the
+//     same image is read back as an MN-major operand by the weight-gradient kernel.
+//
+// Three kernels: mlp_fwd_tc (10 tensor layers + alpha/rgb heads on CUDA cores in the epilogue),
+// mlp_dgrad_tc (9 tensor layers, ReLU masks from the bitmask stash), mlp_wgrad_tc (per-layer dY^T X with the
+// 256x256 fp32 accumulator resident in TMEM over a row range, flushed once with red.global.add).
+#include "common.cuh"
+#include "mlp_layout.h"
+#include "tc_ptx.cuh"
+
+namespace tc {
+
+using namespace mlp_layout;
+
+constexpr int kThreads = 320;  // 10 warps
+constexpr int kEpiWarp0 = 2;
+constexpr uint32_t ACT_BYTES = 65536, SLAB_BYTES = 16384, PE_BYTES = 16384, WSTAGE = 32768;
+constexpr int NSTAGE = 2;
+constexpr uint32_t OFF_ACT = 0, OFF_PE = 2 * ACT_BYTES, OFF_W = OFF_PE + 2 * PE_BYTES, OFF_BAR = OFF_W + NSTAGE * WSTAGE;
+constexpr uint32_t SMEM_FWD = OFF_BAR + 256;
+static_assert(SMEM_FWD <= 232448, "shared memory budget");
+
+// packed weight image of one net
+constexpr int FWD_CHUNKS = 38, DG_CHUNKS = 34;
+constexpr size_t FWD_BYTES = (size_t)34 * 32768 + 4 * 16384;
+constexpr size_t DG_BYTES = (size_t)34 * 32768;
+constexpr size_t PACKED_BYTES = FWD_BYTES + DG_BYTES;
+
+// stash (bf16 mode): [viewbias B*128 fp32 (1 KB aligned)] [acts: tiles x 10 x 64 KB] [masks: tiles x 9 x 128 x 32 B]
+constexpr size_t TILE_ACT_BYTES = 10 * 65536;
+constexpr size_t TILE_MASK_BYTES = 9 * 128 * 32;
+
+struct ChunkSrc {
+  int base;     // float offset of element (row 0, col 0) in the flat parameter buffer
+  int row_mul;  // float stride per chunk row
+  int col_mul;  // float stride per chunk column
+  int kvalid;   // columns >= kvalid are zero
+  int nrows;    // 256 or 128
+  int byte_off; // byte offset of the chunk in the packed image
+};
+__constant__ ChunkSrc c_chunks[FWD_CHUNKS + DG_CHUNKS];
+
+// one thread = one 16-byte chunk (8 bf16) of the packed image
+__global__ void pack_weights_kernel(const float *__restrict__ P, uint8_t *__restrict__ packed) {
+  int ci = blockIdx.y;
+  ChunkSrc s = c_chunks[ci];
+  int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= s.nrows * 8) return;
+  int r = idx >> 3, q = idx & 7;
+  uint32_t w[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    int c0 = q * 8 + 2 * e;
+    float a = (c0 < s.kvalid) ? P[s.base + r * s.row_mul + c0 * s.col_mul] : 0.f;
+    float b = (c0 + 1 < s.kvalid) ? P[s.base + r * s.row_mul + (c0 + 1) * s.col_mul] : 0.f;
+    w[e] = pack_bf16(a, b);
+  }
+  *reinterpret_cast<uint4 *>(packed + s.byte_off + sw128_offset(r, q * 8)) = make_uint4(w[0], w[1], w[2], w[3]);
+}
+
+// viewbias[ray][c] = b_v[c] + sum_j W_v[c][256+j] * PE4(viewdir)[j]  -- the 27 view-direction inputs of
+// views_linears.0 are constant along a ray, so their contribution is a per-ray bias (fp32, exact)
+__global__ void viewbias_kernel(int64_t B, const float *__restrict__ P, const float *__restrict__ dirpe,
+                                float *__restrict__ vb) {
+  int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= B * 128) return;
+  int64_t ray = idx >> 7;
+  int c = (int)(idx & 127);
+  const float *w = P + W_VIEWS + c * 283 + 256;
+  const float *pe = dirpe + ray * 32;
+  float s = P[B_VIEWS + c];
+#pragma unroll
+  for (int j = 0; j < 27; ++j) s = fmaf(w[j], pe[j], s);
+  vb[idx] = s;
+}
+
+struct Bars {
+  uint32_t w_full[NSTAGE], w_empty[NSTAGE], pe_full, pe_empty, acc_full, act_ready;
+};
+__device__ __forceinline__ Bars make_bars(uint32_t base) {
+  Bars b;
+  for (int i = 0; i < NSTAGE; ++i) {
+    b.w_full[i] = base + 8 * i;
+    b.w_empty[i] = base + 8 * (NSTAGE + i);
+  }
+  b.pe_full = base + 8 * (2 * NSTAGE);
+  b.pe_empty = base + 8 * (2 * NSTAGE + 1);
+  b.acc_full = base + 8 * (2 * NSTAGE + 2);
+  b.act_ready = base + 8 * (2 * NSTAGE + 3);
+  return b;
+}
+
+struct Ring {
+  uint32_t stage = 0, phase = 0;
+  __device__ __forceinline__ void next() {
+    if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+  }
+};
+
+// A operand: K-major SW128 slab [128 rows x 64]; B operand: K-major SW128 chunk [N rows x 64]; 4 k-steps of 16
+__device__ __forceinline__ void issue_chunk(uint32_t tmem_d, uint32_t a_smem, uint32_t b_smem, uint32_t idesc,
+                                            bool first) {
+  uint64_t da = make_smem_desc(a_smem, 0, 1024), db = make_smem_desc(b_smem, 0, 1024);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) umma_bf16(tmem_d, da + 2 * k, db + 2 * k, idesc, (first && k == 0) ? 0u : 1u);
+}
+
+__device__ __forceinline__ void common_setup(uint8_t *smem, const Bars &bars, uint32_t *tmem_slot, int warp) {
+  if ((smem_u32(smem) & 1023u) != 0) {
+    if (threadIdx.x == 0) printf("flnerf: dynamic smem base not 1024-byte aligned\n");
+    __trap();
+  }
+  if (warp == 1 && lane_id() == 0) {
+    for (int i = 0; i < NSTAGE; ++i) { mbar_init(bars.w_full[i], 1); mbar_init(bars.w_empty[i], 1); }
+    mbar_init(bars.pe_full, 1);
+    mbar_init(bars.pe_empty, 1);
+    mbar_init(bars.acc_full, 1);
+    mbar_init(bars.act_ready, 8);
+    fence_mbar_init();
+  }
+  if (warp == 0) {
+    tmem_alloc(smem_u32(tmem_slot), 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+}
+
+// epilogue helper: store 32 consecutive bf16 columns [c0, c0+32) of row r (packed as 16 u32) into an act tile
+__device__ __forceinline__ void store_cols32(uint8_t *act_tile, uint32_t r, uint32_t c0, const uint32_t pk[16]) {
+  uint8_t *slab = act_tile + (c0 >> 6) * SLAB_BYTES + (r >> 3) * 1024u + (r & 7u) * 128u;
+  uint32_t q0 = (c0 & 63u) >> 3;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    uint32_t pos = ((q0 + q) ^ (r & 7u)) << 4;
+    *reinterpret_cast<uint4 *>(slab + pos) = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+  }
+}
+
+// =================================================================================================
+// forward
+// =================================================================================================
+struct FwdParams {
+  const float *P;          // fp32 parameters (biases, alpha / rgb / view weights)
+  const uint8_t *packed;   // bf16 chunks
+  const uint8_t *pe_tiles; // [tiles][16 KB]
+  const float *viewbias;   // [B][128]
+  float *raw;              // [n][4]
+  uint8_t *stash_act;      // or null
+  uint32_t *stash_mask;    // or null
+  int64_t n;
+  int S;
+  int n_pairs;
+};
+
+__global__ void __launch_bounds__(kThreads, 1) mlp_fwd_tc(FwdParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const int warp = threadIdx.x >> 5;
+  const uint32_t lane = lane_id();
+  const Bars bars = make_bars(smem_u32(smem + OFF_BAR));
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + OFF_BAR + 128);
+  common_setup(smem, bars, tmem_slot, warp);
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t s_act = smem_u32(smem + OFF_ACT), s_pe = smem_u32(smem + OFF_PE), s_w = smem_u32(smem + OFF_W);
+
+  if (warp == 0) {
+    // ---------------------------------------------------------------- producer
+    if (lane == 0) {
+      Ring ring;
+      uint32_t it = 0;
+      auto load_pe = [&](int pair, uint32_t k) {
+        if (k > 0) mbar_wait(bars.pe_empty, (k - 1) & 1);
+        mbar_arrive_expect_tx(bars.pe_full, 2 * PE_BYTES);
+        bulk_g2s(s_pe, p.pe_tiles + (size_t)pair * 2 * PE_BYTES, 2 * PE_BYTES, bars.pe_full);
+      };
+      auto load_chunks = [&](int c_begin, int c_end) {
+        for (int ci = c_begin; ci < c_end; ++ci) {
+          uint32_t bytes = ci < 34 ? 32768u : 16384u;
+          size_t off = ci < 34 ? (size_t)ci * 32768 : (size_t)34 * 32768 + (size_t)(ci - 34) * 16384;
+          mbar_wait(bars.w_empty[ring.stage], ring.phase ^ 1);
+          mbar_arrive_expect_tx(bars.w_full[ring.stage], bytes);
+          bulk_g2s(s_w + ring.stage * WSTAGE, p.packed + off, bytes, bars.w_full[ring.stage]);
+          ring.next();
+        }
+      };
+      int first_pair = blockIdx.x;
+      if (first_pair < p.n_pairs) load_pe(first_pair, 0);
+      for (int pair = first_pair; pair < p.n_pairs; pair += gridDim.x, ++it) {
+        load_chunks(0, 22);  // layers 0..5 (1 + 16 + 5 chunks)
+        int next = pair + gridDim.x;
+        if (next < p.n_pairs) load_pe(next, it + 1);  // PE slabs are free once layer 5 has been issued
+        load_chunks(22, 38);
+      }
+    }
+  } else if (warp == 1) {
+    // ---------------------------------------------------------------- MMA issuer
+    if (lane == 0) {
+      Ring ring;
+      uint32_t n_act = 0, it = 0;
+      const uint32_t idesc256 = make_idesc(128, 256, 0, 0), idesc128 = make_idesc(128, 128, 0, 0);
+      for (int pair = blockIdx.x; pair < p.n_pairs; pair += gridDim.x, ++it) {
+        mbar_wait(bars.pe_full, it & 1);
+        for (int L = 0; L < 10; ++L) {
+          if (!(it == 0 && L == 0)) {  // inputs of this layer written / TMEM drained by the epilogue
+            mbar_wait(bars.act_ready, n_act & 1);
+            ++n_act;
+          }
+          tc_fence_after();
+          const int nch = (L == 0) ? 1 : (L == 5 ? 5 : 4);
+          for (int c = 0; c < nch; ++c) {
+            mbar_wait(bars.w_full[ring.stage], ring.phase);
+            tc_fence_after();
+            const bool use_pe = (L == 0) || (L == 5 && c == 0);
+            const int slab = (L == 5) ? c - 1 : c;
+#pragma unroll
+            for (int t = 0; t < 2; ++t) {
+              uint32_t a = use_pe ? s_pe + t * PE_BYTES : s_act + t * ACT_BYTES + slab * SLAB_BYTES;
+              issue_chunk(tmem_base + t * 256, a, s_w + ring.stage * WSTAGE, L == 9 ? idesc128 : idesc256, c == 0);
+            }
+            umma_commit(bars.w_empty[ring.stage]);
+            ring.next();
+          }
+          umma_commit(bars.acc_full);
+          if (L == 5) umma_commit(bars.pe_empty);
+        }
+      }
+    }
+  } else {
+    // ---------------------------------------------------------------- epilogue (8 warps, 2 tiles x 4 lane quarters)
+    const int e = warp - kEpiWarp0;
+    const int t = e >> 2;
+    const uint32_t quarter = warp & 3;
+    const uint32_t r = quarter * 32 + lane;  // row inside the tile == TMEM lane
+    uint8_t *act_tile = smem + OFF_ACT + t * ACT_BYTES;
+    const uint32_t tmem_row = tmem_base + ((quarter * 32) << 16) + t * 256;
+    const bool elected = (e & 3) == 0 && lane == 0;  // one thread per tile drives the bulk stores
+    uint32_t n_acc = 0;
+    bool store_pending = false;
+    for (int pair = blockIdx.x; pair < p.n_pairs; pair += gridDim.x) {
+      const int64_t tile = (int64_t)pair * 2 + t;
+      const int64_t row = tile * 128 + r;
+      float alpha = 0.f;
+      for (int L = 0; L < 10; ++L) {
+        mbar_wait(bars.acc_full, n_acc & 1);
+        ++n_acc;
+        tc_fence_after();
+        if (p.stash_act) {  // the previous layer's bulk store must have finished reading act_tile
+          if (elected && store_pending) bulk_wait_read0();
+          named_bar_sync(1 + t, 128);
+        }
+        uint32_t *mask_dst = p.stash_mask ? p.stash_mask + ((size_t)tile * 9 + (L < 9 ? L : 8)) * 128 * 8 + (size_t)r * 8
+                                          : nullptr;
+        if (L < 9) {
+          const float *bias = p.P + (L < 8 ? b_pts(L) : B_FEAT);
+          const float *wa = p.P + W_ALPHA;
+#pragma unroll 1
+          for (int cb = 0; cb < 8; ++cb) {
+            uint32_t v[32], pk[16];
+            tmem_ld32(tmem_row + cb * 32, v);
+            tmem_ld_wait();
+            uint32_t m = 0;
+#pragma unroll
+            for (int i = 0; i < 32; i += 2) {
+              float x0 = __uint_as_float(v[i]) + __ldg(bias + cb * 32 + i);
+              float x1 = __uint_as_float(v[i + 1]) + __ldg(bias + cb * 32 + i + 1);
+              if (L < 8) { x0 = fmaxf(x0, 0.f); x1 = fmaxf(x1, 0.f); }
+              uint32_t w = pack_bf16(x0, x1);
+              pk[i >> 1] = w;
+              m |= ((w & 0xFFFFu) ? 1u : 0u) << i;
+              m |= ((w >> 16) ? 1u : 0u) << (i + 1);
+              if (L == 7) {  // alpha_linear on the (bf16-rounded) activations the next layers also see
+                alpha = fmaf(bf16_lo(w), __ldg(wa + cb * 32 + i), alpha);
+                alpha = fmaf(bf16_hi(w), __ldg(wa + cb * 32 + i + 1), alpha);
+              }
+            }
+            if (mask_dst && L < 8) mask_dst[cb] = m;
+            store_cols32(act_tile, r, cb * 32, pk);
+          }
+        } else {
+          // views_linears.0 (N=128) + rgb_linear on CUDA cores, then raw = (r,g,b,sigma)
+          const int64_t ray = (row < p.n ? row : p.n - 1) / p.S;
+          const float *vb = p.viewbias + ray * 128;
+          const float *wr = p.P + W_RGB;
+          float c0 = 0.f, c1 = 0.f, c2 = 0.f;
+#pragma unroll 1
+          for (int cb = 0; cb < 4; ++cb) {
+            uint32_t v[32], pk[16];
+            tmem_ld32(tmem_row + cb * 32, v);
+            tmem_ld_wait();
+            uint32_t m = 0;
+#pragma unroll
+            for (int i = 0; i < 32; i += 2) {
+              float x0 = fmaxf(__uint_as_float(v[i]) + __ldg(vb + cb * 32 + i), 0.f);
+              float x1 = fmaxf(__uint_as_float(v[i + 1]) + __ldg(vb + cb * 32 + i + 1), 0.f);
+              uint32_t w = pack_bf16(x0, x1);
+              pk[i >> 1] = w;
+              m |= ((w & 0xFFFFu) ? 1u : 0u) << i;
+              m |= ((w >> 16) ? 1u : 0u) << (i + 1);
+              float h0 = bf16_lo(w), h1 = bf16_hi(w);
+              int k = cb * 32 + i;
+              c0 = fmaf(h0, __ldg(wr + k), c0);           c0 = fmaf(h1, __ldg(wr + k + 1), c0);
+              c1 = fmaf(h0, __ldg(wr + 128 + k), c1);     c1 = fmaf(h1, __ldg(wr + 128 + k + 1), c1);
+              c2 = fmaf(h0, __ldg(wr + 256 + k), c2);     c2 = fmaf(h1, __ldg(wr + 256 + k + 1), c2);
+            }
+            if (mask_dst) mask_dst[cb] = m;
+            store_cols32(act_tile, r, cb * 32, pk);
+          }
+          if (row < p.n) {
+            float4 o = make_float4(c0 + __ldg(p.P + B_RGB), c1 + __ldg(p.P + B_RGB + 1), c2 + __ldg(p.P + B_RGB + 2),
+                                   alpha + __ldg(p.P + B_ALPHA));
+            reinterpret_cast<float4 *>(p.raw)[row] = o;
+          }
+        }
+        tc_fence_before();
+        fence_async_smem();
+        if (p.stash_act) {
+          named_bar_sync(1 + t, 128);  // all 4 warps of this tile have written act_tile
+          if (elected) {
+            bulk_s2g(p.stash_act + (size_t)tile * TILE_ACT_BYTES + (size_t)L * 65536, smem_u32(act_tile),
+                     L == 9 ? 32768u : 65536u);
+            bulk_commit();
+          }
+          store_pending = true;
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bars.act_ready);
+      }
+    }
+    if (elected && store_pending) bulk_wait_all0();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, 512);
+}
+
+// =================================================================================================
+// backward, data gradient chain:  G9 -> dF -> dH7 -> ... -> dH0   (pre-activation gradients, bf16)
+// =================================================================================================
+struct DgradParams {
+  const float *P;
+  const uint8_t *packed_dg;  // 34 chunks of 32 KB
+  const float *draw;         // [n][4]
+  const uint32_t *stash_mask;
+  uint8_t *dy;               // [tiles][10][64 KB]: slot l<8 = dH_l, slot 8 = dF, slot 9 = G9 (32 KB)
+  int64_t n;
+  int n_pairs;
+};
+
+__global__ void __launch_bounds__(kThreads, 1) mlp_dgrad_tc(DgradParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const int warp = threadIdx.x >> 5;
+  const uint32_t lane = lane_id();
+  const Bars bars = make_bars(smem_u32(smem + OFF_BAR));
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + OFF_BAR + 128);
+  common_setup(smem, bars, tmem_slot, warp);
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t s_act = smem_u32(smem + OFF_ACT), s_w = smem_u32(smem + OFF_W);
+
+  if (warp == 0) {
+    if (lane == 0) {
+      Ring ring;
+      for (int pair = blockIdx.x; pair < p.n_pairs; pair += gridDim.x) {
+        for (int ci = 0; ci < DG_CHUNKS; ++ci) {
+          mbar_wait(bars.w_empty[ring.stage], ring.phase ^ 1);
+          mbar_arrive_expect_tx(bars.w_full[ring.stage], 32768u);
+          bulk_g2s(s_w + ring.stage * WSTAGE, p.packed_dg + (size_t)ci * 32768, 32768u, bars.w_full[ring.stage]);
+          ring.next();
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      Ring ring;
+      uint32_t n_act = 0;
+      const uint32_t idesc = make_idesc(128, 256, 0, 0);
+      for (int pair = blockIdx.x; pair < p.n_pairs; pair += gridDim.x) {
+        for (int D = 0; D < 9; ++D) {  // D=0: dF = G9 * Wv (K=128); D>=1: K=256
+          mbar_wait(bars.act_ready, n_act & 1);
+          ++n_act;
+          tc_fence_after();
+          const int nch = (D == 0) ? 2 : 4;
+          for (int c = 0; c < nch; ++c) {
+            mbar_wait(bars.w_full[ring.stage], ring.phase);
+            tc_fence_after();
+#pragma unroll
+            for (int t = 0; t < 2; ++t)
+              issue_chunk(tmem_base + t * 256, s_act + t * ACT_BYTES + c * SLAB_BYTES, s_w + ring.stage * WSTAGE, idesc,
+                          c == 0);
+            umma_commit(bars.w_empty[ring.stage]);
+            ring.next();
+          }
+          umma_commit(bars.acc_full);
+        }
+      }
+    }
+  } else {
+    const int e = warp - kEpiWarp0;
+    const int t = e >> 2;
+    const uint32_t quarter = warp & 3;
+    const uint32_t r = quarter * 32 + lane;
+    uint8_t *act_tile = smem + OFF_ACT + t * ACT_BYTES;
+    const uint32_t tmem_row = tmem_base + ((quarter * 32) << 16) + t * 256;
+    const bool elected = (e & 3) == 0 && lane == 0;
+    uint32_t n_acc = 0;
+    bool store_pending = false;
+    for (int pair = blockIdx.x; pair < p.n_pairs; pair += gridDim.x) {
+      const int64_t tile = (int64_t)pair * 2 + t;
+      const int64_t row = tile * 128 + r;
+      float4 dr = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (row < p.n) dr = reinterpret_cast<const float4 *>(p.draw)[row];
+      const uint32_t *mask_base = p.stash_mask + (size_t)tile * 9 * 128 * 8 + (size_t)r * 8;
+      // stage -1: G9 = (d_rgb * W_rgb) masked by relu(h9) -> act slabs 0,1 ; stages 0..8 = tensor layers
+      for (int D = -1; D < 9; ++D) {
+        if (D >= 0) {
+          mbar_wait(bars.acc_full, n_acc & 1);
+          ++n_acc;
+          tc_fence_after();
+        }
+        if (elected && store_pending) bulk_wait_read0();
+        named_bar_sync(1 + t, 128);
+        // ReLU mask of the activation this gradient flows into: D=-1 -> h9 (slot 8), D=0 -> none (feature is
+        // linear), D=1 -> H7, D=2 -> H6, ..., D=8 -> H0
+        const uint32_t *mk = (D != 0) ? mask_base + (size_t)((D < 0) ? 8 : 8 - D) * 128 * 8 : nullptr;
+        if (D < 0) {
+          const float *wr = p.P + W_RGB;
+#pragma unroll 1
+          for (int cb = 0; cb < 4; ++cb) {
+            uint32_t pk[16];
+            uint32_t m = __ldg(mk + cb);
+#pragma unroll
+            for (int i = 0; i < 32; i += 2) {
+              int k = cb * 32 + i;
+              float g0 = dr.x * __ldg(wr + k) + dr.y * __ldg(wr + 128 + k) + dr.z * __ldg(wr + 256 + k);
+              float g1 = dr.x * __ldg(wr + k + 1) + dr.y * __ldg(wr + 128 + k + 1) + dr.z * __ldg(wr + 256 + k + 1);
+              g0 = ((m >> i) & 1u) ? g0 : 0.f;
+              g1 = ((m >> (i + 1)) & 1u) ? g1 : 0.f;
+              pk[i >> 1] = pack_bf16(g0, g1);
+            }
+            store_cols32(act_tile, r, cb * 32, pk);
+          }
+        } else {
+          const float *wa = p.P + W_ALPHA;
+#pragma unroll 1
+          for (int cb = 0; cb < 8; ++cb) {
+            uint32_t v[32], pk[16];
+            tmem_ld32(tmem_row + cb * 32, v);
+            tmem_ld_wait();
+            uint32_t m = mk ? __ldg(mk + cb) : ~0u;
+#pragma unroll
+            for (int i = 0; i < 32; i += 2) {
+              float g0 = __uint_as_float(v[i]), g1 = __uint_as_float(v[i + 1]);
+              if (D == 1) {  // dH7 also receives d_sigma * w_alpha (alpha_linear reads H7)
+                g0 = fmaf(dr.w, __ldg(wa + cb * 32 + i), g0);
+                g1 = fmaf(dr.w, __ldg(wa + cb * 32 + i + 1), g1);
+              }
+              g0 = ((m >> i) & 1u) ? g0 : 0.f;
+              g1 = ((m >> (i + 1)) & 1u) ? g1 : 0.f;
+              pk[i >> 1] = pack_bf16(g0, g1);
+            }
+            store_cols32(act_tile, r, cb * 32, pk);
+          }
+        }
+        tc_fence_before();
+        fence_async_smem();
+        named_bar_sync(1 + t, 128);
+        if (elected) {
+          int slot = (D < 0) ? 9 : 8 - D;  // D=0 -> dF (8), D=1 -> dH7 (7) ... D=8 -> dH0 (0)
+          bulk_s2g(p.dy + (size_t)tile * TILE_ACT_BYTES + (size_t)slot * 65536, smem_u32(act_tile),
+                   D < 0 ? 32768u : 65536u);
+          bulk_commit();
+        }
+        store_pending = true;
+        __syncwarp();
+        if (D < 8 && lane == 0) mbar_arrive(bars.act_ready);  // the last stage feeds no further MMA
+      }
+    }
+    if (elected && store_pending) bulk_wait_all0();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, 512);
+}
+
+// =================================================================================================
+// backward, weight gradients:  dW[out][in] += sum_rows dY[row][out] * X[row][in]
+// Both operands are the stashed [rows x features] SWIZZLE_128B images read as MN-major UMMA operands
+// (LBO = distance between 64-feature slabs, SBO = 1024 = distance between 8-row groups).
+// =================================================================================================
+struct WUnit {
+  int a_slot;   // dY slot (in dy buffer)
+  int a_slabs;  // 4 (M=256) or 2 (M=128)
+  int b_kind;   // 0 = stash act slot, 1 = PE tiles
+  int b_slot;
+  int b_slabs;  // 4 (N=256) or 1 (N=64)
+  int w_off;    // float offset of dW(0,0)
+  int ldw;
+  int bias_off; // float offset of the bias gradient (column sums of dY), -1 = none
+  int alpha;    // 1: also accumulate d w_alpha = sum_rows d_sigma[row] * X[row][:] and d b_alpha
+  int splits;   // number of row ranges this unit is cut into
+};
+constexpr int kUnits = 11;
+__constant__ WUnit c_units[kUnits];
+
+struct WgradParams {
+  const uint8_t *dy;
+  const uint8_t *stash_act;
+  const uint8_t *pe_tiles;
+  const float *draw;
+  float *G;
+  int64_t n;
+  int n_tiles;  // 128-row tiles
+};
+
+constexpr int WG_STAGES = 3;
+constexpr uint32_t WG_A_BYTES = 32768, WG_B_BYTES = 32768;  // 64 rows x 256 features each
+constexpr uint32_t WG_STAGE_BYTES = WG_A_BYTES + WG_B_BYTES;
+constexpr uint32_t WG_OFF_BAR = WG_STAGES * WG_STAGE_BYTES;
+constexpr uint32_t SMEM_WG = WG_OFF_BAR + 256;
+
+__global__ void __launch_bounds__(kThreads, 1) mlp_wgrad_tc(WgradParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const int warp = threadIdx.x >> 5;
+  const uint32_t lane = lane_id();
+  const uint32_t bar0 = smem_u32(smem + WG_OFF_BAR);
+  // barriers: full[3], empty[3], acc_done
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + WG_OFF_BAR + 128);
+  if ((smem_u32(smem) & 1023u) != 0) __trap();
+  // helpers (8 warps) + MMA commit free a stage: 1 (commit) + 8 (warps)
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < WG_STAGES; ++i) { mbar_init(bar0 + 8 * i, 1); mbar_init(bar0 + 8 * (WG_STAGES + i), 9); }
+    mbar_init(bar0 + 8 * 2 * WG_STAGES, 1);
+    fence_mbar_init();
+  }
+  if (warp == 0) { tmem_alloc(smem_u32(tmem_slot), 512); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // which (unit, row range) does this CTA own?
+  int u = 0, part = blockIdx.x;
+  while (u < kUnits - 1 && part >= c_units[u].splits) { part -= c_units[u].splits; ++u; }
+  const WUnit un = c_units[u];
+  const int nhalf = p.n_tiles * 2;  // 64-row half tiles
+  const int h_begin = (int)((int64_t)nhalf * part / un.splits), h_end = (int)((int64_t)nhalf * (part + 1) / un.splits);
+  const uint32_t a_bytes = un.a_slabs * 8192u, b_bytes = un.b_slabs * 8192u;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      for (int h = h_begin; h < h_end; ++h) {
+        mbar_wait(bar0 + 8 * (WG_STAGES + stage), phase ^ 1);
+        uint32_t full = bar0 + 8 * stage;
+        mbar_arrive_expect_tx(full, a_bytes + b_bytes);
+        const size_t tile = (size_t)(h >> 1), half_off = (size_t)(h & 1) * 8192;
+        const uint8_t *a_src = p.dy + tile * TILE_ACT_BYTES + (size_t)un.a_slot * 65536 + half_off;
+        uint32_t sa = smem_u32(smem + stage * WG_STAGE_BYTES), sb = sa + WG_A_BYTES;
+        for (int s = 0; s < un.a_slabs; ++s) bulk_g2s(sa + s * 8192, a_src + (size_t)s * SLAB_BYTES, 8192u, full);
+        const uint8_t *b_src = un.b_kind == 0 ? p.stash_act + tile * TILE_ACT_BYTES + (size_t)un.b_slot * 65536 + half_off
+                                              : p.pe_tiles + tile * PE_BYTES + half_off;
+        for (int s = 0; s < un.b_slabs; ++s) bulk_g2s(sb + s * 8192, b_src + (size_t)s * SLAB_BYTES, 8192u, full);
+        if (++stage == WG_STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      const uint32_t idesc = make_idesc(128, un.b_slabs * 64, 1, 1);
+      const int mhalves = un.a_slabs / 2;
+      for (int h = h_begin; h < h_end; ++h) {
+        mbar_wait(bar0 + 8 * stage, phase);
+        tc_fence_after();
+        uint32_t sa = smem_u32(smem + stage * WG_STAGE_BYTES), sb = sa + WG_A_BYTES;
+        for (int mh = 0; mh < mhalves; ++mh) {
+          // A: M = 128 out-features = 2 slabs; MN-major: LBO = 8192 (next 64 features), SBO = 1024 (next 8 rows)
+          uint64_t da = make_smem_desc(sa + mh * 2 * 8192, 8192, 1024);
+          uint64_t db = make_smem_desc(sb, 8192, 1024);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)  // 16 rows per k-step = 2048 bytes
+            umma_bf16(tmem_base + mh * 256, da + 128 * k, db + 128 * k, idesc, (h == h_begin && k == 0) ? 0u : 1u);
+        }
+        umma_commit(bar0 + 8 * (WG_STAGES + stage));
+        if (++stage == WG_STAGES) { stage = 0; phase ^= 1; }
+      }
+      umma_commit(bar0 + 8 * 2 * WG_STAGES);
+    }
+  } else {
+    // helper warps: column sums of dY (bias gradients) [+ alpha head] straight from the staged tiles, then the flush
+    const int ht = threadIdx.x - kEpiWarp0 * 32;  // 0..255 = feature column
+    float bsum = 0.f, asum = 0.f, basum = 0.f;
+    uint32_t stage = 0, phase = 0;
+    const bool do_bias = un.bias_off >= 0 && ht < un.a_slabs * 64;
+    for (int h = h_begin; h < h_end; ++h) {
+      mbar_wait(bar0 + 8 * stage, phase);
+      const uint8_t *sa = smem + stage * WG_STAGE_BYTES;
+      const uint8_t *sb = sa + WG_A_BYTES;
+      const int64_t row0 = (int64_t)h * 64;
+      if (do_bias || un.alpha) {
+        const uint32_t slab = ht >> 6, c = ht & 63;
+#pragma unroll 4
+        for (uint32_t rr = 0; rr < 64; ++rr) {
+          uint32_t off = slab * 8192u + sw128_offset(rr, c);
+          if (do_bias) bsum += __bfloat162float(*reinterpret_cast<const __nv_bfloat16 *>(sa + off));
+          if (un.alpha) {
+            int64_t row = row0 + rr;
+            float ds = row < p.n ? __ldg(p.draw + row * 4 + 3) : 0.f;
+            asum = fmaf(ds, __bfloat162float(*reinterpret_cast<const __nv_bfloat16 *>(sb + off)), asum);
+            if (ht == 0) basum += ds;
+          }
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar0 + 8 * (WG_STAGES + stage));
+      if (++stage == WG_STAGES) { stage = 0; phase ^= 1; }
+    }
+    if (h_end > h_begin) {
+      if (do_bias) atomicAdd(p.G + un.bias_off + ht, bsum);
+      if (un.alpha) {
+        atomicAdd(p.G + W_ALPHA + ht, asum);
+        if (ht == 0) atomicAdd(p.G + B_ALPHA, basum);
+      }
+      // flush the accumulators: TMEM lane = out feature (within the 128-row M half), column = in feature
+      mbar_wait(bar0 + 8 * 2 * WG_STAGES, 0);
+      tc_fence_after();
+      const int e = warp - kEpiWarp0;
+      const uint32_t quarter = warp & 3;
+      const int ncol = un.b_slabs * 64;
+      const int mhalves = un.a_slabs / 2;
+      for (int mh = 0; mh < mhalves; ++mh) {
+        const int out = mh * 128 + quarter * 32 + lane;
+        float *dst = p.G + un.w_off + (size_t)out * un.ldw;
+        // the two warps that share a lane quarter split the 32-column blocks between them
+        for (int cb = (e >> 2); cb * 32 < ncol; cb += 2) {
+          uint32_t v[32];
+          tmem_ld32(tmem_base + ((quarter * 32) << 16) + mh * 256 + cb * 32, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            int col = cb * 32 + i;
+            // PE units have 63 valid inputs: column 63 is the zero pad and must not be written
+            if (!(un.b_kind == 1 && col >= 63)) atomicAdd(dst + col, __uint_as_float(v[i]));
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, 512);
+}
+
+// rgb head + view-direction columns of views_linears.0: CUDA cores (0.1% of the FLOPs)
+//   dW_rgb[c][k] += sum_rows d_rgb[row][c] * h9[row][k];  db_rgb += sum d_rgb
+//   dW_v[c][256+j] += sum_rows G9[row][c] * dirpe[ray(row)][j]
+__global__ void __launch_bounds__(128) wgrad_small_kernel(const uint8_t *__restrict__ stash_act,
+                                                          const uint8_t *__restrict__ dy,
+                                                          const float *__restrict__ draw,
+                                                          const float *__restrict__ dirpe, float *__restrict__ G,
+                                                          int64_t n, int S, int n_tiles, int tiles_per_block) {
+  const int k = threadIdx.x;  // feature column 0..127
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, b0 = 0.f, b1 = 0.f, b2 = 0.f;
+  float av[27];
+#pragma unroll
+  for (int j = 0; j < 27; ++j) av[j] = 0.f;
+  const int t0 = blockIdx.x * tiles_per_block, t1 = min(n_tiles, t0 + tiles_per_block);
+  const uint32_t slab = k >> 6, c = k & 63;
+  for (int tile = t0; tile < t1; ++tile) {
+    const uint8_t *h9 = stash_act + (size_t)tile * TILE_ACT_BYTES + (size_t)9 * 65536 + slab * SLAB_BYTES;
+    const uint8_t *g9 = dy + (size_t)tile * TILE_ACT_BYTES + (size_t)9 * 65536 + slab * SLAB_BYTES;
+    for (uint32_t rr = 0; rr < 128; ++rr) {
+      int64_t row = (int64_t)tile * 128 + rr;
+      if (row >= n) break;
+      float4 d = __ldg(reinterpret_cast<const float4 *>(draw) + row);
+      uint32_t off = sw128_offset(rr, c);
+      float h = __bfloat162float(*reinterpret_cast<const __nv_bfloat16 *>(h9 + off));
+      float g = __bfloat162float(*reinterpret_cast<const __nv_bfloat16 *>(g9 + off));
+      a0 = fmaf(d.x, h, a0); a1 = fmaf(d.y, h, a1); a2 = fmaf(d.z, h, a2);
+      if (k == (int)(rr & 127)) { b0 += d.x; b1 += d.y; b2 += d.z; }
+      const float *pe = dirpe + (row / S) * 32;
+#pragma unroll
+      for (int j = 0; j < 27; ++j) av[j] = fmaf(g, __ldg(pe + j), av[j]);
+    }
+  }
+  atomicAdd(G + W_RGB + k, a0);
+  atomicAdd(G + W_RGB + 128 + k, a1);
+  atomicAdd(G + W_RGB + 256 + k, a2);
+  atomicAdd(G + B_RGB, b0);
+  atomicAdd(G + B_RGB + 1, b1);
+  atomicAdd(G + B_RGB + 2, b2);
+#pragma unroll
+  for (int j = 0; j < 27; ++j) atomicAdd(G + W_VIEWS + k * 283 + 256 + j, av[j]);
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+static bool g_tables_ready = false;
+static int g_wgrad_grid = 0;
+
+static int setup_tables(int sm_count) {
+  if (g_tables_ready) return 0;
+  ChunkSrc ch[FWD_CHUNKS + DG_CHUNKS];
+  int ci = 0, off = 0;
+  auto add = [&](int base, int row_mul, int col_mul, int kvalid, int nrows) {
+    ch[ci].base = base; ch[ci].row_mul = row_mul; ch[ci].col_mul = col_mul; ch[ci].kvalid = kvalid;
+    ch[ci].nrows = nrows; ch[ci].byte_off = off;
+    off += nrows * 128;
+    ++ci;
+  };
+  // forward: B operand rows = output feature, columns = 64 consecutive input features
+  add(W_PTS[0], 63, 1, 63, 256);
+  for (int l = 1; l < 8; ++l) {
+    if (l == 5) {
+      add(W_PTS[5], 319, 1, 63, 256);
+      for (int c = 0; c < 4; ++c) add(W_PTS[5] + 63 + c * 64, 319, 1, 64, 256);
+    } else {
+      for (int c = 0; c < 4; ++c) add(W_PTS[l] + c * 64, 256, 1, 64, 256);
+    }
+  }
+  for (int c = 0; c < 4; ++c) add(W_FEAT + c * 64, 256, 1, 64, 256);
+  for (int c = 0; c < 4; ++c) add(W_VIEWS + c * 64, 283, 1, 64, 128);
+  if (ci != FWD_CHUNKS || (size_t)off != FWD_BYTES) return 1;
+  // dgrad: B operand rows = input feature j, columns = 64 consecutive output features: W[out][in_off + j]
+  for (int c = 0; c < 2; ++c) add(W_VIEWS + c * 64 * 283, 1, 283, 64, 256);
+  for (int c = 0; c < 4; ++c) add(W_FEAT + c * 64 * 256, 1, 256, 64, 256);
+  for (int l = 7; l >= 1; --l) {
+    int ld = K_PTS[l], in_off = (l == 5) ? 63 : 0;
+    for (int c = 0; c < 4; ++c) add(W_PTS[l] + in_off + c * 64 * ld, 1, ld, 64, 256);
+  }
+  if (ci != FWD_CHUNKS + DG_CHUNKS || (size_t)off != PACKED_BYTES) return 1;
+  if (cudaMemcpyToSymbol(c_chunks, ch, sizeof(ch)) != cudaSuccess) return 1;
+
+  WUnit un[kUnits] = {
+      // a_slot a_slabs b_kind b_slot b_slabs w_off             ldw  bias_off   alpha splits
+      {0, 4, 1, 0, 1, W_PTS[0], 63, B_PTS[0], 0, 0},
+      {1, 4, 0, 0, 4, W_PTS[1], 256, B_PTS[1], 0, 0},
+      {2, 4, 0, 1, 4, W_PTS[2], 256, B_PTS[2], 0, 0},
+      {3, 4, 0, 2, 4, W_PTS[3], 256, B_PTS[3], 0, 0},
+      {4, 4, 0, 3, 4, W_PTS[4], 256, B_PTS[4], 0, 0},
+      {5, 4, 0, 4, 4, W_PTS[5] + 63, 319, B_PTS[5], 0, 0},
+      {5, 4, 1, 0, 1, W_PTS[5], 319, -1, 0, 0},
+      {6, 4, 0, 5, 4, W_PTS[6], 256, B_PTS[6], 0, 0},
+      {7, 4, 0, 6, 4, W_PTS[7], 256, B_PTS[7], 0, 0},
+      {8, 4, 0, 7, 4, W_FEAT, 256, B_FEAT, 1, 0},
+      {9, 2, 0, 8, 4, W_VIEWS, 283, B_VIEWS, 0, 0},
+  };
+  // split the row range of every unit in proportion to the bytes it streams, one work item per SM
+  double cost[kUnits], total = 0;
+  for (int i = 0; i < kUnits; ++i) { cost[i] = un[i].a_slabs * 8.0 + un[i].b_slabs * 8.0; total += cost[i]; }
+  int used = 0;
+  for (int i = 0; i < kUnits; ++i) {
+    int s = (int)(sm_count * cost[i] / total);
+    if (s < 1) s = 1;
+    un[i].splits = s;
+    used += s;
+  }
+  for (int i = 0; used < sm_count; i = (i + 1) % kUnits) {
+    if (un[i].a_slabs == 4 && un[i].b_slabs == 4) { ++un[i].splits; ++used; }
+  }
+  g_wgrad_grid = used;
+  if (cudaMemcpyToSymbol(c_units, un, sizeof(un)) != cudaSuccess) return 1;
+  if (cudaFuncSetAttribute(mlp_fwd_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_FWD) != cudaSuccess) return 1;
+  if (cudaFuncSetAttribute(mlp_dgrad_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_FWD) != cudaSuccess) return 1;
+  if (cudaFuncSetAttribute(mlp_wgrad_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_WG) != cudaSuccess) return 1;
+  g_tables_ready = true;
+  return 0;
+}
+
+}  // namespace tc
+
+// ---- entry points used by api.cu -------------------------------------------------------------------
+size_t mlp_tc_packed_bytes() { return tc::PACKED_BYTES; }
+
+static size_t tc_vb_bytes(int64_t n, int S) {
+  int64_t B = (n + S - 1) / S;
+  return (size_t)((B * 128 * 4 + 1023) / 1024) * 1024;
+}
+size_t mlp_tc_stash_bytes(int64_t n, int S, int training) {
+  size_t tiles = (size_t)(flnerf_padded_rows(n) / 128);
+  return tc_vb_bytes(n, S) + (training ? tiles * (tc::TILE_ACT_BYTES + tc::TILE_MASK_BYTES) : 0);
+}
+size_t mlp_tc_bwd_workspace_bytes(int64_t n) { return (size_t)(flnerf_padded_rows(n) / 128) * tc::TILE_ACT_BYTES; }
+
+int mlp_tc_pack_weights(flnerf_ctx *ctx, const float *params, void *packed, cudaStream_t st) {
+  FL_REQUIRE(tc::setup_tables(ctx->sm_count) == 0, "mlp_tc: table setup failed: %s", cudaGetErrorString(cudaGetLastError()));
+  dim3 grid(8, tc::FWD_CHUNKS + tc::DG_CHUNKS);
+  FL_LAUNCH(tc::pack_weights_kernel, grid, 256, 0, st, params, (uint8_t *)packed);
+  return 0;
+}
+
+int mlp_tc_forward(flnerf_ctx *ctx, const float *params, const void *packed, int64_t n, int S, const void *pe_tiles,
+                   const float *dirpe, float *raw, void *stash, int training, cudaStream_t st) {
+  FL_REQUIRE(tc::setup_tables(ctx->sm_count) == 0, "mlp_tc: table setup failed: %s", cudaGetErrorString(cudaGetLastError()));
+  FL_REQUIRE(n % S == 0, "mlp_tc_forward: n=%lld is not a multiple of S=%d", (long long)n, S);
+  int64_t B = n / S;
+  float *vb = (float *)stash;
+  FL_LAUNCH(tc::viewbias_kernel, (unsigned)ceil_div64(B * 128, 256), 256, 0, st, B, params, dirpe, vb);
+  tc::FwdParams p{};
+  p.P = params; p.packed = (const uint8_t *)packed; p.pe_tiles = (const uint8_t *)pe_tiles; p.viewbias = vb;
+  p.raw = raw; p.n = n; p.S = S;
+  int64_t n_pad = flnerf_padded_rows(n);
+  p.n_pairs = (int)(n_pad / 256);
+  if (training) {
+    p.stash_act = (uint8_t *)stash + tc_vb_bytes(n, S);
+    p.stash_mask = (uint32_t *)(p.stash_act + (size_t)(n_pad / 128) * tc::TILE_ACT_BYTES);
+  }
+  int grid = p.n_pairs < ctx->sm_count ? p.n_pairs : ctx->sm_count;
+  FL_LAUNCH(tc::mlp_fwd_tc, grid, tc::kThreads, tc::SMEM_FWD, st, p);
+  return 0;
+}
+
+int mlp_tc_backward(flnerf_ctx *ctx, const float *params, const void *packed, int64_t n, int S, const void *pe_tiles,
+                    const float *dirpe, const void *stash, const float *draw, float *grads, void *ws,
+                    cudaStream_t st) {
+  FL_REQUIRE(tc::setup_tables(ctx->sm_count) == 0, "mlp_tc: table setup failed: %s", cudaGetErrorString(cudaGetLastError()));
+  int64_t n_pad = flnerf_padded_rows(n);
+  const uint8_t *stash_act = (const uint8_t *)stash + tc_vb_bytes(n, S);
+  const uint32_t *stash_mask = (const uint32_t *)(stash_act + (size_t)(n_pad / 128) * tc::TILE_ACT_BYTES);
+  tc::DgradParams d{};
+  d.P = params; d.packed_dg = (const uint8_t *)packed + tc::FWD_BYTES; d.draw = draw; d.stash_mask = stash_mask;
+  d.dy = (uint8_t *)ws; d.n = n; d.n_pairs = (int)(n_pad / 256);
+  int grid = d.n_pairs < ctx->sm_count ? d.n_pairs : ctx->sm_count;
+  FL_LAUNCH(tc::mlp_dgrad_tc, grid, tc::kThreads, tc::SMEM_FWD, st, d);
+  tc::WgradParams w{};
+  w.dy = (const uint8_t *)ws; w.stash_act = stash_act; w.pe_tiles = (const uint8_t *)pe_tiles; w.draw = draw;
+  w.G = grads; w.n = n; w.n_tiles = (int)(n_pad / 128);
+  FL_LAUNCH(tc::mlp_wgrad_tc, tc::g_wgrad_grid, tc::kThreads, tc::SMEM_WG, st, w);
+  const int tpb = 16;
+  FL_LAUNCH(tc::wgrad_small_kernel, (unsigned)((w.n_tiles + tpb - 1) / tpb), 128, 0, st, stash_act, w.dy, draw, dirpe,
+            grads, n, S, w.n_tiles, tpb);
+  return 0;
+}

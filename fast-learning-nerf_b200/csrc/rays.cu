@@ -1,0 +1,326 @@
+// rays.cu -- ray generation, NDC warp + packing, stratified depths, positional encoding.
+// Reference: nerf-ours/run_nerf_helpers.py:15-108, render.py:59-80, 244-268, run_nerf.py:50-64.
+//
+// All of these are HBM-bound elementwise kernels: one thread per output element (or per 16-byte
+// output chunk), unit-stride stores, inputs re-read through L1/L2.  Arithmetic uses the *_rn
+// intrinsics wherever the reference performs separate tensor ops, so that no FMA contraction
+// changes the rounding relative to torch (x*freq is exact; sinf/cosf are the accurate versions).
+#include "common.cuh"
+
+namespace {
+
+struct Cam {
+  float cx, cy, fx, fy;
+};
+struct Pose {
+  float m[12];  // 3x4 row-major c2w
+};
+
+__device__ __forceinline__ void pixel_ray(const Cam &c, const float *P, int row, int col, float o[3], float d[3]) {
+  // dirs = [(i-cx)/fx, -(j-cy)/fy, -1]; rays_d[a] = sum_b dirs[b]*R[a][b]   (helpers:72-75)
+  float x = __fdiv_rn(__fsub_rn((float)col, c.cx), c.fx);
+  float y = -__fdiv_rn(__fsub_rn((float)row, c.cy), c.fy);
+  float z = -1.0f;
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    float s = __fadd_rn(__fmul_rn(x, P[a * 4 + 0]), __fmul_rn(y, P[a * 4 + 1]));
+    d[a] = __fadd_rn(s, __fmul_rn(z, P[a * 4 + 2]));
+    o[a] = P[a * 4 + 3];
+  }
+}
+
+__global__ void raygen_kernel(int H, int W, Cam cam, Pose pose, float *__restrict__ ro, float *__restrict__ rd) {
+  int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= (int64_t)H * W) return;
+  int row = (int)(p / W), col = (int)(p % W);
+  float o[3], d[3];
+  pixel_ray(cam, pose.m, row, col, o, d);
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    ro[p * 3 + a] = o[a];
+    rd[p * 3 + a] = d[a];
+  }
+}
+
+__global__ void pack_rays_kernel(int64_t B, const float *__restrict__ ro, const float *__restrict__ rd, float near_,
+                                 float far_, int ndc, float sx, float sy, float *__restrict__ out) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B) return;
+  float o0 = ro[i * 3], o1 = ro[i * 3 + 1], o2 = ro[i * 3 + 2];
+  float d0 = rd[i * 3], d1 = rd[i * 3 + 1], d2 = rd[i * 3 + 2];
+  // viewdirs from the un-warped direction (render.py:59-66)
+  float nrm = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(d0, d0), __fmul_rn(d1, d1)), __fmul_rn(d2, d2)));
+  float v0 = __fdiv_rn(d0, nrm), v1 = __fdiv_rn(d1, nrm), v2 = __fdiv_rn(d2, nrm);
+  if (ndc) {  // run_nerf_helpers.py:91-108 with near = 1
+    const float nr = 1.0f;
+    float t = -__fdiv_rn(__fadd_rn(nr, o2), d2);
+    o0 = __fadd_rn(o0, __fmul_rn(t, d0));
+    o1 = __fadd_rn(o1, __fmul_rn(t, d1));
+    o2 = __fadd_rn(o2, __fmul_rn(t, d2));
+    float a0 = __fdiv_rn(__fmul_rn(sx, o0), o2);
+    float a1 = __fdiv_rn(__fmul_rn(sy, o1), o2);
+    float a2 = __fadd_rn(1.0f, __fdiv_rn(2.0f * nr, o2));
+    float b0 = __fmul_rn(sx, __fsub_rn(__fdiv_rn(d0, d2), __fdiv_rn(o0, o2)));
+    float b1 = __fmul_rn(sy, __fsub_rn(__fdiv_rn(d1, d2), __fdiv_rn(o1, o2)));
+    float b2 = __fdiv_rn(-2.0f * nr, o2);
+    o0 = a0; o1 = a1; o2 = a2; d0 = b0; d1 = b1; d2 = b2;
+  }
+  float *q = out + i * 11;
+  q[0] = o0; q[1] = o1; q[2] = o2; q[3] = d0; q[4] = d1; q[5] = d2;
+  q[6] = near_; q[7] = far_; q[8] = v0; q[9] = v1; q[10] = v2;
+}
+
+__device__ __forceinline__ float base_depth(float near_, float far_, float t, int lindisp) {
+  float omt = __fsub_rn(1.0f, t);
+  if (!lindisp) return __fadd_rn(__fmul_rn(near_, omt), __fmul_rn(far_, t));                       // render.py:246
+  float inv = __fadd_rn(__fmul_rn(__fdiv_rn(1.0f, near_), omt), __fmul_rn(__fdiv_rn(1.0f, far_), t));  // :248
+  return __fdiv_rn(1.0f, inv);
+}
+
+__global__ void coarse_depths_kernel(int64_t B, int Nc, const float *__restrict__ rays11, const float *__restrict__ tv,
+                                     const float *__restrict__ t_rand, int perturb, int lindisp, uint64_t seed,
+                                     uint64_t offset, float *__restrict__ z) {
+  int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= B * Nc) return;
+  int64_t ray = idx / Nc;
+  int j = (int)(idx % Nc);
+  float near_ = rays11[ray * 11 + 6], far_ = rays11[ray * 11 + 7];
+  float zj = base_depth(near_, far_, tv[j], lindisp);
+  if (perturb) {  // render.py:252-266
+    float lo = zj, hi = zj;
+    if (j > 0) lo = __fmul_rn(0.5f, __fadd_rn(zj, base_depth(near_, far_, tv[j - 1], lindisp)));
+    if (j < Nc - 1) hi = __fmul_rn(0.5f, __fadd_rn(base_depth(near_, far_, tv[j + 1], lindisp), zj));
+    float u;
+    if (t_rand) {
+      u = t_rand[idx];
+    } else {
+      uint32_t r[4];
+      philox4x32(seed, offset + (uint64_t)idx, 0x5A17ull, r);
+      u = u32_to_unit(r[0]);
+    }
+    zj = __fadd_rn(lo, __fmul_rn(__fsub_rn(hi, lo), u));
+  }
+  z[idx] = zj;
+}
+
+// channel ch of PE_L(x): ch<3 -> x[ch]; else k=(ch-3)/6, sin for (ch-3)%6<3 else cos, coord=(ch-3)%3
+__device__ __forceinline__ float pe_channel(const float x[3], int ch) {
+  if (ch < 3) return x[ch];
+  int q = ch - 3;
+  int k = q / 6, r = q % 6;
+  float a = x[r % 3] * (float)(1u << k);  // exact: power-of-two scale (helpers:32,38)
+  return r < 3 ? sinf(a) : cosf(a);
+}
+
+__global__ void posenc_kernel(int64_t n, int L, const float *__restrict__ x, float *__restrict__ out) {
+  int C = 3 + 6 * L;
+  int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n * C) return;
+  int64_t p = idx / C;
+  int ch = (int)(idx % C);
+  float v[3] = {x[p * 3], x[p * 3 + 1], x[p * 3 + 2]};
+  out[idx] = pe_channel(v, ch);
+}
+
+__device__ __forceinline__ void sample_point(const float *__restrict__ r11, float z, float p[3]) {
+  // pts = o + d*z with separate rounding (render.py:268)
+#pragma unroll
+  for (int a = 0; a < 3; ++a) p[a] = __fadd_rn(r11[a], __fmul_rn(r11[3 + a], z));
+}
+
+__global__ void encode_f32_kernel(int64_t B, int S, const float *__restrict__ rays11, const float *__restrict__ z,
+                                  float *__restrict__ x90) {
+  int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t n = B * S;
+  if (idx >= n * 90) return;
+  int64_t row = idx / 90;
+  int ch = (int)(idx % 90);
+  const float *r11 = rays11 + (row / S) * 11;
+  float v[3];
+  if (ch < 63) {
+    sample_point(r11, z[row], v);
+    x90[idx] = pe_channel(v, ch);
+  } else {
+    v[0] = r11[8]; v[1] = r11[9]; v[2] = r11[10];
+    x90[idx] = pe_channel(v, ch - 63);
+  }
+}
+
+// one thread = one 16-byte chunk (8 channels) of one row of a [128 x 64] bf16 SWIZZLE_128B tile
+__global__ void encode_tc_kernel(int64_t n, int64_t n_pad, int S, const float *__restrict__ rays11,
+                                 const float *__restrict__ z, uint8_t *__restrict__ tiles) {
+  int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n_pad * 8) return;
+  int64_t row = idx >> 3;
+  int q = (int)(idx & 7);
+  uint32_t packed[4] = {0u, 0u, 0u, 0u};
+  if (row < n) {
+    float p[3];
+    sample_point(rays11 + (row / S) * 11, z[row], p);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      int c0 = q * 8 + 2 * e;
+      float a = pe_channel(p, c0);
+      float b = (c0 + 1 < 63) ? pe_channel(p, c0 + 1) : 0.0f;
+      __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+      packed[e] = *reinterpret_cast<uint32_t *>(&h);
+    }
+  }
+  int64_t tile = row >> 7;
+  uint32_t r = (uint32_t)(row & 127);
+  uint8_t *dst = tiles + tile * 16384 + sw128_offset(r, (uint32_t)q * 8);
+  *reinterpret_cast<uint4 *>(dst) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+}
+
+// generic NeRF.forward(x[n,90]) entry for the tensor-core MLP: already-embedded fp32 rows -> bf16 tile image
+__global__ void pack_x90_kernel(int64_t n, int64_t n_pad, const float *__restrict__ x90, uint8_t *__restrict__ tiles,
+                                float *__restrict__ dirpe) {
+  int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n_pad * 8) return;
+  int64_t row = idx >> 3;
+  int q = (int)(idx & 7);
+  uint32_t packed[4] = {0u, 0u, 0u, 0u};
+  if (row < n) {
+    const float *src = x90 + row * 90;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      int c0 = q * 8 + 2 * e;
+      float a = src[c0];
+      float b = (c0 + 1 < 63) ? src[c0 + 1] : 0.0f;
+      __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+      packed[e] = *reinterpret_cast<uint32_t *>(&h);
+    }
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      int j = q * 4 + e;
+      dirpe[row * 32 + j] = j < 27 ? src[63 + j] : 0.0f;
+    }
+  }
+  int64_t tile = row >> 7;
+  uint32_t r = (uint32_t)(row & 127);
+  *reinterpret_cast<uint4 *>(tiles + tile * 16384 + sw128_offset(r, (uint32_t)q * 8)) =
+      make_uint4(packed[0], packed[1], packed[2], packed[3]);
+}
+
+__global__ void dirpe_kernel(int64_t B, const float *__restrict__ rays11, float *__restrict__ dirpe) {
+  int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= B * 32) return;
+  int64_t ray = idx >> 5;
+  int ch = (int)(idx & 31);
+  float v[3] = {rays11[ray * 11 + 8], rays11[ray * 11 + 9], rays11[ray * 11 + 10]};
+  dirpe[idx] = ch < 27 ? pe_channel(v, ch) : 0.0f;
+}
+
+__global__ void gather_batch_kernel(int64_t B, int64_t first, int64_t stride, const int32_t *__restrict__ ray_pix,
+                                    const int32_t *__restrict__ ray_gid, int cap, int H, int W, Cam cam,
+                                    const float *__restrict__ poses, const float *__restrict__ images,
+                                    float *__restrict__ ro, float *__restrict__ rd, float *__restrict__ target,
+                                    int32_t *__restrict__ leaf_gid) {
+  int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= B) return;
+  int64_t j = first + k * stride;
+  int pix = ray_pix[j], gid = ray_gid[j];
+  int img = gid / cap;
+  int row = pix / W, col = pix % W;
+  float o[3], d[3];
+  pixel_ray(cam, poses + (int64_t)img * 12, row, col, o, d);
+  const float *src = images + (((int64_t)img * H + row) * W + col) * 3;
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    ro[k * 3 + a] = o[a];
+    rd[k * 3 + a] = d[a];
+    target[k * 3 + a] = src[a];
+  }
+  if (leaf_gid) leaf_gid[k] = gid;
+}
+
+Cam make_cam(const double *K) {
+  Cam c;
+  c.fx = (float)K[0]; c.cx = (float)K[2]; c.fy = (float)K[4]; c.cy = (float)K[5];
+  return c;
+}
+
+}  // namespace
+
+extern "C" {
+
+int flnerf_raygen(flnerf_ctx *ctx, int H, int W, const double *h_K, const float *h_c2w, float *rays_o, float *rays_d,
+                  void *stream) {
+  FL_REQUIRE(ctx && h_K && h_c2w && rays_o && rays_d && H > 0 && W > 0, "flnerf_raygen: bad arguments");
+  Pose P;
+  for (int i = 0; i < 12; ++i) P.m[i] = h_c2w[i];
+  int64_t n = (int64_t)H * W;
+  FL_LAUNCH(raygen_kernel, (unsigned)ceil_div64(n, 256), 256, 0, stream, H, W, make_cam(h_K), P, rays_o, rays_d);
+  return 0;
+}
+
+int flnerf_pack_rays(flnerf_ctx *ctx, int64_t B, const float *rays_o, const float *rays_d, float near_, float far_,
+                     int ndc, int H, int W, double focal, float *rays11, void *stream) {
+  FL_REQUIRE(ctx && rays_o && rays_d && rays11 && B >= 0, "flnerf_pack_rays: bad arguments");
+  if (B == 0) return 0;
+  float sx = (float)(-1.0 / (W / (2.0 * focal))), sy = (float)(-1.0 / (H / (2.0 * focal)));
+  FL_LAUNCH(pack_rays_kernel, (unsigned)ceil_div64(B, 256), 256, 0, stream, B, rays_o, rays_d, near_, far_, ndc, sx, sy,
+            rays11);
+  return 0;
+}
+
+int flnerf_coarse_depths(flnerf_ctx *ctx, int64_t B, int Nc, const float *rays11, const float *t_vals,
+                         const float *t_rand, int perturb, int lindisp, uint64_t seed, uint64_t offset, float *z,
+                         void *stream) {
+  FL_REQUIRE(ctx && rays11 && t_vals && z && Nc > 0 && B >= 0, "flnerf_coarse_depths: bad arguments");
+  if (B == 0) return 0;
+  FL_LAUNCH(coarse_depths_kernel, (unsigned)ceil_div64(B * Nc, 256), 256, 0, stream, B, Nc, rays11, t_vals, t_rand,
+            perturb, lindisp, seed, offset, z);
+  return 0;
+}
+
+int flnerf_posenc(flnerf_ctx *ctx, int64_t n, int L, const float *x, float *out, void *stream) {
+  FL_REQUIRE(ctx && x && out && L >= 0 && L <= 16 && n >= 0, "flnerf_posenc: bad arguments");
+  if (n == 0) return 0;
+  FL_LAUNCH(posenc_kernel, (unsigned)ceil_div64(n * (3 + 6 * L), 256), 256, 0, stream, n, L, x, out);
+  return 0;
+}
+
+int flnerf_encode_f32(flnerf_ctx *ctx, int64_t B, int S, const float *rays11, const float *z, float *x90,
+                      void *stream) {
+  FL_REQUIRE(ctx && rays11 && z && x90 && S > 0 && B >= 0, "flnerf_encode_f32: bad arguments");
+  if (B == 0) return 0;
+  FL_LAUNCH(encode_f32_kernel, (unsigned)ceil_div64(B * S * 90, 256), 256, 0, stream, B, S, rays11, z, x90);
+  return 0;
+}
+
+int64_t flnerf_padded_rows(int64_t n) { return ceil_div64(n, FLNERF_PAIR_ROWS) * FLNERF_PAIR_ROWS; }
+
+int flnerf_encode_tc(flnerf_ctx *ctx, int64_t B, int S, const float *rays11, const float *z, void *pe_tiles,
+                     float *dirpe, void *stream) {
+  FL_REQUIRE(ctx && rays11 && z && pe_tiles && dirpe && S > 0 && B >= 0, "flnerf_encode_tc: bad arguments");
+  if (B == 0) return 0;
+  int64_t n = B * S, n_pad = flnerf_padded_rows(n);
+  FL_LAUNCH(encode_tc_kernel, (unsigned)ceil_div64(n_pad * 8, 256), 256, 0, stream, n, n_pad, S, rays11, z,
+            (uint8_t *)pe_tiles);
+  FL_LAUNCH(dirpe_kernel, (unsigned)ceil_div64(B * 32, 256), 256, 0, stream, B, rays11, dirpe);
+  return 0;
+}
+
+int flnerf_pack_x90(flnerf_ctx *ctx, int64_t n, const float *x90, void *pe_tiles, float *dirpe, void *stream) {
+  FL_REQUIRE(ctx && x90 && pe_tiles && dirpe && n >= 0, "flnerf_pack_x90: bad arguments");
+  if (n == 0) return 0;
+  int64_t n_pad = flnerf_padded_rows(n);
+  FL_LAUNCH(pack_x90_kernel, (unsigned)ceil_div64(n_pad * 8, 256), 256, 0, stream, n, n_pad, x90, (uint8_t *)pe_tiles,
+            dirpe);
+  return 0;
+}
+
+int flnerf_gather_batch(flnerf_ctx *ctx, int64_t B, int64_t first, int64_t stride, const int32_t *ray_pix,
+                        const int32_t *ray_gid, int cap, int H, int W, const double *h_K, const float *poses,
+                        const float *images, float *rays_o, float *rays_d, float *target, int32_t *leaf_gid,
+                        void *stream) {
+  FL_REQUIRE(ctx && ray_pix && ray_gid && h_K && poses && images && rays_o && rays_d && target && cap > 0,
+             "flnerf_gather_batch: bad arguments");
+  if (B == 0) return 0;
+  FL_LAUNCH(gather_batch_kernel, (unsigned)ceil_div64(B, 256), 256, 0, stream, B, first, stride, ray_pix, ray_gid, cap,
+            H, W, make_cam(h_K), poses, images, rays_o, rays_d, target, leaf_gid);
+  return 0;
+}
+
+}  // extern "C"

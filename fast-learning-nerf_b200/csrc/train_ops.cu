@@ -1,0 +1,324 @@
+// train_ops.cu -- loss (+ per-leaf max table), Adam, and the GPU-resident quadtree ray selector.
+// Reference: run_nerf_helpers.py:9 (img2mse), run_nerf.py:99,482-502 (loss, Adam),
+// tree.py:17-94 (QuadTree), :569-626 (gen_rays_v3_1_subThread), :533-557,629-652 (adjust_tree).
+#include "common.cuh"
+#include <math.h>
+
+namespace {
+
+// ------------------------------------------------------------------------------------------------
+// a9 + a13 accumulation.  One block (deterministic sums); B*3 elements is tiny next to the MLP.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024)
+mse_leafmax_kernel(int64_t B, const float *__restrict__ rgb, const float *__restrict__ rgb0,
+                   const float *__restrict__ target, float inv_count, const int32_t *__restrict__ leaf_gid,
+                   float *__restrict__ loss_out, float *__restrict__ d_rgb, float *__restrict__ d_rgb0,
+                   float *__restrict__ leaf_max) {
+  __shared__ float red[2][32];
+  float s_f = 0.f, s_c = 0.f;
+  for (int64_t r = threadIdx.x; r < B; r += blockDim.x) {
+    float mx = 0.f;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      float t = target[r * 3 + c];
+      float df = rgb[r * 3 + c] - t;
+      s_f += df * df;
+      if (d_rgb) d_rgb[r * 3 + c] = 2.0f * df * inv_count;
+      mx = fmaxf(mx, fabsf(t - rgb[r * 3 + c]));  // |gt - pred| (tree.py:538), max over channels (:642)
+      if (rgb0) {
+        float dc = rgb0[r * 3 + c] - t;
+        s_c += dc * dc;
+        if (d_rgb0) d_rgb0[r * 3 + c] = 2.0f * dc * inv_count;
+      }
+    }
+    if (leaf_gid && leaf_max) {
+      int g = leaf_gid[r];
+      // non-negative floats order like their int patterns; the table is initialised to -1.0f
+      if (g >= 0) atomicMax(reinterpret_cast<int *>(leaf_max) + g, __float_as_int(mx));
+    }
+  }
+  int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    s_f += __shfl_xor_sync(0xffffffffu, s_f, o);
+    s_c += __shfl_xor_sync(0xffffffffu, s_c, o);
+  }
+  if (lane == 0) { red[0][w] = s_f; red[1][w] = s_c; }
+  __syncthreads();
+  if (w == 0) {
+    s_f = lane < (int)(blockDim.x >> 5) ? red[0][lane] : 0.f;
+    s_c = lane < (int)(blockDim.x >> 5) ? red[1][lane] : 0.f;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      s_f += __shfl_xor_sync(0xffffffffu, s_f, o);
+      s_c += __shfl_xor_sync(0xffffffffu, s_c, o);
+    }
+    if (lane == 0) {
+      loss_out[0] = s_f * inv_count;
+      loss_out[1] = s_c * inv_count;
+    }
+  }
+}
+
+// torch.optim.Adam single-tensor update order (exp_avg.lerp, exp_avg_sq.mul.addcmul, sqrt/bc2_sqrt + eps, addcdiv)
+__global__ void adam_kernel(int64_t n, float *__restrict__ p, float *__restrict__ m, float *__restrict__ v,
+                            const float *__restrict__ g, float omb1, float b2, float omb2, float eps, float step_size,
+                            float bc2_sqrt) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float gi = g[i];
+  float mi = m[i] + (gi - m[i]) * omb1;
+  float vi = v[i] * b2 + omb2 * gi * gi;
+  m[i] = mi;
+  v[i] = vi;
+  float den = sqrtf(vi) / bc2_sqrt + eps;
+  p[i] = p[i] - step_size * (mi / den);
+}
+
+// ------------------------------------------------------------------------------------------------
+// quadtree
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void child_box(const double b[4], int q, double out[4]) {
+  // tree.py:61-72: TL (x0,y0,mx,my), (mx,y0,x1,my), (x0,my,mx,y1), (mx,my,x1,y1)
+  double mx = (b[0] + b[2]) / 2, my = (b[1] + b[3]) / 2;
+  out[0] = (q & 1) ? mx : b[0];
+  out[2] = (q & 1) ? b[2] : mx;
+  out[1] = (q & 2) ? my : b[1];
+  out[3] = (q & 2) ? b[3] : my;
+}
+
+__global__ void qt_init_kernel(int n_images, int cap, int H, int W, int levels, int leaves, double *__restrict__ boxes,
+                               int32_t *__restrict__ count, double *__restrict__ min_area) {
+  int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (int64_t)n_images * leaves) return;
+  int img = (int)(idx / leaves), j = (int)(idx % leaves);
+  double b[4] = {0.0, 0.0, (double)H, (double)W}, c[4];
+  for (int l = levels - 1; l >= 0; --l) {  // most significant base-4 digit = first split (DFS order)
+    child_box(b, (j >> (2 * l)) & 3, c);
+    b[0] = c[0]; b[1] = c[1]; b[2] = c[2]; b[3] = c[3];
+  }
+  double *o = boxes + ((int64_t)img * cap + j) * 4;
+  o[0] = b[0]; o[1] = b[1]; o[2] = b[2]; o[3] = b[3];
+  if (j == 0) {
+    count[img] = leaves;
+    min_area[img] = (double)H * (double)W / (double)leaves;  // tree.py:94
+  }
+}
+
+// block-wide exclusive scan of one int per thread (blockDim.x = 256)
+__device__ __forceinline__ int block_excl_scan(int v, int *total, int *s_warp) {
+  int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  int incl = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    int t = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += t;
+  }
+  if (lane == 31) s_warp[w] = incl;
+  __syncthreads();
+  if (w == 0) {
+    int x = lane < (int)(blockDim.x >> 5) ? s_warp[lane] : 0;
+    int xi = x;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      int t = __shfl_up_sync(0xffffffffu, xi, o);
+      if (lane >= o) xi += t;
+    }
+    s_warp[lane] = xi - x;  // exclusive warp offsets
+    if (lane == 31) s_warp[32] = xi;
+  }
+  __syncthreads();
+  int res = s_warp[w] + incl - v;
+  *total = s_warp[32];
+  __syncthreads();
+  return res;
+}
+
+// one block per image
+__global__ void __launch_bounds__(256)
+qt_refine_kernel(int cap, const double *__restrict__ boxes_in, const int32_t *__restrict__ count_in,
+                 double *__restrict__ min_area, const float *__restrict__ leaf_max, float thres,
+                 double *__restrict__ boxes_out, int32_t *__restrict__ count_out) {
+  __shared__ int s_warp[33];
+  __shared__ int s_any;
+  int img = blockIdx.x;
+  int n = count_in[img];
+  double ma = min_area[img];
+  const double *bi = boxes_in + (int64_t)img * cap * 4;
+  double *bo = boxes_out + (int64_t)img * cap * 4;
+  if (threadIdx.x == 0) s_any = 0;
+  __syncthreads();
+  int base_out = 0;
+  for (int base = 0; base < n; base += blockDim.x) {
+    int j = base + threadIdx.x;
+    double b[4] = {0, 0, 0, 0};
+    int split = 0;
+    if (j < n) {
+      b[0] = bi[j * 4]; b[1] = bi[j * 4 + 1]; b[2] = bi[j * 4 + 2]; b[3] = bi[j * 4 + 3];
+      double area = (b[2] - b[0]) * (b[3] - b[1]);
+      // tree.py:642-646: loss.max() > thres (fp32 compare) and area == minArea (float equality)
+      split = (leaf_max[(int64_t)img * cap + j] > thres) && (area == ma);
+    }
+    int total;
+    int pos = base_out + block_excl_scan(j < n ? (split ? 4 : 1) : 0, &total, s_warp);
+    if (j < n) {
+      if (split) {
+        s_any = 1;
+        for (int q = 0; q < 4; ++q) {
+          if (pos + q < cap) child_box(b, q, bo + (int64_t)(pos + q) * 4);
+        }
+      } else if (pos < cap) {
+        bo[pos * 4] = b[0]; bo[pos * 4 + 1] = b[1]; bo[pos * 4 + 2] = b[2]; bo[pos * 4 + 3] = b[3];
+      }
+    }
+    base_out += total;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    count_out[img] = min(base_out, cap);
+    if (s_any) min_area[img] = ma / 4;  // tree.py:649-650 (once per tree per adjust)
+  }
+}
+
+// single block: per-leaf ray counts + exclusive scan over all (image, leaf) slots
+__global__ void __launch_bounds__(256)
+qt_count_kernel(int n_images, int cap, const double *__restrict__ boxes, const int32_t *__restrict__ count,
+                const double *__restrict__ min_area, double rays_per_pixel, int64_t *__restrict__ ray_offset) {
+  __shared__ int s_warp[33];
+  int64_t running = 0;
+  int64_t slots = (int64_t)n_images * cap;
+  for (int64_t base = 0; base < slots; base += blockDim.x) {
+    int64_t s = base + threadIdx.x;
+    int c = 0;
+    if (s < slots) {
+      int img = (int)(s / cap), j = (int)(s % cap);
+      if (j < count[img]) {
+        const double *b = boxes + s * 4;
+        double area = (b[2] - b[0]) * (b[3] - b[1]);
+        c = (area > min_area[img] + 0.01) ? 10 : (int)(area * rays_per_pixel);  // tree.py:578-581
+      }
+    }
+    int total;
+    int ex = block_excl_scan(c, &total, s_warp);
+    if (s < slots) ray_offset[s] = running + ex;
+    running += total;
+  }
+  if (threadIdx.x == 0) ray_offset[slots] = running;
+}
+
+__device__ __forceinline__ uint32_t mix32(uint32_t x) {
+  x ^= x >> 16; x *= 0x7feb352dU; x ^= x >> 15; x *= 0x846ca68bU; x ^= x >> 16;
+  return x;
+}
+// keyed bijection of [0,N): balanced Feistel network on 2*half bits + cycle walking
+__host__ __device__ inline uint64_t feistel_perm(uint64_t j, uint64_t N, int half, uint64_t seed) {
+  uint64_t mask = (1ull << half) - 1;
+  uint64_t x = j;
+  do {
+    uint32_t L = (uint32_t)(x >> half), R = (uint32_t)(x & mask);
+#pragma unroll
+    for (int r = 0; r < 6; ++r) {
+      uint32_t k = (uint32_t)(seed >> ((r & 1) * 32)) + 0x9E3779B9u * (uint32_t)(r + 1);
+      uint32_t f = R * 0x85EBCA6Bu + k;
+      f ^= f >> 16; f *= 0x7feb352dU; f ^= f >> 15; f *= 0x846ca68bU; f ^= f >> 16;
+      uint32_t nl = R;
+      R = (L ^ f) & (uint32_t)mask;
+      L = nl;
+    }
+    x = ((uint64_t)L << half) | R;
+  } while (x >= N);
+  return x;
+}
+
+__global__ void qt_emit_kernel(int n_images, int cap, int W, const double *__restrict__ boxes,
+                               const int64_t *__restrict__ ray_offset, int64_t N, int half, uint64_t seed,
+                               int32_t *__restrict__ ray_pix, int32_t *__restrict__ ray_gid) {
+  int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= N) return;
+  // slot = last s with ray_offset[s] <= j  (empty slots have equal offsets, upper bound skips them)
+  int64_t lo = 0, hi = (int64_t)n_images * cap;
+  while (hi - lo > 1) {
+    int64_t mid = (lo + hi) >> 1;
+    if (ray_offset[mid] <= j) lo = mid; else hi = mid;
+  }
+  const double *b = boxes + lo * 4;
+  // tree.py:598-599: x ~ randint[ceil(x0), ceil(x1)), y ~ randint[ceil(y0), ceil(y1-0.01)), with replacement
+  int x_lo = (int)ceil(b[0]), x_hi = (int)ceil(b[2]);
+  int y_lo = (int)ceil(b[1]), y_hi = (int)ceil(b[3] - 0.01);
+  uint32_t r[4];
+  philox4x32(seed, (uint64_t)j, 0x9E17ull, r);
+  int row = x_lo + (int)(r[0] % (uint32_t)max(1, x_hi - x_lo));
+  int col = y_lo + (int)(r[1] % (uint32_t)max(1, y_hi - y_lo));
+  int64_t pos = (int64_t)feistel_perm((uint64_t)j, (uint64_t)N, half, seed ^ 0xA5A5A5A55A5A5A5Aull);
+  ray_pix[pos] = row * W + col;
+  ray_gid[pos] = (int32_t)lo;
+}
+
+}  // namespace
+
+extern "C" {
+
+int flnerf_mse_leafmax(flnerf_ctx *ctx, int64_t B, const float *rgb, const float *rgb0, const float *target,
+                       int64_t denom, const int32_t *leaf_gid, float *loss_out, float *d_rgb, float *d_rgb0,
+                       float *leaf_max, void *stream) {
+  FL_REQUIRE(ctx && rgb && target && loss_out && denom > 0 && B >= 0, "flnerf_mse_leafmax: bad arguments");
+  float inv = (float)(1.0 / (3.0 * (double)denom));
+  FL_LAUNCH(mse_leafmax_kernel, 1, 1024, 0, stream, B, rgb, rgb0, target, inv, leaf_gid, loss_out, d_rgb, d_rgb0,
+            leaf_max);
+  return 0;
+}
+
+int flnerf_adam_step(flnerf_ctx *ctx, int64_t n, float *param, float *m, float *v, const float *grad, double lr,
+                     double b1, double b2, double eps, int64_t t, void *stream) {
+  FL_REQUIRE(ctx && param && m && v && grad && n >= 0 && t >= 1, "flnerf_adam_step: bad arguments");
+  if (n == 0) return 0;
+  double bc1 = 1.0 - pow(b1, (double)t), bc2 = 1.0 - pow(b2, (double)t);
+  FL_LAUNCH(adam_kernel, (unsigned)ceil_div64(n, 256), 256, 0, stream, n, param, m, v, grad, (float)(1.0 - b1),
+            (float)b2, (float)(1.0 - b2), (float)eps, (float)(lr / bc1), (float)sqrt(bc2));
+  return 0;
+}
+
+int flnerf_qt_init(flnerf_ctx *ctx, int n_images, int cap, int H, int W, int max_depth, double *boxes, int32_t *count,
+                   double *min_area, void *stream) {
+  FL_REQUIRE(ctx && boxes && count && min_area && n_images > 0 && max_depth >= 1 && max_depth <= 12,
+             "flnerf_qt_init: bad arguments");
+  int levels = max_depth - 1;
+  int leaves = 1 << (2 * levels);
+  FL_REQUIRE(leaves <= cap, "flnerf_qt_init: capacity %d < %d leaves", cap, leaves);
+  FL_LAUNCH(qt_init_kernel, (unsigned)ceil_div64((int64_t)n_images * leaves, 256), 256, 0, stream, n_images, cap, H, W,
+            levels, leaves, boxes, count, min_area);
+  return 0;
+}
+
+int flnerf_qt_refine(flnerf_ctx *ctx, int n_images, int cap, const double *boxes_in, const int32_t *count_in,
+                     double *min_area, const float *leaf_max, float thres, double *boxes_out, int32_t *count_out,
+                     void *stream) {
+  FL_REQUIRE(ctx && boxes_in && count_in && min_area && leaf_max && boxes_out && count_out && boxes_in != boxes_out,
+             "flnerf_qt_refine: bad arguments");
+  FL_LAUNCH(qt_refine_kernel, n_images, 256, 0, stream, cap, boxes_in, count_in, min_area, leaf_max, thres, boxes_out,
+            count_out);
+  return 0;
+}
+
+int flnerf_qt_count(flnerf_ctx *ctx, int n_images, int cap, const double *boxes, const int32_t *count,
+                    const double *min_area, double rays_per_pixel, int64_t *ray_offset, void *stream) {
+  FL_REQUIRE(ctx && boxes && count && min_area && ray_offset, "flnerf_qt_count: bad arguments");
+  FL_LAUNCH(qt_count_kernel, 1, 256, 0, stream, n_images, cap, boxes, count, min_area, rays_per_pixel, ray_offset);
+  return 0;
+}
+
+int flnerf_qt_emit(flnerf_ctx *ctx, int n_images, int cap, int W, const double *boxes, const int32_t *count,
+                   const int64_t *ray_offset, int64_t n_rays, uint64_t seed, int32_t *ray_pix, int32_t *ray_gid,
+                   void *stream) {
+  (void)count;
+  FL_REQUIRE(ctx && boxes && ray_offset && ray_pix && ray_gid && n_rays >= 0, "flnerf_qt_emit: bad arguments");
+  if (n_rays == 0) return 0;
+  int bits = 2;
+  while ((1ull << bits) < (uint64_t)n_rays) ++bits;
+  int half = (bits + 1) / 2;
+  FL_LAUNCH(qt_emit_kernel, (unsigned)ceil_div64(n_rays, 256), 256, 0, stream, n_images, cap, W, boxes, ray_offset,
+            n_rays, half, seed, ray_pix, ray_gid);
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,170 @@
+"""Host-side runtime of the training hot loop (run_nerf.py:470-516): one call = render coarse+fine, both
+MSE losses, backward, (gradient all-reduce), Adam -- as a straight sequence of libflnerf.so kernels with no
+autograd graph, no per-iteration D2H copy and no host synchronisation.  ``FusedAdam`` keeps
+torch.optim.Adam's state_dict format (checkpoints stay interchangeable with the reference).
+"""
+import math
+from typing import List, Optional
+
+import torch
+
+from . import ops
+from .lib import MLP_PARAMS, FlnerfError
+
+
+def share_grad_bucket(nets) -> torch.Tensor:
+    """Puts the flat gradients of all nets into ONE contiguous fp32 bucket so that data parallelism needs a
+    single NCCL all-reduce per step."""
+    dev = nets[0].flat_parameters().device
+    bucket = torch.zeros(len(nets) * MLP_PARAMS, dtype=torch.float32, device=dev)
+    for i, net in enumerate(nets):
+        net._ensure_flat()
+        net._flat_grad = bucket[i * MLP_PARAMS:(i + 1) * MLP_PARAMS]
+        off = 0
+        for p in net.parameters():
+            n = p.numel()
+            p.grad = net._flat_grad[off:off + n].view(p.shape)
+            off += n
+    return bucket
+
+
+class FusedAdam(torch.optim.Adam):
+    """torch.optim.Adam(lr, betas, eps=1e-8) (run_nerf.py:99) whose step() is one fused kernel per net over the
+    flat parameter / gradient / moment buffers.  state_dict()/load_state_dict() are the stock ones: exp_avg and
+    exp_avg_sq of every parameter are views into the flat moment buffers."""
+
+    def __init__(self, params, nets, lr=5e-4, betas=(0.9, 0.999), eps=1e-8):
+        super().__init__(params, lr=lr, betas=betas, eps=eps)
+        self._nets = list(nets)
+        self._m, self._v, self._step = {}, {}, {}
+        self._bind()
+
+    def _bind(self):
+        for net in self._nets:
+            flat = net.flat_parameters()
+            m = self._m.get(id(net))
+            if m is None or m.device != flat.device:
+                m, v = torch.zeros_like(flat), torch.zeros_like(flat)
+                self._m[id(net)], self._v[id(net)] = m, v
+            else:
+                v = self._v[id(net)]
+            step = None
+            off = 0
+            for p in net.parameters():
+                n = p.numel()
+                st = self.state[p]
+                if "exp_avg" in st and st["exp_avg"].data_ptr() != m[off:off + n].data_ptr():
+                    m[off:off + n].copy_(st["exp_avg"].reshape(-1))
+                    v[off:off + n].copy_(st["exp_avg_sq"].reshape(-1))
+                if step is None:
+                    step = st.get("step", torch.tensor(0.0))
+                    step = step.detach().cpu().float() if torch.is_tensor(step) else torch.tensor(float(step))
+                st["exp_avg"] = m[off:off + n].view(p.shape)
+                st["exp_avg_sq"] = v[off:off + n].view(p.shape)
+                st["step"] = step
+                off += n
+            self._step[id(net)] = step
+
+    def load_state_dict(self, state_dict):
+        super().load_state_dict(state_dict)
+        self._bind()
+
+    def zero_grad(self, set_to_none: bool = True):
+        for net in self._nets:
+            net._grad_bucket().zero_()
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        g = self.param_groups[0]
+        b1, b2 = g["betas"]
+        for net in self._nets:
+            step = self._step[id(net)]
+            step += 1
+            ops.adam_step(net.flat_parameters(), self._m[id(net)], self._v[id(net)], net._grad_bucket(), float(g["lr"]),
+                          b1, b2, g["eps"], int(step.item()))
+            net.weights_version += 1
+
+
+class Trainer:
+    """The fused training step.  Rays come either from the caller (``step``) or from the GPU-resident quadtree
+    index buffer (``step_from_tree``)."""
+
+    def __init__(self, net_coarse, net_fine, optimizer: FusedAdam, H, W, K, near, far, N_samples=64, N_importance=128,
+                 white_bkgd=True, perturb=1.0, lindisp=False, ndc=False, raw_noise_std=0.0, seed=0, world_size=1,
+                 rank=0):
+        if N_importance <= 0 or net_fine is None:
+            raise FlnerfError("Trainer implements the coarse+fine loop (N_importance > 0), like run_nerf.train()")
+        self.nc, self.nf, self.opt = net_coarse, net_fine, optimizer
+        self.H, self.W, self.K = int(H), int(W), K
+        self.near, self.far = float(near), float(far)
+        self.Nc, self.Nf = int(N_samples), int(N_importance)
+        self.white, self.perturb, self.lindisp, self.ndc = bool(white_bkgd), float(perturb), bool(lindisp), bool(ndc)
+        self.noise_std = float(raw_noise_std)
+        self.seed, self.calls = int(seed), 0
+        self.world, self.rank = int(world_size), int(rank)
+        self.bucket = share_grad_bucket([net_coarse, net_fine])
+        self.last = {}
+
+    # -- one MLP evaluation over [B,S] samples without autograd
+    def _forward_net(self, net, rays11, z):
+        B, S = z.shape
+        flat, packed = net._weights()
+        if net.mode == ops.MODE_FP32:
+            x, dirpe = ops.encode_f32(rays11, z), None
+        else:
+            x, dirpe = ops.encode_tc(rays11, z)
+        raw, stash = ops.mlp_forward(net.mode, flat, packed, x, dirpe, B * S, S, True)
+        return raw, (x, dirpe, stash)
+
+    def _backward_net(self, net, saved, draw, n, S):
+        x, dirpe, stash = saved
+        flat, packed = net._weights()
+        ops.mlp_backward(net.mode, flat, packed, x, dirpe, stash, draw, net._flat_grad, n, S)
+
+    @torch.no_grad()
+    def step(self, rays_o, rays_d, target, leaf_gid=None, leaf_max=None, global_batch: Optional[int] = None):
+        """Returns loss[2] = (fine mse, coarse mse) as a DEVICE tensor (no sync)."""
+        B = rays_o.shape[0]
+        Nc, Nf = self.Nc, self.Nf
+        rays11 = ops.pack_rays(rays_o, rays_d, self.near, self.far, self.ndc, self.H, self.W, float(self.K[0][0]))
+        off = self.calls
+        self.calls += B * (Nc + Nf)
+        z_c = ops.coarse_depths(rays11, Nc, self.perturb > 0, self.lindisp, None, self.seed, off)
+        noise_c = noise_f = None
+        if self.noise_std > 0:
+            noise_c = torch.randn(B, Nc, device=rays11.device) * self.noise_std
+            noise_f = torch.randn(B, Nc + Nf, device=rays11.device) * self.noise_std
+        raw_c, sv_c = self._forward_net(self.nc, rays11, z_c)
+        rgb0, _, _, w_c, _ = ops.composite_forward(raw_c, z_c, rays11[:, 3:6], noise_c, self.white, rays_d_stride=11)
+        z_f, _, _ = ops.sample_pdf_merge(z_c, w_c, Nf, self.perturb == 0, None, self.seed + 1, off, want_samples=False)
+        raw_f, sv_f = self._forward_net(self.nf, rays11, z_f)
+        rgb, disp, acc, _, _ = ops.composite_forward(raw_f, z_f, rays11[:, 3:6], noise_f, self.white, rays_d_stride=11,
+                                                     want_weights=False)
+        denom = int(global_batch) if global_batch is not None else B * self.world
+        loss, d_rgb, d_rgb0 = ops.mse_leafmax(rgb, rgb0, target, denom, leaf_gid, leaf_max)
+        self.opt.zero_grad()
+        draw_f = ops.composite_backward(raw_f, z_f, rays11[:, 3:6], noise_f, self.white, d_rgb, None, None, None,
+                                        rays_d_stride=11)
+        self._backward_net(self.nf, sv_f, draw_f, B * (Nc + Nf), Nc + Nf)
+        draw_c = ops.composite_backward(raw_c, z_c, rays11[:, 3:6], noise_c, self.white, d_rgb0, None, None, None,
+                                        rays_d_stride=11)
+        self._backward_net(self.nc, sv_c, draw_c, B * Nc, Nc)
+        if self.world > 1:
+            torch.distributed.all_reduce(self.bucket)       # the ONE collective of the step
+        self.opt.step()
+        self.last = {"rgb": rgb, "rgb0": rgb0, "disp": disp, "acc": acc}
+        return loss
+
+    @torch.no_grad()
+    def step_from_tree(self, mgr, first, n_rand):
+        """One batch of ``n_rand`` rows of the quadtree index buffer starting at ``first``; under data parallelism
+        rank r consumes rows first + r, first + r + world, ... (every rank holds the same index buffer)."""
+        rows = min(n_rand, mgr.n_rays - first)
+        local = (rows - self.rank + self.world - 1) // self.world
+        o, d, tgt, gid = mgr.batch(first + self.rank, local, self.world)
+        return self.step(o, d, tgt, gid, mgr.leaf_max, global_batch=rows)
+
+
+def lr_at(lrate, lrate_decay, global_iter):
+    """run_nerf.py:498-502"""
+    return lrate * (0.1 ** (global_iter / (lrate_decay * 1000)))

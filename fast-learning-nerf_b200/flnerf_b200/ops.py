@@ -1,0 +1,273 @@
+"""Thin torch-facing wrappers over the C ABI: torch owns device memory and streams, libflnerf.so does
+the arithmetic.  Every function here launches hand-written sm_100a kernels; nothing falls back to
+torch math.  Autograd is provided for the two differentiable stages of the reference render loop
+(the MLP query and raw2outputs); everything else is data (render.py:281 detaches the samples).
+"""
+import ctypes as C
+from typing import Optional, Tuple
+
+import numpy as np
+import torch
+
+from . import lib as L
+
+MODE_FP32, MODE_BF16 = L.MODE_FP32, L.MODE_BF16
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ctx(t: torch.Tensor):
+    if not t.is_cuda:
+        raise L.FlnerfError("flnerf ops need CUDA tensors (got %s); there is no CPU fallback" % t.device)
+    return C.c_void_p(L.context(t.device.index if t.device.index is not None else torch.cuda.current_device()))
+
+
+def _f32c(t: torch.Tensor) -> torch.Tensor:
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def _alloc_bytes(nbytes: int, device) -> torch.Tensor:
+    """1 KB-aligned byte buffer (torch's caching allocator hands out 512-byte aligned blocks)."""
+    buf = torch.empty(int(nbytes) + 1024, dtype=torch.uint8, device=device)
+    off = (-buf.data_ptr()) % 1024
+    return buf[off:off + int(nbytes)]
+
+
+# ------------------------------------------------------------------------------------------ rays
+def raygen(H: int, W: int, K, c2w: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    """get_rays (run_nerf_helpers.py:68-78)."""
+    dev = c2w.device
+    o = torch.empty(H, W, 3, dtype=torch.float32, device=dev)
+    d = torch.empty(H, W, 3, dtype=torch.float32, device=dev)
+    Kh = (C.c_double * 9)(*[float(K[i][j]) for i in range(3) for j in range(3)])
+    Ph = (C.c_float * 12)(*c2w[:3, :4].detach().float().cpu().reshape(-1).tolist())
+    L.check(L.load().flnerf_raygen(_ctx(o), H, W, Kh, Ph, _ptr(o), _ptr(d), _stream()), "flnerf_raygen")
+    return o, d
+
+
+def pack_rays(rays_o, rays_d, near: float, far: float, ndc: bool, H: int, W: int, focal: float) -> torch.Tensor:
+    """ndc_rays + [o,d,near,far,viewdir] packing (run_nerf_helpers.py:91-108, render.py:59-80)."""
+    o, d = _f32c(rays_o.reshape(-1, 3)), _f32c(rays_d.reshape(-1, 3))
+    B = o.shape[0]
+    out = torch.empty(B, 11, dtype=torch.float32, device=o.device)
+    L.check(L.load().flnerf_pack_rays(_ctx(o), B, _ptr(o), _ptr(d), float(near), float(far), int(bool(ndc)), int(H),
+                                      int(W), float(focal), _ptr(out), _stream()), "flnerf_pack_rays")
+    return out
+
+
+_TVALS = {}
+
+
+def _t_vals(n: int, device) -> torch.Tensor:
+    key = (n, str(device))
+    if key not in _TVALS:
+        _TVALS[key] = torch.linspace(0.0, 1.0, steps=n).to(device)   # render.py:244 (host, bit-identical to torch)
+    return _TVALS[key]
+
+
+def coarse_depths(rays11, n_samples: int, perturb: bool, lindisp: bool, t_rand=None, seed: int = 0, offset: int = 0):
+    """render.py:244-266."""
+    B = rays11.shape[0]
+    z = torch.empty(B, n_samples, dtype=torch.float32, device=rays11.device)
+    tr = None if t_rand is None else _f32c(t_rand)
+    L.check(L.load().flnerf_coarse_depths(_ctx(z), B, n_samples, _ptr(rays11), _ptr(_t_vals(n_samples, z.device)),
+                                          _ptr(tr), int(bool(perturb)), int(bool(lindisp)), seed, offset, _ptr(z),
+                                          _stream()), "flnerf_coarse_depths")
+    return z
+
+
+def posenc(x: torch.Tensor, n_freq: int) -> torch.Tensor:
+    """Embedder.embed (run_nerf_helpers.py:15-45) for 3-vectors."""
+    shp = x.shape
+    xf = _f32c(x.reshape(-1, 3))
+    out = torch.empty(xf.shape[0], 3 + 6 * n_freq, dtype=torch.float32, device=x.device)
+    L.check(L.load().flnerf_posenc(_ctx(xf), xf.shape[0], n_freq, _ptr(xf), _ptr(out), _stream()), "flnerf_posenc")
+    return out.reshape(*shp[:-1], 3 + 6 * n_freq)
+
+
+def encode_f32(rays11, z) -> torch.Tensor:
+    B, S = z.shape
+    x = torch.empty(B * S, 90, dtype=torch.float32, device=z.device)
+    L.check(L.load().flnerf_encode_f32(_ctx(z), B, S, _ptr(rays11), _ptr(z), _ptr(x), _stream()), "flnerf_encode_f32")
+    return x
+
+
+def padded_rows(n: int) -> int:
+    return (n + 255) // 256 * 256
+
+
+def encode_tc(rays11, z):
+    B, S = z.shape
+    tiles = _alloc_bytes(padded_rows(B * S) // 128 * 16384, z.device)
+    dirpe = torch.empty(B, 32, dtype=torch.float32, device=z.device)
+    L.check(L.load().flnerf_encode_tc(_ctx(z), B, S, _ptr(rays11), _ptr(z), _ptr(tiles), _ptr(dirpe), _stream()),
+            "flnerf_encode_tc")
+    return tiles, dirpe
+
+
+def pack_x90(x90):
+    n = x90.shape[0]
+    tiles = _alloc_bytes(padded_rows(n) // 128 * 16384, x90.device)
+    dirpe = torch.empty(n, 32, dtype=torch.float32, device=x90.device)
+    L.check(L.load().flnerf_pack_x90(_ctx(x90), n, _ptr(x90), _ptr(tiles), _ptr(dirpe), _stream()), "flnerf_pack_x90")
+    return tiles, dirpe
+
+
+# ------------------------------------------------------------------------------------------ MLP
+def mlp_pack_weights(flat_params: torch.Tensor, packed: Optional[torch.Tensor] = None) -> torch.Tensor:
+    if packed is None:
+        packed = _alloc_bytes(L.load().flnerf_mlp_packed_bytes(), flat_params.device)
+    L.check(L.load().flnerf_mlp_pack_weights(_ctx(flat_params), _ptr(flat_params), _ptr(packed), _stream()),
+            "flnerf_mlp_pack_weights")
+    return packed
+
+
+def mlp_forward(mode, flat_params, packed, x, dirpe, n: int, S: int, training: bool):
+    """Returns (raw[n,4], stash)."""
+    dev = flat_params.device
+    raw = torch.empty(n, 4, dtype=torch.float32, device=dev)
+    stash = _alloc_bytes(L.load().flnerf_mlp_stash_bytes(mode, n, S, int(training)), dev)
+    L.check(L.load().flnerf_mlp_forward(_ctx(raw), mode, _ptr(flat_params), _ptr(packed), n, S, _ptr(x), _ptr(dirpe),
+                                        _ptr(raw), _ptr(stash), int(training), _stream()), "flnerf_mlp_forward")
+    return raw, stash
+
+
+def mlp_backward(mode, flat_params, packed, x, dirpe, stash, draw, flat_grad, n: int, S: int):
+    """flat_grad += dL/dparams."""
+    ws_bytes = L.load().flnerf_mlp_bwd_workspace_bytes(mode, n)
+    ws = _alloc_bytes(ws_bytes, flat_params.device)
+    draw = _f32c(draw.reshape(n, 4))
+    L.check(L.load().flnerf_mlp_backward(_ctx(draw), mode, _ptr(flat_params), _ptr(packed), n, S, _ptr(x), _ptr(dirpe),
+                                         _ptr(stash), _ptr(draw), _ptr(flat_grad), _ptr(ws), ws_bytes, _stream()),
+            "flnerf_mlp_backward")
+
+
+# ------------------------------------------------------------------------------------------ compositing
+def composite_forward(raw, z, rays_d, noise, white_bkgd: bool, rays_d_stride: int = 3, want_weights: bool = True):
+    B, S = z.shape
+    dev = z.device
+    rgb = torch.empty(B, 3, dtype=torch.float32, device=dev)
+    disp = torch.empty(B, dtype=torch.float32, device=dev)
+    acc = torch.empty(B, dtype=torch.float32, device=dev)
+    depth = torch.empty(B, dtype=torch.float32, device=dev)
+    w = torch.empty(B, S, dtype=torch.float32, device=dev) if want_weights else None
+    L.check(L.load().flnerf_composite_forward(_ctx(z), B, S, _ptr(raw), _ptr(z), _ptr(rays_d), rays_d_stride,
+                                              _ptr(noise), int(bool(white_bkgd)), _ptr(rgb), _ptr(disp), _ptr(acc),
+                                              _ptr(depth), _ptr(w), _stream()), "flnerf_composite_forward")
+    return rgb, disp, acc, w, depth
+
+
+def composite_backward(raw, z, rays_d, noise, white_bkgd, g_rgb, g_disp, g_acc, g_depth, rays_d_stride: int = 3):
+    B, S = z.shape
+    draw = torch.empty(B, S, 4, dtype=torch.float32, device=z.device)
+    gs = [None if g is None else _f32c(g) for g in (g_rgb, g_disp, g_acc, g_depth)]
+    L.check(L.load().flnerf_composite_backward(_ctx(z), B, S, _ptr(raw), _ptr(z), _ptr(rays_d), rays_d_stride,
+                                               _ptr(noise), int(bool(white_bkgd)), _ptr(gs[0]), _ptr(gs[1]),
+                                               _ptr(gs[2]), _ptr(gs[3]), _ptr(draw), _stream()),
+            "flnerf_composite_backward")
+    return draw
+
+
+class CompositeFn(torch.autograd.Function):
+    """raw2outputs (render.py:149-192) with the analytic backward of SURVEY appendix A.2."""
+
+    @staticmethod
+    def forward(ctx, raw, z, rays_d, noise, white_bkgd):
+        raw, z, rays_d = _f32c(raw), _f32c(z), _f32c(rays_d)
+        noise = None if noise is None else _f32c(noise)
+        rgb, disp, acc, w, depth = composite_forward(raw, z, rays_d, noise, white_bkgd)
+        ctx.save_for_backward(raw, z, rays_d, noise)
+        ctx.white = bool(white_bkgd)
+        ctx.mark_non_differentiable(w)     # only consumed by sample_pdf, which the reference detaches
+        return rgb, disp, acc, w, depth
+
+    @staticmethod
+    def backward(ctx, g_rgb, g_disp, g_acc, g_w, g_depth):
+        raw, z, rays_d, noise = ctx.saved_tensors
+        draw = composite_backward(raw, z, rays_d, noise, ctx.white, g_rgb, g_disp, g_acc, g_depth)
+        return draw, None, None, None, None
+
+
+def sample_pdf_merge(z, weights, n_fine: int, det: bool, u=None, seed: int = 0, offset: int = 0, want_samples=True):
+    """sample_pdf + sort-merge + z_std (run_nerf_helpers.py:112-155, render.py:279-284,299)."""
+    B, Nc = z.shape
+    dev = z.device
+    merged = torch.empty(B, Nc + n_fine, dtype=torch.float32, device=dev)
+    zs = torch.empty(B, n_fine, dtype=torch.float32, device=dev) if want_samples else None
+    zstd = torch.empty(B, dtype=torch.float32, device=dev)
+    uu = None if u is None else _f32c(u)
+    L.check(L.load().flnerf_sample_pdf_merge(_ctx(z), B, Nc, n_fine, _ptr(_f32c(z)), _ptr(_f32c(weights)), _ptr(uu),
+                                             int(bool(det)), seed, offset, _ptr(merged), _ptr(zs), _ptr(zstd),
+                                             _stream()), "flnerf_sample_pdf_merge")
+    return merged, zs, zstd
+
+
+def sample_pdf_bins(bins, weights, n_samples: int, det: bool, u=None, seed: int = 0, offset: int = 0):
+    """sample_pdf on explicit bins (run_nerf_helpers.py:112-155)."""
+    B, nb = bins.shape
+    out = torch.empty(B, n_samples, dtype=torch.float32, device=bins.device)
+    uu = None if u is None else _f32c(u)
+    L.check(L.load().flnerf_sample_pdf(_ctx(bins), B, nb, n_samples, _ptr(_f32c(bins)), _ptr(_f32c(weights)), _ptr(uu),
+                                       int(bool(det)), seed, offset, _ptr(out), _stream()), "flnerf_sample_pdf")
+    return out
+
+
+# ------------------------------------------------------------------------------------------ loss / optimiser
+def mse_leafmax(rgb, rgb0, target, denom: int, leaf_gid=None, leaf_max=None, want_grads=True):
+    B = rgb.shape[0]
+    dev = rgb.device
+    loss = torch.empty(2, dtype=torch.float32, device=dev)
+    d_rgb = torch.empty(B, 3, dtype=torch.float32, device=dev) if want_grads else None
+    d_rgb0 = torch.empty(B, 3, dtype=torch.float32, device=dev) if (want_grads and rgb0 is not None) else None
+    L.check(L.load().flnerf_mse_leafmax(_ctx(rgb), B, _ptr(_f32c(rgb)), _ptr(None if rgb0 is None else _f32c(rgb0)),
+                                        _ptr(_f32c(target)), int(denom), _ptr(leaf_gid), _ptr(loss), _ptr(d_rgb),
+                                        _ptr(d_rgb0), _ptr(leaf_max), _stream()), "flnerf_mse_leafmax")
+    return loss, d_rgb, d_rgb0
+
+
+def adam_step(param, m, v, grad, lr: float, b1: float, b2: float, eps: float, t: int):
+    L.check(L.load().flnerf_adam_step(_ctx(param), param.numel(), _ptr(param), _ptr(m), _ptr(v), _ptr(grad), lr, b1, b2,
+                                      eps, int(t), _stream()), "flnerf_adam_step")
+
+
+# ------------------------------------------------------------------------------------------ quadtree
+def qt_init(n_images, cap, H, W, max_depth, boxes, count, min_area):
+    L.check(L.load().flnerf_qt_init(_ctx(boxes), n_images, cap, H, W, max_depth, _ptr(boxes), _ptr(count),
+                                    _ptr(min_area), _stream()), "flnerf_qt_init")
+
+
+def qt_refine(n_images, cap, boxes_in, count_in, min_area, leaf_max, thres, boxes_out, count_out):
+    L.check(L.load().flnerf_qt_refine(_ctx(boxes_in), n_images, cap, _ptr(boxes_in), _ptr(count_in), _ptr(min_area),
+                                      _ptr(leaf_max), float(thres), _ptr(boxes_out), _ptr(count_out), _stream()),
+            "flnerf_qt_refine")
+
+
+def qt_count(n_images, cap, boxes, count, min_area, rays_per_pixel, ray_offset):
+    L.check(L.load().flnerf_qt_count(_ctx(boxes), n_images, cap, _ptr(boxes), _ptr(count), _ptr(min_area),
+                                     float(rays_per_pixel), _ptr(ray_offset), _stream()), "flnerf_qt_count")
+
+
+def qt_emit(n_images, cap, W, boxes, count, ray_offset, n_rays, seed, ray_pix, ray_gid):
+    L.check(L.load().flnerf_qt_emit(_ctx(boxes), n_images, cap, W, _ptr(boxes), _ptr(count), _ptr(ray_offset),
+                                    int(n_rays), int(seed), _ptr(ray_pix), _ptr(ray_gid), _stream()), "flnerf_qt_emit")
+
+
+def gather_batch(B, first, stride, ray_pix, ray_gid, cap, H, W, K, poses, images, want_gid=True):
+    dev = images.device
+    o = torch.empty(B, 3, dtype=torch.float32, device=dev)
+    d = torch.empty(B, 3, dtype=torch.float32, device=dev)
+    t = torch.empty(B, 3, dtype=torch.float32, device=dev)
+    gid = torch.empty(B, dtype=torch.int32, device=dev) if want_gid else None
+    Kh = (C.c_double * 9)(*[float(K[i][j]) for i in range(3) for j in range(3)])
+    L.check(L.load().flnerf_gather_batch(_ctx(images), int(B), int(first), int(stride), _ptr(ray_pix), _ptr(ray_gid),
+                                         int(cap), int(H), int(W), Kh, _ptr(poses), _ptr(images), _ptr(o), _ptr(d),
+                                         _ptr(t), _ptr(gid), _stream()), "flnerf_gather_batch")
+    return o, d, t, gid

@@ -1,0 +1,248 @@
+"""Drop-in for nerf-ours/tree.py: ``QuadTreeNode``, ``QuadTree``, ``QuadTreeManager``, ``get_children``,
+``recursive_subdivide`` keep their names/attributes (``treeDivide_*.pkl`` pickles them by qualified name),
+but the per-image trees LIVE ON THE GPU as structure-of-arrays: DFS-ordered leaf boxes
+``boxes[n_images, cap, 4]`` (float64, exact dyadic fractions of H and W), ``count[n_images]``,
+``min_area[n_images]``.  Ray emission (tree.py:569-626), the per-leaf max-|gt-pred| statistic and the
+refinement (tree.py:533-557, 629-652) are kernels in csrc/train_ops.cu; the Python node objects are a
+lazily rebuilt mirror used only for (de)serialisation.
+"""
+import math
+from typing import List
+
+import numpy as np
+import torch
+
+from flnerf_b200 import ops
+from flnerf_b200.lib import FlnerfError
+
+
+class QuadTreeNode:
+    """A box (x0, y0, x1, y1): x = image row in [0, H], y = column in [0, W] (tree.py:92)."""
+
+    def __init__(self, x0, y0, x1, y1):
+        self.x0, self.y0, self.x1, self.y1 = x0, y0, x1, y1
+        self.children = []
+
+    def box(self):
+        return (self.x0, self.y0, self.x1, self.y1)
+
+    def get_error(self, img):
+        """Sum over channels of the per-channel pixel variance inside the box (tree.py:28-56)."""
+        px = img[math.ceil(self.x0):math.floor(self.x1), math.ceil(self.y0):math.floor(self.y1), :]
+        px = px.detach().cpu().numpy() if torch.is_tensor(px) else np.asarray(px)
+        return float(sum(np.square(px[:, :, c] - px[:, :, c].mean()).mean() for c in range(3)))
+
+    def subdivide_once(self):
+        mx, my = (self.x0 + self.x1) / 2, (self.y0 + self.y1) / 2
+        self.children = [QuadTreeNode(self.x0, self.y0, mx, my), QuadTreeNode(mx, self.y0, self.x1, my),
+                         QuadTreeNode(self.x0, my, mx, self.y1), QuadTreeNode(mx, my, self.x1, self.y1)]
+
+    @property
+    def area(self):
+        return (self.x1 - self.x0) * (self.y1 - self.y0)
+
+    def __str__(self):
+        return "({:.1f}, {:.1f}), ({:.1f}, {:.1f})".format(self.x0, self.y0, self.x1, self.y1)
+
+
+def recursive_subdivide(node, thres, image, cur_depth, max_depth):
+    """tree.py:655-676: split while depth < max_depth and the block variance is >= thres."""
+    if cur_depth >= max_depth:
+        return
+    if thres > 0 and node.get_error(image) < thres:     # with thres <= 0 the variance test can never fire
+        return
+    node.subdivide_once()
+    for c in node.children:
+        recursive_subdivide(c, thres, image, cur_depth + 1, max_depth)
+
+
+def get_children(node):
+    """Leaves in depth-first order (tree.py:679-686); the index in this list is the leaf id."""
+    if not node.children:
+        return [node]
+    out = []
+    for c in node.children:
+        out += get_children(c)
+    return out
+
+
+class QuadTree:
+    def __init__(self, image, stdThres, max_depth, _boxes=None, _min_area=None):
+        self.H, self.W = (image.shape[0], image.shape[1]) if not isinstance(image, tuple) else image
+        self.threshold = stdThres
+        self.image = None if isinstance(image, tuple) else image
+        self.root = QuadTreeNode(0, 0, self.H, self.W)
+        if _boxes is None:
+            recursive_subdivide(self.root, self.threshold, self.image, 1, max_depth)
+            self.minArea = self.H * self.W / (4 ** (max_depth - 1))
+        else:
+            it = iter([tuple(float(v) for v in b) for b in _boxes])
+            self._rebuild(self.root, it, [next(it)])
+            self.minArea = _min_area
+
+    @staticmethod
+    def _rebuild(node, it, head):
+        """Inverse of get_children for a tree produced by midpoint splits: a node is a leaf iff the next DFS leaf is
+        exactly its box."""
+        if head[0] == node.box():
+            head[0] = next(it, None)
+            return
+        node.subdivide_once()
+        for c in node.children:
+            QuadTree._rebuild(c, it, head)
+
+
+class QuadTreeManager:
+    """GPU-resident replacement of tree.py:159-566 (constructor and the two methods run_nerf.py calls)."""
+
+    def __init__(self, H, W, K, images, poses, mseThres=0.1, max_depth=5, max_level=None, device=None, seed=0):
+        if mseThres > 0:
+            raise FlnerfError("flnerf QuadTreeManager builds the uniform initial tree (mseThres<=0, what run_nerf.py "
+                              "passes, run_nerf.py:337); variance-driven initial splits are not implemented")
+        self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+        self.n_images, self.h, self.w = int(poses.shape[0]), int(H), int(W)
+        self.K = np.asarray(K, dtype=np.float64)
+        self.images = images
+        self.epoch_size = self.n_images * self.h * self.w
+        self.processor = None           # ImageProcessor sharpness maps are only used with prob=True (tree.py:583-595)
+        self._images_dev = torch.as_tensor(images, dtype=torch.float32).to(self.device).contiguous()
+        self._poses_dev = torch.as_tensor(poses, dtype=torch.float32)[:, :3, :4].to(self.device).contiguous()
+        self.max_level = int(max_level) if max_level is not None else int(max_depth) + 6
+        self.cap = 4 ** (self.max_level - 1)
+        n = self.n_images
+        self._boxes = [torch.zeros(n, self.cap, 4, dtype=torch.float64, device=self.device) for _ in range(2)]
+        self._count = [torch.zeros(n, dtype=torch.int32, device=self.device) for _ in range(2)]
+        self._min_area = torch.zeros(n, dtype=torch.float64, device=self.device)
+        self._cur = 0
+        ops.qt_init(n, self.cap, self.h, self.w, int(max_depth), self._boxes[0], self._count[0], self._min_area)
+        self.cur_level = max_depth
+        self.leaf_max = torch.full((n * self.cap,), -1.0, dtype=torch.float32, device=self.device)
+        self._ray_offset = torch.zeros(n * self.cap + 1, dtype=torch.int64, device=self.device)
+        self.ray_pix = self.ray_gid = None
+        self.n_rays = 0
+        self._epoch = 0
+        self.seed = int(seed)
+        self._mirror = None
+
+    # ------------------------------------------------------------------ GPU state
+    @property
+    def boxes(self):
+        return self._boxes[self._cur]
+
+    @property
+    def counts(self):
+        return self._count[self._cur]
+
+    def leaf_lists(self):
+        """[(boxes float64 [n_i,4] numpy, min_area)] per image -- DFS order."""
+        cnt = self.counts.cpu().numpy()
+        bx = self.boxes.cpu().numpy()
+        ma = self._min_area.cpu().numpy()
+        return [(bx[i, :cnt[i]].copy(), float(ma[i])) for i in range(self.n_images)]
+
+    # ------------------------------------------------------------------ reference attributes (lazy mirrors)
+    @property
+    def quadTrees(self) -> List[QuadTree]:
+        if self._mirror is None:
+            self._mirror = [QuadTree((self.h, self.w), 0.0, 1, _boxes=b, _min_area=m) for b, m in self.leaf_lists()]
+        return self._mirror
+
+    @quadTrees.setter
+    def quadTrees(self, trees):
+        """Resume path (run_nerf.py:339-345): upload pickled trees into the SoA."""
+        bx = np.zeros((self.n_images, self.cap, 4), np.float64)
+        cnt = np.zeros(self.n_images, np.int32)
+        ma = np.zeros(self.n_images, np.float64)
+        for i, t in enumerate(trees):
+            leaves = get_children(t.root)
+            if len(leaves) > self.cap:
+                raise FlnerfError("pickled tree %d has %d leaves > capacity %d" % (i, len(leaves), self.cap))
+            bx[i, :len(leaves)] = np.array([l.box() for l in leaves], np.float64)
+            cnt[i], ma[i] = len(leaves), t.minArea
+        self._boxes[self._cur].copy_(torch.from_numpy(bx))
+        self._count[self._cur].copy_(torch.from_numpy(cnt))
+        self._min_area.copy_(torch.from_numpy(ma))
+        self._mirror = list(trees)
+
+    @property
+    def childrens(self):
+        return [get_children(t.root) for t in self.quadTrees]
+
+    @childrens.setter
+    def childrens(self, value):      # derived from quadTrees; the reference assigns it after unpickling
+        pass
+
+    @property
+    def dirs(self):
+        return torch.stack([ops.raygen(self.h, self.w, self.K, self._poses_dev[i])[1] for i in range(self.n_images)], 0)
+
+    @property
+    def origins(self):
+        return torch.stack([ops.raygen(self.h, self.w, self.K, self._poses_dev[i])[0] for i in range(self.n_images)], 0)
+
+    @property
+    def result_leaf_id(self):
+        """[N,2] float32 rows (image, leaf) in emission order (tree.py:606)."""
+        g = self.ray_gid.long()
+        return torch.stack([g // self.cap, g % self.cap], 1).float()
+
+    # ------------------------------------------------------------------ emission
+    def emit_epoch(self, down_scale=1, last_epoch=False, seed=None):
+        """Builds the epoch's shuffled ray index buffer on the GPU; returns the number of rays."""
+        rpp = self.epoch_size / self.n_images / down_scale / self.h / self.w      # tree.py:381-382
+        n = self.n_images
+        if last_epoch:   # throw-away depth-1 trees: H*W uniform draws per image (tree.py:390-400)
+            boxes = torch.zeros(n, self.cap, 4, dtype=torch.float64, device=self.device)
+            count = torch.zeros(n, dtype=torch.int32, device=self.device)
+            min_area = torch.zeros(n, dtype=torch.float64, device=self.device)
+            ops.qt_init(n, self.cap, self.h, self.w, 1, boxes, count, min_area)
+        else:
+            boxes, count, min_area = self.boxes, self.counts, self._min_area
+        ops.qt_count(n, self.cap, boxes, count, min_area, rpp, self._ray_offset)
+        self.n_rays = int(self._ray_offset[-1].item())        # one 8-byte D2H per epoch
+        self.ray_pix = torch.empty(self.n_rays, dtype=torch.int32, device=self.device)
+        self.ray_gid = torch.empty(self.n_rays, dtype=torch.int32, device=self.device)
+        self._epoch += 1
+        s = self.seed * 1000003 + self._epoch if seed is None else int(seed)
+        ops.qt_emit(n, self.cap, self.w, boxes, count, self._ray_offset, self.n_rays, s, self.ray_pix, self.ray_gid)
+        self._emitted_last = bool(last_epoch)
+        return self.n_rays
+
+    def batch(self, first, B, stride=1):
+        """rays_o, rays_d, target_rgb, leaf_gid for rows first, first+stride, ... of the index buffer."""
+        return ops.gather_batch(B, first, stride, self.ray_pix, self.ray_gid, self.cap, self.h, self.w, self.K,
+                                self._poses_dev, self._images_dev)
+
+    def gen_rays_v3_multiThread(self, down_scale=16, prob=True, randSamp_proc=0.95, debug=False, last_epoch=False):
+        """tree.py:377-428 -> (origins[N,3], dirs[N,3], rgb[N,3]) (GPU tensors, already shuffled)."""
+        if prob:
+            raise FlnerfError("probability-guided pixel sampling (prob=True, image_process.py) is not implemented; "
+                              "nerf-ours/run_nerf.py always passes prob=False (run_nerf.py:440,452)")
+        n = self.emit_epoch(down_scale, last_epoch)
+        o, d, rgb, _ = ops.gather_batch(n, 0, 1, self.ray_pix, self.ray_gid, self.cap, self.h, self.w, self.K,
+                                        self._poses_dev, self._images_dev, want_gid=False)
+        return o, d, rgb
+
+    # ------------------------------------------------------------------ refinement
+    def reset_leaf_stats(self):
+        self.leaf_max.fill_(-1.0)
+
+    def refine(self, thres):
+        """adjust_tree on the accumulated per-leaf table (tree.py:629-652), then clears the table."""
+        nxt = 1 - self._cur
+        ops.qt_refine(self.n_images, self.cap, self._boxes[self._cur], self._count[self._cur], self._min_area,
+                      self.leaf_max, thres, self._boxes[nxt], self._count[nxt])
+        self._cur = nxt
+        self._mirror = None
+        self.cur_level += 1
+        self.reset_leaf_stats()
+
+    def adjust_tree_multiThread(self, rgb_gt, rgb_pred, thres=0.001, debug=False):
+        """tree.py:533-557: rgb_gt / rgb_pred are the epoch's [N,3] targets and predictions in emission order."""
+        gt = torch.as_tensor(rgb_gt, dtype=torch.float32).to(self.device)
+        pr = torch.as_tensor(rgb_pred, dtype=torch.float32).to(self.device)
+        n = gt.shape[0]
+        self.reset_leaf_stats()
+        ops.mse_leafmax(pr, None, gt, max(n, 1), self.ray_gid[:n].contiguous(), self.leaf_max, want_grads=False)
+        self.refine(thres)
+        print('After sudivide, there are {} child nodes'.format(int(self.counts.sum().item())))

@@ -1,0 +1,156 @@
+/* flnerf.h -- C ABI of libflnerf.so: the B200 (sm_100a) hot path of Fast-Learning-NeRF.
+ *
+ * The reference (wen-yuan-zhang/Fast-Learning-NeRF, nerf-ours/) has no FFI of its own: the path
+ * is Python functions wired by name (run_nerf.py:21-33).  Each entry point below replaces the
+ * arithmetic of the cited reference function; the Python modules in fast-learning-nerf_b200/
+ * (render.py, run_nerf_helpers.py, model.py, tree.py) keep the reference signatures and bind
+ * these symbols with ctypes (see INTEGRATION.md for the stub a maintainer would add).
+ *
+ * Conventions
+ *  - every pointer is a DEVICE pointer unless the parameter name starts with h_ (host);
+ *  - all work is enqueued on the caller's cudaStream_t (passed as void*), nothing synchronises;
+ *  - the library never allocates or frees caller memory; scratch comes from caller workspaces
+ *    sized by the *_bytes() queries;
+ *  - return value: 0 = OK, non-zero = error, text via flnerf_last_error() (thread-local);
+ *  - fp32 unless stated; "rays11" is [B,11] = o(3) d(3) near far viewdir(3) (render.py:74-80).
+ */
+#ifndef FLNERF_H
+#define FLNERF_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct flnerf_ctx flnerf_ctx;
+
+/* MLP arithmetic modes (model.py:38-63 is fp32; see DESIGN.md "precision modes") */
+#define FLNERF_MODE_FP32 0 /* CUDA-core fp32 GEMMs: the parity path (<=1e-4 rel of the reference)      */
+#define FLNERF_MODE_BF16 1 /* tcgen05 bf16 x bf16 -> fp32 TMEM accumulators: the throughput path        */
+
+#define FLNERF_MLP_PARAMS 595844 /* parameters of one NeRF(D=8,W=256,skips=[4],use_viewdirs) (model.py:20-34) */
+#define FLNERF_TILE_ROWS 128
+#define FLNERF_PAIR_ROWS 256     /* the tensor-core kernels process rows in pairs of 128-row tiles */
+
+int flnerf_version(void);
+const char *flnerf_last_error(void);
+flnerf_ctx *flnerf_create(int device);
+void flnerf_destroy(flnerf_ctx *ctx);
+int flnerf_sm_count(flnerf_ctx *ctx);
+
+/* ---- a1: get_rays (run_nerf_helpers.py:68-78). h_K = 3x3 row-major doubles, h_c2w = 3x4 floats. */
+int flnerf_raygen(flnerf_ctx *, int H, int W, const double *h_K, const float *h_c2w, float *rays_o, float *rays_d,
+                  void *stream);
+
+/* ---- a2+a3: ndc_rays + ray packing (run_nerf_helpers.py:91-108, render.py:59-80). */
+int flnerf_pack_rays(flnerf_ctx *, int64_t B, const float *rays_o, const float *rays_d, float near_, float far_,
+                     int ndc, int H, int W, double focal, float *rays11, void *stream);
+
+/* ---- a4: stratified depths (render.py:244-266). t_vals = linspace(0,1,Nc) [Nc]; t_rand [B,Nc] or NULL
+ * (NULL with perturb!=0 draws Philox uniforms from (seed, offset)). */
+int flnerf_coarse_depths(flnerf_ctx *, int64_t B, int Nc, const float *rays11, const float *t_vals,
+                         const float *t_rand, int perturb, int lindisp, uint64_t seed, uint64_t offset, float *z,
+                         void *stream);
+
+/* ---- a5: positional encoding (run_nerf_helpers.py:15-63, run_nerf.py:50-64). */
+/* generic embedder: x[n,3] -> out[n,3+6L] */
+int flnerf_posenc(flnerf_ctx *, int64_t n, int L, const float *x, float *out, void *stream);
+/* fused sample-point + PE, reference layout: x90[B*S,90] = [PE10(o+d*z), PE4(viewdir)] */
+int flnerf_encode_f32(flnerf_ctx *, int64_t B, int S, const float *rays11, const float *z, float *x90, void *stream);
+/* fused sample-point + PE for the tensor-core MLP: pe_tiles = ceil(B*S/256)*2 tiles of [128 rows x 64] bf16 in
+ * the SWIZZLE_128B K-major shared-memory image (16 KB each, column 63 = 0); dirpe[B,32] fp32 (27 used). */
+int flnerf_encode_tc(flnerf_ctx *, int64_t B, int S, const float *rays11, const float *z, void *pe_tiles,
+                     float *dirpe, void *stream);
+/* already-embedded rows x90[n,90] (NeRF.forward API) -> pe_tiles + dirpe[n,32] (one "ray" per row, S = 1) */
+int flnerf_pack_x90(flnerf_ctx *, int64_t n, const float *x90, void *pe_tiles, float *dirpe, void *stream);
+int64_t flnerf_padded_rows(int64_t n);                  /* n rounded up to FLNERF_PAIR_ROWS */
+
+/* ---- a6: NeRF MLP (model.py:38-63).  params/grads: flat fp32[FLNERF_MLP_PARAMS] in parameters() order:
+ * pts_linears.0..7 {weight,bias}, views_linears.0, feature_linear, alpha_linear, rgb_linear. */
+/* scratch + activations kept for backward.  S = samples per ray (n = B*S rows, ray-major); training=0 sizes the
+ * buffer for inference (FP32 mode always keeps the per-layer activations). */
+size_t flnerf_mlp_stash_bytes(int mode, int64_t n, int S, int training);
+size_t flnerf_mlp_bwd_workspace_bytes(int mode, int64_t n);
+size_t flnerf_mlp_packed_bytes(void);                   /* bf16 tensor-core weight image of one net */
+/* fp32 master weights -> pre-swizzled bf16 chunks (forward and transposed for dgrad) + fp32 small tensors */
+int flnerf_mlp_pack_weights(flnerf_ctx *, const float *params, void *packed, void *stream);
+/* mode FP32: x = x90 fp32 [n,90];  mode BF16: x = pe_tiles, dirpe[B,32], S = samples per ray (row -> ray = row/S).
+ * raw_out [n,4] = (r,g,b,sigma).  stash: flnerf_mlp_stash_bytes(mode, n, S, training) bytes, 1 KB aligned. */
+int flnerf_mlp_forward(flnerf_ctx *, int mode, const float *params, const void *packed, int64_t n, int S,
+                       const void *x, const float *dirpe, float *raw_out, void *stash, int training, void *stream);
+/* grads += d(loss)/d(params) given draw[n,4]; no input gradient is produced (z, pts carry no grad: render.py:281) */
+int flnerf_mlp_backward(flnerf_ctx *, int mode, const float *params, const void *packed, int64_t n, int S,
+                        const void *x, const float *dirpe, const void *stash, const float *draw, float *grads,
+                        void *workspace, size_t workspace_bytes, void *stream);
+
+/* ---- a7: raw2outputs (render.py:149-192) and its backward. One warp per ray. */
+int flnerf_composite_forward(flnerf_ctx *, int64_t B, int S, const float *raw, const float *z, const float *rays_d,
+                             int64_t rays_d_stride, const float *noise, int white_bkgd, float *rgb, float *disp,
+                             float *acc, float *depth, float *weights, void *stream);
+/* g_* may be NULL (treated as zero). draw[B,S,4] is overwritten. */
+int flnerf_composite_backward(flnerf_ctx *, int64_t B, int S, const float *raw, const float *z, const float *rays_d,
+                              int64_t rays_d_stride, const float *noise, int white_bkgd, const float *g_rgb,
+                              const float *g_disp, const float *g_acc, const float *g_depth, float *draw,
+                              void *stream);
+
+/* ---- a8: sample_pdf + sort-merge (run_nerf_helpers.py:112-155, render.py:279-284, 299).
+ * u [B,Nf] or NULL; det!=0 -> u = linspace(0,1,Nf); NULL & det==0 -> Philox(seed, offset).
+ * Outputs: z_merged[B,Nc+Nf] ascending, z_samples[B,Nf] (may be NULL), z_std[B] (may be NULL). */
+int flnerf_sample_pdf_merge(flnerf_ctx *, int64_t B, int Nc, int Nf, const float *z, const float *weights,
+                            const float *u, int det, uint64_t seed, uint64_t offset, float *z_merged,
+                            float *z_samples, float *z_std, void *stream);
+
+/* the plain sample_pdf(bins[B,n_bins], weights[B,n_bins-1], N_samples) API (run_nerf_helpers.py:112-155) */
+int flnerf_sample_pdf(flnerf_ctx *, int64_t B, int n_bins, int Nf, const float *bins, const float *weights,
+                      const float *u, int det, uint64_t seed, uint64_t offset, float *z_samples, void *stream);
+
+/* ---- a9 + a13 accumulation: img2mse for fine and coarse (run_nerf_helpers.py:9, run_nerf.py:482-490), their
+ * gradients, and the per-leaf max |gt - pred| table adjust_tree consumes (tree.py:538,642).
+ * loss_out[2] = {mse(rgb), mse(rgb0)} (written, not accumulated); denom = number of rays the mean runs over
+ * (global batch under data parallelism); rgb0/d_rgb0 may be NULL; leaf_gid (int32 [B], <0 = skip) and
+ * leaf_max (fp32 table, atomicMax) may be NULL. */
+int flnerf_mse_leafmax(flnerf_ctx *, int64_t B, const float *rgb, const float *rgb0, const float *target,
+                       int64_t denom, const int32_t *leaf_gid, float *loss_out, float *d_rgb, float *d_rgb0,
+                       float *leaf_max, void *stream);
+
+/* ---- torch.optim.Adam step (run_nerf.py:99,494) over flat buffers, t = 1-based step number; the bias
+ * corrections are computed on the host in double like torch does. */
+int flnerf_adam_step(flnerf_ctx *, int64_t n, float *param, float *m, float *v, const float *grad, double lr,
+                     double b1, double b2, double eps, int64_t t, void *stream);
+
+/* ---- a10-a13: GPU-resident quadtrees. Leaves of image i live at boxes[(i*cap + j)*4 .. +3] =
+ * (x0,y0,x1,y1) doubles in DFS order (tree.py:61-72,679-686), count[i] leaves, min_area[i]. */
+/* uniform tree of depth max_depth (tree.py:84-94 with mseThres=0) */
+int flnerf_qt_init(flnerf_ctx *, int n_images, int cap, int H, int W, int max_depth, double *boxes, int32_t *count,
+                   double *min_area, void *stream);
+/* adjust_tree (tree.py:533-557,629-652): split leaves with leaf_max > thres and area == min_area; shrink min_area
+ * of trees that split.  boxes_out must not alias boxes_in.  leaf_max is [n_images*cap]. */
+int flnerf_qt_refine(flnerf_ctx *, int n_images, int cap, const double *boxes_in, const int32_t *count_in,
+                     double *min_area, const float *leaf_max, float thres, double *boxes_out, int32_t *count_out,
+                     void *stream);
+/* gen_rays_v3_1 (tree.py:569-626) per-leaf ray counts: 10 if area > min_area+0.01 else int(area*rays_per_pixel);
+ * ray_offset[n_images*cap+1] = exclusive scan over (image, leaf); total rays is ray_offset[n_images*cap]. */
+int flnerf_qt_count(flnerf_ctx *, int n_images, int cap, const double *boxes, const int32_t *count,
+                    const double *min_area, double rays_per_pixel, int64_t *ray_offset, void *stream);
+/* emits the epoch's shuffled ray index buffer: for ray j of leaf (i,l): row ~ U[ceil(x0),ceil(x1)),
+ * col ~ U[ceil(y0),ceil(y1-0.01)) (Philox(seed)), written at position perm(j) where perm is a keyed bijection of
+ * [0,N) (replaces torch.randperm, tree.py:416).  ray_pix[N] = row*W+col, ray_gid[N] = i*cap+l. */
+int flnerf_qt_emit(flnerf_ctx *, int n_images, int cap, int W, const double *boxes, const int32_t *count,
+                   const int64_t *ray_offset, int64_t n_rays, uint64_t seed, int32_t *ray_pix, int32_t *ray_gid,
+                   void *stream);
+/* gathers a batch: for k in [0,B): ray = first + k*stride; target rgb from images (fp32 [n,H,W,3]) and the ray
+ * (o,d) regenerated from pose/intrinsics (== get_rays at that pixel).  poses fp32 [n_images,12]. */
+int flnerf_gather_batch(flnerf_ctx *, int64_t B, int64_t first, int64_t stride, const int32_t *ray_pix,
+                        const int32_t *ray_gid, int cap, int H, int W, const double *h_K, const float *poses,
+                        const float *images, float *rays_o, float *rays_d, float *target, int32_t *leaf_gid,
+                        void *stream);
+
+/* ---- diagnostics: number of kernels this library launched since the counter was last reset */
+int64_t flnerf_launch_count(int reset);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

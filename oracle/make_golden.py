@@ -1,0 +1,277 @@
+"""TEST INFRASTRUCTURE -- generates tests/golden/*.npz by executing the UNMODIFIED reference
+(/root/reference/nerf-ours, imported through oracle/ref_shim.py) on seeded inputs.
+
+Run in the build container:   python oracle/make_golden.py
+The fixtures are committed; this script is how they were made.  Weights are not stored:
+they are regenerated from a numpy seed by ``nerf_oracle.init_params``.
+"""
+import math
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+import nerf_oracle as O  # noqa: E402
+import ref_shim  # noqa: E402
+
+OUT = os.path.join(os.path.dirname(HERE), "tests", "golden")
+
+
+def pose_spherical(theta, phi, radius):
+    """load_blender.py:10-34 restated with numpy (camera on a sphere looking at the origin)."""
+    t = np.eye(4); t[2, 3] = radius
+    ph = phi / 180.0 * np.pi
+    rp = np.array([[1, 0, 0, 0], [0, np.cos(ph), -np.sin(ph), 0], [0, np.sin(ph), np.cos(ph), 0], [0, 0, 0, 1.0]])
+    th = theta / 180.0 * np.pi
+    rt = np.array([[np.cos(th), 0, -np.sin(th), 0], [0, 1, 0, 0], [np.sin(th), 0, np.cos(th), 0], [0, 0, 0, 1.0]])
+    c2w = rt @ rp @ t
+    c2w = np.array([[-1, 0, 0, 0], [0, 0, 1, 0], [0, 1, 0, 0], [0, 0, 0, 1.0]]) @ c2w
+    return c2w.astype(np.float32)
+
+
+def lego_K(H, W, focal):
+    return np.array([[focal, 0, 0.5 * W], [0, focal, 0.5 * H], [0, 0, 1]])
+
+
+def ref_model(ref, params):
+    m = ref.model.NeRF(D=8, W=256, input_ch=63, input_ch_views=27, output_ch=5, skips=[4], use_viewdirs=True)
+    m.load_state_dict({k: v.clone() for k, v in params.items()})
+    return m
+
+
+def t2n(d):
+    return {k: (v.detach().numpy() if torch.is_tensor(v) else np.asarray(v)) for k, v in d.items()}
+
+
+def close(a, b, tol=0.0, what=""):
+    a = torch.as_tensor(a); b = torch.as_tensor(b)
+    err = (a.double() - b.double()).abs().max().item() if a.numel() else 0.0
+    assert err <= tol, "%s: oracle vs reference max abs err %g > %g" % (what, err, tol)
+    return err
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    ref = ref_shim.load()
+    H = ref.helpers
+    torch.manual_seed(0)
+    np.random.seed(0)
+
+    # ---------------------------------------------------------------- rays (a1, a2, a3)
+    Hh, Ww, focal = 20, 24, 33.333
+    K = lego_K(Hh, Ww, focal)
+    c2w = torch.from_numpy(pose_spherical(37.0, -30.0, 4.0)[:3, :4])
+    ro, rd = H.get_rays(Hh, Ww, K, c2w)
+    oo, od = O.camera_rays(Hh, Ww, K, c2w)
+    close(oo, ro, 0, "rays_o"); close(od, rd, 0, "rays_d")
+    rnp_o, rnp_d = H.get_rays_np(Hh, Ww, K, c2w.numpy())
+    # fern-like NDC
+    Hf, Wf, ff = 18, 24, 19.4
+    Kf = lego_K(Hf, Wf, ff)
+    c2wf = torch.eye(4)[:3, :4].clone(); c2wf[:, 3] = torch.tensor([0.1, -0.05, 0.02])
+    fo, fd = H.get_rays(Hf, Wf, Kf, c2wf)
+    no, nd = H.ndc_rays(Hf, Wf, Kf[0][0], 1.0, fo.reshape(-1, 3), fd.reshape(-1, 3))
+    oo2, od2 = O.ndc_warp(Hf, Wf, Kf[0][0], 1.0, fo.reshape(-1, 3), fd.reshape(-1, 3))
+    close(oo2, no, 0, "ndc_o"); close(od2, nd, 0, "ndc_d")
+    np.savez_compressed(os.path.join(OUT, "rays.npz"), **t2n(dict(
+        H=Hh, W=Ww, K=K, c2w=c2w, rays_o=ro.contiguous(), rays_d=rd, rays_o_np=rnp_o, rays_d_np=rnp_d,
+        Hf=Hf, Wf=Wf, Kf=Kf, c2wf=c2wf, fern_o=fo.contiguous(), fern_d=fd, ndc_o=no, ndc_d=nd)))
+
+    # ---------------------------------------------------------------- PE (a5)
+    pts = (torch.rand(96, 3) * 8 - 4)
+    dirs = torch.nn.functional.normalize(torch.randn(96, 3), dim=-1)
+    e10, d10 = H.get_embedder(10, 0)
+    e4, d4 = H.get_embedder(4, 0)
+    assert d10 == 63 and d4 == 27
+    pe_p, pe_d = e10(pts), e4(dirs)
+    close(O.posenc(pts, 10), pe_p, 0, "pe10"); close(O.posenc(dirs, 4), pe_d, 0, "pe4")
+    np.savez_compressed(os.path.join(OUT, "posenc.npz"), **t2n(dict(pts=pts, dirs=dirs, pe_pts=pe_p, pe_dirs=pe_d)))
+
+    # ---------------------------------------------------------------- MLP fwd + grads (a6)
+    seed_c, seed_f = 11, 12
+    pc, pf = O.init_params(seed_c), O.init_params(seed_f)
+    mc, mf = ref_model(ref, pc), ref_model(ref, pf)
+    x = torch.cat([e10(pts), e4(dirs)], -1)
+    y = mc(x)
+    close(O.mlp_forward(pc, x), y, 1e-6, "mlp_forward")
+    gout = torch.randn(96, 4) * 0.1
+    mc.zero_grad()
+    (y * gout).sum().backward()
+    grads = {n: p_.grad.clone() for n, p_ in mc.named_parameters()}
+    # oracle grads
+    pc_req = {k: v.clone().requires_grad_(True) for k, v in pc.items()}
+    (O.mlp_forward(pc_req, x) * gout).sum().backward()
+    for n in grads:
+        close(pc_req[n].grad, grads[n], 2e-6, "grad " + n)
+    np.savez_compressed(os.path.join(OUT, "mlp.npz"), **t2n(dict(
+        seed=seed_c, x=x, y=y, gout=gout,
+        **{"grad." + n: g for n, g in grads.items() if g.numel() <= 4096},          # biases, alpha, rgb weights
+        **{"gradrow." + n: g[:4] for n, g in grads.items() if g.numel() > 4096},      # first 4 rows of big weights
+        **{"gradnorm." + n: g.double().norm() for n, g in grads.items()})))
+
+    # ---------------------------------------------------------------- compositing (a7)
+    B, S = 24, 64
+    raw = torch.randn(B, S, 4) * torch.tensor([1.0, 1.0, 1.0, 10.0])
+    raw[0, :, 3] = -5.0                      # fully transparent ray -> acc 0, disp NaN (reference behaviour)
+    raw[1, :, 3] = 50.0                      # opaque at first sample
+    z = torch.sort(torch.rand(B, S) * 4 + 2, -1)[0]
+    rd_c = torch.randn(B, 3)
+    comp = {}
+    for wb in (False, True):
+        r = ref.render.raw2outputs(raw, z, rd_c, 0, wb)
+        o = O.composite(raw, z, rd_c, None, wb)
+        for a, b, n in zip(o, r, ["rgb", "disp", "acc", "w", "depth"]):
+            close(torch.nan_to_num(a, nan=-7.0), torch.nan_to_num(b, nan=-7.0), 0, "composite " + n)
+            comp[f"{n}_wb{int(wb)}"] = b
+    # gradient of a scalar of rgb_map w.r.t. raw (what training uses)
+    raw_g = raw.clone().requires_grad_(True)
+    g_rgb = torch.randn(B, 3)
+    r = ref.render.raw2outputs(raw_g, z, rd_c, 0, True)
+    (r[0] * g_rgb).sum().backward()
+    comp["g_rgb"] = g_rgb
+    comp["draw_wb1"] = raw_g.grad.clone()
+    # all differentiable outputs (rgb, disp, acc, depth) on rays that are not fully transparent
+    raw_g2 = raw[1:].clone().requires_grad_(True)
+    g_all = torch.randn(B - 1, 6)
+    r = ref.render.raw2outputs(raw_g2, z[1:], rd_c[1:], 0, False)
+    ((r[0] * g_all[:, :3]).sum() + (r[1] * g_all[:, 3]).sum() + (r[2] * g_all[:, 4]).sum() + (r[4] * g_all[:, 5]).sum()).backward()
+    comp["g_all"] = g_all
+    comp["draw_all_wb0"] = raw_g2.grad.clone()
+    np.savez_compressed(os.path.join(OUT, "composite.npz"), **t2n(dict(raw=raw, z=z, rays_d=rd_c, **comp)))
+
+    # ---------------------------------------------------------------- sample_pdf + merge (a8)
+    w = comp["w_wb0"].detach()
+    zmid = 0.5 * (z[:, 1:] + z[:, :-1])
+    zs_det = H.sample_pdf(zmid, w[:, 1:-1], 128, det=True)
+    close(O.inverse_cdf(zmid, w[:, 1:-1], 128, None), zs_det, 0, "sample_pdf det")
+    zs_py = H.sample_pdf(zmid, w[:, 1:-1], 128, det=False, pytest=True)     # u = np.random.seed(0); rand(B,128)
+    np.random.seed(0)
+    u_py = torch.Tensor(np.random.rand(B, 128))
+    close(O.inverse_cdf(zmid, w[:, 1:-1], 128, u_py), zs_py, 0, "sample_pdf pytest")
+    merged_det = torch.sort(torch.cat([z, zs_det], -1), -1)[0]
+    merged_py = torch.sort(torch.cat([z, zs_py], -1), -1)[0]
+    np.savez_compressed(os.path.join(OUT, "sample_pdf.npz"), **t2n(dict(
+        z=z, weights=w, zs_det=zs_det, zs_u=zs_py, u=u_py, merged_det=merged_det, merged_u=merged_py,
+        zstd_det=torch.std(zs_det, -1, unbiased=False), zstd_u=torch.std(zs_py, -1, unbiased=False))))
+
+    # ---------------------------------------------------------------- render_rays end to end
+    def ref_query(inputs, viewdirs, fn):
+        return ref_shim.ref_run_network(ref, inputs, viewdirs, fn, e10, e4)
+
+    Br = 16
+    Hl, Wl, fl = 800, 800, 1111.111
+    Kl = lego_K(Hl, Wl, fl)
+    c2wl = torch.from_numpy(pose_spherical(-60.0, -30.0, 4.0)[:3, :4])
+    ro, rd = H.get_rays(Hl, Wl, Kl, c2wl)
+    sel = torch.from_numpy(np.random.RandomState(3).choice(Hl * Wl, Br, replace=False))
+    bo, bd = ro.reshape(-1, 3)[sel], rd.reshape(-1, 3)[sel]
+    target = torch.from_numpy(np.random.RandomState(4).uniform(0, 1, (Br, 3)).astype(np.float32))
+    rr = {}
+    for name, kw in [("det", dict(perturb=0.0, pytest=False)), ("jit", dict(perturb=1.0, pytest=True))]:
+        mc.zero_grad(); mf.zero_grad()
+        rgb, disp, acc, ex = ref.render.render(
+            Hl, Wl, Kl, chunk=32768, rays=torch.stack([bo, bd], 0), ndc=False, near=2.0, far=6.0, use_viewdirs=True,
+            network_query_fn=ref_query, network_fn=mc, network_fine=mf, N_samples=64, N_importance=128,
+            white_bkgd=True, raw_noise_std=0.0, retraw=True, **kw)
+        loss = H.img2mse(rgb, target) + H.img2mse(ex["rgb0"], target)
+        loss.backward()
+        rr.update({f"{name}.rgb": rgb, f"{name}.disp": disp, f"{name}.acc": acc, f"{name}.rgb0": ex["rgb0"],
+                   f"{name}.disp0": ex["disp0"], f"{name}.acc0": ex["acc0"], f"{name}.z_std": ex["z_std"],
+                   f"{name}.raw": ex["raw"], f"{name}.loss": loss.detach()})
+        for tag, m in (("c", mc), ("f", mf)):
+            for n, p_ in m.named_parameters():
+                rr[f"{name}.gnorm.{tag}.{n}"] = p_.grad.double().norm()
+                if p_.grad.numel() <= 4096:
+                    rr[f"{name}.grad.{tag}.{n}"] = p_.grad.clone()
+        # oracle agreement on the same inputs
+        rays11 = O.pack_rays(Hl, Wl, Kl, bo, bd, 2.0, 6.0, ndc=False)
+        if name == "det":
+            oo = O.render_rays(rays11, pc, pf, 64, 128, white_bkgd=True)
+        else:
+            np.random.seed(0); tr = torch.Tensor(np.random.rand(Br, 64))
+            np.random.seed(0); uu = torch.Tensor(np.random.rand(Br, 128))
+            oo = O.render_rays(rays11, pc, pf, 64, 128, white_bkgd=True, t_rand=tr, u=uu, det_fine=False)
+        close(oo["rgb0"], ex["rgb0"], 2e-6, name + " rgb0")
+        close(oo["rgb_map"], rgb, 5e-5, name + " rgb")
+    np.savez_compressed(os.path.join(OUT, "render_rays.npz"), **t2n(dict(
+        seed_c=seed_c, seed_f=seed_f, H=Hl, W=Wl, K=Kl, rays_o=bo, rays_d=bd, target=target, near=2.0, far=6.0, **rr)))
+
+    # ---------------------------------------------------------------- fern-like NDC render (config 3 shape)
+    mc.zero_grad(); mf.zero_grad()
+    fo_b, fd_b = fo.reshape(-1, 3)[::37][:8].contiguous(), fd.reshape(-1, 3)[::37][:8].contiguous()
+    rgb, disp, acc, ex = ref.render.render(
+        Hf, Wf, Kf, chunk=32768, rays=torch.stack([fo_b, fd_b], 0), ndc=True, near=0.0, far=1.0, use_viewdirs=True,
+        network_query_fn=ref_query, network_fn=mc, network_fine=mf, N_samples=64, N_importance=128,
+        white_bkgd=False, raw_noise_std=0.0, retraw=False, perturb=0.0)
+    np.savez_compressed(os.path.join(OUT, "render_ndc.npz"), **t2n(dict(
+        seed_c=seed_c, seed_f=seed_f, H=Hf, W=Wf, K=Kf, rays_o=fo_b, rays_d=fd_b, rgb=rgb, disp=disp, acc=acc,
+        rgb0=ex["rgb0"], z_std=ex["z_std"])))
+
+    # ---------------------------------------------------------------- quadtree (a10-a13)
+    T = ref.tree
+    Hq = Wq = 64
+    n_img = 3
+    imgs = torch.from_numpy(np.random.RandomState(5).uniform(0, 1, (n_img, Hq, Wq, 3)).astype(np.float32))
+    poses = torch.stack([torch.from_numpy(pose_spherical(a, -30.0, 4.0)[:3, :4]) for a in (0.0, 120.0, 240.0)])
+    Kq = lego_K(Hq, Wq, 80.0)
+    mgr = T.QuadTreeManager(Hq, Wq, Kq, imgs, poses, mseThres=0.0, max_depth=2)
+    q = {}
+    hist = []
+    rs = np.random.RandomState(6)
+    for rnd in range(4):
+        torch.manual_seed(100 + rnd)
+        o_, d_, c_ = mgr.gen_rays_v3_multiThread(down_scale=1, prob=False, randSamp_proc=1.0)
+        lid = mgr.result_leaf_id.clone()
+        boxes = [[(n.x0, n.y0, n.x1, n.y1) for n in ch] for ch in mgr.childrens]
+        mina = [t.minArea for t in mgr.quadTrees]
+        # per-leaf counts and pixel ranges vs oracle
+        for i in range(n_img):
+            cnt = torch.bincount(lid[lid[:, 0] == i][:, 1].long(), minlength=len(boxes[i]))
+            exp = [O.leaf_ray_count(b, mina[i], 1.0) for b in boxes[i]]
+            assert cnt.tolist() == exp, (rnd, i)
+        # the emitted rays are integer pixels of the right image: check colour gather identity
+        pred = c_ + torch.from_numpy(rs.normal(0, 0.004, c_.shape).astype(np.float32)) * (rs.rand(c_.shape[0], 1) > 0.6)
+        pred = pred.float()
+        table = O.leaf_max_table(lid.numpy(), c_.numpy(), pred.numpy(), n_img, [len(b) for b in boxes])
+        thres = 0.005
+        mgr.adjust_tree_multiThread(c_, pred, thres=thres)
+        new_boxes = [[(n.x0, n.y0, n.x1, n.y1) for n in ch] for ch in mgr.childrens]
+        new_min = [t.minArea for t in mgr.quadTrees]
+        for i in range(n_img):
+            ob, om = O.refine(boxes[i], mina[i], table[i], thres)
+            assert ob == new_boxes[i] and om == new_min[i], (rnd, i)
+        for i in range(n_img):
+            q[f"r{rnd}.boxes{i}"] = np.array(boxes[i], np.float64)
+            q[f"r{rnd}.table{i}"] = table[i]
+            q[f"r{rnd}.newboxes{i}"] = np.array(new_boxes[i], np.float64)
+        q[f"r{rnd}.minarea"] = np.array(mina, np.float64)
+        q[f"r{rnd}.newminarea"] = np.array(new_min, np.float64)
+        q[f"r{rnd}.n_rays"] = lid.shape[0]
+        hist.append([len(b) for b in new_boxes])
+    # threshold-tie case: stat exactly equal to fp32(thres) must NOT split; one ulp above must
+    tie = np.float32(0.005)
+    q["tie.thres"] = 0.005
+    q["tie.stat"] = np.array([tie, np.nextafter(tie, np.float32(1)), np.float32(0.0), np.float32(1.0)], np.float32)
+    t_one = T.QuadTree(imgs[0].numpy(), 0.0, 2)
+    ch = T.get_children(t_one.root)
+    fake_lid = torch.tensor([[0.0, j] for j in range(4)])
+    gt = torch.zeros(4, 3); pr = torch.zeros(4, 3); pr[:, 1] = torch.from_numpy(q["tie.stat"])
+
+    class M:  # minimal manager stand-in for adjust_tree_subThread
+        childrens = [ch]
+    T.adjust_tree_subThread(M, 0, fake_lid, torch.abs(gt - pr), ch, 0.005, t_one)
+    q["tie.newboxes"] = np.array([(n.x0, n.y0, n.x1, n.y1) for n in M.childrens[0]], np.float64)
+    ob, om = O.refine([(n.x0, n.y0, n.x1, n.y1) for n in ch], 64 * 64 / 4, q["tie.stat"], 0.005)
+    assert np.array_equal(np.array(ob), q["tie.newboxes"]) and om == t_one.minArea
+    q["H"] = Hq; q["W"] = Wq; q["n_img"] = n_img; q["leaf_hist"] = np.array(hist)
+    np.savez_compressed(os.path.join(OUT, "quadtree.npz"), **q)
+    print("golden fixtures written to", OUT)
+    for f in sorted(os.listdir(OUT)):
+        print("  %-20s %8d bytes" % (f, os.path.getsize(os.path.join(OUT, f))))
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,100 @@
+"""TEST INFRASTRUCTURE -- loads the UNMODIFIED reference modules from /root/reference.
+
+Only usable inside the build container (the GPU box has no /root/reference).  It is
+used by ``oracle/make_golden.py`` to generate the committed fixtures under
+``tests/golden/`` and by ``tests/test_oracle_vs_reference.py`` (skipped when the
+reference tree is absent) to pin the oracle restatement against the real code.
+
+The reference hot path (nerf-ours/{run_nerf_helpers,render,model,tree}.py) imports a
+few modules that are not installed here (imageio, matplotlib, colour, threadpool,
+``from cv2 import cv2``) and hard-codes ``.cuda()``; we stub those *modules* and make
+``Tensor.cuda`` the identity on a GPU-less host.  No reference file is edited or copied.
+"""
+import importlib
+import os
+import sys
+import types
+
+REF_ROOT = os.environ.get("FLNERF_REFERENCE_ROOT", "/root/reference")
+REF_NERF = os.path.join(REF_ROOT, "nerf-ours")
+
+
+def available() -> bool:
+    return os.path.isfile(os.path.join(REF_NERF, "render.py"))
+
+
+class _SerialPool:
+    """Serial stand-in for threadpool.ThreadPool (tree.py:410-414, 547-550)."""
+
+    def __init__(self, n):
+        self.q = []
+
+    def putRequest(self, r):
+        self.q.append(r)
+
+    def wait(self):
+        q, self.q = self.q, []
+        for fn, kw in q:
+            fn(**kw)
+
+
+def load():
+    """Returns a namespace with the reference modules: helpers, model, render, tree."""
+    if not available():
+        raise RuntimeError("reference tree not present at %s" % REF_NERF)
+    import torch
+
+    for name in ["imageio", "matplotlib", "matplotlib.pyplot", "matplotlib.patches", "colour"]:
+        if name not in sys.modules:
+            sys.modules[name] = types.ModuleType(name)
+    sys.modules["colour"].Color = object
+    try:
+        import cv2
+        cv2.cv2 = cv2
+        sys.modules["cv2.cv2"] = cv2
+    except Exception:  # pragma: no cover
+        pass
+    if "threadpool" not in sys.modules:
+        tp = types.ModuleType("threadpool")
+        tp.ThreadPool = _SerialPool
+        tp.makeRequests = lambda fn, vs: [(fn, kw) for _, kw in vs]
+        sys.modules["threadpool"] = tp
+    if not torch.cuda.is_available():
+        torch.Tensor.cuda = lambda self, *a, **k: self
+
+    saved_path = list(sys.path)
+    saved_mods = {k: sys.modules.get(k) for k in
+                  ["run_nerf_helpers", "model", "render", "tree", "image_process", "tree_utils"]}
+    for k in saved_mods:
+        sys.modules.pop(k, None)
+    sys.path.insert(0, REF_NERF)
+    try:
+        ns = types.SimpleNamespace()
+        ns.helpers = importlib.import_module("run_nerf_helpers")
+        ns.model = importlib.import_module("model")
+        ns.render = importlib.import_module("render")
+        ns.tree = importlib.import_module("tree")
+    finally:
+        sys.path[:] = saved_path
+        # keep the reference modules out of the global namespace so that the product's
+        # same-named modules (fast-learning-nerf_b200/render.py ...) can be imported later
+        for k, v in saved_mods.items():
+            cur = sys.modules.pop(k, None)
+            if v is not None:
+                sys.modules[k] = v
+            setattr(ns, "_" + k, cur)
+    return ns
+
+
+def ref_run_network(ns, inputs, viewdirs, fn, embed_fn, embeddirs_fn, netchunk=1024 * 64):
+    """run_network is defined in run_nerf.py (50-64), which cannot be imported without
+    configargparse/imageio/loaders; this is its 12-line call sequence expressed over the
+    reference's own embedders and model (no new arithmetic)."""
+    import torch
+    flat = inputs.reshape(-1, inputs.shape[-1])
+    emb = embed_fn(flat)
+    if viewdirs is not None:
+        dirs = viewdirs[:, None].expand(inputs.shape).reshape(-1, inputs.shape[-1])
+        emb = torch.cat([emb, embeddirs_fn(dirs)], -1)
+    out = torch.cat([fn(emb[i:i + netchunk]) for i in range(0, emb.shape[0], netchunk)], 0)
+    return out.reshape(list(inputs.shape[:-1]) + [out.shape[-1]])

@@ -1,0 +1,80 @@
+"""CPU: host-side logic that needs no device -- CLI/config surface, tree (de)serialisation mirror, parameter
+layout, checkpoint key compatibility."""
+import io
+import os
+import pickle
+
+import numpy as np
+import torch
+
+import nerf_oracle as O
+from conftest import PKG
+
+
+def test_config_parser_defaults_match_reference_flags():
+    import argument_parser
+    a = argument_parser.config_parser().parse_args([])
+    exp = dict(basedir='./logs/', netdepth=8, netwidth=256, N_rand=4096, lrate=5e-4, lrate_decay=250, chunk=32768,
+               netchunk=65536, N_samples=64, N_importance=0, perturb=1.0, multires=10, multires_views=4,
+               raw_noise_std=0.0, n_epoch=12, init_level=3, subdivide_every=1, subdivide_thres=0.015,
+               randSamp_perc=0.5, dataset_type='llff', testskip=8, factor=8, llffhold=8, precrop_frac=0.5,
+               i_embed=0, use_viewdirs=False, white_bkgd=False, no_ndc=False, lindisp=False, render_only=False)
+    for k, v in exp.items():
+        assert getattr(a, k) == v, k
+
+
+def test_config_file_and_cli_override():
+    import argument_parser
+    cfg = os.path.join(PKG, "configs", "lego.txt")
+    a = argument_parser.config_parser().parse_args(["--config", cfg, "--N_rand", "4096"])
+    assert a.N_rand == 4096 and a.white_bkgd and a.use_viewdirs and a.no_batching
+    assert (a.N_samples, a.N_importance, a.n_epoch, a.init_level, a.subdivide_every) == (64, 128, 18, 2, 3)
+    assert a.subdivide_thres == 0.001 and a.lrate_decay == 500 and a.dataset_type == 'blender'
+
+
+def test_tree_mirror_roundtrip_and_pickle(golden):
+    import tree
+    g = golden("quadtree")
+    for rnd in (0, 3):
+        boxes = g[f"r{rnd}.newboxes1"]
+        t = tree.QuadTree((int(g["H"]), int(g["W"])), 0.0, 1, _boxes=boxes, _min_area=float(g[f"r{rnd}.newminarea"][1]))
+        leaves = tree.get_children(t.root)
+        assert np.array_equal(np.array([l.box() for l in leaves], np.float64), boxes)       # DFS order preserved
+        t2 = pickle.load(io.BytesIO(pickle.dumps([t])))[0]                                   # pickled by qualified name
+        assert type(t2).__module__ == "tree" and t2.minArea == t.minArea
+        assert [l.box() for l in tree.get_children(t2.root)] == [l.box() for l in leaves]
+    # reference-style construction still works (uniform tree when thres <= 0)
+    t = tree.QuadTree(np.zeros((64, 64, 3), np.float32), 0.0, 3)
+    assert len(tree.get_children(t.root)) == 16 and t.minArea == 64 * 64 / 16
+    assert [l.box() for l in tree.get_children(t.root)] == O.uniform_tree(64, 64, 3)[0]
+    import tree_utils
+    assert len(tree.get_children(tree_utils.SimpleQuadTree(32, 32, 2).root)) == 4
+
+
+def test_parameter_layout_matches_reference_order():
+    import model
+    net = model.NeRF(D=8, W=256, input_ch=63, input_ch_views=27, output_ch=5, skips=[4], use_viewdirs=True)
+    names = [n for n, _ in net.named_parameters()]
+    ref = list(O.init_params(0).keys())
+    assert names == ref
+    shapes = {n: tuple(p.shape) for n, p in net.named_parameters()}
+    assert shapes["pts_linears.5.weight"] == (256, 319) and shapes["views_linears.0.weight"] == (128, 283)
+    assert sum(p.numel() for p in net.parameters()) == 595844
+    # offsets used by the kernels (csrc/mlp_layout.h) == running sum over parameters()
+    off, table = 0, {}
+    for n, p in net.named_parameters():
+        table[n] = off
+        off += p.numel()
+    assert table["pts_linears.5.weight"] == 279552 and table["views_linears.0.weight"] == 493056
+    assert table["feature_linear.weight"] == 529408 and table["alpha_linear.weight"] == 595200
+    assert table["rgb_linear.weight"] == 595457 and table["rgb_linear.bias"] == 595841
+    # DataParallel-style checkpoint keys
+    import run_nerf
+    sd = run_nerf.ModuleHolder(net).state_dict()
+    assert all(k.startswith("module.") for k in sd) and "module.pts_linears.0.weight" in sd
+
+
+def test_lr_schedule_and_feistel_free_logic():
+    from flnerf_b200.engine import lr_at
+    assert abs(lr_at(5e-4, 500, 0) - 5e-4) < 1e-12
+    assert abs(lr_at(5e-4, 500, 500000) - 5e-5) < 1e-12

@@ -1,0 +1,55 @@
+"""CPU, build container only: the oracle against the live, unmodified reference (skipped where /root/reference is
+absent, e.g. on the GPU box).  Complements the golden fixtures with fresh random inputs."""
+import numpy as np
+import pytest
+import torch
+
+import nerf_oracle as O
+import ref_shim
+
+pytestmark = pytest.mark.skipif(not ref_shim.available(), reason="reference tree not present")
+
+
+@pytest.fixture(scope="module")
+def ref():
+    return ref_shim.load()
+
+
+def test_composite_and_sample_pdf_random(ref):
+    torch.manual_seed(7)
+    raw = torch.randn(9, 40, 4) * 3
+    z = torch.sort(torch.rand(9, 40) * 4 + 2, -1)[0]
+    d = torch.randn(9, 3)
+    for wb in (False, True):
+        a = O.composite(raw, z, d, None, wb)
+        b = ref.render.raw2outputs(raw, z, d, 0, wb)
+        for x, y in zip(a, b):
+            assert torch.equal(torch.nan_to_num(x, nan=-7), torch.nan_to_num(y, nan=-7))
+    w = a[3]
+    mid = 0.5 * (z[:, 1:] + z[:, :-1])
+    assert torch.equal(O.inverse_cdf(mid, w[:, 1:-1], 33, None), ref.helpers.sample_pdf(mid, w[:, 1:-1], 33, det=True))
+
+
+def test_mlp_matches_reference_module(ref):
+    p = O.init_params(5)
+    m = ref.model.NeRF(D=8, W=256, input_ch=63, input_ch_views=27, output_ch=5, skips=[4], use_viewdirs=True)
+    m.load_state_dict(p)
+    assert [k for k, _ in m.named_parameters()] == list(p.keys())            # parameters() order == flat layout
+    x = torch.randn(50, 90)
+    np.testing.assert_allclose(O.mlp_forward(p, x).numpy(), m(x).detach().numpy(), atol=2e-6, rtol=0)
+
+
+def test_adam_matches_torch():
+    torch.manual_seed(0)
+    w = [torch.randn(7, 5), torch.randn(5)]
+    ref_w = [t.clone().requires_grad_(True) for t in w]
+    opt = torch.optim.Adam(ref_w, lr=5e-4, betas=(0.9, 0.999))
+    mine = O.AdamState([t.clone() for t in w])
+    for _ in range(5):
+        gs = [torch.randn_like(t) for t in w]
+        for t, g in zip(ref_w, gs):
+            t.grad = g.clone()
+        opt.step()
+        mine.step(gs)
+    for a, b in zip(mine.params, ref_w):
+        np.testing.assert_allclose(a.numpy(), b.detach().numpy(), rtol=1e-6, atol=1e-8)
