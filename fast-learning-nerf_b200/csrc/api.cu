@@ -26,7 +26,8 @@ int mlp_tc_pack_weights(flnerf_ctx *ctx, const float *params, void *packed, cuda
 int mlp_tc_forward(flnerf_ctx *ctx, const float *params, const void *packed, int64_t n, int S, const void *pe_tiles,
                    const float *dirpe, float *raw, void *stash, int training, cudaStream_t st);
 int mlp_tc_backward(flnerf_ctx *ctx, const float *params, const void *packed, int64_t n, int S, const void *pe_tiles,
-                    const float *dirpe, const void *stash, const float *draw, float *grads, void *ws, cudaStream_t st);
+                    const float *dirpe, const void *stash, const float *draw, float *grads, void *ws, int stages,
+                    cudaStream_t st);
 
 extern "C" {
 
@@ -96,9 +97,20 @@ int flnerf_mlp_forward(flnerf_ctx *ctx, int mode, const float *params, const voi
   return mlp_tc_forward(ctx, params, packed, n, S, x, dirpe, raw_out, stash, training, (cudaStream_t)stream);
 }
 
+int flnerf_mlp_backward_stages(flnerf_ctx *ctx, int mode, const float *params, const void *packed, int64_t n, int S,
+                               const void *x, const float *dirpe, const void *stash, const float *draw, float *grads,
+                               void *workspace, size_t workspace_bytes, int stages, void *stream);
+
 int flnerf_mlp_backward(flnerf_ctx *ctx, int mode, const float *params, const void *packed, int64_t n, int S,
                         const void *x, const float *dirpe, const void *stash, const float *draw, float *grads,
                         void *workspace, size_t workspace_bytes, void *stream) {
+  return flnerf_mlp_backward_stages(ctx, mode, params, packed, n, S, x, dirpe, stash, draw, grads, workspace,
+                                    workspace_bytes, 7, stream);
+}
+
+int flnerf_mlp_backward_stages(flnerf_ctx *ctx, int mode, const float *params, const void *packed, int64_t n, int S,
+                               const void *x, const float *dirpe, const void *stash, const float *draw, float *grads,
+                               void *workspace, size_t workspace_bytes, int stages, void *stream) {
   FL_REQUIRE(ctx && params && x && stash && draw && grads && workspace && n > 0 && S > 0,
              "flnerf_mlp_backward: bad arguments");
   FL_REQUIRE(workspace_bytes >= flnerf_mlp_bwd_workspace_bytes(mode, n), "flnerf_mlp_backward: workspace too small");
@@ -110,7 +122,8 @@ int flnerf_mlp_backward(flnerf_ctx *ctx, int mode, const float *params, const vo
   FL_REQUIRE(packed && dirpe, "flnerf_mlp_backward: bf16 mode needs packed weights and dirpe");
   FL_REQUIRE((((uintptr_t)packed | (uintptr_t)x | (uintptr_t)stash | (uintptr_t)workspace) & 1023) == 0,
              "flnerf_mlp_backward: packed / pe_tiles / stash / workspace must be 1024-byte aligned");
-  return mlp_tc_backward(ctx, params, packed, n, S, x, dirpe, stash, draw, grads, workspace, (cudaStream_t)stream);
+  return mlp_tc_backward(ctx, params, packed, n, S, x, dirpe, stash, draw, grads, workspace, stages,
+                         (cudaStream_t)stream);
 }
 
 }  // extern "C"

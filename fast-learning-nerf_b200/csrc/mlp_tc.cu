@@ -821,7 +821,7 @@ int mlp_tc_forward(flnerf_ctx *ctx, const float *params, const void *packed, int
 }
 
 int mlp_tc_backward(flnerf_ctx *ctx, const float *params, const void *packed, int64_t n, int S, const void *pe_tiles,
-                    const float *dirpe, const void *stash, const float *draw, float *grads, void *ws,
+                    const float *dirpe, const void *stash, const float *draw, float *grads, void *ws, int stages,
                     cudaStream_t st) {
   FL_REQUIRE(tc::setup_tables(ctx->sm_count) == 0, "mlp_tc: table setup failed: %s", cudaGetErrorString(cudaGetLastError()));
   int64_t n_pad = flnerf_padded_rows(n);
@@ -831,13 +831,13 @@ int mlp_tc_backward(flnerf_ctx *ctx, const float *params, const void *packed, in
   d.P = params; d.packed_dg = (const uint8_t *)packed + tc::FWD_BYTES; d.draw = draw; d.stash_mask = stash_mask;
   d.dy = (uint8_t *)ws; d.n = n; d.n_pairs = (int)(n_pad / 256);
   int grid = d.n_pairs < ctx->sm_count ? d.n_pairs : ctx->sm_count;
-  FL_LAUNCH(tc::mlp_dgrad_tc, grid, tc::kThreads, tc::SMEM_FWD, st, d);
+  if (stages & 1) FL_LAUNCH(tc::mlp_dgrad_tc, grid, tc::kThreads, tc::SMEM_FWD, st, d);
   tc::WgradParams w{};
   w.dy = (const uint8_t *)ws; w.stash_act = stash_act; w.pe_tiles = (const uint8_t *)pe_tiles; w.draw = draw;
   w.G = grads; w.n = n; w.n_tiles = (int)(n_pad / 128);
-  FL_LAUNCH(tc::mlp_wgrad_tc, tc::g_wgrad_grid, tc::kThreads, tc::SMEM_WG, st, w);
+  if (stages & 2) FL_LAUNCH(tc::mlp_wgrad_tc, tc::g_wgrad_grid, tc::kThreads, tc::SMEM_WG, st, w);
   const int tpb = 16;
-  FL_LAUNCH(tc::wgrad_small_kernel, (unsigned)((w.n_tiles + tpb - 1) / tpb), 128, 0, st, stash_act, w.dy, draw, dirpe,
+  if (stages & 4) FL_LAUNCH(tc::wgrad_small_kernel, (unsigned)((w.n_tiles + tpb - 1) / tpb), 128, 0, st, stash_act, w.dy, draw, dirpe,
             grads, n, S, w.n_tiles, tpb);
   return 0;
 }

@@ -37,6 +37,7 @@ SIGNATURES = {
     "flnerf_mlp_pack_weights": (_i, [_vp, _vp, _vp, _vp]),
     "flnerf_mlp_forward": (_i, [_vp, _i, _vp, _vp, _i64, _i, _vp, _vp, _vp, _vp, _i, _vp]),
     "flnerf_mlp_backward": (_i, [_vp, _i, _vp, _vp, _i64, _i, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "flnerf_mlp_backward_stages": (_i, [_vp, _i, _vp, _vp, _i64, _i, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _i, _vp]),
     "flnerf_composite_forward": (_i, [_vp, _i64, _i, _vp, _vp, _vp, _i64, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
     "flnerf_composite_backward": (_i, [_vp, _i64, _i, _vp, _vp, _vp, _i64, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
     "flnerf_sample_pdf_merge": (_i, [_vp, _i64, _i, _i, _vp, _vp, _vp, _i, _u64, _u64, _vp, _vp, _vp, _vp]),

@@ -140,14 +140,16 @@ def mlp_forward(mode, flat_params, packed, x, dirpe, n: int, S: int, training: b
     return raw, stash
 
 
-def mlp_backward(mode, flat_params, packed, x, dirpe, stash, draw, flat_grad, n: int, S: int):
-    """flat_grad += dL/dparams."""
+def mlp_backward(mode, flat_params, packed, x, dirpe, stash, draw, flat_grad, n: int, S: int, stages: int = 7, ws=None):
+    """flat_grad += dL/dparams.  ``stages`` selects kernels (1 dgrad, 2 wgrad, 4 heads) for per-kernel timing."""
     ws_bytes = L.load().flnerf_mlp_bwd_workspace_bytes(mode, n)
-    ws = _alloc_bytes(ws_bytes, flat_params.device)
+    if ws is None:
+        ws = _alloc_bytes(ws_bytes, flat_params.device)
     draw = _f32c(draw.reshape(n, 4))
-    L.check(L.load().flnerf_mlp_backward(_ctx(draw), mode, _ptr(flat_params), _ptr(packed), n, S, _ptr(x), _ptr(dirpe),
-                                         _ptr(stash), _ptr(draw), _ptr(flat_grad), _ptr(ws), ws_bytes, _stream()),
-            "flnerf_mlp_backward")
+    L.check(L.load().flnerf_mlp_backward_stages(_ctx(draw), mode, _ptr(flat_params), _ptr(packed), n, S, _ptr(x),
+                                                _ptr(dirpe), _ptr(stash), _ptr(draw), _ptr(flat_grad), _ptr(ws),
+                                                ws_bytes, int(stages), _stream()), "flnerf_mlp_backward")
+    return ws
 
 
 # ------------------------------------------------------------------------------------------ compositing

@@ -85,6 +85,12 @@ int flnerf_mlp_backward(flnerf_ctx *, int mode, const float *params, const void 
                         const void *x, const float *dirpe, const void *stash, const float *draw, float *grads,
                         void *workspace, size_t workspace_bytes, void *stream);
 
+/* same, running only the selected backward kernels (bit 0: data-gradient chain, bit 1: weight gradients, bit 2:
+ * rgb/view-direction heads) -- used by bench.py to time each kernel with CUDA events; FP32 mode ignores it */
+int flnerf_mlp_backward_stages(flnerf_ctx *, int mode, const float *params, const void *packed, int64_t n, int S,
+                               const void *x, const float *dirpe, const void *stash, const float *draw, float *grads,
+                               void *workspace, size_t workspace_bytes, int stages, void *stream);
+
 /* ---- a7: raw2outputs (render.py:149-192) and its backward. One warp per ray. */
 int flnerf_composite_forward(flnerf_ctx *, int64_t B, int S, const float *raw, const float *z, const float *rays_d,
                              int64_t rays_d_stride, const float *noise, int white_bkgd, float *rgb, float *disp,

@@ -1,0 +1,309 @@
+"""GPU (-m gpu): the MLP kernels, the reference-facing render API and the training step, through the C ABI.
+
+Tolerances:
+  * FLNERF_MODE_FP32 (parity path): outputs and loss within 1e-4 relative of the reference/oracle, gradients
+    within 2e-3 relative per tensor (fp32 summation order over up to 10^5 rows);
+  * FLNERF_MODE_BF16 (tcgen05 path): bf16 operands, fp32 accumulation.  Checked against an fp32 emulation that
+    rounds weights/activations to bf16 at the same places (max abs err <= 4e-3 of the output scale, mean <= 4e-4),
+    gradients within 3e-2 relative L2 per tensor; and against the fp32 path (relative L2 <= 2e-2).
+"""
+import math
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import nerf_oracle as O
+
+pytestmark = pytest.mark.gpu
+P = 595844
+
+
+def T(a, dev="cuda"):
+    return torch.from_numpy(np.asarray(a)).to(dev)
+
+
+def make_net(seed, precision):
+    import model
+    net = model.NeRF(D=8, W=256, input_ch=63, input_ch_views=27, output_ch=5, skips=[4], use_viewdirs=True,
+                     precision=precision)
+    net.load_state_dict(O.init_params(seed))
+    return net.cuda()
+
+
+def rb(x):
+    """bf16 rounding with a straight-through gradient (what the tensor-core path does to operands)."""
+    return x + (x.to(torch.bfloat16).float() - x).detach()
+
+
+def mlp_bf16_emulation(p, x, dirpe_rows):
+    """fp32 emulation of csrc/mlp_tc.cu: bf16 weights and activations, fp32 accumulate, fp32 heads."""
+    lin = torch.nn.functional.linear
+    xp = rb(x[:, :63])
+    h = xp
+    for i in range(8):
+        h = rb(torch.relu(lin(h, rb(p[f"pts_linears.{i}.weight"]), p[f"pts_linears.{i}.bias"])))
+        if i == 4:
+            h = torch.cat([xp, h], -1)
+    sigma = lin(h, p["alpha_linear.weight"], p["alpha_linear.bias"])
+    feat = rb(lin(h, rb(p["feature_linear.weight"]), p["feature_linear.bias"]))
+    wv = p["views_linears.0.weight"]
+    vb = lin(dirpe_rows, wv[:, 256:], p["views_linears.0.bias"])
+    h9 = rb(torch.relu(lin(feat, rb(wv[:, :256])) + vb))
+    rgb = lin(h9, p["rgb_linear.weight"], p["rgb_linear.bias"])
+    return torch.cat([rgb, sigma], -1)
+
+
+def rel_l2(a, b):
+    return float((a.double() - b.double()).norm() / b.double().norm().clamp(min=1e-30))
+
+
+# ------------------------------------------------------------------------------------------- fp32 parity path
+def test_mlp_fp32_forward_backward_golden(golden):
+    g = golden("mlp")
+    net = make_net(int(g["seed"]), "fp32")
+    x = T(g["x"])
+    y = net(x)
+    np.testing.assert_allclose(y.detach().cpu().numpy(), g["y"], atol=1e-5, rtol=1e-4)
+    net.zero_grad()
+    (y * T(g["gout"])).sum().backward()
+    grads = {n: p.grad.detach().cpu() for n, p in net.named_parameters()}
+    for k in g.files:
+        if k.startswith("grad."):
+            np.testing.assert_allclose(grads[k[5:]].numpy(), g[k], rtol=2e-3, atol=2e-5)
+        elif k.startswith("gradrow."):
+            np.testing.assert_allclose(grads[k[8:]][:4].numpy(), g[k], rtol=2e-3, atol=2e-5)
+        elif k.startswith("gradnorm."):
+            np.testing.assert_allclose(float(grads[k[9:]].double().norm()), float(g[k]), rtol=1e-4)
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_render_api_matches_reference_goldens(golden, precision):
+    import render as R
+    import run_nerf
+    g = golden("render_rays")
+    nc, nf = make_net(int(g["seed_c"]), precision), make_net(int(g["seed_f"]), precision)
+    import run_nerf_helpers as H
+    q = run_nerf.NetworkQuery(H.get_embedder(10)[0], H.get_embedder(4)[0], 65536)
+    tgt = T(g["target"])
+    tol = dict(fp32=(2e-5, 1e-4, 1e-4), bf16=(2e-2, 4e-2, 5e-2))[precision]
+    for name, kw in (("det", dict(perturb=0.0, pytest=False)), ("jit", dict(perturb=1.0, pytest=True))):
+        nc.zero_grad(); nf.zero_grad()
+        rgb, disp, acc, ex = R.render(int(g["H"]), int(g["W"]), g["K"], chunk=32768,
+                                      rays=torch.stack([T(g["rays_o"]), T(g["rays_d"])], 0), ndc=False, near=2.0, far=6.0,
+                                      use_viewdirs=True, network_query_fn=q, network_fn=nc, network_fine=nf,
+                                      N_samples=64, N_importance=128, white_bkgd=True, raw_noise_std=0.0, retraw=True, **kw)
+        assert rgb.shape == (16, 3) and ex["raw"].shape == (16, 192, 4) and set(ex) == {"raw", "rgb0", "disp0", "acc0", "z_std"}
+        np.testing.assert_allclose(ex["rgb0"].detach().cpu().numpy(), g[f"{name}.rgb0"], atol=tol[0], rtol=0)
+        np.testing.assert_allclose(rgb.detach().cpu().numpy(), g[f"{name}.rgb"], atol=tol[1], rtol=0)
+        loss = H.img2mse(rgb, tgt) + H.img2mse(ex["rgb0"], tgt)
+        np.testing.assert_allclose(float(loss), float(g[f"{name}.loss"]), rtol=tol[2])
+        if precision == "fp32":
+            np.testing.assert_allclose(acc.detach().cpu().numpy(), g[f"{name}.acc"], atol=1e-4)
+            np.testing.assert_allclose(ex["z_std"].cpu().numpy(), g[f"{name}.z_std"], atol=2e-4)
+            loss.backward()
+            for tag, net in (("c", nc), ("f", nf)):
+                for n_, p_ in net.named_parameters():
+                    ref = float(g[f"{name}.gnorm.{tag}.{n_}"])
+                    np.testing.assert_allclose(float(p_.grad.double().norm()), ref, rtol=5e-3, atol=1e-9)
+                    key = f"{name}.grad.{tag}.{n_}"
+                    if key in g.files:
+                        np.testing.assert_allclose(p_.grad.cpu().numpy(), g[key], rtol=5e-3, atol=2e-5 * max(ref, 1e-6))
+
+
+def test_ndc_render_golden(golden):
+    import render as R, run_nerf, run_nerf_helpers as H
+    g = golden("render_ndc")
+    nc, nf = make_net(int(g["seed_c"]), "fp32"), make_net(int(g["seed_f"]), "fp32")
+    q = run_nerf.NetworkQuery(H.get_embedder(10)[0], H.get_embedder(4)[0], 65536)
+    with torch.no_grad():
+        rgb, disp, acc, ex = R.render(int(g["H"]), int(g["W"]), g["K"], rays=torch.stack([T(g["rays_o"]), T(g["rays_d"])], 0),
+                                      ndc=True, near=0.0, far=1.0, use_viewdirs=True, network_query_fn=q, network_fn=nc,
+                                      network_fine=nf, N_samples=64, N_importance=128, white_bkgd=False, perturb=0.0)
+    np.testing.assert_allclose(ex["rgb0"].cpu().numpy(), g["rgb0"], atol=2e-5)
+    np.testing.assert_allclose(rgb.cpu().numpy(), g["rgb"], atol=1e-4)
+
+
+# ------------------------------------------------------------------------------------------- tcgen05 path
+def test_mlp_bf16_forward_backward_vs_emulation():
+    torch.manual_seed(0)
+    B, S = 40, 24                                   # 960 rows: 7.5 tiles -> exercises the padded last pair
+    rays = torch.cat([torch.randn(B, 3) * 0.5, torch.nn.functional.normalize(torch.randn(B, 3), dim=-1),
+                      2 * torch.ones(B, 1), 6 * torch.ones(B, 1), torch.nn.functional.normalize(torch.randn(B, 3), dim=-1)], -1)
+    z = torch.sort(torch.rand(B, S) * 4 + 2, -1)[0]
+    net = make_net(21, "bf16")
+    raw = net.query_rays(rays.cuda(), z.cuda())
+    assert raw.shape == (B, S, 4)
+    p = {k: v.clone().requires_grad_(True) for k, v in O.init_params(21).items()}
+    pts = rays[:, None, 0:3] + rays[:, None, 3:6] * z[:, :, None]
+    x = torch.cat([O.posenc(pts.reshape(-1, 3), 10), O.posenc(rays[:, None, 8:11].expand(B, S, 3).reshape(-1, 3), 4)], -1)
+    ref = mlp_bf16_emulation(p, x, x[:, 63:])
+    got = raw.detach().cpu().reshape(-1, 4)
+    scale = float(ref.abs().max())
+    err = (got - ref.detach()).abs()
+    assert float(err.max()) <= 4e-3 * scale and float(err.mean()) <= 4e-4 * scale, (float(err.max()), float(err.mean()), scale)
+    f32 = O.mlp_forward({k: v.detach() for k, v in p.items()}, x)
+    assert rel_l2(got, f32) < 2e-2
+    gout = torch.randn(B * S, 4) * 0.1
+    net.zero_grad()
+    (raw.reshape(-1, 4) * gout.cuda()).sum().backward()
+    (ref * gout).sum().backward()
+    for n_, q in net.named_parameters():
+        r = rel_l2(q.grad.cpu(), p[n_].grad)
+        assert r < 3e-2, (n_, r)
+
+
+def test_nerf_forward_api_on_embedded_rows():
+    torch.manual_seed(1)
+    x = torch.randn(300, 90)
+    p = O.init_params(3)
+    ref = O.mlp_forward(p, x)
+    y32 = make_net(3, "fp32")(x.cuda())
+    np.testing.assert_allclose(y32.detach().cpu().numpy(), ref.numpy(), atol=2e-5, rtol=1e-4)
+    y16 = make_net(3, "bf16")(x.cuda().reshape(3, 100, 90))
+    assert y16.shape == (3, 100, 4) and rel_l2(y16.detach().cpu().reshape(-1, 4), ref) < 2e-2
+    with torch.no_grad():
+        y_ng = make_net(3, "bf16")(x.cuda())
+    assert torch.equal(y_ng.cpu(), y16.detach().cpu().reshape(-1, 4))       # inference (no stash) == training forward
+
+
+# ------------------------------------------------------------------------------------------- training step
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_fused_trainer_matches_autograd_path_and_oracle(golden, precision):
+    import render as R, run_nerf, run_nerf_helpers as H
+    from flnerf_b200.engine import FusedAdam, Trainer
+    g = golden("render_rays")
+    ro, rd, tgt = T(g["rays_o"]), T(g["rays_d"]), T(g["target"])
+    K, Hh, Ww = g["K"], int(g["H"]), int(g["W"])
+
+    def fresh():
+        nc, nf = make_net(int(g["seed_c"]), precision), make_net(int(g["seed_f"]), precision)
+        opt = FusedAdam(list(nc.parameters()) + list(nf.parameters()), [nc, nf], lr=5e-4)
+        return nc, nf, opt
+
+    # (1) public API: render + loss.backward + optimizer.step  (run_nerf.py:479-494)
+    nc, nf, opt = fresh()
+    q = run_nerf.NetworkQuery(H.get_embedder(10)[0], H.get_embedder(4)[0], 65536)
+    rgb, _, _, ex = R.render(Hh, Ww, K, rays=torch.stack([ro, rd], 0), ndc=False, near=2.0, far=6.0, use_viewdirs=True,
+                             network_query_fn=q, network_fn=nc, network_fine=nf, N_samples=64, N_importance=128,
+                             white_bkgd=True, perturb=0.0, retraw=True)
+    opt.zero_grad()
+    loss = H.img2mse(rgb, tgt) + H.img2mse(ex["rgb0"], tgt)
+    loss.backward()
+    g_api = torch.cat([nc._flat_grad, nf._flat_grad]).clone()
+    opt.step()
+    w_api = torch.cat([nc.flat_parameters(), nf.flat_parameters()]).clone()
+    # (2) fused trainer (no autograd)
+    nc2, nf2, opt2 = fresh()
+    tr = Trainer(nc2, nf2, opt2, Hh, Ww, K, 2.0, 6.0, 64, 128, white_bkgd=True, perturb=0.0)
+    l2 = tr.step(ro, rd, tgt)
+    np.testing.assert_allclose(float(l2.sum()), float(loss), rtol=1e-5)
+    w_tr = torch.cat([nc2.flat_parameters(), nf2.flat_parameters()])
+    assert rel_l2(tr.bucket, g_api) < (1e-4 if precision == "fp32" else 2e-3)
+    assert float((w_tr - w_api).abs().max()) <= 2.1 * 5e-4          # same Adam step up to sign flips of ~zero grads
+    assert float((w_tr - w_api).abs().mean()) < 2e-5
+    # (3) oracle: one full reference iteration (render + 2 MSE + backward + Adam) on the CPU
+    pc, pf = O.init_params(int(g["seed_c"])), O.init_params(int(g["seed_f"]))
+    o_opt = O.AdamState(list(pc.values()) + list(pf.values()))
+    rays11 = O.pack_rays(Hh, Ww, K, ro.cpu(), rd.cpu(), 2.0, 6.0, ndc=False)
+    res = O.train_step(rays11, tgt.cpu(), pc, pf, o_opt, 64, 128, white_bkgd=True)
+    g_or = torch.cat([x.reshape(-1) for x in res["grads"]])
+    np.testing.assert_allclose(float(l2.sum()), res["loss"], rtol=1e-4 if precision == "fp32" else 5e-2)
+    assert rel_l2(tr.bucket.cpu(), g_or) < (2e-3 if precision == "fp32" else 1e-1)
+
+
+def test_fused_adam_state_dict_is_stock_adam_compatible(tmp_path):
+    from flnerf_b200.engine import FusedAdam
+    import run_nerf
+    nc, nf = make_net(1, "fp32"), make_net(2, "fp32")
+    params = list(nc.parameters()) + list(nf.parameters())
+    opt = FusedAdam(params, [nc, nf], lr=5e-4)
+    for net in (nc, nf):
+        net._grad_bucket().normal_()
+    opt.step(); opt.step()
+    sd = opt.state_dict()
+    assert len(sd["state"]) == 48 and len(sd["param_groups"]) == 1 and len(sd["param_groups"][0]["params"]) == 48
+    assert float(sd["state"][0]["step"]) == 2.0 and sd["state"][0]["exp_avg"].shape == (256, 63)
+    # checkpoint exactly as run_nerf.py:532-539 writes it, reloaded by stock torch objects
+    path = os.path.join(tmp_path, "001.tar")
+    torch.save({"global_epoch": 1, "global_iter": 2, "network_fn_state_dict": run_nerf.ModuleHolder(nc).state_dict(),
+                "network_fine_state_dict": run_nerf.ModuleHolder(nf).state_dict(), "optimizer_state_dict": sd}, path)
+    ck = torch.load(path, weights_only=False)
+    stock_params = [torch.nn.Parameter(p.detach().clone()) for p in params]
+    stock = torch.optim.Adam(stock_params, lr=5e-4, betas=(0.9, 0.999))
+    stock.load_state_dict(ck["optimizer_state_dict"])
+    # one more identical step on both sides
+    gnew = [torch.randn_like(p) for p in params]
+    off = 0
+    for net in (nc, nf):
+        b = net._grad_bucket()
+        o2 = 0
+        for p in net.parameters():
+            b[o2:o2 + p.numel()].copy_(gnew[off].reshape(-1)); o2 += p.numel(); off += 1
+    for sp, gg in zip(stock_params, gnew):
+        sp.grad = gg.clone()
+    opt.step(); stock.step()
+    for a, b in zip(params, stock_params):
+        np.testing.assert_allclose(a.detach().cpu().numpy(), b.detach().cpu().numpy(), rtol=3e-6, atol=2e-7)
+    # and the other direction: our optimiser resumes from a stock state dict
+    opt2 = FusedAdam(params, [nc, nf], lr=5e-4)
+    opt2.load_state_dict(stock.state_dict())
+    assert float(opt2.state_dict()["state"][5]["step"]) == 3.0
+    assert all(k.startswith("module.") for k in ck["network_fn_state_dict"])
+
+
+def test_training_reduces_loss_bf16():
+    """30 fused steps on a fixed synthetic batch: the tcgen05 training path must actually learn."""
+    from flnerf_b200.engine import FusedAdam, Trainer
+    from flnerf_b200 import synthetic
+    torch.manual_seed(0)
+    H = W = 100
+    K = synthetic.intrinsics(H, W, 138.9)
+    poses = synthetic.lego_like_poses(4)
+    imgs = synthetic.render_scene(H, W, K, poses, n_samples=64)
+    nc, nf = make_net(5, "bf16"), make_net(6, "bf16")
+    opt = FusedAdam(list(nc.parameters()) + list(nf.parameters()), [nc, nf], lr=5e-4)
+    tr = Trainer(nc, nf, opt, H, W, K, 2.0, 6.0, 64, 128, white_bkgd=True, perturb=1.0)
+    import tree
+    mgr = tree.QuadTreeManager(H, W, K, imgs, torch.as_tensor(poses[:, :3, :4]), mseThres=0.0, max_depth=2, max_level=4)
+    n = mgr.emit_epoch()
+    losses = []
+    for i, first in enumerate(range(0, min(n, 30 * 1024), 1024)):
+        losses.append(tr.step_from_tree(mgr, first, 1024))
+    l = torch.stack(losses).sum(-1).cpu().numpy()
+    assert np.all(np.isfinite(l)) and l[-5:].mean() < 0.9 * l[:3].mean(), l
+    assert float(mgr.leaf_max.max()) > 0                                 # per-leaf statistic accumulated on the device
+
+
+# ------------------------------------------------------------------------------------------- BASELINE-size properties
+def test_full_size_properties():
+    """config 2 sizes (4096 rays, 64+128 samples): properties that do not need the (slow) CPU oracle."""
+    from flnerf_b200 import ops
+    torch.manual_seed(0)
+    B, Nc, Nf = 4096, 64, 128
+    rays = torch.cat([torch.randn(B, 3) * 0.3 + torch.tensor([0., 0., 4.]), -torch.nn.functional.normalize(torch.randn(B, 3) * 0.2 + torch.tensor([0., 0., 1.]), dim=-1),
+                      2 * torch.ones(B, 1), 6 * torch.ones(B, 1), torch.nn.functional.normalize(torch.randn(B, 3), dim=-1)], -1).cuda()
+    z = ops.coarse_depths(rays, Nc, True, False, None, 1, 0)
+    net16, net32 = make_net(8, "bf16"), make_net(8, "fp32")
+    with torch.no_grad():
+        raw16 = net16.query_rays(rays, z)
+        raw32 = net32.query_rays(rays, z)
+        assert rel_l2(raw16, raw32) < 2e-2                                       # bf16 tensor path tracks the fp32 path
+        perm = torch.randperm(B, device="cuda")
+        raw16p = net16.query_rays(rays[perm].contiguous(), z[perm].contiguous())
+        assert torch.equal(raw16p, raw16[perm])                                  # row-permutation equivariance, bit-exact
+        rgb, disp, acc, w, depth = ops.composite_forward(raw16.contiguous(), z, rays[:, 3:6].contiguous(), None, True)
+        assert float(acc.max()) <= 1 + 1e-5 and float(w.min()) >= 0
+        np.testing.assert_allclose(w.sum(-1).cpu().numpy(), acc.cpu().numpy(), atol=1e-5)
+        zf, zs, zstd = ops.sample_pdf_merge(z, w, Nf, False, None, 2, 0)
+        assert zf.shape == (B, Nc + Nf) and bool((zf[:, 1:] >= zf[:, :-1]).all())
+        assert torch.equal(zf, torch.sort(torch.cat([z, zs], -1), -1)[0])
+    # linearity of the backward pass in the upstream gradient (both nets see 2x the gradient -> 2x the bucket)
+    raw = net16.query_rays(rays, zf)
+    gout = torch.randn_like(raw) * 1e-3
+    net16.zero_grad(); (raw * gout).sum().backward(); g1 = net16._flat_grad.clone()
+    raw = net16.query_rays(rays, zf)
+    net16.zero_grad(); (raw * (2 * gout)).sum().backward(); g2 = net16._flat_grad.clone()
+    assert rel_l2(g2, 2 * g1) < 1e-4
+    assert float(g1.abs().max()) > 0 and bool(torch.isfinite(g1).all())
