@@ -256,8 +256,8 @@ int flnerf_raygen(flnerf_ctx *ctx, int H, int W, const double *h_K, const float 
 
 int flnerf_pack_rays(flnerf_ctx *ctx, int64_t B, const float *rays_o, const float *rays_d, float near_, float far_,
                      int ndc, int H, int W, double focal, float *rays11, void *stream) {
-  FL_REQUIRE(ctx && rays_o && rays_d && rays11 && B >= 0, "flnerf_pack_rays: bad arguments");
   if (B == 0) return 0;
+  FL_REQUIRE(ctx && rays_o && rays_d && rays11 && B > 0, "flnerf_pack_rays: bad arguments");
   float sx = (float)(-1.0 / (W / (2.0 * focal))), sy = (float)(-1.0 / (H / (2.0 * focal)));
   FL_LAUNCH(pack_rays_kernel, (unsigned)ceil_div64(B, 256), 256, 0, stream, B, rays_o, rays_d, near_, far_, ndc, sx, sy,
             rays11);

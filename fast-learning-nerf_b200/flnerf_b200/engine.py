@@ -57,17 +57,22 @@ class FusedAdam(torch.optim.Adam):
                     m[off:off + n].copy_(st["exp_avg"].reshape(-1))
                     v[off:off + n].copy_(st["exp_avg_sq"].reshape(-1))
                 if step is None:
-                    step = st.get("step", torch.tensor(0.0))
-                    step = step.detach().cpu().float() if torch.is_tensor(step) else torch.tensor(float(step))
+                    step = int(float(st["step"])) if "step" in st else 0
                 st["exp_avg"] = m[off:off + n].view(p.shape)
                 st["exp_avg_sq"] = v[off:off + n].view(p.shape)
-                st["step"] = step
+                st["step"] = torch.tensor(float(step))      # one tensor per parameter, like stock Adam
                 off += n
             self._step[id(net)] = step
 
     def load_state_dict(self, state_dict):
         super().load_state_dict(state_dict)
         self._bind()
+
+    def state_dict(self):
+        for net in self._nets:      # the fused step keeps ONE counter per net; publish it per parameter
+            for p in net.parameters():
+                self.state[p]["step"] = torch.tensor(float(self._step[id(net)]))
+        return super().state_dict()
 
     def zero_grad(self, set_to_none: bool = True):
         for net in self._nets:
@@ -78,10 +83,9 @@ class FusedAdam(torch.optim.Adam):
         g = self.param_groups[0]
         b1, b2 = g["betas"]
         for net in self._nets:
-            step = self._step[id(net)]
-            step += 1
+            self._step[id(net)] += 1
             ops.adam_step(net.flat_parameters(), self._m[id(net)], self._v[id(net)], net._grad_bucket(), float(g["lr"]),
-                          b1, b2, g["eps"], int(step.item()))
+                          b1, b2, g["eps"], self._step[id(net)])
             net.weights_version += 1
 
 
