@@ -221,13 +221,19 @@ sample_pdf_merge_kernel(int64_t B, int Nc, int Nf, int P2, const float *__restri
   float part = 0.f;
   for (int k = lane; k < M; k += 32) part += __fadd_rn(ww[k + 1], 1e-5f);
   float total = warp_sum(part);
-  float carry = 0.f;
+  // torch.cumsum on the CPU accumulates fp32 inputs in double and rounds every prefix once; do the same so that the
+  // searchsorted / den<1e-5 decisions below see the reference's cdf
+  double carry = 0.0;
   if (lane == 0) cdf[0] = 0.f;
   for (int base = 0; base < M; base += 32) {
     int k = base + lane;
-    float p = (k < M) ? __fdiv_rn(__fadd_rn(ww[k + 1], 1e-5f), total) : 0.f;
-    float incl = warp_scan_add(p, lane);
-    if (k < M) cdf[k + 1] = carry + incl;
+    double incl = (k < M) ? (double)__fdiv_rn(__fadd_rn(ww[k + 1], 1e-5f), total) : 0.0;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      double t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += t;
+    }
+    if (k < M) cdf[k + 1] = (float)(carry + incl);
     carry += __shfl_sync(0xffffffffu, incl, 31);
   }
   __syncwarp();

@@ -27,7 +27,9 @@ constexpr int kEpiWarp0 = 2;
 constexpr uint32_t ACT_BYTES = 65536, SLAB_BYTES = 16384, PE_BYTES = 16384, WSTAGE = 32768;
 constexpr int NSTAGE = 2;
 constexpr uint32_t OFF_ACT = 0, OFF_PE = 2 * ACT_BYTES, OFF_W = OFF_PE + 2 * PE_BYTES, OFF_BAR = OFF_W + NSTAGE * WSTAGE;
-constexpr uint32_t SMEM_FWD = OFF_BAR + 256;
+// fp32 copies of the small heads: W_rgb[3][128], b_rgb[3], b_alpha[1], w_alpha[256]
+constexpr uint32_t OFF_HEAD = OFF_BAR + 256, HEAD_FLOATS = 384 + 4 + 256;
+constexpr uint32_t SMEM_FWD = OFF_HEAD + HEAD_FLOATS * 4;
 static_assert(SMEM_FWD <= 232448, "shared memory budget");
 
 // packed weight image of one net
@@ -115,11 +117,15 @@ __device__ __forceinline__ void issue_chunk(uint32_t tmem_d, uint32_t a_smem, ui
   for (int k = 0; k < 4; ++k) umma_bf16(tmem_d, da + 2 * k, db + 2 * k, idesc, (first && k == 0) ? 0u : 1u);
 }
 
-__device__ __forceinline__ void common_setup(uint8_t *smem, const Bars &bars, uint32_t *tmem_slot, int warp) {
+__device__ __forceinline__ void common_setup(uint8_t *smem, const Bars &bars, uint32_t *tmem_slot, int warp,
+                                             const float *P) {
   if ((smem_u32(smem) & 1023u) != 0) {
     if (threadIdx.x == 0) printf("flnerf: dynamic smem base not 1024-byte aligned\n");
     __trap();
   }
+  float *head = reinterpret_cast<float *>(smem + OFF_HEAD);
+  for (int i = threadIdx.x; i < (int)HEAD_FLOATS; i += blockDim.x)
+    head[i] = i < 387 ? P[W_RGB + i] : (i == 387 ? P[B_ALPHA] : P[W_ALPHA + (i - 388)]);
   if (warp == 1 && lane_id() == 0) {
     for (int i = 0; i < NSTAGE; ++i) { mbar_init(bars.w_full[i], 1); mbar_init(bars.w_empty[i], 1); }
     mbar_init(bars.pe_full, 1);
@@ -148,6 +154,99 @@ __device__ __forceinline__ void store_cols32(uint8_t *act_tile, uint32_t r, uint
   }
 }
 
+// ---- epilogue building blocks ---------------------------------------------------------------------
+// forward: 32 accumulator columns [c0, c0+32) of row r -> +bias -> (relu) -> bf16 -> act tile; kType 0 relu,
+// 1 relu + alpha head, 2 linear.  Returns the non-zero mask of the 32 outputs (0 when not needed).
+template <int kType, bool kMask>
+__device__ __forceinline__ uint32_t fwd_block(const uint32_t v[32], const float *__restrict__ bias, uint8_t *act_tile,
+                                              uint32_t r, uint32_t c0, const float *s_wa, float &alpha) {
+  uint32_t pk[16], m = 0;
+  const float4 *b4 = reinterpret_cast<const float4 *>(bias + c0);
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    const float4 b = __ldg(b4 + q);
+    const float x0 = __uint_as_float(v[4 * q]) + b.x, x1 = __uint_as_float(v[4 * q + 1]) + b.y;
+    const float x2 = __uint_as_float(v[4 * q + 2]) + b.z, x3 = __uint_as_float(v[4 * q + 3]) + b.w;
+    const uint32_t w0 = kType == 2 ? pack_bf16_fast(x0, x1) : pack_bf16_relu(x0, x1);
+    const uint32_t w1 = kType == 2 ? pack_bf16_fast(x2, x3) : pack_bf16_relu(x2, x3);
+    pk[2 * q] = w0;
+    pk[2 * q + 1] = w1;
+    if (kMask) m |= nz_bits(w0, 4 * q) | nz_bits(w1, 4 * q + 2);
+    if (kType == 1) {  // alpha_linear on the bf16-rounded activations the next layers also see
+      const float4 a = *reinterpret_cast<const float4 *>(s_wa + c0 + 4 * q);
+      alpha = fmaf(bf16_lo(w0), a.x, alpha);
+      alpha = fmaf(bf16_hi(w0), a.y, alpha);
+      alpha = fmaf(bf16_lo(w1), a.z, alpha);
+      alpha = fmaf(bf16_hi(w1), a.w, alpha);
+    }
+  }
+  store_cols32(act_tile, r, c0, pk);
+  return m;
+}
+
+// all 256 columns of one row, TMEM loads double-buffered against the math
+template <int kType, bool kMask>
+__device__ __forceinline__ void fwd_epilogue_256(uint32_t tmem_row, const float *__restrict__ bias, uint8_t *act_tile,
+                                                 uint32_t r, uint32_t *mask_dst, const float *s_wa, float &alpha) {
+  uint32_t va[32], vb[32], mk[8];
+  tmem_ld32(tmem_row, va);
+#pragma unroll
+  for (int cb = 0; cb < 8; cb += 2) {
+    tmem_ld_wait(va);
+    tmem_ld32(tmem_row + (cb + 1) * 32, vb);
+    mk[cb] = fwd_block<kType, kMask>(va, bias, act_tile, r, cb * 32, s_wa, alpha);
+    tmem_ld_wait(vb);
+    if (cb + 2 < 8) tmem_ld32(tmem_row + (cb + 2) * 32, va);
+    mk[cb + 1] = fwd_block<kType, kMask>(vb, bias, act_tile, r, (cb + 1) * 32, s_wa, alpha);
+  }
+  if (kMask) {
+    uint4 *d = reinterpret_cast<uint4 *>(mask_dst);
+    d[0] = make_uint4(mk[0], mk[1], mk[2], mk[3]);
+    d[1] = make_uint4(mk[4], mk[5], mk[6], mk[7]);
+  }
+}
+
+// backward: gradient columns [c0, c0+32) -> (+ d_sigma * w_alpha) -> relu mask -> bf16 -> act tile
+template <bool kAlpha, bool kUseMask>
+__device__ __forceinline__ void dgrad_block(const uint32_t v[32], uint32_t m, float dsig, const float *s_wa,
+                                            uint8_t *act_tile, uint32_t r, uint32_t c0) {
+  uint32_t pk[16];
+#pragma unroll
+  for (int i = 0; i < 32; i += 2) {
+    float g0 = __uint_as_float(v[i]), g1 = __uint_as_float(v[i + 1]);
+    if (kAlpha) {
+      g0 = fmaf(dsig, s_wa[c0 + i], g0);
+      g1 = fmaf(dsig, s_wa[c0 + i + 1], g1);
+    }
+    if (kUseMask) {
+      g0 = (m & (1u << i)) ? g0 : 0.f;
+      g1 = (m & (2u << i)) ? g1 : 0.f;
+    }
+    pk[i >> 1] = pack_bf16_fast(g0, g1);
+  }
+  store_cols32(act_tile, r, c0, pk);
+}
+
+template <bool kAlpha, bool kUseMask>
+__device__ __forceinline__ void dgrad_epilogue_256(uint32_t tmem_row, const uint32_t *__restrict__ mask_row, float dsig,
+                                                   const float *s_wa, uint8_t *act_tile, uint32_t r) {
+  uint32_t va[32], vb[32], mk[8];
+  tmem_ld32(tmem_row, va);
+  if (kUseMask) {
+    const uint4 a = __ldg(reinterpret_cast<const uint4 *>(mask_row)), b = __ldg(reinterpret_cast<const uint4 *>(mask_row) + 1);
+    mk[0] = a.x; mk[1] = a.y; mk[2] = a.z; mk[3] = a.w; mk[4] = b.x; mk[5] = b.y; mk[6] = b.z; mk[7] = b.w;
+  }
+#pragma unroll
+  for (int cb = 0; cb < 8; cb += 2) {
+    tmem_ld_wait(va);
+    tmem_ld32(tmem_row + (cb + 1) * 32, vb);
+    dgrad_block<kAlpha, kUseMask>(va, kUseMask ? mk[cb] : 0u, dsig, s_wa, act_tile, r, cb * 32);
+    tmem_ld_wait(vb);
+    if (cb + 2 < 8) tmem_ld32(tmem_row + (cb + 2) * 32, va);
+    dgrad_block<kAlpha, kUseMask>(vb, kUseMask ? mk[cb + 1] : 0u, dsig, s_wa, act_tile, r, (cb + 1) * 32);
+  }
+}
+
 // =================================================================================================
 // forward
 // =================================================================================================
@@ -170,7 +269,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_fwd_tc(FwdParams p) {
   const uint32_t lane = lane_id();
   const Bars bars = make_bars(smem_u32(smem + OFF_BAR));
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + OFF_BAR + 128);
-  common_setup(smem, bars, tmem_slot, warp);
+  common_setup(smem, bars, tmem_slot, warp, p.P);
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t s_act = smem_u32(smem + OFF_ACT), s_pe = smem_u32(smem + OFF_PE), s_w = smem_u32(smem + OFF_W);
 
@@ -261,66 +360,53 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_fwd_tc(FwdParams p) {
         }
         uint32_t *mask_dst = p.stash_mask ? p.stash_mask + ((size_t)tile * 9 + (L < 9 ? L : 8)) * 128 * 8 + (size_t)r * 8
                                           : nullptr;
-        if (L < 9) {
-          const float *bias = p.P + (L < 8 ? b_pts(L) : B_FEAT);
-          const float *wa = p.P + W_ALPHA;
-#pragma unroll 1
-          for (int cb = 0; cb < 8; ++cb) {
-            uint32_t v[32], pk[16];
-            tmem_ld32(tmem_row + cb * 32, v);
-            tmem_ld_wait();
-            uint32_t m = 0;
-#pragma unroll
-            for (int i = 0; i < 32; i += 2) {
-              float x0 = __uint_as_float(v[i]) + __ldg(bias + cb * 32 + i);
-              float x1 = __uint_as_float(v[i + 1]) + __ldg(bias + cb * 32 + i + 1);
-              if (L < 8) { x0 = fmaxf(x0, 0.f); x1 = fmaxf(x1, 0.f); }
-              uint32_t w = pack_bf16(x0, x1);
-              pk[i >> 1] = w;
-              m |= ((w & 0xFFFFu) ? 1u : 0u) << i;
-              m |= ((w >> 16) ? 1u : 0u) << (i + 1);
-              if (L == 7) {  // alpha_linear on the (bf16-rounded) activations the next layers also see
-                alpha = fmaf(bf16_lo(w), __ldg(wa + cb * 32 + i), alpha);
-                alpha = fmaf(bf16_hi(w), __ldg(wa + cb * 32 + i + 1), alpha);
-              }
-            }
-            if (mask_dst && L < 8) mask_dst[cb] = m;
-            store_cols32(act_tile, r, cb * 32, pk);
-          }
+        const float *s_head = reinterpret_cast<const float *>(smem + OFF_HEAD);
+        const float *s_wa = s_head + 388;
+        if (L < 7) {
+          const float *bias = p.P + b_pts(L);
+          if (mask_dst) fwd_epilogue_256<0, true>(tmem_row, bias, act_tile, r, mask_dst, s_wa, alpha);
+          else fwd_epilogue_256<0, false>(tmem_row, bias, act_tile, r, nullptr, s_wa, alpha);
+        } else if (L == 7) {
+          alpha = 0.f;
+          if (mask_dst) fwd_epilogue_256<1, true>(tmem_row, p.P + b_pts(7), act_tile, r, mask_dst, s_wa, alpha);
+          else fwd_epilogue_256<1, false>(tmem_row, p.P + b_pts(7), act_tile, r, nullptr, s_wa, alpha);
+        } else if (L == 8) {
+          fwd_epilogue_256<2, false>(tmem_row, p.P + B_FEAT, act_tile, r, nullptr, s_wa, alpha);
         } else {
           // views_linears.0 (N=128) + rgb_linear on CUDA cores, then raw = (r,g,b,sigma)
           const int64_t ray = (row < p.n ? row : p.n - 1) / p.S;
-          const float *vb = p.viewbias + ray * 128;
-          const float *wr = p.P + W_RGB;
+          const float4 *vb4 = reinterpret_cast<const float4 *>(p.viewbias + ray * 128);
           float c0 = 0.f, c1 = 0.f, c2 = 0.f;
-#pragma unroll 1
-          for (int cb = 0; cb < 4; ++cb) {
-            uint32_t v[32], pk[16];
-            tmem_ld32(tmem_row + cb * 32, v);
-            tmem_ld_wait();
-            uint32_t m = 0;
+          uint32_t mk4[4];
 #pragma unroll
-            for (int i = 0; i < 32; i += 2) {
-              float x0 = fmaxf(__uint_as_float(v[i]) + __ldg(vb + cb * 32 + i), 0.f);
-              float x1 = fmaxf(__uint_as_float(v[i + 1]) + __ldg(vb + cb * 32 + i + 1), 0.f);
-              uint32_t w = pack_bf16(x0, x1);
-              pk[i >> 1] = w;
-              m |= ((w & 0xFFFFu) ? 1u : 0u) << i;
-              m |= ((w >> 16) ? 1u : 0u) << (i + 1);
-              float h0 = bf16_lo(w), h1 = bf16_hi(w);
-              int k = cb * 32 + i;
-              c0 = fmaf(h0, __ldg(wr + k), c0);           c0 = fmaf(h1, __ldg(wr + k + 1), c0);
-              c1 = fmaf(h0, __ldg(wr + 128 + k), c1);     c1 = fmaf(h1, __ldg(wr + 128 + k + 1), c1);
-              c2 = fmaf(h0, __ldg(wr + 256 + k), c2);     c2 = fmaf(h1, __ldg(wr + 256 + k + 1), c2);
+          for (int cb = 0; cb < 4; ++cb) {
+            uint32_t v[32], pk[16], m = 0;
+            tmem_ld32(tmem_row + cb * 32, v);
+            tmem_ld_wait(v);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              const float4 b = __ldg(vb4 + cb * 8 + q);
+              const uint32_t w0 = pack_bf16_relu(__uint_as_float(v[4 * q]) + b.x, __uint_as_float(v[4 * q + 1]) + b.y);
+              const uint32_t w1 = pack_bf16_relu(__uint_as_float(v[4 * q + 2]) + b.z, __uint_as_float(v[4 * q + 3]) + b.w);
+              pk[2 * q] = w0;
+              pk[2 * q + 1] = w1;
+              m |= nz_bits(w0, 4 * q) | nz_bits(w1, 4 * q + 2);
+              const float h[4] = {bf16_lo(w0), bf16_hi(w0), bf16_lo(w1), bf16_hi(w1)};
+              const int k = cb * 32 + 4 * q;
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                c0 = fmaf(h[e], s_head[k + e], c0);
+                c1 = fmaf(h[e], s_head[128 + k + e], c1);
+                c2 = fmaf(h[e], s_head[256 + k + e], c2);
+              }
             }
-            if (mask_dst) mask_dst[cb] = m;
+            mk4[cb] = m;
             store_cols32(act_tile, r, cb * 32, pk);
           }
-          if (row < p.n) {
-            float4 o = make_float4(c0 + __ldg(p.P + B_RGB), c1 + __ldg(p.P + B_RGB + 1), c2 + __ldg(p.P + B_RGB + 2),
-                                   alpha + __ldg(p.P + B_ALPHA));
-            reinterpret_cast<float4 *>(p.raw)[row] = o;
-          }
+          if (row < p.n)
+            reinterpret_cast<float4 *>(p.raw)[row] =
+                make_float4(c0 + s_head[384], c1 + s_head[385], c2 + s_head[386], alpha + s_head[387]);
+          if (mask_dst) *reinterpret_cast<uint4 *>(mask_dst) = make_uint4(mk4[0], mk4[1], mk4[2], mk4[3]);
         }
         tc_fence_before();
         fence_async_smem();
@@ -363,7 +449,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_dgrad_tc(DgradParams p) {
   const uint32_t lane = lane_id();
   const Bars bars = make_bars(smem_u32(smem + OFF_BAR));
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + OFF_BAR + 128);
-  common_setup(smem, bars, tmem_slot, warp);
+  common_setup(smem, bars, tmem_slot, warp, p.P);
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t s_act = smem_u32(smem + OFF_ACT), s_w = smem_u32(smem + OFF_W);
 
@@ -432,44 +518,31 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_dgrad_tc(DgradParams p) {
         // ReLU mask of the activation this gradient flows into: D=-1 -> h9 (slot 8), D=0 -> none (feature is
         // linear), D=1 -> H7, D=2 -> H6, ..., D=8 -> H0
         const uint32_t *mk = (D != 0) ? mask_base + (size_t)((D < 0) ? 8 : 8 - D) * 128 * 8 : nullptr;
+        const float *s_head = reinterpret_cast<const float *>(smem + OFF_HEAD);
+        const float *s_wa = s_head + 388;
         if (D < 0) {
-          const float *wr = p.P + W_RGB;
-#pragma unroll 1
+          const uint4 m4 = __ldg(reinterpret_cast<const uint4 *>(mk));
+          const uint32_t mw[4] = {m4.x, m4.y, m4.z, m4.w};
+#pragma unroll
           for (int cb = 0; cb < 4; ++cb) {
             uint32_t pk[16];
-            uint32_t m = __ldg(mk + cb);
 #pragma unroll
             for (int i = 0; i < 32; i += 2) {
-              int k = cb * 32 + i;
-              float g0 = dr.x * __ldg(wr + k) + dr.y * __ldg(wr + 128 + k) + dr.z * __ldg(wr + 256 + k);
-              float g1 = dr.x * __ldg(wr + k + 1) + dr.y * __ldg(wr + 128 + k + 1) + dr.z * __ldg(wr + 256 + k + 1);
-              g0 = ((m >> i) & 1u) ? g0 : 0.f;
-              g1 = ((m >> (i + 1)) & 1u) ? g1 : 0.f;
-              pk[i >> 1] = pack_bf16(g0, g1);
+              const int k = cb * 32 + i;
+              float g0 = dr.x * s_head[k] + dr.y * s_head[128 + k] + dr.z * s_head[256 + k];
+              float g1 = dr.x * s_head[k + 1] + dr.y * s_head[128 + k + 1] + dr.z * s_head[256 + k + 1];
+              g0 = (mw[cb] & (1u << i)) ? g0 : 0.f;
+              g1 = (mw[cb] & (2u << i)) ? g1 : 0.f;
+              pk[i >> 1] = pack_bf16_fast(g0, g1);
             }
             store_cols32(act_tile, r, cb * 32, pk);
           }
+        } else if (D == 0) {
+          dgrad_epilogue_256<false, false>(tmem_row, nullptr, 0.f, s_wa, act_tile, r);
+        } else if (D == 1) {  // dH7 also receives d_sigma * w_alpha (alpha_linear reads H7)
+          dgrad_epilogue_256<true, true>(tmem_row, mk, dr.w, s_wa, act_tile, r);
         } else {
-          const float *wa = p.P + W_ALPHA;
-#pragma unroll 1
-          for (int cb = 0; cb < 8; ++cb) {
-            uint32_t v[32], pk[16];
-            tmem_ld32(tmem_row + cb * 32, v);
-            tmem_ld_wait();
-            uint32_t m = mk ? __ldg(mk + cb) : ~0u;
-#pragma unroll
-            for (int i = 0; i < 32; i += 2) {
-              float g0 = __uint_as_float(v[i]), g1 = __uint_as_float(v[i + 1]);
-              if (D == 1) {  // dH7 also receives d_sigma * w_alpha (alpha_linear reads H7)
-                g0 = fmaf(dr.w, __ldg(wa + cb * 32 + i), g0);
-                g1 = fmaf(dr.w, __ldg(wa + cb * 32 + i + 1), g1);
-              }
-              g0 = ((m >> i) & 1u) ? g0 : 0.f;
-              g1 = ((m >> (i + 1)) & 1u) ? g1 : 0.f;
-              pk[i >> 1] = pack_bf16(g0, g1);
-            }
-            store_cols32(act_tile, r, cb * 32, pk);
-          }
+          dgrad_epilogue_256<false, true>(tmem_row, mk, 0.f, s_wa, act_tile, r);
         }
         tc_fence_before();
         fence_async_smem();
@@ -601,24 +674,36 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_wgrad_tc(WgradParams p) {
     float bsum = 0.f, asum = 0.f, basum = 0.f;
     uint32_t stage = 0, phase = 0;
     const bool do_bias = un.bias_off >= 0 && ht < un.a_slabs * 64;
+    // byte offset of column c inside row j of an 8-row group of a SWIZZLE_128B slab (the XOR only involves j)
+    const uint32_t slab = ht >> 6, c = ht & 63;
+    uint32_t offj[8];
+#pragma unroll
+    for (uint32_t j = 0; j < 8; ++j) offj[j] = slab * 8192u + j * 128u + ((((c >> 3) ^ j) & 7u) << 4) + ((c & 7u) << 1);
     for (int h = h_begin; h < h_end; ++h) {
       mbar_wait(bar0 + 8 * stage, phase);
       const uint8_t *sa = smem + stage * WG_STAGE_BYTES;
       const uint8_t *sb = sa + WG_A_BYTES;
-      const int64_t row0 = (int64_t)h * 64;
-      if (do_bias || un.alpha) {
-        const uint32_t slab = ht >> 6, c = ht & 63;
-#pragma unroll 4
-        for (uint32_t rr = 0; rr < 64; ++rr) {
-          uint32_t off = slab * 8192u + sw128_offset(rr, c);
-          if (do_bias) bsum += __bfloat162float(*reinterpret_cast<const __nv_bfloat16 *>(sa + off));
-          if (un.alpha) {
-            int64_t row = row0 + rr;
-            float ds = row < p.n ? __ldg(p.draw + row * 4 + 3) : 0.f;
-            asum = fmaf(ds, __bfloat162float(*reinterpret_cast<const __nv_bfloat16 *>(sb + off)), asum);
-            if (ht == 0) basum += ds;
+      if (do_bias) {
+#pragma unroll
+        for (uint32_t g = 0; g < 8; ++g)
+#pragma unroll
+          for (uint32_t j = 0; j < 8; ++j)
+            bsum += __uint_as_float((uint32_t)(*reinterpret_cast<const uint16_t *>(sa + g * 1024u + offj[j])) << 16);
+      }
+      if (un.alpha) {
+        // d_sigma of the 64 rows of this half tile: lane l holds rows l and l+32, broadcast by shuffle
+        const int64_t row0 = (int64_t)h * 64;
+        float d0 = (row0 + lane < p.n) ? __ldg(p.draw + (row0 + lane) * 4 + 3) : 0.f;
+        float d1 = (row0 + 32 + lane < p.n) ? __ldg(p.draw + (row0 + 32 + lane) * 4 + 3) : 0.f;
+        if (warp == kEpiWarp0) basum += d0 + d1;
+#pragma unroll
+        for (uint32_t g = 0; g < 8; ++g)
+#pragma unroll
+          for (uint32_t j = 0; j < 8; ++j) {
+            const uint32_t rr = g * 8 + j;
+            float ds = __shfl_sync(0xffffffffu, rr < 32 ? d0 : d1, rr & 31);
+            asum = fmaf(ds, __uint_as_float((uint32_t)(*reinterpret_cast<const uint16_t *>(sb + g * 1024u + offj[j])) << 16), asum);
           }
-        }
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(bar0 + 8 * (WG_STAGES + stage));
@@ -628,7 +713,11 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_wgrad_tc(WgradParams p) {
       if (do_bias) atomicAdd(p.G + un.bias_off + ht, bsum);
       if (un.alpha) {
         atomicAdd(p.G + W_ALPHA + ht, asum);
-        if (ht == 0) atomicAdd(p.G + B_ALPHA, basum);
+        if (warp == kEpiWarp0) {
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) basum += __shfl_xor_sync(0xffffffffu, basum, o);
+          if (lane == 0) atomicAdd(p.G + B_ALPHA, basum);
+        }
       }
       // flush the accumulators: TMEM lane = out feature (within the 128-row M half), column = in feature
       mbar_wait(bar0 + 8 * 2 * WG_STAGES, 0);
@@ -669,27 +758,45 @@ __global__ void __launch_bounds__(128) wgrad_small_kernel(const uint8_t *__restr
                                                           const float *__restrict__ dirpe, float *__restrict__ G,
                                                           int64_t n, int S, int n_tiles, int tiles_per_block) {
   const int k = threadIdx.x;  // feature column 0..127
-  float a0 = 0.f, a1 = 0.f, a2 = 0.f, b0 = 0.f, b1 = 0.f, b2 = 0.f;
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, b0 = 0.f, b1 = 0.f, b2 = 0.f, gsum = 0.f;
   float av[27];
 #pragma unroll
   for (int j = 0; j < 27; ++j) av[j] = 0.f;
   const int t0 = blockIdx.x * tiles_per_block, t1 = min(n_tiles, t0 + tiles_per_block);
   const uint32_t slab = k >> 6, c = k & 63;
+  const int64_t row_end = min(n, (int64_t)t1 * 128);
+  auto flush_ray = [&](int64_t ray) {  // sum_s G9[row][k] of one ray is multiplied once with that ray's 27 PE values
+    const float *pe = dirpe + ray * 32;
+#pragma unroll
+    for (int j = 0; j < 27; ++j) av[j] = fmaf(gsum, __ldg(pe + j), av[j]);
+    gsum = 0.f;
+  };
   for (int tile = t0; tile < t1; ++tile) {
     const uint8_t *h9 = stash_act + (size_t)tile * TILE_ACT_BYTES + (size_t)9 * 65536 + slab * SLAB_BYTES;
     const uint8_t *g9 = dy + (size_t)tile * TILE_ACT_BYTES + (size_t)9 * 65536 + slab * SLAB_BYTES;
-    for (uint32_t rr = 0; rr < 128; ++rr) {
-      int64_t row = (int64_t)tile * 128 + rr;
-      if (row >= n) break;
-      float4 d = __ldg(reinterpret_cast<const float4 *>(draw) + row);
-      uint32_t off = sw128_offset(rr, c);
-      float h = __bfloat162float(*reinterpret_cast<const __nv_bfloat16 *>(h9 + off));
-      float g = __bfloat162float(*reinterpret_cast<const __nv_bfloat16 *>(g9 + off));
-      a0 = fmaf(d.x, h, a0); a1 = fmaf(d.y, h, a1); a2 = fmaf(d.z, h, a2);
-      if (k == (int)(rr & 127)) { b0 += d.x; b1 += d.y; b2 += d.z; }
-      const float *pe = dirpe + (row / S) * 32;
+    const int64_t row0 = (int64_t)tile * 128;
+#pragma unroll 1
+    for (uint32_t r8 = 0; r8 < 128; r8 += 8) {
+      if (row0 + r8 >= row_end) break;
+      float hv[8], gv[8];
+      float4 d[8];
 #pragma unroll
-      for (int j = 0; j < 27; ++j) av[j] = fmaf(g, __ldg(pe + j), av[j]);
+      for (uint32_t j = 0; j < 8; ++j) {  // 8 rows in flight
+        const uint32_t off = (r8 >> 3) * 1024u + j * 128u + ((((c >> 3) ^ j) & 7u) << 4) + ((c & 7u) << 1);
+        hv[j] = __uint_as_float((uint32_t)(*reinterpret_cast<const uint16_t *>(h9 + off)) << 16);
+        gv[j] = __uint_as_float((uint32_t)(*reinterpret_cast<const uint16_t *>(g9 + off)) << 16);
+        const int64_t row = row0 + r8 + j;
+        d[j] = row < n ? __ldg(reinterpret_cast<const float4 *>(draw) + row) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (uint32_t j = 0; j < 8; ++j) {
+        const int64_t row = row0 + r8 + j;
+        if (row >= n) break;
+        a0 = fmaf(d[j].x, hv[j], a0); a1 = fmaf(d[j].y, hv[j], a1); a2 = fmaf(d[j].z, hv[j], a2);
+        if (k == (int)((r8 + j) & 127)) { b0 += d[j].x; b1 += d[j].y; b2 += d[j].z; }
+        gsum += gv[j];
+        if ((row + 1) % S == 0 || row + 1 == row_end) flush_ray(row / S);
+      }
     }
   }
   atomicAdd(G + W_RGB + k, a0);
@@ -836,7 +943,7 @@ int mlp_tc_backward(flnerf_ctx *ctx, const float *params, const void *packed, in
   w.dy = (const uint8_t *)ws; w.stash_act = stash_act; w.pe_tiles = (const uint8_t *)pe_tiles; w.draw = draw;
   w.G = grads; w.n = n; w.n_tiles = (int)(n_pad / 128);
   if (stages & 2) FL_LAUNCH(tc::mlp_wgrad_tc, tc::g_wgrad_grid, tc::kThreads, tc::SMEM_WG, st, w);
-  const int tpb = 16;
+  const int tpb = 4;
   if (stages & 4) FL_LAUNCH(tc::wgrad_small_kernel, (unsigned)((w.n_tiles + tpb - 1) / tpb), 128, 0, st, stash_act, w.dy, draw, dirpe,
             grads, n, S, w.n_tiles, tpb);
   return 0;

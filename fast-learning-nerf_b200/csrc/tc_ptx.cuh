@@ -102,6 +102,16 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t v[32]) {
       : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// wait + make every later use of v[] data-dependent on the wait (the loaded registers are only valid after it)
+__device__ __forceinline__ void tmem_ld_wait(uint32_t v[32]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]), "+r"(v[8]),
+                 "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15]), "+r"(v[16]),
+                 "+r"(v[17]), "+r"(v[18]), "+r"(v[19]), "+r"(v[20]), "+r"(v[21]), "+r"(v[22]), "+r"(v[23]), "+r"(v[24]),
+                 "+r"(v[25]), "+r"(v[26]), "+r"(v[27]), "+r"(v[28]), "+r"(v[29]), "+r"(v[30]), "+r"(v[31])
+               :
+               : "memory");
+}
 
 // ----- UMMA descriptors (cute/arch/mma_sm100_desc.hpp bit layout) --------------------------------
 // shared-memory matrix descriptor: start>>4 [0,14), LBO>>4 [16,30), SBO>>4 [32,46), version=1 [46,48),
@@ -119,6 +129,24 @@ __host__ __device__ constexpr uint32_t make_idesc(uint32_t M, uint32_t N, uint32
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t *>(&h);
+}
+// {lo = a, hi = b} rounded to bf16; the relu variant clamps negatives to +0 in the same instruction
+__device__ __forceinline__ uint32_t pack_bf16_relu(float a, float b) {
+  uint32_t d;
+  asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(b), "f"(a));
+  return d;
+}
+__device__ __forceinline__ uint32_t pack_bf16_fast(float a, float b) {
+  uint32_t d;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(b), "f"(a));
+  return d;
+}
+// bits e and e+1 of a 32-bit row mask from a packed pair of NON-NEGATIVE bf16 (halfword != 0); e is a constant
+__device__ __forceinline__ uint32_t nz_bits(uint32_t w, int e) {
+  uint32_t t = w + 0x7FFF7FFFu;  // bit 15 / bit 31 set iff the low / high halfword is non-zero (no carry: h <= 0x7F80)
+  uint32_t lo = (e <= 15) ? (t >> (15 - e)) : (t << (e - 15));
+  uint32_t hi = t >> (30 - e);
+  return (lo & (1u << e)) | (hi & (2u << e));
 }
 __device__ __forceinline__ float bf16_lo(uint32_t p) { return __uint_as_float(p << 16); }
 __device__ __forceinline__ float bf16_hi(uint32_t p) { return __uint_as_float(p & 0xFFFF0000u); }

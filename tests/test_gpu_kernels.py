@@ -139,9 +139,7 @@ def test_sample_pdf_merge(golden, ops):
     np.testing.assert_allclose(zstd.cpu().numpy(), g["zstd_det"], atol=1e-3)
     m, zs, zstd = ops.sample_pdf_merge(z, w, 128, False, T(g["u"]))
     ref = g["zs_u"]
-    err = np.abs(zs.cpu().numpy() - ref)
-    # the den<1e-5 snap (appendix A.3) makes a handful of samples discontinuous in the cdf rounding: allow 0.1 %
-    assert float((err > 3e-5).mean()) < 1e-3, float(err.max())
+    mostly_close(zs.cpu().numpy(), ref)
     mm = m.cpu()
     assert bool((mm[:, 1:] >= mm[:, :-1]).all())                                                 # sortedness (property)
     assert torch.equal(mm, torch.sort(torch.cat([z.cpu(), zs.cpu()], -1), -1)[0])                # merge == sort(cat), exact
@@ -153,7 +151,7 @@ def test_sample_pdf_merge(golden, ops):
     mostly_close(got.cpu().numpy(), g["zs_det"])
     got = H.sample_pdf(mid.cpu(), w[:, 1:-1].cpu(), 128, det=False, pytest=True)                  # numpy seed-0 hook
     assert got.device.type == "cpu"
-    assert float((np.abs(got.numpy() - g["zs_u"]) > 3e-5).mean()) < 1e-3
+    mostly_close(got.numpy(), g["zs_u"])
     # Philox path: samples stay inside [first bin, last bin] and follow the pdf mass ordering
     m, zs, _ = ops.sample_pdf_merge(z, w, 128, False, None, seed=9, offset=0)
     assert bool((zs >= mid[:, :1] - 1e-5).all()) and bool((zs <= mid[:, -1:] + 1e-5).all())
