@@ -17,16 +17,19 @@
 #include "common.cuh"
 #include "mlp_layout.h"
 #include "tc_ptx.cuh"
+#include <stdlib.h>
 
 namespace tc {
 
 using namespace mlp_layout;
 
-constexpr int kThreads = 320;  // 10 warps
+// CTA = 18 warps: warp 0 producer, warp 1 MMA issuer, warps 2..17 epilogue (2 tiles x 4 lane quarters x 2 column halves)
+constexpr int kEpiWarps = 16;
+constexpr int kThreads = (2 + kEpiWarps) * 32;  // 576
 constexpr int kEpiWarp0 = 2;
 constexpr uint32_t ACT_BYTES = 65536, SLAB_BYTES = 16384, PE_BYTES = 16384, WSTAGE = 32768;
-constexpr int NSTAGE = 2;
-constexpr uint32_t OFF_ACT = 0, OFF_PE = 2 * ACT_BYTES, OFF_W = OFF_PE + 2 * PE_BYTES, OFF_BAR = OFF_W + NSTAGE * WSTAGE;
+constexpr int NSTAGE = 3;  // 3 x 32 KB ring: weight chunks AND the PE slabs of the pair travel through it
+constexpr uint32_t OFF_ACT = 0, OFF_W = 2 * ACT_BYTES, OFF_BAR = OFF_W + NSTAGE * WSTAGE;
 // fp32 copies of the small heads: W_rgb[3][128], b_rgb[3], b_alpha[1], w_alpha[256]
 constexpr uint32_t OFF_HEAD = OFF_BAR + 256, HEAD_FLOATS = 384 + 4 + 256;
 constexpr uint32_t SMEM_FWD = OFF_HEAD + HEAD_FLOATS * 4;
@@ -86,20 +89,18 @@ __global__ void viewbias_kernel(int64_t B, const float *__restrict__ P, const fl
   vb[idx] = s;
 }
 
-struct Bars {
-  uint32_t w_full[NSTAGE], w_empty[NSTAGE], pe_full, pe_empty, acc_full, act_ready;
-};
-__device__ __forceinline__ Bars make_bars(uint32_t base) {
-  Bars b;
-  for (int i = 0; i < NSTAGE; ++i) {
-    b.w_full[i] = base + 8 * i;
-    b.w_empty[i] = base + 8 * (NSTAGE + i);
-  }
-  b.pe_full = base + 8 * (2 * NSTAGE);
-  b.pe_empty = base + 8 * (2 * NSTAGE + 1);
-  b.acc_full = base + 8 * (2 * NSTAGE + 2);
-  b.act_ready = base + 8 * (2 * NSTAGE + 3);
-  return b;
+// mbarrier addresses (bytes from the barrier block): no arrays, so nothing lands in local memory
+__device__ __forceinline__ uint32_t bar_w_full(uint32_t base, uint32_t i) { return base + 8u * i; }
+__device__ __forceinline__ uint32_t bar_w_empty(uint32_t base, uint32_t i) { return base + 8u * (NSTAGE + i); }
+__device__ __forceinline__ uint32_t bar_acc_full(uint32_t base) { return base + 8u * (2 * NSTAGE); }
+__device__ __forceinline__ uint32_t bar_act_ready(uint32_t base) { return base + 8u * (2 * NSTAGE + 1); }
+
+// All CTAs execute the same chunk sequence at the same speed; started together they would all pull the SAME 32 KB
+// weight chunk from the same few L2 slices at the same time.  CTA i therefore starts i * stagger cycles late.
+__device__ __forceinline__ void stagger_start(int cycles_per_cta) {
+  if (cycles_per_cta <= 0) return;
+  const long long t0 = clock64(), wait = (long long)blockIdx.x * cycles_per_cta;
+  while (clock64() - t0 < wait) __nanosleep(200);
 }
 
 struct Ring {
@@ -117,8 +118,7 @@ __device__ __forceinline__ void issue_chunk(uint32_t tmem_d, uint32_t a_smem, ui
   for (int k = 0; k < 4; ++k) umma_bf16(tmem_d, da + 2 * k, db + 2 * k, idesc, (first && k == 0) ? 0u : 1u);
 }
 
-__device__ __forceinline__ void common_setup(uint8_t *smem, const Bars &bars, uint32_t *tmem_slot, int warp,
-                                             const float *P) {
+__device__ __forceinline__ void common_setup(uint8_t *smem, uint32_t bar, uint32_t *tmem_slot, int warp, const float *P) {
   if ((smem_u32(smem) & 1023u) != 0) {
     if (threadIdx.x == 0) printf("flnerf: dynamic smem base not 1024-byte aligned\n");
     __trap();
@@ -127,11 +127,9 @@ __device__ __forceinline__ void common_setup(uint8_t *smem, const Bars &bars, ui
   for (int i = threadIdx.x; i < (int)HEAD_FLOATS; i += blockDim.x)
     head[i] = i < 387 ? P[W_RGB + i] : (i == 387 ? P[B_ALPHA] : P[W_ALPHA + (i - 388)]);
   if (warp == 1 && lane_id() == 0) {
-    for (int i = 0; i < NSTAGE; ++i) { mbar_init(bars.w_full[i], 1); mbar_init(bars.w_empty[i], 1); }
-    mbar_init(bars.pe_full, 1);
-    mbar_init(bars.pe_empty, 1);
-    mbar_init(bars.acc_full, 1);
-    mbar_init(bars.act_ready, 8);
+    for (int i = 0; i < NSTAGE; ++i) { mbar_init(bar_w_full(bar, i), 1); mbar_init(bar_w_empty(bar, i), 1); }
+    mbar_init(bar_acc_full(bar), 1);
+    mbar_init(bar_act_ready(bar), kEpiWarps);
     fence_mbar_init();
   }
   if (warp == 0) {
@@ -158,13 +156,12 @@ __device__ __forceinline__ void store_cols32(uint8_t *act_tile, uint32_t r, uint
 // forward: 32 accumulator columns [c0, c0+32) of row r -> +bias -> (relu) -> bf16 -> act tile; kType 0 relu,
 // 1 relu + alpha head, 2 linear.  Returns the non-zero mask of the 32 outputs (0 when not needed).
 template <int kType, bool kMask>
-__device__ __forceinline__ uint32_t fwd_block(const uint32_t v[32], const float *__restrict__ bias, uint8_t *act_tile,
+__device__ __forceinline__ uint32_t fwd_block(const uint32_t v[32], const float4 bq[8], uint8_t *act_tile,
                                               uint32_t r, uint32_t c0, const float *s_wa, float &alpha) {
   uint32_t pk[16], m = 0;
-  const float4 *b4 = reinterpret_cast<const float4 *>(bias + c0);
 #pragma unroll
   for (int q = 0; q < 8; ++q) {
-    const float4 b = __ldg(b4 + q);
+    const float4 b = bq[q];
     const float x0 = __uint_as_float(v[4 * q]) + b.x, x1 = __uint_as_float(v[4 * q + 1]) + b.y;
     const float x2 = __uint_as_float(v[4 * q + 2]) + b.z, x3 = __uint_as_float(v[4 * q + 3]) + b.w;
     const uint32_t w0 = kType == 2 ? pack_bf16_fast(x0, x1) : pack_bf16_relu(x0, x1);
@@ -184,26 +181,23 @@ __device__ __forceinline__ uint32_t fwd_block(const uint32_t v[32], const float 
   return m;
 }
 
-// all 256 columns of one row, TMEM loads double-buffered against the math
+// 128 columns [ch*128, ch*128+128) of one row (the other column half belongs to the partner warp)
 template <int kType, bool kMask>
-__device__ __forceinline__ void fwd_epilogue_256(uint32_t tmem_row, const float *__restrict__ bias, uint8_t *act_tile,
-                                                 uint32_t r, uint32_t *mask_dst, const float *s_wa, float &alpha) {
-  uint32_t va[32], vb[32], mk[8];
-  tmem_ld32(tmem_row, va);
+__device__ __forceinline__ void fwd_epilogue_half(uint32_t tmem_row, uint32_t ch, const float *__restrict__ bias,
+                                                  uint8_t *act_tile, uint32_t r, uint32_t *mask_dst, const float *s_wa,
+                                                  float &alpha) {
+  uint32_t v[32], mk[4];
 #pragma unroll
-  for (int cb = 0; cb < 8; cb += 2) {
-    tmem_ld_wait(va);
-    tmem_ld32(tmem_row + (cb + 1) * 32, vb);
-    mk[cb] = fwd_block<kType, kMask>(va, bias, act_tile, r, cb * 32, s_wa, alpha);
-    tmem_ld_wait(vb);
-    if (cb + 2 < 8) tmem_ld32(tmem_row + (cb + 2) * 32, va);
-    mk[cb + 1] = fwd_block<kType, kMask>(vb, bias, act_tile, r, (cb + 1) * 32, s_wa, alpha);
+  for (int i = 0; i < 4; ++i) {
+    const uint32_t cb = ch * 4 + i;
+    tmem_ld32(tmem_row + cb * 32, v);
+    float4 bq[8];  // bias loads are independent of the accumulator: issue them before waiting on TMEM
+#pragma unroll
+    for (int q = 0; q < 8; ++q) bq[q] = __ldg(reinterpret_cast<const float4 *>(bias + cb * 32) + q);
+    tmem_ld_wait(v);
+    mk[i] = fwd_block<kType, kMask>(v, bq, act_tile, r, cb * 32, s_wa, alpha);
   }
-  if (kMask) {
-    uint4 *d = reinterpret_cast<uint4 *>(mask_dst);
-    d[0] = make_uint4(mk[0], mk[1], mk[2], mk[3]);
-    d[1] = make_uint4(mk[4], mk[5], mk[6], mk[7]);
-  }
+  if (kMask) *reinterpret_cast<uint4 *>(mask_dst + ch * 4) = make_uint4(mk[0], mk[1], mk[2], mk[3]);
 }
 
 // backward: gradient columns [c0, c0+32) -> (+ d_sigma * w_alpha) -> relu mask -> bf16 -> act tile
@@ -228,22 +222,19 @@ __device__ __forceinline__ void dgrad_block(const uint32_t v[32], uint32_t m, fl
 }
 
 template <bool kAlpha, bool kUseMask>
-__device__ __forceinline__ void dgrad_epilogue_256(uint32_t tmem_row, const uint32_t *__restrict__ mask_row, float dsig,
-                                                   const float *s_wa, uint8_t *act_tile, uint32_t r) {
-  uint32_t va[32], vb[32], mk[8];
-  tmem_ld32(tmem_row, va);
+__device__ __forceinline__ void dgrad_epilogue_half(uint32_t tmem_row, uint32_t ch, const uint32_t *__restrict__ mask_row,
+                                                    float dsig, const float *s_wa, uint8_t *act_tile, uint32_t r) {
+  uint32_t v[32], mk[4] = {0u, 0u, 0u, 0u};
   if (kUseMask) {
-    const uint4 a = __ldg(reinterpret_cast<const uint4 *>(mask_row)), b = __ldg(reinterpret_cast<const uint4 *>(mask_row) + 1);
-    mk[0] = a.x; mk[1] = a.y; mk[2] = a.z; mk[3] = a.w; mk[4] = b.x; mk[5] = b.y; mk[6] = b.z; mk[7] = b.w;
+    const uint4 a = __ldg(reinterpret_cast<const uint4 *>(mask_row) + ch);
+    mk[0] = a.x; mk[1] = a.y; mk[2] = a.z; mk[3] = a.w;
   }
 #pragma unroll
-  for (int cb = 0; cb < 8; cb += 2) {
-    tmem_ld_wait(va);
-    tmem_ld32(tmem_row + (cb + 1) * 32, vb);
-    dgrad_block<kAlpha, kUseMask>(va, kUseMask ? mk[cb] : 0u, dsig, s_wa, act_tile, r, cb * 32);
-    tmem_ld_wait(vb);
-    if (cb + 2 < 8) tmem_ld32(tmem_row + (cb + 2) * 32, va);
-    dgrad_block<kAlpha, kUseMask>(vb, kUseMask ? mk[cb + 1] : 0u, dsig, s_wa, act_tile, r, (cb + 1) * 32);
+  for (int i = 0; i < 4; ++i) {
+    const uint32_t cb = ch * 4 + i;
+    tmem_ld32(tmem_row + cb * 32, v);
+    tmem_ld_wait(v);
+    dgrad_block<kAlpha, kUseMask>(v, mk[i], dsig, s_wa, act_tile, r, cb * 32);
   }
 }
 
@@ -255,51 +246,46 @@ struct FwdParams {
   const uint8_t *packed;   // bf16 chunks
   const uint8_t *pe_tiles; // [tiles][16 KB]
   const float *viewbias;   // [B][128]
-  float *raw;              // [n][4]
+  float *raw;              // [n][4], ZEROED by the host: the two column-half warps of a row accumulate into it
   uint8_t *stash_act;      // or null
   uint32_t *stash_mask;    // or null
   int64_t n;
   int S;
   int n_pairs;
+  int stagger_cycles;
 };
 
+// ring items of one pair, in consumption order: PE(both tiles), W(L0), W(L1)x4 .. W(L4)x4, PE, W(L5)x5, W(L6)x4,
+// W(L7)x4, W(L8)x4, W(L9)x4  = 40 items
 __global__ void __launch_bounds__(kThreads, 1) mlp_fwd_tc(FwdParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const int warp = threadIdx.x >> 5;
   const uint32_t lane = lane_id();
-  const Bars bars = make_bars(smem_u32(smem + OFF_BAR));
+  const uint32_t bar = smem_u32(smem + OFF_BAR);
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + OFF_BAR + 128);
-  common_setup(smem, bars, tmem_slot, warp, p.P);
+  common_setup(smem, bar, tmem_slot, warp, p.P);
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t s_act = smem_u32(smem + OFF_ACT), s_pe = smem_u32(smem + OFF_PE), s_w = smem_u32(smem + OFF_W);
+  const uint32_t s_act = smem_u32(smem + OFF_ACT), s_w = smem_u32(smem + OFF_W);
 
   if (warp == 0) {
     // ---------------------------------------------------------------- producer
     if (lane == 0) {
       Ring ring;
-      uint32_t it = 0;
-      auto load_pe = [&](int pair, uint32_t k) {
-        if (k > 0) mbar_wait(bars.pe_empty, (k - 1) & 1);
-        mbar_arrive_expect_tx(bars.pe_full, 2 * PE_BYTES);
-        bulk_g2s(s_pe, p.pe_tiles + (size_t)pair * 2 * PE_BYTES, 2 * PE_BYTES, bars.pe_full);
+      stagger_start(p.stagger_cycles);
+      auto push = [&](const uint8_t *src, uint32_t bytes) {
+        mbar_wait(bar_w_empty(bar, ring.stage), ring.phase ^ 1);
+        mbar_arrive_expect_tx(bar_w_full(bar, ring.stage), bytes);
+        bulk_g2s(s_w + ring.stage * WSTAGE, src, bytes, bar_w_full(bar, ring.stage));
+        ring.next();
       };
-      auto load_chunks = [&](int c_begin, int c_end) {
-        for (int ci = c_begin; ci < c_end; ++ci) {
-          uint32_t bytes = ci < 34 ? 32768u : 16384u;
-          size_t off = ci < 34 ? (size_t)ci * 32768 : (size_t)34 * 32768 + (size_t)(ci - 34) * 16384;
-          mbar_wait(bars.w_empty[ring.stage], ring.phase ^ 1);
-          mbar_arrive_expect_tx(bars.w_full[ring.stage], bytes);
-          bulk_g2s(s_w + ring.stage * WSTAGE, p.packed + off, bytes, bars.w_full[ring.stage]);
-          ring.next();
+      for (int pair = blockIdx.x; pair < p.n_pairs; pair += gridDim.x) {
+        const uint8_t *pe = p.pe_tiles + (size_t)pair * 2 * PE_BYTES;
+        for (int ci = 0; ci < FWD_CHUNKS; ++ci) {
+          if (ci == 0 || ci == 17) push(pe, 2 * PE_BYTES);  // layer 0 and the skip slab of layer 5
+          const uint32_t bytes = ci < 34 ? 32768u : 16384u;
+          const size_t off = ci < 34 ? (size_t)ci * 32768 : (size_t)34 * 32768 + (size_t)(ci - 34) * 16384;
+          push(p.packed + off, bytes);
         }
-      };
-      int first_pair = blockIdx.x;
-      if (first_pair < p.n_pairs) load_pe(first_pair, 0);
-      for (int pair = first_pair; pair < p.n_pairs; pair += gridDim.x, ++it) {
-        load_chunks(0, 22);  // layers 0..5 (1 + 16 + 5 chunks)
-        int next = pair + gridDim.x;
-        if (next < p.n_pairs) load_pe(next, it + 1);  // PE slabs are free once layer 5 has been issued
-        load_chunks(22, 38);
       }
     }
   } else if (warp == 1) {
@@ -309,77 +295,84 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_fwd_tc(FwdParams p) {
       uint32_t n_act = 0, it = 0;
       const uint32_t idesc256 = make_idesc(128, 256, 0, 0), idesc128 = make_idesc(128, 128, 0, 0);
       for (int pair = blockIdx.x; pair < p.n_pairs; pair += gridDim.x, ++it) {
-        mbar_wait(bars.pe_full, it & 1);
         for (int L = 0; L < 10; ++L) {
           if (!(it == 0 && L == 0)) {  // inputs of this layer written / TMEM drained by the epilogue
-            mbar_wait(bars.act_ready, n_act & 1);
+            mbar_wait(bar_act_ready(bar), n_act & 1);
             ++n_act;
           }
           tc_fence_after();
           const int nch = (L == 0) ? 1 : (L == 5 ? 5 : 4);
           for (int c = 0; c < nch; ++c) {
-            mbar_wait(bars.w_full[ring.stage], ring.phase);
-            tc_fence_after();
             const bool use_pe = (L == 0) || (L == 5 && c == 0);
+            uint32_t pe_stage = 0;
+            if (use_pe) {  // the PE slabs occupy the ring stage right before their weight chunk
+              mbar_wait(bar_w_full(bar, ring.stage), ring.phase);
+              pe_stage = ring.stage;
+              ring.next();
+            }
+            mbar_wait(bar_w_full(bar, ring.stage), ring.phase);
+            tc_fence_after();
             const int slab = (L == 5) ? c - 1 : c;
 #pragma unroll
             for (int t = 0; t < 2; ++t) {
-              uint32_t a = use_pe ? s_pe + t * PE_BYTES : s_act + t * ACT_BYTES + slab * SLAB_BYTES;
+              uint32_t a = use_pe ? s_w + pe_stage * WSTAGE + t * PE_BYTES : s_act + t * ACT_BYTES + slab * SLAB_BYTES;
               issue_chunk(tmem_base + t * 256, a, s_w + ring.stage * WSTAGE, L == 9 ? idesc128 : idesc256, c == 0);
             }
-            umma_commit(bars.w_empty[ring.stage]);
+            if (use_pe) umma_commit(bar_w_empty(bar, pe_stage));
+            umma_commit(bar_w_empty(bar, ring.stage));
             ring.next();
           }
-          umma_commit(bars.acc_full);
-          if (L == 5) umma_commit(bars.pe_empty);
+          umma_commit(bar_acc_full(bar));
         }
       }
     }
   } else {
-    // ---------------------------------------------------------------- epilogue (8 warps, 2 tiles x 4 lane quarters)
+    // ---------------------------------------------------------------- epilogue: 16 warps
     const int e = warp - kEpiWarp0;
-    const int t = e >> 2;
-    const uint32_t quarter = warp & 3;
-    const uint32_t r = quarter * 32 + lane;  // row inside the tile == TMEM lane
+    const int t = e >> 3;                         // tile of the pair
+    const uint32_t ch = (uint32_t)(e >> 2) & 1u;  // column half
+    const uint32_t quarter = warp & 3;            // TMEM lane quarter this warp may access
+    const uint32_t r = quarter * 32 + lane;       // row inside the tile == TMEM lane
     uint8_t *act_tile = smem + OFF_ACT + t * ACT_BYTES;
     const uint32_t tmem_row = tmem_base + ((quarter * 32) << 16) + t * 256;
-    const bool elected = (e & 3) == 0 && lane == 0;  // one thread per tile drives the bulk stores
+    const bool elected = (e & 7) == 0 && lane == 0;  // one thread per tile drives the bulk stores
+    const float *s_head = reinterpret_cast<const float *>(smem + OFF_HEAD);
+    const float *s_wa = s_head + 388;
     uint32_t n_acc = 0;
     bool store_pending = false;
     for (int pair = blockIdx.x; pair < p.n_pairs; pair += gridDim.x) {
       const int64_t tile = (int64_t)pair * 2 + t;
       const int64_t row = tile * 128 + r;
-      float alpha = 0.f;
       for (int L = 0; L < 10; ++L) {
-        mbar_wait(bars.acc_full, n_acc & 1);
+        mbar_wait(bar_acc_full(bar), n_acc & 1);
         ++n_acc;
         tc_fence_after();
         if (p.stash_act) {  // the previous layer's bulk store must have finished reading act_tile
           if (elected && store_pending) bulk_wait_read0();
-          named_bar_sync(1 + t, 128);
+          named_bar_sync(1 + t, 256);
         }
         uint32_t *mask_dst = p.stash_mask ? p.stash_mask + ((size_t)tile * 9 + (L < 9 ? L : 8)) * 128 * 8 + (size_t)r * 8
                                           : nullptr;
-        const float *s_head = reinterpret_cast<const float *>(smem + OFF_HEAD);
-        const float *s_wa = s_head + 388;
+        float alpha = 0.f;
         if (L < 7) {
           const float *bias = p.P + b_pts(L);
-          if (mask_dst) fwd_epilogue_256<0, true>(tmem_row, bias, act_tile, r, mask_dst, s_wa, alpha);
-          else fwd_epilogue_256<0, false>(tmem_row, bias, act_tile, r, nullptr, s_wa, alpha);
+          if (mask_dst) fwd_epilogue_half<0, true>(tmem_row, ch, bias, act_tile, r, mask_dst, s_wa, alpha);
+          else fwd_epilogue_half<0, false>(tmem_row, ch, bias, act_tile, r, nullptr, s_wa, alpha);
         } else if (L == 7) {
-          alpha = 0.f;
-          if (mask_dst) fwd_epilogue_256<1, true>(tmem_row, p.P + b_pts(7), act_tile, r, mask_dst, s_wa, alpha);
-          else fwd_epilogue_256<1, false>(tmem_row, p.P + b_pts(7), act_tile, r, nullptr, s_wa, alpha);
+          if (mask_dst) fwd_epilogue_half<1, true>(tmem_row, ch, p.P + b_pts(7), act_tile, r, mask_dst, s_wa, alpha);
+          else fwd_epilogue_half<1, false>(tmem_row, ch, p.P + b_pts(7), act_tile, r, nullptr, s_wa, alpha);
+          if (row < p.n) atomicAdd(p.raw + row * 4 + 3, alpha + (ch == 0 ? s_head[387] : 0.f));
         } else if (L == 8) {
-          fwd_epilogue_256<2, false>(tmem_row, p.P + B_FEAT, act_tile, r, nullptr, s_wa, alpha);
+          fwd_epilogue_half<2, false>(tmem_row, ch, p.P + B_FEAT, act_tile, r, nullptr, s_wa, alpha);
         } else {
-          // views_linears.0 (N=128) + rgb_linear on CUDA cores, then raw = (r,g,b,sigma)
+          // views_linears.0 (N=128: 64 columns per warp) + rgb_linear on CUDA cores -> raw[row].rgb (accumulated)
           const int64_t ray = (row < p.n ? row : p.n - 1) / p.S;
           const float4 *vb4 = reinterpret_cast<const float4 *>(p.viewbias + ray * 128);
           float c0 = 0.f, c1 = 0.f, c2 = 0.f;
-          uint32_t mk4[4];
+          uint32_t mk2[2];
 #pragma unroll
-          for (int cb = 0; cb < 4; ++cb) {
+          for (int i = 0; i < 2; ++i) {
+            const uint32_t cb = ch * 2 + i;
             uint32_t v[32], pk[16], m = 0;
             tmem_ld32(tmem_row + cb * 32, v);
             tmem_ld_wait(v);
@@ -394,24 +387,27 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_fwd_tc(FwdParams p) {
               const float h[4] = {bf16_lo(w0), bf16_hi(w0), bf16_lo(w1), bf16_hi(w1)};
               const int k = cb * 32 + 4 * q;
 #pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                c0 = fmaf(h[e], s_head[k + e], c0);
-                c1 = fmaf(h[e], s_head[128 + k + e], c1);
-                c2 = fmaf(h[e], s_head[256 + k + e], c2);
+              for (int x = 0; x < 4; ++x) {
+                c0 = fmaf(h[x], s_head[k + x], c0);
+                c1 = fmaf(h[x], s_head[128 + k + x], c1);
+                c2 = fmaf(h[x], s_head[256 + k + x], c2);
               }
             }
-            mk4[cb] = m;
+            mk2[i] = m;
             store_cols32(act_tile, r, cb * 32, pk);
           }
-          if (row < p.n)
-            reinterpret_cast<float4 *>(p.raw)[row] =
-                make_float4(c0 + s_head[384], c1 + s_head[385], c2 + s_head[386], alpha + s_head[387]);
-          if (mask_dst) *reinterpret_cast<uint4 *>(mask_dst) = make_uint4(mk4[0], mk4[1], mk4[2], mk4[3]);
+          if (row < p.n) {
+            const float bsel = ch == 0 ? 1.f : 0.f;
+            atomicAdd(p.raw + row * 4 + 0, c0 + bsel * s_head[384]);
+            atomicAdd(p.raw + row * 4 + 1, c1 + bsel * s_head[385]);
+            atomicAdd(p.raw + row * 4 + 2, c2 + bsel * s_head[386]);
+          }
+          if (mask_dst) *reinterpret_cast<uint2 *>(mask_dst + ch * 2) = make_uint2(mk2[0], mk2[1]);
         }
         tc_fence_before();
         fence_async_smem();
         if (p.stash_act) {
-          named_bar_sync(1 + t, 128);  // all 4 warps of this tile have written act_tile
+          named_bar_sync(1 + t, 256);  // all 8 warps of this tile have written act_tile
           if (elected) {
             bulk_s2g(p.stash_act + (size_t)tile * TILE_ACT_BYTES + (size_t)L * 65536, smem_u32(act_tile),
                      L == 9 ? 32768u : 65536u);
@@ -420,7 +416,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_fwd_tc(FwdParams p) {
           store_pending = true;
         }
         __syncwarp();
-        if (lane == 0) mbar_arrive(bars.act_ready);
+        if (lane == 0) mbar_arrive(bar_act_ready(bar));
       }
     }
     if (elected && store_pending) bulk_wait_all0();
@@ -441,26 +437,28 @@ struct DgradParams {
   uint8_t *dy;               // [tiles][10][64 KB]: slot l<8 = dH_l, slot 8 = dF, slot 9 = G9 (32 KB)
   int64_t n;
   int n_pairs;
+  int stagger_cycles;
 };
 
 __global__ void __launch_bounds__(kThreads, 1) mlp_dgrad_tc(DgradParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const int warp = threadIdx.x >> 5;
   const uint32_t lane = lane_id();
-  const Bars bars = make_bars(smem_u32(smem + OFF_BAR));
+  const uint32_t bar = smem_u32(smem + OFF_BAR);
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + OFF_BAR + 128);
-  common_setup(smem, bars, tmem_slot, warp, p.P);
+  common_setup(smem, bar, tmem_slot, warp, p.P);
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t s_act = smem_u32(smem + OFF_ACT), s_w = smem_u32(smem + OFF_W);
 
   if (warp == 0) {
     if (lane == 0) {
       Ring ring;
+      stagger_start(p.stagger_cycles);
       for (int pair = blockIdx.x; pair < p.n_pairs; pair += gridDim.x) {
         for (int ci = 0; ci < DG_CHUNKS; ++ci) {
-          mbar_wait(bars.w_empty[ring.stage], ring.phase ^ 1);
-          mbar_arrive_expect_tx(bars.w_full[ring.stage], 32768u);
-          bulk_g2s(s_w + ring.stage * WSTAGE, p.packed_dg + (size_t)ci * 32768, 32768u, bars.w_full[ring.stage]);
+          mbar_wait(bar_w_empty(bar, ring.stage), ring.phase ^ 1);
+          mbar_arrive_expect_tx(bar_w_full(bar, ring.stage), 32768u);
+          bulk_g2s(s_w + ring.stage * WSTAGE, p.packed_dg + (size_t)ci * 32768, 32768u, bar_w_full(bar, ring.stage));
           ring.next();
         }
       }
@@ -472,32 +470,35 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_dgrad_tc(DgradParams p) {
       const uint32_t idesc = make_idesc(128, 256, 0, 0);
       for (int pair = blockIdx.x; pair < p.n_pairs; pair += gridDim.x) {
         for (int D = 0; D < 9; ++D) {  // D=0: dF = G9 * Wv (K=128); D>=1: K=256
-          mbar_wait(bars.act_ready, n_act & 1);
+          mbar_wait(bar_act_ready(bar), n_act & 1);
           ++n_act;
           tc_fence_after();
           const int nch = (D == 0) ? 2 : 4;
           for (int c = 0; c < nch; ++c) {
-            mbar_wait(bars.w_full[ring.stage], ring.phase);
+            mbar_wait(bar_w_full(bar, ring.stage), ring.phase);
             tc_fence_after();
 #pragma unroll
             for (int t = 0; t < 2; ++t)
               issue_chunk(tmem_base + t * 256, s_act + t * ACT_BYTES + c * SLAB_BYTES, s_w + ring.stage * WSTAGE, idesc,
                           c == 0);
-            umma_commit(bars.w_empty[ring.stage]);
+            umma_commit(bar_w_empty(bar, ring.stage));
             ring.next();
           }
-          umma_commit(bars.acc_full);
+          umma_commit(bar_acc_full(bar));
         }
       }
     }
   } else {
     const int e = warp - kEpiWarp0;
-    const int t = e >> 2;
+    const int t = e >> 3;
+    const uint32_t ch = (uint32_t)(e >> 2) & 1u;
     const uint32_t quarter = warp & 3;
     const uint32_t r = quarter * 32 + lane;
     uint8_t *act_tile = smem + OFF_ACT + t * ACT_BYTES;
     const uint32_t tmem_row = tmem_base + ((quarter * 32) << 16) + t * 256;
-    const bool elected = (e & 3) == 0 && lane == 0;
+    const bool elected = (e & 7) == 0 && lane == 0;
+    const float *s_head = reinterpret_cast<const float *>(smem + OFF_HEAD);
+    const float *s_wa = s_head + 388;
     uint32_t n_acc = 0;
     bool store_pending = false;
     for (int pair = blockIdx.x; pair < p.n_pairs; pair += gridDim.x) {
@@ -509,44 +510,43 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_dgrad_tc(DgradParams p) {
       // stage -1: G9 = (d_rgb * W_rgb) masked by relu(h9) -> act slabs 0,1 ; stages 0..8 = tensor layers
       for (int D = -1; D < 9; ++D) {
         if (D >= 0) {
-          mbar_wait(bars.acc_full, n_acc & 1);
+          mbar_wait(bar_acc_full(bar), n_acc & 1);
           ++n_acc;
           tc_fence_after();
         }
         if (elected && store_pending) bulk_wait_read0();
-        named_bar_sync(1 + t, 128);
+        named_bar_sync(1 + t, 256);
         // ReLU mask of the activation this gradient flows into: D=-1 -> h9 (slot 8), D=0 -> none (feature is
         // linear), D=1 -> H7, D=2 -> H6, ..., D=8 -> H0
         const uint32_t *mk = (D != 0) ? mask_base + (size_t)((D < 0) ? 8 : 8 - D) * 128 * 8 : nullptr;
-        const float *s_head = reinterpret_cast<const float *>(smem + OFF_HEAD);
-        const float *s_wa = s_head + 388;
         if (D < 0) {
-          const uint4 m4 = __ldg(reinterpret_cast<const uint4 *>(mk));
-          const uint32_t mw[4] = {m4.x, m4.y, m4.z, m4.w};
+          const uint2 m2 = __ldg(reinterpret_cast<const uint2 *>(mk) + ch);
+          const uint32_t mw[2] = {m2.x, m2.y};
 #pragma unroll
-          for (int cb = 0; cb < 4; ++cb) {
+          for (int j = 0; j < 2; ++j) {
+            const uint32_t cb = ch * 2 + j;
             uint32_t pk[16];
 #pragma unroll
             for (int i = 0; i < 32; i += 2) {
               const int k = cb * 32 + i;
               float g0 = dr.x * s_head[k] + dr.y * s_head[128 + k] + dr.z * s_head[256 + k];
               float g1 = dr.x * s_head[k + 1] + dr.y * s_head[128 + k + 1] + dr.z * s_head[256 + k + 1];
-              g0 = (mw[cb] & (1u << i)) ? g0 : 0.f;
-              g1 = (mw[cb] & (2u << i)) ? g1 : 0.f;
+              g0 = (mw[j] & (1u << i)) ? g0 : 0.f;
+              g1 = (mw[j] & (2u << i)) ? g1 : 0.f;
               pk[i >> 1] = pack_bf16_fast(g0, g1);
             }
             store_cols32(act_tile, r, cb * 32, pk);
           }
         } else if (D == 0) {
-          dgrad_epilogue_256<false, false>(tmem_row, nullptr, 0.f, s_wa, act_tile, r);
+          dgrad_epilogue_half<false, false>(tmem_row, ch, nullptr, 0.f, s_wa, act_tile, r);
         } else if (D == 1) {  // dH7 also receives d_sigma * w_alpha (alpha_linear reads H7)
-          dgrad_epilogue_256<true, true>(tmem_row, mk, dr.w, s_wa, act_tile, r);
+          dgrad_epilogue_half<true, true>(tmem_row, ch, mk, dr.w, s_wa, act_tile, r);
         } else {
-          dgrad_epilogue_256<false, true>(tmem_row, mk, 0.f, s_wa, act_tile, r);
+          dgrad_epilogue_half<false, true>(tmem_row, ch, mk, 0.f, s_wa, act_tile, r);
         }
         tc_fence_before();
         fence_async_smem();
-        named_bar_sync(1 + t, 128);
+        named_bar_sync(1 + t, 256);
         if (elected) {
           int slot = (D < 0) ? 9 : 8 - D;  // D=0 -> dF (8), D=1 -> dH7 (7) ... D=8 -> dH0 (0)
           bulk_s2g(p.dy + (size_t)tile * TILE_ACT_BYTES + (size_t)slot * 65536, smem_u32(act_tile),
@@ -555,7 +555,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_dgrad_tc(DgradParams p) {
         }
         store_pending = true;
         __syncwarp();
-        if (D < 8 && lane == 0) mbar_arrive(bars.act_ready);  // the last stage feeds no further MMA
+        if (D < 8 && lane == 0) mbar_arrive(bar_act_ready(bar));  // the last stage feeds no further MMA
       }
     }
     if (elected && store_pending) bulk_wait_all0();
@@ -580,6 +580,8 @@ struct WUnit {
   int ldw;
   int bias_off; // float offset of the bias gradient (column sums of dY), -1 = none
   int alpha;    // 1: also accumulate d w_alpha = sum_rows d_sigma[row] * X[row][:] and d b_alpha
+                // 2: the views unit also carries the CUDA-core heads: d W_rgb, d b_rgb (needs the h9 half tile as a
+                //    third operand) and the 27 view-direction columns of d W_views (per-ray sums of G9 x PE(dir))
   int splits;   // number of row ranges this unit is cut into
 };
 constexpr int kUnits = 11;
@@ -590,8 +592,11 @@ struct WgradParams {
   const uint8_t *stash_act;
   const uint8_t *pe_tiles;
   const float *draw;
+  const float *dirpe;   // [B][32]
   float *G;
+  long long *dbg;       // per-CTA {unit, cycles main loop, cycles total} when profiling the work split, else null
   int64_t n;
+  int S;
   int n_tiles;  // 128-row tiles
 };
 
@@ -599,9 +604,16 @@ constexpr int WG_STAGES = 3;
 constexpr uint32_t WG_A_BYTES = 32768, WG_B_BYTES = 32768;  // 64 rows x 256 features each
 constexpr uint32_t WG_STAGE_BYTES = WG_A_BYTES + WG_B_BYTES;
 constexpr uint32_t WG_OFF_BAR = WG_STAGES * WG_STAGE_BYTES;
-constexpr uint32_t SMEM_WG = WG_OFF_BAR + 256;
+constexpr uint32_t WG_OFF_DRAW = WG_OFF_BAR + 256;            // per stage: draw[64 rows][4] fp32 (units with heads)
+constexpr uint32_t SMEM_WG = WG_OFF_DRAW + WG_STAGES * 1024;
+static_assert(SMEM_WG <= 232448, "shared memory budget");
 
-__global__ void __launch_bounds__(kThreads, 1) mlp_wgrad_tc(WgradParams p) {
+__device__ __forceinline__ float bf16_at(const uint8_t *p) {
+  return __uint_as_float((uint32_t)(*reinterpret_cast<const uint16_t *>(p)) << 16);
+}
+
+constexpr int kWgThreads = 320;
+__global__ void __launch_bounds__(kWgThreads, 1) mlp_wgrad_tc(WgradParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const int warp = threadIdx.x >> 5;
   const uint32_t lane = lane_id();
@@ -635,7 +647,10 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_wgrad_tc(WgradParams p) {
       for (int h = h_begin; h < h_end; ++h) {
         mbar_wait(bar0 + 8 * (WG_STAGES + stage), phase ^ 1);
         uint32_t full = bar0 + 8 * stage;
-        mbar_arrive_expect_tx(full, a_bytes + b_bytes);
+        const int64_t row0 = (int64_t)h * 64;
+        const int64_t nv = p.n - row0;   // valid rows of this half tile (the tail of the last pair is padding)
+        const uint32_t draw_bytes = (un.alpha && nv > 0) ? (uint32_t)(nv < 64 ? nv : 64) * 16u : 0u;
+        mbar_arrive_expect_tx(full, a_bytes + b_bytes + (un.alpha == 2 ? 16384u : 0u) + draw_bytes);
         const size_t tile = (size_t)(h >> 1), half_off = (size_t)(h & 1) * 8192;
         const uint8_t *a_src = p.dy + tile * TILE_ACT_BYTES + (size_t)un.a_slot * 65536 + half_off;
         uint32_t sa = smem_u32(smem + stage * WG_STAGE_BYTES), sb = sa + WG_A_BYTES;
@@ -643,6 +658,11 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_wgrad_tc(WgradParams p) {
         const uint8_t *b_src = un.b_kind == 0 ? p.stash_act + tile * TILE_ACT_BYTES + (size_t)un.b_slot * 65536 + half_off
                                               : p.pe_tiles + tile * PE_BYTES + half_off;
         for (int s = 0; s < un.b_slabs; ++s) bulk_g2s(sb + s * 8192, b_src + (size_t)s * SLAB_BYTES, 8192u, full);
+        if (un.alpha == 2) {  // h9 (stash slot 9, 2 slabs) rides in the unused upper half of the A region
+          const uint8_t *h9 = p.stash_act + tile * TILE_ACT_BYTES + (size_t)9 * 65536 + half_off;
+          for (int s = 0; s < 2; ++s) bulk_g2s(sa + 16384 + s * 8192, h9 + (size_t)s * SLAB_BYTES, 8192u, full);
+        }
+        if (draw_bytes) bulk_g2s(smem_u32(smem + WG_OFF_DRAW + stage * 1024), p.draw + row0 * 4, draw_bytes, full);
         if (++stage == WG_STAGES) { stage = 0; phase ^= 1; }
       }
     }
@@ -669,79 +689,198 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_wgrad_tc(WgradParams p) {
       umma_commit(bar0 + 8 * 2 * WG_STAGES);
     }
   } else {
-    // helper warps: column sums of dY (bias gradients) [+ alpha head] straight from the staged tiles, then the flush
-    const int ht = threadIdx.x - kEpiWarp0 * 32;  // 0..255 = feature column
-    float bsum = 0.f, asum = 0.f, basum = 0.f;
-    uint32_t stage = 0, phase = 0;
-    const bool do_bias = un.bias_off >= 0 && ht < un.a_slabs * 64;
-    // byte offset of column c inside row j of an 8-row group of a SWIZZLE_128B slab (the XOR only involves j)
-    const uint32_t slab = ht >> 6, c = ht & 63;
-    uint32_t offj[8];
+    // ------------------------------------------------------------------------------------------------------------
+    // helper warps (256 threads): CUDA-core reductions straight from the staged tiles, then the accumulator flush.
+    //   every unit : bias gradient = column sums of dY; thread = column PAIR (packed bf16x2), half of the 64 rows
+    //   alpha == 1 : lower 128 threads do the bias sums (all rows), upper 128 threads accumulate
+    //                d w_alpha[c] = sum_rows d_sigma[row] * H7[row][c] for a column pair (d_sigma from the staged draw rows)
+    //   alpha == 2 : lower 128 threads: column sums of G9 per ray segment -> d b_views and the 27 view-direction
+    //                columns of d W_views; upper 128 threads: d W_rgb[:, k] = sum_rows d_rgb[row] * h9[row][k]
+    // ------------------------------------------------------------------------------------------------------------
+    const int ht = threadIdx.x - kEpiWarp0 * 32;  // 0..255
+    const bool upper = ht >= 128;
+    const uint32_t hh = (uint32_t)ht & 127u;
+    float s0 = 0.f, s1 = 0.f, t0 = 0.f, t1 = 0.f, t2 = 0.f, gsum = 0.f, db0 = 0.f, db1 = 0.f, db2 = 0.f, db3 = 0.f;
+    float av[27];
 #pragma unroll
-    for (uint32_t j = 0; j < 8; ++j) offj[j] = slab * 8192u + j * 128u + ((((c >> 3) ^ j) & 7u) << 4) + ((c & 7u) << 1);
+    for (int x = 0; x < 27; ++x) av[x] = 0.f;
+    // byte offsets inside an 8-row group of a SWIZZLE_128B slab: column pair (2hh, 2hh+1) and single column hh
+    uint32_t offp[8], offs[8];
+#pragma unroll
+    for (uint32_t j = 0; j < 8; ++j) {
+      const uint32_t cp = (2u * hh) & 63u, c1 = hh & 63u;
+      offp[j] = ((2u * hh) >> 6) * 8192u + j * 128u + ((((cp >> 3) ^ j) & 7u) << 4) + ((cp & 7u) << 1);
+      offs[j] = (hh >> 6) * 8192u + j * 128u + ((((c1 >> 3) ^ j) & 7u) << 4) + ((c1 & 7u) << 1);
+    }
+    const bool pair_valid = 2 * (int)hh < un.a_slabs * 64;
+    int rem = (int)(((int64_t)h_begin * 64) % p.S);  // position of the next row inside its ray (heads unit)
+    uint32_t stage = 0, phase = 0;
+    const long long t_start = clock64();
     for (int h = h_begin; h < h_end; ++h) {
       mbar_wait(bar0 + 8 * stage, phase);
       const uint8_t *sa = smem + stage * WG_STAGE_BYTES;
       const uint8_t *sb = sa + WG_A_BYTES;
-      if (do_bias) {
+      const float4 *sd = reinterpret_cast<const float4 *>(smem + WG_OFF_DRAW + stage * 1024);
+      const int64_t row0 = (int64_t)h * 64;
+      const int nv = (int)((p.n - row0) < 64 ? (p.n - row0 < 0 ? 0 : p.n - row0) : 64);
+      if (un.alpha == 0) {
+        if (un.bias_off >= 0 && pair_valid) {  // rows [32*upper, 32*upper + 32)
 #pragma unroll
-        for (uint32_t g = 0; g < 8; ++g)
+          for (uint32_t g = 0; g < 4; ++g)
 #pragma unroll
-          for (uint32_t j = 0; j < 8; ++j)
-            bsum += __uint_as_float((uint32_t)(*reinterpret_cast<const uint16_t *>(sa + g * 1024u + offj[j])) << 16);
-      }
-      if (un.alpha) {
-        // d_sigma of the 64 rows of this half tile: lane l holds rows l and l+32, broadcast by shuffle
-        const int64_t row0 = (int64_t)h * 64;
-        float d0 = (row0 + lane < p.n) ? __ldg(p.draw + (row0 + lane) * 4 + 3) : 0.f;
-        float d1 = (row0 + 32 + lane < p.n) ? __ldg(p.draw + (row0 + 32 + lane) * 4 + 3) : 0.f;
-        if (warp == kEpiWarp0) basum += d0 + d1;
+            for (uint32_t j = 0; j < 8; ++j) {
+              const uint32_t w = *reinterpret_cast<const uint32_t *>(sa + ((upper ? 4u : 0u) + g) * 1024u + offp[j]);
+              s0 += bf16_lo(w);
+              s1 += bf16_hi(w);
+            }
+        }
+      } else if (un.alpha == 1) {
+        if (!upper) {
 #pragma unroll
-        for (uint32_t g = 0; g < 8; ++g)
+          for (uint32_t g = 0; g < 8; ++g)
 #pragma unroll
-          for (uint32_t j = 0; j < 8; ++j) {
-            const uint32_t rr = g * 8 + j;
-            float ds = __shfl_sync(0xffffffffu, rr < 32 ? d0 : d1, rr & 31);
-            asum = fmaf(ds, __uint_as_float((uint32_t)(*reinterpret_cast<const uint16_t *>(sb + g * 1024u + offj[j])) << 16), asum);
+            for (uint32_t j = 0; j < 8; ++j) {
+              const uint32_t w = *reinterpret_cast<const uint32_t *>(sa + g * 1024u + offp[j]);
+              s0 += bf16_lo(w);
+              s1 += bf16_hi(w);
+            }
+        } else {
+#pragma unroll
+          for (uint32_t g = 0; g < 8; ++g)
+#pragma unroll
+            for (uint32_t j = 0; j < 8; ++j) {
+              const int rr = (int)(g * 8 + j);
+              const float ds = rr < nv ? sd[rr].w : 0.f;
+              const uint32_t w = *reinterpret_cast<const uint32_t *>(sb + g * 1024u + offp[j]);
+              t0 = fmaf(ds, bf16_lo(w), t0);
+              t1 = fmaf(ds, bf16_hi(w), t1);
+              if (hh == 0) db3 += ds;
+            }
+        }
+      } else {
+        if (!upper) {
+          // the ray segment sum is carried across the consecutive half tiles of this CTA: it is folded with the ray's
+          // 27 PE values only when the ray ends (every S rows) or at the CTA's last row
+          const bool last_stage = (h == h_end - 1);
+          auto fold = [&](int64_t row) {
+            if (row < p.n) {
+              const float *pe = p.dirpe + (row / p.S) * 32;
+#pragma unroll
+              for (int x = 0; x < 27; ++x) av[x] = fmaf(gsum, __ldg(pe + x), av[x]);
+            }
+            s0 += gsum;
+            gsum = 0.f;
+          };
+          if (rem + 64 <= p.S) {  // no ray boundary strictly inside this half tile: straight 64-row sum
+#pragma unroll
+            for (uint32_t g = 0; g < 8; ++g)
+#pragma unroll
+              for (uint32_t j = 0; j < 8; ++j) gsum += bf16_at(sa + g * 1024u + offs[j]);
+            rem += 64;
+            if (rem == p.S || last_stage) {
+              fold(row0 + 63);
+              if (rem == p.S) rem = 0;
+            }
+          } else {  // general case (S not a multiple of 64): per-row boundary test, computed addresses
+            const uint32_t c1 = hh & 63u, sl = (hh >> 6) * 8192u;
+#pragma unroll 1
+            for (uint32_t rr = 0; rr < 64; ++rr) {
+              const uint32_t j = rr & 7u;
+              gsum += bf16_at(sa + sl + (rr >> 3) * 1024u + j * 128u + ((((c1 >> 3) ^ j) & 7u) << 4) + ((c1 & 7u) << 1));
+              if (++rem == p.S || (last_stage && rr == 63)) {
+                fold(row0 + rr);
+                if (rem == p.S) rem = 0;
+              }
+            }
           }
+        } else {
+#pragma unroll
+          for (uint32_t g = 0; g < 8; ++g)
+#pragma unroll
+            for (uint32_t j = 0; j < 8; ++j) {
+              const int rr = (int)(g * 8 + j);
+              const float4 d = rr < nv ? sd[rr] : make_float4(0.f, 0.f, 0.f, 0.f);
+              const float hv = bf16_at(sa + 16384 + g * 1024u + offs[j]);
+              t0 = fmaf(d.x, hv, t0);
+              t1 = fmaf(d.y, hv, t1);
+              t2 = fmaf(d.z, hv, t2);
+              if (hh == 0) { db0 += d.x; db1 += d.y; db2 += d.z; }
+            }
+        }
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(bar0 + 8 * (WG_STAGES + stage));
       if (++stage == WG_STAGES) { stage = 0; phase ^= 1; }
     }
+    const long long t_loop = clock64();
     if (h_end > h_begin) {
-      if (do_bias) atomicAdd(p.G + un.bias_off + ht, bsum);
-      if (un.alpha) {
-        atomicAdd(p.G + W_ALPHA + ht, asum);
-        if (warp == kEpiWarp0) {
+      if (un.alpha == 0) {
+        if (un.bias_off >= 0 && pair_valid) {
+          atomicAdd(p.G + un.bias_off + 2 * hh, s0);
+          atomicAdd(p.G + un.bias_off + 2 * hh + 1, s1);
+        }
+      } else if (un.alpha == 1) {
+        if (!upper) {
+          atomicAdd(p.G + un.bias_off + 2 * hh, s0);
+          atomicAdd(p.G + un.bias_off + 2 * hh + 1, s1);
+        } else {
+          atomicAdd(p.G + W_ALPHA + 2 * hh, t0);
+          atomicAdd(p.G + W_ALPHA + 2 * hh + 1, t1);
+          if (hh == 0) atomicAdd(p.G + B_ALPHA, db3);
+        }
+      } else {
+        if (!upper) {
+          atomicAdd(p.G + un.bias_off + hh, s0);
 #pragma unroll
-          for (int o = 16; o > 0; o >>= 1) basum += __shfl_xor_sync(0xffffffffu, basum, o);
-          if (lane == 0) atomicAdd(p.G + B_ALPHA, basum);
+          for (int x = 0; x < 27; ++x) atomicAdd(p.G + W_VIEWS + hh * 283 + 256 + x, av[x]);
+        } else {
+          atomicAdd(p.G + W_RGB + hh, t0);
+          atomicAdd(p.G + W_RGB + 128 + hh, t1);
+          atomicAdd(p.G + W_RGB + 256 + hh, t2);
+          if (hh == 0) {
+            atomicAdd(p.G + B_RGB, db0);
+            atomicAdd(p.G + B_RGB + 1, db1);
+            atomicAdd(p.G + B_RGB + 2, db2);
+          }
         }
       }
-      // flush the accumulators: TMEM lane = out feature (within the 128-row M half), column = in feature
+      // flush the accumulators: TMEM lane = out feature (within the 128-row M half), column = in feature.  A thread
+      // owns a ROW, so direct atomics would touch 32 different lines per instruction; each warp transposes its
+      // 32x32 block through the (now idle: all helpers are past their last stage) stage memory and issues
+      // line-coalesced reductions instead.
       mbar_wait(bar0 + 8 * 2 * WG_STAGES, 0);
       tc_fence_after();
+      named_bar_sync(1, 256);
       const int e = warp - kEpiWarp0;
       const uint32_t quarter = warp & 3;
       const int ncol = un.b_slabs * 64;
       const int mhalves = un.a_slabs / 2;
+      float *tr = reinterpret_cast<float *>(smem) + e * (32 * 33);
       for (int mh = 0; mh < mhalves; ++mh) {
-        const int out = mh * 128 + quarter * 32 + lane;
-        float *dst = p.G + un.w_off + (size_t)out * un.ldw;
+        const int out0 = mh * 128 + quarter * 32;
         // the two warps that share a lane quarter split the 32-column blocks between them
         for (int cb = (e >> 2); cb * 32 < ncol; cb += 2) {
           uint32_t v[32];
           tmem_ld32(tmem_base + ((quarter * 32) << 16) + mh * 256 + cb * 32, v);
-          tmem_ld_wait();
+          tmem_ld_wait(v);
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            int col = cb * 32 + i;
-            // PE units have 63 valid inputs: column 63 is the zero pad and must not be written
-            if (!(un.b_kind == 1 && col >= 63)) atomicAdd(dst + col, __uint_as_float(v[i]));
-          }
+          for (int i = 0; i < 32; ++i) tr[lane * 33 + i] = __uint_as_float(v[i]);
+          __syncwarp();
+          const int col = cb * 32 + lane;
+          // PE units have 63 valid inputs: column 63 is the zero pad and must not be written
+          const bool ok = !(un.b_kind == 1 && col >= 63);
+#pragma unroll 4
+          for (int rr = 0; rr < 32; ++rr)
+            if (ok) atomicAdd(p.G + un.w_off + (size_t)(out0 + rr) * un.ldw + col, tr[rr * 33 + lane]);
+          __syncwarp();
         }
       }
+    }
+    if (p.dbg && threadIdx.x == kEpiWarp0 * 32) {
+      p.dbg[blockIdx.x * 4 + 0] = u;
+      p.dbg[blockIdx.x * 4 + 1] = t_loop - t_start;
+      p.dbg[blockIdx.x * 4 + 2] = clock64() - t_start;
+      p.dbg[blockIdx.x * 4 + 3] = h_end - h_begin;
     }
   }
   tc_fence_before();
@@ -752,20 +891,21 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_wgrad_tc(WgradParams p) {
 // rgb head + view-direction columns of views_linears.0: CUDA cores (0.1% of the FLOPs)
 //   dW_rgb[c][k] += sum_rows d_rgb[row][c] * h9[row][k];  db_rgb += sum d_rgb
 //   dW_v[c][256+j] += sum_rows G9[row][c] * dirpe[ray(row)][j]
-__global__ void __launch_bounds__(128) wgrad_small_kernel(const uint8_t *__restrict__ stash_act,
+__global__ void __launch_bounds__(512) wgrad_small_kernel(const uint8_t *__restrict__ stash_act,
                                                           const uint8_t *__restrict__ dy,
                                                           const float *__restrict__ draw,
                                                           const float *__restrict__ dirpe, float *__restrict__ G,
                                                           int64_t n, int S, int n_tiles, int tiles_per_block) {
-  const int k = threadIdx.x;  // feature column 0..127
+  __shared__ float red[33][128];  // partial sums of one row-quarter at a time
+  const int k = threadIdx.x & 127;   // feature column 0..127
+  const int qr = threadIdx.x >> 7;   // row quarter 0..3 (32 rows of every tile)
   float a0 = 0.f, a1 = 0.f, a2 = 0.f, b0 = 0.f, b1 = 0.f, b2 = 0.f, gsum = 0.f;
   float av[27];
 #pragma unroll
   for (int j = 0; j < 27; ++j) av[j] = 0.f;
   const int t0 = blockIdx.x * tiles_per_block, t1 = min(n_tiles, t0 + tiles_per_block);
   const uint32_t slab = k >> 6, c = k & 63;
-  const int64_t row_end = min(n, (int64_t)t1 * 128);
-  auto flush_ray = [&](int64_t ray) {  // sum_s G9[row][k] of one ray is multiplied once with that ray's 27 PE values
+  auto flush_ray = [&](int64_t ray) {  // sum_s G9[row][k] over a ray segment, multiplied once with the ray's 27 PE values
     const float *pe = dirpe + ray * 32;
 #pragma unroll
     for (int j = 0; j < 27; ++j) av[j] = fmaf(gsum, __ldg(pe + j), av[j]);
@@ -774,15 +914,16 @@ __global__ void __launch_bounds__(128) wgrad_small_kernel(const uint8_t *__restr
   for (int tile = t0; tile < t1; ++tile) {
     const uint8_t *h9 = stash_act + (size_t)tile * TILE_ACT_BYTES + (size_t)9 * 65536 + slab * SLAB_BYTES;
     const uint8_t *g9 = dy + (size_t)tile * TILE_ACT_BYTES + (size_t)9 * 65536 + slab * SLAB_BYTES;
-    const int64_t row0 = (int64_t)tile * 128;
-#pragma unroll 1
-    for (uint32_t r8 = 0; r8 < 128; r8 += 8) {
-      if (row0 + r8 >= row_end) break;
+    const int64_t row0 = (int64_t)tile * 128 + qr * 32;
+    const int64_t seg_end = min(n, row0 + 32);
+#pragma unroll
+    for (uint32_t r8 = 0; r8 < 32; r8 += 8) {
+      if (row0 + r8 >= seg_end) break;
       float hv[8], gv[8];
       float4 d[8];
 #pragma unroll
       for (uint32_t j = 0; j < 8; ++j) {  // 8 rows in flight
-        const uint32_t off = (r8 >> 3) * 1024u + j * 128u + ((((c >> 3) ^ j) & 7u) << 4) + ((c & 7u) << 1);
+        const uint32_t off = ((uint32_t)qr * 4 + (r8 >> 3)) * 1024u + j * 128u + ((((c >> 3) ^ j) & 7u) << 4) + ((c & 7u) << 1);
         hv[j] = __uint_as_float((uint32_t)(*reinterpret_cast<const uint16_t *>(h9 + off)) << 16);
         gv[j] = __uint_as_float((uint32_t)(*reinterpret_cast<const uint16_t *>(g9 + off)) << 16);
         const int64_t row = row0 + r8 + j;
@@ -793,25 +934,60 @@ __global__ void __launch_bounds__(128) wgrad_small_kernel(const uint8_t *__restr
         const int64_t row = row0 + r8 + j;
         if (row >= n) break;
         a0 = fmaf(d[j].x, hv[j], a0); a1 = fmaf(d[j].y, hv[j], a1); a2 = fmaf(d[j].z, hv[j], a2);
-        if (k == (int)((r8 + j) & 127)) { b0 += d[j].x; b1 += d[j].y; b2 += d[j].z; }
+        if (k == (int)(r8 + j)) { b0 += d[j].x; b1 += d[j].y; b2 += d[j].z; }
         gsum += gv[j];
-        if ((row + 1) % S == 0 || row + 1 == row_end) flush_ray(row / S);
+        if ((row + 1) % S == 0 || row + 1 == seg_end) flush_ray(row / S);
       }
     }
   }
-  atomicAdd(G + W_RGB + k, a0);
-  atomicAdd(G + W_RGB + 128 + k, a1);
-  atomicAdd(G + W_RGB + 256 + k, a2);
-  atomicAdd(G + B_RGB, b0);
-  atomicAdd(G + B_RGB + 1, b1);
-  atomicAdd(G + B_RGB + 2, b2);
+  // reduce the four row-quarters (one at a time through shared memory), then one atomic per (column, output)
+  for (int q = 1; q < 4; ++q) {
+    if (qr == q) {
+      float *dst = &red[0][k];
+      dst[0] = a0; dst[128] = a1; dst[256] = a2; dst[3 * 128] = b0; dst[4 * 128] = b1; dst[5 * 128] = b2;
 #pragma unroll
-  for (int j = 0; j < 27; ++j) atomicAdd(G + W_VIEWS + k * 283 + 256 + j, av[j]);
+      for (int j = 0; j < 27; ++j) dst[(6 + j) * 128] = av[j];
+    }
+    __syncthreads();
+    if (qr == 0) {
+      const float *src = &red[0][k];
+      a0 += src[0]; a1 += src[128]; a2 += src[256]; b0 += src[3 * 128]; b1 += src[4 * 128]; b2 += src[5 * 128];
+#pragma unroll
+      for (int j = 0; j < 27; ++j) av[j] += src[(6 + j) * 128];
+    }
+    __syncthreads();
+  }
+  if (qr == 0) {
+    atomicAdd(G + W_RGB + k, a0);
+    atomicAdd(G + W_RGB + 128 + k, a1);
+    atomicAdd(G + W_RGB + 256 + k, a2);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      b0 += __shfl_xor_sync(0xffffffffu, b0, o);
+      b1 += __shfl_xor_sync(0xffffffffu, b1, o);
+      b2 += __shfl_xor_sync(0xffffffffu, b2, o);
+    }
+    if ((k & 31) == 0) {
+      atomicAdd(G + B_RGB, b0);
+      atomicAdd(G + B_RGB + 1, b1);
+      atomicAdd(G + B_RGB + 2, b2);
+    }
+#pragma unroll
+    for (int j = 0; j < 27; ++j) atomicAdd(G + W_VIEWS + k * 283 + 256 + j, av[j]);
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
+static int stagger_setting() {
+  static int v = -1;
+  if (v < 0) {
+    const char *e = getenv("FLNERF_STAGGER");
+    v = e ? atoi(e) : 600;
+  }
+  return v;
+}
 static bool g_tables_ready = false;
 static int g_wgrad_grid = 0;
 
@@ -860,11 +1036,15 @@ static int setup_tables(int sm_count) {
       {6, 4, 0, 5, 4, W_PTS[6], 256, B_PTS[6], 0, 0},
       {7, 4, 0, 6, 4, W_PTS[7], 256, B_PTS[7], 0, 0},
       {8, 4, 0, 7, 4, W_FEAT, 256, B_FEAT, 1, 0},
-      {9, 2, 0, 8, 4, W_VIEWS, 283, B_VIEWS, 0, 0},
+      {9, 2, 0, 8, 4, W_VIEWS, 283, B_VIEWS, 2, 0},
   };
   // split the row range of every unit in proportion to the bytes it streams, one work item per SM
   double cost[kUnits], total = 0;
-  for (int i = 0; i < kUnits; ++i) { cost[i] = un[i].a_slabs * 8.0 + un[i].b_slabs * 8.0; total += cost[i]; }
+  for (int i = 0; i < kUnits; ++i) {
+    // relative time per half tile, measured per unit with FLNERF_WG_DEBUG (bytes streamed + CUDA-core helper work)
+    cost[i] = un[i].b_slabs == 1 ? 0.85 : (un[i].alpha ? 1.2 : 1.0);
+    total += cost[i];
+  }
   int used = 0;
   for (int i = 0; i < kUnits; ++i) {
     int s = (int)(sm_count * cost[i] / total);
@@ -923,6 +1103,8 @@ int mlp_tc_forward(flnerf_ctx *ctx, const float *params, const void *packed, int
     p.stash_mask = (uint32_t *)(p.stash_act + (size_t)(n_pad / 128) * tc::TILE_ACT_BYTES);
   }
   int grid = p.n_pairs < ctx->sm_count ? p.n_pairs : ctx->sm_count;
+  p.stagger_cycles = p.n_pairs >= 4 * grid ? tc::stagger_setting() : 0;   // only worth it for long launches
+  FL_CHECK_CUDA(cudaMemsetAsync(raw, 0, (size_t)n * 4 * sizeof(float), st));  // column-half warps accumulate into it
   FL_LAUNCH(tc::mlp_fwd_tc, grid, tc::kThreads, tc::SMEM_FWD, st, p);
   return 0;
 }
@@ -938,13 +1120,28 @@ int mlp_tc_backward(flnerf_ctx *ctx, const float *params, const void *packed, in
   d.P = params; d.packed_dg = (const uint8_t *)packed + tc::FWD_BYTES; d.draw = draw; d.stash_mask = stash_mask;
   d.dy = (uint8_t *)ws; d.n = n; d.n_pairs = (int)(n_pad / 256);
   int grid = d.n_pairs < ctx->sm_count ? d.n_pairs : ctx->sm_count;
+  d.stagger_cycles = d.n_pairs >= 4 * grid ? tc::stagger_setting() : 0;
   if (stages & 1) FL_LAUNCH(tc::mlp_dgrad_tc, grid, tc::kThreads, tc::SMEM_FWD, st, d);
   tc::WgradParams w{};
   w.dy = (const uint8_t *)ws; w.stash_act = stash_act; w.pe_tiles = (const uint8_t *)pe_tiles; w.draw = draw;
-  w.G = grads; w.n = n; w.n_tiles = (int)(n_pad / 128);
-  if (stages & 2) FL_LAUNCH(tc::mlp_wgrad_tc, tc::g_wgrad_grid, tc::kThreads, tc::SMEM_WG, st, w);
-  const int tpb = 4;
-  if (stages & 4) FL_LAUNCH(tc::wgrad_small_kernel, (unsigned)((w.n_tiles + tpb - 1) / tpb), 128, 0, st, stash_act, w.dy, draw, dirpe,
+  w.G = grads; w.n = n; w.n_tiles = (int)(n_pad / 128); w.dirpe = dirpe; w.S = S;
+  static long long *dbg = nullptr;
+  const bool want_dbg = getenv("FLNERF_WG_DEBUG") != nullptr;
+  if (want_dbg && !dbg) cudaMalloc(&dbg, sizeof(long long) * 4 * 1024);
+  w.dbg = want_dbg ? dbg : nullptr;
+  if (stages & 2) FL_LAUNCH(tc::mlp_wgrad_tc, tc::g_wgrad_grid, tc::kWgThreads, tc::SMEM_WG, st, w);
+  if (want_dbg && (stages & 2)) {
+    static int printed = 0;
+    if (printed++ == 3) {  // a warmed-up launch
+      long long h[4 * 1024];
+      cudaStreamSynchronize(st);
+      cudaMemcpy(h, dbg, sizeof(long long) * 4 * tc::g_wgrad_grid, cudaMemcpyDeviceToHost);
+      for (int i = 0; i < tc::g_wgrad_grid; ++i)
+        fprintf(stderr, "wgdbg cta %d unit %lld loop %lld total %lld halves %lld\n", i, h[i * 4], h[i * 4 + 1], h[i * 4 + 2], h[i * 4 + 3]);
+    }
+  }
+  const int tpb = 8;
+  if (stages & 8) FL_LAUNCH(tc::wgrad_small_kernel, (unsigned)((w.n_tiles + tpb - 1) / tpb), 512, 0, st, stash_act, w.dy, draw, dirpe,
             grads, n, S, w.n_tiles, tpb);
   return 0;
 }

@@ -31,13 +31,14 @@ __device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity)
   return ok;
 }
 // Bounded wait: a protocol bug must surface as a trapped kernel (error code to the host), never as a hung GPU.
+__device__ __noinline__ void mbar_timeout(uint32_t bar, uint32_t parity) {
+  printf("flnerf: mbarrier timeout block %d thread %d bar %u parity %u\n", blockIdx.x, threadIdx.x, bar, parity);
+  __trap();
+}
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins > (1u << 26)) {
-      printf("flnerf: mbarrier timeout block %d thread %d bar %u parity %u\n", blockIdx.x, threadIdx.x, bar, parity);
-      __trap();
-    }
+    if (++spins > (1u << 26)) mbar_timeout(bar, parity);
   }
 }
 
