@@ -141,9 +141,9 @@ def load_dataset(args):
     ``dataset_type = synthetic`` needs no files; the real loaders are the reference's own load_*.py (host-side
     I/O, out of scope here) found on $FLNERF_LOADERS (a directory holding load_blender.py / load_llff.py)."""
     if args.dataset_type == 'synthetic':
-        H = W = 400 if args.half_res else 800
+        H = W = int(os.environ.get("FLNERF_SYN_RES", 400 if args.half_res else 800))
         focal = 0.5 * W / np.tan(0.5 * 0.6911112070083618)
-        n_train, n_test = 100, 8
+        n_train, n_test = int(os.environ.get("FLNERF_SYN_VIEWS", 100)), 8
         poses = np.concatenate([synthetic.lego_like_poses(n_train), synthetic.lego_like_poses(n_test, phi=-20.0)], 0)
         K = synthetic.intrinsics(H, W, focal)
         images = synthetic.render_scene(H, W, K, poses, device=device).cpu().numpy()
