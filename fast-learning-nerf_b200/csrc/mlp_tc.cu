@@ -427,6 +427,217 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_fwd_tc(FwdParams p) {
 }
 
 // =================================================================================================
+// forward, generation 2: 2-CTA cluster, weight chunks fetched ONCE per cluster and multicast into both rings
+// (each CTA requests one half), which halves the L2 traffic per SM and makes it affordable to run the two tiles
+// of a CTA half a period apart: tile A's MMAs overlap tile B's epilogue (cta_group::1 MMAs, per-tile barriers).
+// =================================================================================================
+__device__ __forceinline__ uint32_t bar2_w_full(uint32_t base, uint32_t i) { return base + 8u * i; }
+__device__ __forceinline__ uint32_t bar2_w_empty(uint32_t base, uint32_t i) { return base + 8u * (NSTAGE + i); }
+__device__ __forceinline__ uint32_t bar2_acc_full(uint32_t base, uint32_t t) { return base + 8u * (2 * NSTAGE + t); }
+__device__ __forceinline__ uint32_t bar2_act_ready(uint32_t base, uint32_t t) { return base + 8u * (2 * NSTAGE + 2 + t); }
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) mlp_fwd_tc2(FwdParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const int warp = threadIdx.x >> 5;
+  const uint32_t lane = lane_id();
+  const uint32_t bar = smem_u32(smem + OFF_BAR);
+  const uint32_t cr = cluster_ctarank();
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + OFF_BAR + 128);
+  if ((smem_u32(smem) & 1023u) != 0) __trap();
+  float *head = reinterpret_cast<float *>(smem + OFF_HEAD);
+  for (int i = threadIdx.x; i < (int)HEAD_FLOATS; i += blockDim.x)
+    head[i] = i < 387 ? p.P[W_RGB + i] : (i == 387 ? p.P[B_ALPHA] : p.P[W_ALPHA + (i - 388)]);
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < NSTAGE; ++i) { mbar_init(bar2_w_full(bar, i), 1); mbar_init(bar2_w_empty(bar, i), 2); }
+    for (int t = 0; t < 2; ++t) { mbar_init(bar2_acc_full(bar, t), 1); mbar_init(bar2_act_ready(bar, t), kEpiWarps / 2); }
+    fence_mbar_init();
+  }
+  if (warp == 0) { tmem_alloc(smem_u32(tmem_slot), 512); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();  // the peer's barriers must be initialised before our multicast copies / commits reach them
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t s_act = smem_u32(smem + OFF_ACT), s_w = smem_u32(smem + OFF_W);
+  // both CTAs of a cluster must walk the weight ring the same number of times: surplus iterations recompute the
+  // last pair without side effects
+  const int iters = (p.n_pairs + (int)gridDim.x - 1) / (int)gridDim.x;
+
+  if (warp == 0) {
+    // ---------------------------------------------------------------- producer
+    if (lane == 0) {
+      Ring ring;
+      for (int it = 0; it < iters; ++it) {
+        const int pair = min(p.n_pairs - 1, (int)blockIdx.x + it * (int)gridDim.x);
+        const uint8_t *pe = p.pe_tiles + (size_t)pair * 2 * PE_BYTES;
+        int ci = 0;
+        for (int L = 0; L < 10; ++L) {
+          const int nch = (L == 0) ? 1 : (L == 5 ? 5 : 4);
+          for (int t = 0; t < 2; ++t) {
+            for (int c = 0; c < nch; ++c) {
+              if (c == 0 && (L == 0 || L == 5)) {  // this tile's PE slab: CTA-local item
+                mbar_wait(bar2_w_empty(bar, ring.stage), ring.phase ^ 1);
+                mbar_arrive_expect_tx(bar2_w_full(bar, ring.stage), PE_BYTES);
+                bulk_g2s(s_w + ring.stage * WSTAGE, pe + (size_t)t * PE_BYTES, PE_BYTES, bar2_w_full(bar, ring.stage));
+                ring.next();
+              }
+              const int cc = ci + c;
+              const uint32_t bytes = cc < 34 ? 32768u : 16384u, half = bytes / 2;
+              const size_t off = cc < 34 ? (size_t)cc * 32768 : (size_t)34 * 32768 + (size_t)(cc - 34) * 16384;
+              mbar_wait(bar2_w_empty(bar, ring.stage), ring.phase ^ 1);
+              mbar_arrive_expect_tx(bar2_w_full(bar, ring.stage), bytes);   // my half + the peer's half
+              bulk_g2s_multicast(s_w + ring.stage * WSTAGE + cr * half, p.packed + off + (size_t)cr * half, half,
+                                 bar2_w_full(bar, ring.stage), (uint16_t)3);
+              ring.next();
+            }
+          }
+          ci += nch;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ---------------------------------------------------------------- MMA issuer
+    if (lane == 0) {
+      Ring ring;
+      uint32_t n_act[2] = {0u, 0u};
+      const uint32_t idesc256 = make_idesc(128, 256, 0, 0), idesc128 = make_idesc(128, 128, 0, 0);
+      for (int it = 0; it < iters; ++it) {
+        for (int L = 0; L < 10; ++L) {
+          const int nch = (L == 0) ? 1 : (L == 5 ? 5 : 4);
+#pragma unroll
+          for (int t = 0; t < 2; ++t) {
+            if (!(it == 0 && L == 0)) {  // this tile's inputs written / its accumulator drained by its epilogue warps
+              mbar_wait(bar2_act_ready(bar, t), n_act[t] & 1);
+              ++n_act[t];
+            }
+            tc_fence_after();
+            for (int c = 0; c < nch; ++c) {
+              const bool use_pe = (L == 0) || (L == 5 && c == 0);
+              uint32_t pe_stage = 0;
+              if (use_pe) {
+                mbar_wait(bar2_w_full(bar, ring.stage), ring.phase);
+                pe_stage = ring.stage;
+                ring.next();
+              }
+              mbar_wait(bar2_w_full(bar, ring.stage), ring.phase);
+              tc_fence_after();
+              const int slab = (L == 5) ? c - 1 : c;
+              const uint32_t a = use_pe ? s_w + pe_stage * WSTAGE : s_act + t * ACT_BYTES + slab * SLAB_BYTES;
+              issue_chunk(tmem_base + t * 256, a, s_w + ring.stage * WSTAGE, L == 9 ? idesc128 : idesc256, c == 0);
+              if (use_pe) umma_commit_multicast(bar2_w_empty(bar, pe_stage), (uint16_t)3);
+              umma_commit_multicast(bar2_w_empty(bar, ring.stage), (uint16_t)3);
+              ring.next();
+            }
+            umma_commit(bar2_acc_full(bar, t));
+          }
+        }
+      }
+    }
+  } else {
+    // ---------------------------------------------------------------- epilogue: 8 warps per tile
+    const int e = warp - kEpiWarp0;
+    const int t = e >> 3;
+    const uint32_t ch = (uint32_t)(e >> 2) & 1u;
+    const uint32_t quarter = warp & 3;
+    const uint32_t r = quarter * 32 + lane;
+    uint8_t *act_tile = smem + OFF_ACT + t * ACT_BYTES;
+    const uint32_t tmem_row = tmem_base + ((quarter * 32) << 16) + t * 256;
+    const bool elected = (e & 7) == 0 && lane == 0;
+    const float *s_head = reinterpret_cast<const float *>(smem + OFF_HEAD);
+    const float *s_wa = s_head + 388;
+    uint32_t n_acc = 0;
+    bool store_pending = false;
+    for (int it = 0; it < iters; ++it) {
+      const int pair_raw = (int)blockIdx.x + it * (int)gridDim.x;
+      const bool live = pair_raw < p.n_pairs;          // surplus iteration: compute, but write nothing
+      const int pair = live ? pair_raw : p.n_pairs - 1;
+      const int64_t tile = (int64_t)pair * 2 + t;
+      const int64_t row = tile * 128 + r;
+      uint8_t *stash_act = live ? p.stash_act : nullptr;
+      uint32_t *stash_mask = live ? p.stash_mask : nullptr;
+      for (int L = 0; L < 10; ++L) {
+        mbar_wait(bar2_acc_full(bar, t), n_acc & 1);
+        ++n_acc;
+        tc_fence_after();
+        if (p.stash_act) {
+          if (elected && store_pending) bulk_wait_read0();
+          named_bar_sync(1 + t, 256);
+        }
+        uint32_t *mask_dst = stash_mask ? stash_mask + ((size_t)tile * 9 + (L < 9 ? L : 8)) * 128 * 8 + (size_t)r * 8 : nullptr;
+        float alpha = 0.f;
+        if (L < 7) {
+          const float *bias = p.P + b_pts(L);
+          if (mask_dst) fwd_epilogue_half<0, true>(tmem_row, ch, bias, act_tile, r, mask_dst, s_wa, alpha);
+          else fwd_epilogue_half<0, false>(tmem_row, ch, bias, act_tile, r, nullptr, s_wa, alpha);
+        } else if (L == 7) {
+          if (mask_dst) fwd_epilogue_half<1, true>(tmem_row, ch, p.P + b_pts(7), act_tile, r, mask_dst, s_wa, alpha);
+          else fwd_epilogue_half<1, false>(tmem_row, ch, p.P + b_pts(7), act_tile, r, nullptr, s_wa, alpha);
+          if (live && row < p.n) atomicAdd(p.raw + row * 4 + 3, alpha + (ch == 0 ? s_head[387] : 0.f));
+        } else if (L == 8) {
+          fwd_epilogue_half<2, false>(tmem_row, ch, p.P + B_FEAT, act_tile, r, nullptr, s_wa, alpha);
+        } else {
+          const int64_t ray = (row < p.n ? row : p.n - 1) / p.S;
+          const float4 *vb4 = reinterpret_cast<const float4 *>(p.viewbias + ray * 128);
+          float c0 = 0.f, c1 = 0.f, c2 = 0.f;
+          uint32_t mk2[2];
+#pragma unroll
+          for (int i = 0; i < 2; ++i) {
+            const uint32_t cb = ch * 2 + i;
+            uint32_t v[32], pk[16], m = 0;
+            tmem_ld32(tmem_row + cb * 32, v);
+            tmem_ld_wait(v);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              const float4 b = __ldg(vb4 + cb * 8 + q);
+              const uint32_t w0 = pack_bf16_relu(__uint_as_float(v[4 * q]) + b.x, __uint_as_float(v[4 * q + 1]) + b.y);
+              const uint32_t w1 = pack_bf16_relu(__uint_as_float(v[4 * q + 2]) + b.z, __uint_as_float(v[4 * q + 3]) + b.w);
+              pk[2 * q] = w0;
+              pk[2 * q + 1] = w1;
+              m |= nz_bits(w0, 4 * q) | nz_bits(w1, 4 * q + 2);
+              const float h[4] = {bf16_lo(w0), bf16_hi(w0), bf16_lo(w1), bf16_hi(w1)};
+              const int k = cb * 32 + 4 * q;
+#pragma unroll
+              for (int x = 0; x < 4; ++x) {
+                c0 = fmaf(h[x], s_head[k + x], c0);
+                c1 = fmaf(h[x], s_head[128 + k + x], c1);
+                c2 = fmaf(h[x], s_head[256 + k + x], c2);
+              }
+            }
+            mk2[i] = m;
+            store_cols32(act_tile, r, cb * 32, pk);
+          }
+          if (live && row < p.n) {
+            const float bsel = ch == 0 ? 1.f : 0.f;
+            atomicAdd(p.raw + row * 4 + 0, c0 + bsel * s_head[384]);
+            atomicAdd(p.raw + row * 4 + 1, c1 + bsel * s_head[385]);
+            atomicAdd(p.raw + row * 4 + 2, c2 + bsel * s_head[386]);
+          }
+          if (mask_dst) *reinterpret_cast<uint2 *>(mask_dst + ch * 2) = make_uint2(mk2[0], mk2[1]);
+        }
+        tc_fence_before();
+        fence_async_smem();
+        if (p.stash_act) {
+          named_bar_sync(1 + t, 256);
+          if (elected && stash_act) {
+            bulk_s2g(stash_act + (size_t)tile * TILE_ACT_BYTES + (size_t)L * 65536, smem_u32(act_tile),
+                     L == 9 ? 32768u : 65536u);
+            bulk_commit();
+            store_pending = true;
+          }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar2_act_ready(bar, t));
+      }
+    }
+    if (elected && store_pending) bulk_wait_all0();
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();  // nobody leaves while the peer may still multicast into this CTA
+  if (warp == 0) tmem_dealloc(tmem_base, 512);
+}
+
+// =================================================================================================
 // backward, data gradient chain:  G9 -> dF -> dH7 -> ... -> dH0   (pre-activation gradients, bf16)
 // =================================================================================================
 struct DgradParams {
@@ -562,6 +773,157 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_dgrad_tc(DgradParams p) {
   }
   tc_fence_before();
   __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, 512);
+}
+
+// =================================================================================================
+// data-gradient chain, generation 2 (same scheme as mlp_fwd_tc2: cluster of 2, multicast weight chunks, the two
+// tiles of a CTA half a period apart)
+// =================================================================================================
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) mlp_dgrad_tc2(DgradParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const int warp = threadIdx.x >> 5;
+  const uint32_t lane = lane_id();
+  const uint32_t bar = smem_u32(smem + OFF_BAR);
+  const uint32_t cr = cluster_ctarank();
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + OFF_BAR + 128);
+  if ((smem_u32(smem) & 1023u) != 0) __trap();
+  float *head = reinterpret_cast<float *>(smem + OFF_HEAD);
+  for (int i = threadIdx.x; i < (int)HEAD_FLOATS; i += blockDim.x)
+    head[i] = i < 387 ? p.P[W_RGB + i] : (i == 387 ? p.P[B_ALPHA] : p.P[W_ALPHA + (i - 388)]);
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < NSTAGE; ++i) { mbar_init(bar2_w_full(bar, i), 1); mbar_init(bar2_w_empty(bar, i), 2); }
+    for (int t = 0; t < 2; ++t) { mbar_init(bar2_acc_full(bar, t), 1); mbar_init(bar2_act_ready(bar, t), kEpiWarps / 2); }
+    fence_mbar_init();
+  }
+  if (warp == 0) { tmem_alloc(smem_u32(tmem_slot), 512); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t s_act = smem_u32(smem + OFF_ACT), s_w = smem_u32(smem + OFF_W);
+  const int iters = (p.n_pairs + (int)gridDim.x - 1) / (int)gridDim.x;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      Ring ring;
+      for (int it = 0; it < iters; ++it) {
+        int ci = 0;
+        for (int D = 0; D < 9; ++D) {
+          const int nch = (D == 0) ? 2 : 4;
+          for (int t = 0; t < 2; ++t)
+            for (int c = 0; c < nch; ++c) {
+              mbar_wait(bar2_w_empty(bar, ring.stage), ring.phase ^ 1);
+              mbar_arrive_expect_tx(bar2_w_full(bar, ring.stage), 32768u);
+              bulk_g2s_multicast(s_w + ring.stage * WSTAGE + cr * 16384u,
+                                 p.packed_dg + (size_t)(ci + c) * 32768 + (size_t)cr * 16384, 16384u,
+                                 bar2_w_full(bar, ring.stage), (uint16_t)3);
+              ring.next();
+            }
+          ci += nch;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      Ring ring;
+      uint32_t n_act[2] = {0u, 0u};
+      const uint32_t idesc = make_idesc(128, 256, 0, 0);
+      for (int it = 0; it < iters; ++it) {
+        for (int D = 0; D < 9; ++D) {
+          const int nch = (D == 0) ? 2 : 4;
+#pragma unroll
+          for (int t = 0; t < 2; ++t) {
+            mbar_wait(bar2_act_ready(bar, t), n_act[t] & 1);
+            ++n_act[t];
+            tc_fence_after();
+            for (int c = 0; c < nch; ++c) {
+              mbar_wait(bar2_w_full(bar, ring.stage), ring.phase);
+              tc_fence_after();
+              issue_chunk(tmem_base + t * 256, s_act + t * ACT_BYTES + c * SLAB_BYTES, s_w + ring.stage * WSTAGE, idesc, c == 0);
+              umma_commit_multicast(bar2_w_empty(bar, ring.stage), (uint16_t)3);
+              ring.next();
+            }
+            umma_commit(bar2_acc_full(bar, t));
+          }
+        }
+      }
+    }
+  } else {
+    const int e = warp - kEpiWarp0;
+    const int t = e >> 3;
+    const uint32_t ch = (uint32_t)(e >> 2) & 1u;
+    const uint32_t quarter = warp & 3;
+    const uint32_t r = quarter * 32 + lane;
+    uint8_t *act_tile = smem + OFF_ACT + t * ACT_BYTES;
+    const uint32_t tmem_row = tmem_base + ((quarter * 32) << 16) + t * 256;
+    const bool elected = (e & 7) == 0 && lane == 0;
+    const float *s_head = reinterpret_cast<const float *>(smem + OFF_HEAD);
+    const float *s_wa = s_head + 388;
+    uint32_t n_acc = 0;
+    bool store_pending = false;
+    for (int it = 0; it < iters; ++it) {
+      const int pair_raw = (int)blockIdx.x + it * (int)gridDim.x;
+      const bool live = pair_raw < p.n_pairs;
+      const int pair = live ? pair_raw : p.n_pairs - 1;
+      const int64_t tile = (int64_t)pair * 2 + t;
+      const int64_t row = tile * 128 + r;
+      float4 dr = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (row < p.n) dr = reinterpret_cast<const float4 *>(p.draw)[row];
+      const uint32_t *mask_base = p.stash_mask + (size_t)tile * 9 * 128 * 8 + (size_t)r * 8;
+      for (int D = -1; D < 9; ++D) {
+        if (D >= 0) {
+          mbar_wait(bar2_acc_full(bar, t), n_acc & 1);
+          ++n_acc;
+          tc_fence_after();
+        }
+        if (elected && store_pending) bulk_wait_read0();
+        named_bar_sync(1 + t, 256);
+        const uint32_t *mk = (D != 0) ? mask_base + (size_t)((D < 0) ? 8 : 8 - D) * 128 * 8 : nullptr;
+        if (D < 0) {
+          const uint2 m2 = __ldg(reinterpret_cast<const uint2 *>(mk) + ch);
+          const uint32_t mw[2] = {m2.x, m2.y};
+#pragma unroll
+          for (int j = 0; j < 2; ++j) {
+            const uint32_t cb = ch * 2 + j;
+            uint32_t pk[16];
+#pragma unroll
+            for (int i = 0; i < 32; i += 2) {
+              const int k = cb * 32 + i;
+              float g0 = dr.x * s_head[k] + dr.y * s_head[128 + k] + dr.z * s_head[256 + k];
+              float g1 = dr.x * s_head[k + 1] + dr.y * s_head[128 + k + 1] + dr.z * s_head[256 + k + 1];
+              g0 = (mw[j] & (1u << i)) ? g0 : 0.f;
+              g1 = (mw[j] & (2u << i)) ? g1 : 0.f;
+              pk[i >> 1] = pack_bf16_fast(g0, g1);
+            }
+            store_cols32(act_tile, r, cb * 32, pk);
+          }
+        } else if (D == 0) {
+          dgrad_epilogue_half<false, false>(tmem_row, ch, nullptr, 0.f, s_wa, act_tile, r);
+        } else if (D == 1) {
+          dgrad_epilogue_half<true, true>(tmem_row, ch, mk, dr.w, s_wa, act_tile, r);
+        } else {
+          dgrad_epilogue_half<false, true>(tmem_row, ch, mk, 0.f, s_wa, act_tile, r);
+        }
+        tc_fence_before();
+        fence_async_smem();
+        named_bar_sync(1 + t, 256);
+        if (elected && live) {
+          int slot = (D < 0) ? 9 : 8 - D;
+          bulk_s2g(p.dy + (size_t)tile * TILE_ACT_BYTES + (size_t)slot * 65536, smem_u32(act_tile), D < 0 ? 32768u : 65536u);
+          bulk_commit();
+          store_pending = true;
+        }
+        __syncwarp();
+        if (D < 8 && lane == 0) mbar_arrive(bar2_act_ready(bar, t));
+      }
+    }
+    if (elected && store_pending) bulk_wait_all0();
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
   if (warp == 0) tmem_dealloc(tmem_base, 512);
 }
 
@@ -988,6 +1350,14 @@ static int stagger_setting() {
   }
   return v;
 }
+static int kernel_generation() {
+  static int v = -1;
+  if (v < 0) {
+    const char *e = getenv("FLNERF_TC_GEN");
+    v = e ? atoi(e) : 2;
+  }
+  return v;
+}
 static bool g_tables_ready = false;
 static int g_wgrad_grid = 0;
 
@@ -1059,6 +1429,8 @@ static int setup_tables(int sm_count) {
   if (cudaMemcpyToSymbol(c_units, un, sizeof(un)) != cudaSuccess) return 1;
   if (cudaFuncSetAttribute(mlp_fwd_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_FWD) != cudaSuccess) return 1;
   if (cudaFuncSetAttribute(mlp_dgrad_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_FWD) != cudaSuccess) return 1;
+  if (cudaFuncSetAttribute(mlp_fwd_tc2, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_FWD) != cudaSuccess) return 1;
+  if (cudaFuncSetAttribute(mlp_dgrad_tc2, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_FWD) != cudaSuccess) return 1;
   if (cudaFuncSetAttribute(mlp_wgrad_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_WG) != cudaSuccess) return 1;
   g_tables_ready = true;
   return 0;
@@ -1105,7 +1477,12 @@ int mlp_tc_forward(flnerf_ctx *ctx, const float *params, const void *packed, int
   int grid = p.n_pairs < ctx->sm_count ? p.n_pairs : ctx->sm_count;
   p.stagger_cycles = p.n_pairs >= 4 * grid ? tc::stagger_setting() : 0;   // only worth it for long launches
   FL_CHECK_CUDA(cudaMemsetAsync(raw, 0, (size_t)n * 4 * sizeof(float), st));  // column-half warps accumulate into it
-  FL_LAUNCH(tc::mlp_fwd_tc, grid, tc::kThreads, tc::SMEM_FWD, st, p);
+  if (tc::kernel_generation() >= 2 && p.n_pairs >= 2) {
+    grid &= ~1;  // clusters of 2
+    FL_LAUNCH(tc::mlp_fwd_tc2, grid, tc::kThreads, tc::SMEM_FWD, st, p);
+  } else {
+    FL_LAUNCH(tc::mlp_fwd_tc, grid, tc::kThreads, tc::SMEM_FWD, st, p);
+  }
   return 0;
 }
 
@@ -1121,7 +1498,13 @@ int mlp_tc_backward(flnerf_ctx *ctx, const float *params, const void *packed, in
   d.dy = (uint8_t *)ws; d.n = n; d.n_pairs = (int)(n_pad / 256);
   int grid = d.n_pairs < ctx->sm_count ? d.n_pairs : ctx->sm_count;
   d.stagger_cycles = d.n_pairs >= 4 * grid ? tc::stagger_setting() : 0;
-  if (stages & 1) FL_LAUNCH(tc::mlp_dgrad_tc, grid, tc::kThreads, tc::SMEM_FWD, st, d);
+  if (stages & 1) {
+    if (tc::kernel_generation() >= 2 && d.n_pairs >= 2) {
+      FL_LAUNCH(tc::mlp_dgrad_tc2, grid & ~1, tc::kThreads, tc::SMEM_FWD, st, d);
+    } else {
+      FL_LAUNCH(tc::mlp_dgrad_tc, grid, tc::kThreads, tc::SMEM_FWD, st, d);
+    }
+  }
   tc::WgradParams w{};
   w.dy = (const uint8_t *)ws; w.stash_act = stash_act; w.pe_tiles = (const uint8_t *)pe_tiles; w.draw = draw;
   w.G = grads; w.n = n; w.n_tiles = (int)(n_pad / 128); w.dirpe = dirpe; w.S = S;
