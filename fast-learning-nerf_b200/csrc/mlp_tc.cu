@@ -168,7 +168,7 @@ __device__ __forceinline__ uint32_t fwd_block(const uint32_t v[32], const float4
     const uint32_t w1 = kType == 2 ? pack_bf16_fast(x2, x3) : pack_bf16_relu(x2, x3);
     pk[2 * q] = w0;
     pk[2 * q + 1] = w1;
-    if (kMask) m |= nz_bits(w0, 4 * q) | nz_bits(w1, 4 * q + 2);
+    if (kMask) m += nz_nibble(w0, w1) << (4 * q);
     if (kType == 1) {  // alpha_linear on the bf16-rounded activations the next layers also see
       const float4 a = *reinterpret_cast<const float4 *>(s_wa + c0 + 4 * q);
       alpha = fmaf(bf16_lo(w0), a.x, alpha);
@@ -253,6 +253,7 @@ struct FwdParams {
   int S;
   int n_pairs;
   int stagger_cycles;
+  int dbg;   // profiling switches (bit 0: skip mask generation, bit 1: skip the activation bulk stores)
 };
 
 // ring items of one pair, in consumption order: PE(both tiles), W(L0), W(L1)x4 .. W(L4)x4, PE, W(L5)x5, W(L6)x4,
@@ -383,7 +384,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_fwd_tc(FwdParams p) {
               const uint32_t w1 = pack_bf16_relu(__uint_as_float(v[4 * q + 2]) + b.z, __uint_as_float(v[4 * q + 3]) + b.w);
               pk[2 * q] = w0;
               pk[2 * q + 1] = w1;
-              m |= nz_bits(w0, 4 * q) | nz_bits(w1, 4 * q + 2);
+              m += nz_nibble(w0, w1) << (4 * q);
               const float h[4] = {bf16_lo(w0), bf16_hi(w0), bf16_lo(w1), bf16_hi(w1)};
               const int k = cb * 32 + 4 * q;
 #pragma unroll
@@ -554,7 +555,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) mlp_fwd
       const int64_t tile = (int64_t)pair * 2 + t;
       const int64_t row = tile * 128 + r;
       uint8_t *stash_act = live ? p.stash_act : nullptr;
-      uint32_t *stash_mask = live ? p.stash_mask : nullptr;
+      uint32_t *stash_mask = (live && !(p.dbg & 1)) ? p.stash_mask : nullptr;
       for (int L = 0; L < 10; ++L) {
         mbar_wait(bar2_acc_full(bar, t), n_acc & 1);
         ++n_acc;
@@ -593,7 +594,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) mlp_fwd
               const uint32_t w1 = pack_bf16_relu(__uint_as_float(v[4 * q + 2]) + b.z, __uint_as_float(v[4 * q + 3]) + b.w);
               pk[2 * q] = w0;
               pk[2 * q + 1] = w1;
-              m |= nz_bits(w0, 4 * q) | nz_bits(w1, 4 * q + 2);
+              m += nz_nibble(w0, w1) << (4 * q);
               const float h[4] = {bf16_lo(w0), bf16_hi(w0), bf16_lo(w1), bf16_hi(w1)};
               const int k = cb * 32 + 4 * q;
 #pragma unroll
@@ -618,8 +619,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) mlp_fwd
         fence_async_smem();
         if (p.stash_act) {
           named_bar_sync(1 + t, 256);
-          if (elected && stash_act) {
-            bulk_s2g(stash_act + (size_t)tile * TILE_ACT_BYTES + (size_t)L * 65536, smem_u32(act_tile),
+          if (elected && stash_act && !(p.dbg & 2)) {
+            bulk_s2g(stash_act + ((p.dbg & 4) ? (size_t)blockIdx.x * 131072 + t * 65536 : (size_t)tile * TILE_ACT_BYTES + (size_t)L * 65536), smem_u32(act_tile),
                      L == 9 ? 32768u : 65536u);
             bulk_commit();
             store_pending = true;
@@ -1477,6 +1478,7 @@ int mlp_tc_forward(flnerf_ctx *ctx, const float *params, const void *packed, int
   int grid = p.n_pairs < ctx->sm_count ? p.n_pairs : ctx->sm_count;
   p.stagger_cycles = p.n_pairs >= 4 * grid ? tc::stagger_setting() : 0;   // only worth it for long launches
   FL_CHECK_CUDA(cudaMemsetAsync(raw, 0, (size_t)n * 4 * sizeof(float), st));  // column-half warps accumulate into it
+  { const char *e = getenv("FLNERF_FWD_DBG"); p.dbg = e ? atoi(e) : 0; }
   if (tc::kernel_generation() >= 2 && p.n_pairs >= 2) {
     grid &= ~1;  // clusters of 2
     FL_LAUNCH(tc::mlp_fwd_tc2, grid, tc::kThreads, tc::SMEM_FWD, st, p);

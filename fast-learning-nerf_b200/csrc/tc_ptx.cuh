@@ -173,6 +173,14 @@ __device__ __forceinline__ uint32_t nz_bits(uint32_t w, int e) {
   uint32_t hi = t >> (30 - e);
   return (lo & (1u << e)) | (hi & (2u << e));
 }
+// 4 mask bits (bit i = element i != 0) from two packed pairs of NON-NEGATIVE bf16: w + 0x7FFF7FFF puts the "non-zero"
+// flags into bits 15/31 (IMAD, fma pipe); PRMT gathers the four flag bytes; (u & 0x80808080) * 0x00204081 moves the
+// flags at bits 7,15,23,31 to bits 28..31 without carries (all 16 partial products land on distinct bits)
+__device__ __forceinline__ uint32_t nz_nibble(uint32_t w0, uint32_t w1) {
+  const uint32_t t0 = w0 + 0x7FFF7FFFu, t1 = w1 + 0x7FFF7FFFu;
+  const uint32_t u = __byte_perm(t0, t1, 0x7531);
+  return ((u & 0x80808080u) * 0x00204081u) >> 28;
+}
 __device__ __forceinline__ float bf16_lo(uint32_t p) { return __uint_as_float(p << 16); }
 __device__ __forceinline__ float bf16_hi(uint32_t p) { return __uint_as_float(p & 0xFFFF0000u); }
 
