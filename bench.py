@@ -230,7 +230,11 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_value = gb * args.steps / (float(t.item()) * 1e-3)
 
+    if world > 1:
+        dist.barrier()
     if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
         return
     # ---------------- per-kernel roofline (rank 0, fine pass: 4096 x 192 rows), CUDA events on the launch stream
     peaks = measured_peaks()
@@ -296,6 +300,8 @@ def run_ours(args):
         "e2e": {"value": e2e_value, "unit": "rays/s", "h2d_bytes_per_step": bytes_in, "d2h_bytes_per_step": 8},
         "gpu_launches": int(launches), "clocks": clk, "roofline": roof, "cpu_baseline": cpu,
         "loss": loss_host}))
+    if world > 1:
+        dist.destroy_process_group()
 
 
 def main():

@@ -1,0 +1,127 @@
+"""GPU (-m gpu): ragged / tiny / maximum sizes through the public API, and the data-parallel step with two ranks
+sharing one GPU (gloo), against the single-process step on the same global batch."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+import nerf_oracle as O
+from conftest import ROOT, PKG
+
+pytestmark = pytest.mark.gpu
+
+
+def make_net(seed, precision):
+    import model
+    net = model.NeRF(D=8, W=256, input_ch=63, input_ch_views=27, output_ch=5, skips=[4], use_viewdirs=True,
+                     precision=precision)
+    net.load_state_dict(O.init_params(seed))
+    return net.cuda()
+
+
+def rays(B, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    o = torch.randn(B, 3, generator=g) * 0.2 + torch.tensor([0., 0., 4.])
+    d = -torch.nn.functional.normalize(torch.randn(B, 3, generator=g) * 0.2 + torch.tensor([0., 0., 1.]), dim=-1)
+    return o.cuda(), d.cuda(), torch.rand(B, 3, generator=g).cuda()
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("B,Nc,Nf", [(1, 64, 128), (3, 7, 5), (257, 64, 128), (130, 32, 64)])
+def test_ragged_batches_through_render(B, Nc, Nf, precision):
+    """Row counts that are not multiples of the 128/256-row tiles, a single ray, odd sample counts."""
+    import render as R, run_nerf, run_nerf_helpers as H
+    nc, nf = make_net(1, precision), make_net(2, precision)
+    q = run_nerf.NetworkQuery(H.get_embedder(10)[0], H.get_embedder(4)[0], 65536)
+    o, d, tgt = rays(B)
+    K = np.array([[100.0, 0, 50], [0, 100.0, 50], [0, 0, 1]])
+    rgb, disp, acc, ex = R.render(100, 100, K, rays=torch.stack([o, d], 0), ndc=False, near=2.0, far=6.0, use_viewdirs=True,
+                                  network_query_fn=q, network_fn=nc, network_fine=nf, N_samples=Nc, N_importance=Nf,
+                                  white_bkgd=True, perturb=0.0, retraw=True)
+    assert rgb.shape == (B, 3) and ex["raw"].shape == (B, Nc + Nf, 4) and bool(torch.isfinite(rgb).all())
+    pc, pf = O.init_params(1), O.init_params(2)
+    r11 = O.pack_rays(100, 100, K, o.cpu(), d.cpu(), 2.0, 6.0, ndc=False)
+    ref = O.render_rays(r11, pc, pf, Nc, Nf, white_bkgd=True)
+    tol = 2e-4 if precision == "fp32" else 5e-2
+    np.testing.assert_allclose(ex["rgb0"].detach().cpu().numpy(), ref["rgb0"].numpy(), atol=tol)
+    np.testing.assert_allclose(rgb.detach().cpu().numpy(), ref["rgb_map"].numpy(), atol=tol)
+    (rgb.sum() + ex["rgb0"].sum()).backward()
+    g = nc._grad_bucket()
+    assert bool(torch.isfinite(g).all()) and float(g.abs().max()) > 0
+
+
+def test_render_full_image_c2w_and_chunking():
+    """render(c2w=...) generates the rays itself; chunking must not change the result (render.py:12-24)."""
+    import render as R, run_nerf, run_nerf_helpers as H
+    from flnerf_b200 import synthetic
+    nc, nf = make_net(3, "bf16"), make_net(4, "bf16")
+    q = run_nerf.NetworkQuery(H.get_embedder(10)[0], H.get_embedder(4)[0], 65536)
+    K = synthetic.intrinsics(40, 48, 60.0)
+    c2w = torch.as_tensor(synthetic.pose_spherical(20.0, -30.0, 4.0)[:3, :4]).cuda()
+    kw = dict(c2w=c2w, ndc=False, near=2.0, far=6.0, use_viewdirs=True, network_query_fn=q, network_fn=nc,
+              network_fine=nf, N_samples=16, N_importance=16, white_bkgd=True, perturb=0.0)
+    with torch.no_grad():
+        a = R.render(40, 48, K, chunk=32768, **kw)
+        b = R.render(40, 48, K, chunk=500, **kw)
+    assert a[0].shape == (40, 48, 3) and a[1].shape == (40, 48)
+    assert torch.equal(a[0], b[0]) and torch.equal(a[2], b[2])
+
+
+def _dp_worker(rank, world, port, out):
+    sys.path.insert(0, PKG)
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.cuda.set_device(0)
+    import nerf_oracle as O2
+    import model
+    from flnerf_b200.engine import FusedAdam, Trainer
+
+    def net(seed):
+        n = model.NeRF(D=8, W=256, input_ch=63, input_ch_views=27, output_ch=5, skips=[4], use_viewdirs=True, precision="fp32")
+        n.load_state_dict(O2.init_params(seed))
+        return n.cuda()
+    B = 37                                              # ragged: ranks get 19 and 18 rays
+    o, d, tgt = rays(B)
+    K = np.array([[100.0, 0, 50], [0, 100.0, 50], [0, 0, 1]])
+    nc, nf = net(5), net(6)
+    opt = FusedAdam(list(nc.parameters()) + list(nf.parameters()), [nc, nf], lr=5e-4)
+    tr = Trainer(nc, nf, opt, 100, 100, K, 2.0, 6.0, 16, 16, white_bkgd=True, perturb=0.0, world_size=world, rank=rank)
+    sel = torch.arange(rank, B, world).cuda()
+    loss = tr.step(o[sel].contiguous(), d[sel].contiguous(), tgt[sel].contiguous(), global_batch=B)
+    dist.all_reduce(loss)
+    w = torch.cat([nc.flat_parameters(), nf.flat_parameters()]).cpu()
+    if rank == 0:
+        out.put((loss.cpu().numpy(), w.numpy(), tr.bucket.cpu().numpy()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_data_parallel_step_matches_single_process():
+    from flnerf_b200.engine import FusedAdam, Trainer
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29600 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_dp_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    loss2, w2, g2 = q.get(timeout=300)
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    B = 37
+    o, d, tgt = rays(B)
+    K = np.array([[100.0, 0, 50], [0, 100.0, 50], [0, 0, 1]])
+    nc, nf = make_net(5, "fp32"), make_net(6, "fp32")
+    opt = FusedAdam(list(nc.parameters()) + list(nf.parameters()), [nc, nf], lr=5e-4)
+    tr = Trainer(nc, nf, opt, 100, 100, K, 2.0, 6.0, 16, 16, white_bkgd=True, perturb=0.0)
+    loss1 = tr.step(o, d, tgt)
+    np.testing.assert_allclose(loss2, loss1.cpu().numpy(), rtol=1e-5)
+    g1 = tr.bucket.cpu().numpy()
+    assert np.linalg.norm(g2 - g1) <= 1e-4 * np.linalg.norm(g1)          # one all-reduce reproduces the full-batch gradient
+    w1 = torch.cat([nc.flat_parameters(), nf.flat_parameters()]).cpu().numpy()
+    assert float(np.abs(w2 - w1).mean()) < 1e-5
