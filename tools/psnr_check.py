@@ -1,5 +1,6 @@
 """PSNR at equal iterations: the bf16 tensor-core path vs the fp32 parity path (== the reference arithmetic, see
-tests/test_gpu_mlp.py) on the synthetic blob scene, same seeds / same ray batches.  Prints one JSON line."""
+tests/test_gpu_mlp.py) on the synthetic blob scene; same seed => same init, same ray batches, same jitter.
+Reports PSNR on training views (fit) and held-out views.  Prints one JSON line."""
 import json, os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "fast-learning-nerf_b200"))
@@ -9,15 +10,31 @@ import model, tree, render as R, run_nerf, run_nerf_helpers as H
 from flnerf_b200 import synthetic
 from flnerf_b200.engine import FusedAdam, Trainer
 
-RES, VIEWS, ITERS, NRAND = int(os.environ.get("PC_RES", 160)), 24, int(os.environ.get("PC_ITERS", 1500)), 2048
+RES, VIEWS = int(os.environ.get("PC_RES", 100)), int(os.environ.get("PC_VIEWS", 40))
+ITERS, NRAND = int(os.environ.get("PC_ITERS", 2000)), int(os.environ.get("PC_NRAND", 1024))
+SEEDS = [int(s) for s in os.environ.get("PC_SEEDS", "0,1,2").split(",")]
 dev = torch.device("cuda")
 K = synthetic.intrinsics(RES, RES, 0.5 * RES / np.tan(0.5 * 0.6911112070083618))
 poses = synthetic.lego_like_poses(VIEWS)
-test_poses = synthetic.lego_like_poses(4, phi=-20.0)
+test_poses = synthetic.lego_like_poses(4, phi=-25.0)
 imgs = synthetic.render_scene(RES, RES, K, poses, n_samples=128)
 test_imgs = synthetic.render_scene(RES, RES, K, test_poses, n_samples=128)
-out = {}
-for seed in (0, 1):
+q = run_nerf.NetworkQuery(H.get_embedder(10)[0], H.get_embedder(4)[0], 65536)
+
+
+def psnr_on(nc, nf, ps, gts):
+    out = []
+    with torch.no_grad():
+        for c2w, gt in zip(ps, gts):
+            rgb = R.render(RES, RES, K, chunk=32768, c2w=torch.as_tensor(c2w[:3, :4], device=dev), ndc=False, near=2.0, far=6.0,
+                           use_viewdirs=True, network_query_fn=q, network_fn=nc, network_fine=nf, N_samples=64,
+                           N_importance=128, white_bkgd=True, perturb=0.0)[0]
+            out.append(float(-10 * torch.log10(torch.mean((rgb - gt) ** 2))))
+    return float(np.mean(out))
+
+
+res = {}
+for seed in SEEDS:
     for prec in ("fp32", "bf16"):
         torch.manual_seed(seed)
         nc = model.NeRF(8, 256, 63, 27, 5, [4], True, precision=prec).to(dev)
@@ -31,21 +48,13 @@ for seed in (0, 1):
             for first in range(0, n - NRAND, NRAND):
                 tr.step_from_tree(mgr, first, NRAND)
                 it += 1
-                for g in opt.param_groups:
-                    g["lr"] = 5e-4 * 0.1 ** (it / 500000)
                 if it >= ITERS:
                     break
             mgr.refine(0.001)
-        q = run_nerf.NetworkQuery(H.get_embedder(10)[0], H.get_embedder(4)[0], 65536)
-        ps = []
-        with torch.no_grad():
-            for i, c2w in enumerate(test_poses):
-                rgb, _, _, _ = R.render(RES, RES, K, chunk=32768, c2w=torch.as_tensor(c2w[:3, :4], device=dev), ndc=False, near=2.0,
-                                        far=6.0, use_viewdirs=True, network_query_fn=q, network_fn=nc, network_fine=nf,
-                                        N_samples=64, N_importance=128, white_bkgd=True, perturb=0.0)
-                ps.append(float(-10 * torch.log10(torch.mean((rgb - test_imgs[i]) ** 2))))
-        out["%s.seed%d" % (prec, seed)] = float(np.mean(ps))
-d = [out["bf16.seed%d" % s] - out["fp32.seed%d" % s] for s in (0, 1)]
-out["delta_db"] = d
-out["config"] = dict(res=RES, views=VIEWS, iters=ITERS, n_rand=NRAND, leaves=int(mgr.counts.sum()))
-print(json.dumps(out))
+        res["%s.seed%d" % (prec, seed)] = {"train": psnr_on(nc, nf, poses[::10], imgs[::10]), "test": psnr_on(nc, nf, test_poses, test_imgs)}
+for k in ("train", "test"):
+    d = [res["bf16.seed%d" % s][k] - res["fp32.seed%d" % s][k] for s in SEEDS]
+    res["delta_%s_db" % k] = d
+    res["mean_delta_%s_db" % k] = float(np.mean(d))
+res["config"] = dict(res=RES, views=VIEWS, iters=ITERS, n_rand=NRAND)
+print(json.dumps(res))
