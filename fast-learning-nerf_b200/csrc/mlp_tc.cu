@@ -254,6 +254,7 @@ struct FwdParams {
   int n_pairs;
   int stagger_cycles;
   int dbg;   // profiling switches (bit 0: skip mask generation, bit 1: skip the activation bulk stores)
+  long long *prof;  // per-CTA cycle accounting of the three roles (16 slots per CTA) when FLNERF_TC_PROF is set, else null
 };
 
 // ring items of one pair, in consumption order: PE(both tiles), W(L0), W(L1)x4 .. W(L4)x4, PE, W(L5)x5, W(L6)x4,
@@ -468,6 +469,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) mlp_fwd
     // ---------------------------------------------------------------- producer
     if (lane == 0) {
       Ring ring;
+      const bool prof = p.prof != nullptr;
+      long long pw = 0;
+      const long long pt0 = prof ? clock64() : 0;
       for (int it = 0; it < iters; ++it) {
         const int pair = min(p.n_pairs - 1, (int)blockIdx.x + it * (int)gridDim.x);
         const uint8_t *pe = p.pe_tiles + (size_t)pair * 2 * PE_BYTES;
@@ -485,7 +489,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) mlp_fwd
               const int cc = ci + c;
               const uint32_t bytes = cc < 34 ? 32768u : 16384u, half = bytes / 2;
               const size_t off = cc < 34 ? (size_t)cc * 32768 : (size_t)34 * 32768 + (size_t)(cc - 34) * 16384;
+              const long long q0 = prof ? clock64() : 0;
               mbar_wait(bar2_w_empty(bar, ring.stage), ring.phase ^ 1);
+              if (prof) pw += clock64() - q0;
               mbar_arrive_expect_tx(bar2_w_full(bar, ring.stage), bytes);   // my half + the peer's half
               bulk_g2s_multicast(s_w + ring.stage * WSTAGE + cr * half, p.packed + off + (size_t)cr * half, half,
                                  bar2_w_full(bar, ring.stage), (uint16_t)3);
@@ -495,6 +501,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) mlp_fwd
           ci += nch;
         }
       }
+      if (prof) { p.prof[blockIdx.x * 16 + 4] = pw; p.prof[blockIdx.x * 16 + 5] = clock64() - pt0; }
     }
   } else if (warp == 1) {
     // ---------------------------------------------------------------- MMA issuer
@@ -502,25 +509,32 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) mlp_fwd
       Ring ring;
       uint32_t n_act[2] = {0u, 0u};
       const uint32_t idesc256 = make_idesc(128, 256, 0, 0), idesc128 = make_idesc(128, 128, 0, 0);
+      const bool prof = p.prof != nullptr;
+      long long wa0 = 0, wa1 = 0, ww = 0;
+      const long long mt0 = prof ? clock64() : 0;
       for (int it = 0; it < iters; ++it) {
         for (int L = 0; L < 10; ++L) {
           const int nch = (L == 0) ? 1 : (L == 5 ? 5 : 4);
 #pragma unroll
           for (int t = 0; t < 2; ++t) {
             if (!(it == 0 && L == 0)) {  // this tile's inputs written / its accumulator drained by its epilogue warps
+              const long long q0 = prof ? clock64() : 0;
               mbar_wait(bar2_act_ready(bar, t), n_act[t] & 1);
+              if (prof) { if (t == 0) wa0 += clock64() - q0; else wa1 += clock64() - q0; }
               ++n_act[t];
             }
             tc_fence_after();
             for (int c = 0; c < nch; ++c) {
               const bool use_pe = (L == 0) || (L == 5 && c == 0);
               uint32_t pe_stage = 0;
+              const long long q1 = prof ? clock64() : 0;
               if (use_pe) {
                 mbar_wait(bar2_w_full(bar, ring.stage), ring.phase);
                 pe_stage = ring.stage;
                 ring.next();
               }
               mbar_wait(bar2_w_full(bar, ring.stage), ring.phase);
+              if (prof) ww += clock64() - q1;
               tc_fence_after();
               const int slab = (L == 5) ? c - 1 : c;
               const uint32_t a = use_pe ? s_w + pe_stage * WSTAGE : s_act + t * ACT_BYTES + slab * SLAB_BYTES;
@@ -532,6 +546,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) mlp_fwd
             umma_commit(bar2_acc_full(bar, t));
           }
         }
+      }
+      if (prof) {
+        long long *o = p.prof + blockIdx.x * 16;
+        o[0] = clock64() - mt0; o[1] = wa0; o[2] = wa1; o[3] = ww;
       }
     }
   } else {
@@ -548,6 +566,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) mlp_fwd
     const float *s_wa = s_head + 388;
     uint32_t n_acc = 0;
     bool store_pending = false;
+    const bool prof = p.prof != nullptr && (e & 7) == 0 && lane == 0;
+    long long e_acc = 0, e_st = 0, e_body = 0, e_tail = 0;
+    const long long et0 = prof ? clock64() : 0;
     for (int it = 0; it < iters; ++it) {
       const int pair_raw = (int)blockIdx.x + it * (int)gridDim.x;
       const bool live = pair_raw < p.n_pairs;          // surplus iteration: compute, but write nothing
@@ -557,13 +578,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) mlp_fwd
       uint8_t *stash_act = live ? p.stash_act : nullptr;
       uint32_t *stash_mask = (live && !(p.dbg & 1)) ? p.stash_mask : nullptr;
       for (int L = 0; L < 10; ++L) {
+        const long long q0 = prof ? clock64() : 0;
         mbar_wait(bar2_acc_full(bar, t), n_acc & 1);
         ++n_acc;
         tc_fence_after();
+        const long long q1 = prof ? clock64() : 0;
         if (p.stash_act) {
           if (elected && store_pending) bulk_wait_read0();
           named_bar_sync(1 + t, 256);
         }
+        const long long q2 = prof ? clock64() : 0;
         uint32_t *mask_dst = stash_mask ? stash_mask + ((size_t)tile * 9 + (L < 9 ? L : 8)) * 128 * 8 + (size_t)r * 8 : nullptr;
         float alpha = 0.f;
         if (L < 7) {
@@ -617,6 +641,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) mlp_fwd
         }
         tc_fence_before();
         fence_async_smem();
+        const long long q3 = prof ? clock64() : 0;
         if (p.stash_act) {
           named_bar_sync(1 + t, 256);
           if (elected && stash_act && !(p.dbg & 2)) {
@@ -628,7 +653,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) mlp_fwd
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(bar2_act_ready(bar, t));
+        if (prof) { e_acc += q1 - q0; e_st += q2 - q1; e_body += q3 - q2; e_tail += clock64() - q3; }
       }
+    }
+    if (prof) {
+      long long *o = p.prof + blockIdx.x * 16 + 6 + t * 5;
+      o[0] = clock64() - et0; o[1] = e_acc; o[2] = e_st; o[3] = e_body; o[4] = e_tail;
     }
     if (elected && store_pending) bulk_wait_all0();
   }
@@ -650,6 +680,7 @@ struct DgradParams {
   int64_t n;
   int n_pairs;
   int stagger_cycles;
+  long long *prof;
 };
 
 __global__ void __launch_bounds__(kThreads, 1) mlp_dgrad_tc(DgradParams p) {
@@ -809,13 +840,18 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) mlp_dgr
   if (warp == 0) {
     if (lane == 0) {
       Ring ring;
+      const bool prof = p.prof != nullptr;
+      long long pw = 0;
+      const long long pt0 = prof ? clock64() : 0;
       for (int it = 0; it < iters; ++it) {
         int ci = 0;
         for (int D = 0; D < 9; ++D) {
           const int nch = (D == 0) ? 2 : 4;
           for (int t = 0; t < 2; ++t)
             for (int c = 0; c < nch; ++c) {
+              const long long q0 = prof ? clock64() : 0;
               mbar_wait(bar2_w_empty(bar, ring.stage), ring.phase ^ 1);
+              if (prof) pw += clock64() - q0;
               mbar_arrive_expect_tx(bar2_w_full(bar, ring.stage), 32768u);
               bulk_g2s_multicast(s_w + ring.stage * WSTAGE + cr * 16384u,
                                  p.packed_dg + (size_t)(ci + c) * 32768 + (size_t)cr * 16384, 16384u,
@@ -825,22 +861,30 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) mlp_dgr
           ci += nch;
         }
       }
+      if (prof) { p.prof[blockIdx.x * 16 + 4] = pw; p.prof[blockIdx.x * 16 + 5] = clock64() - pt0; }
     }
   } else if (warp == 1) {
     if (lane == 0) {
       Ring ring;
       uint32_t n_act[2] = {0u, 0u};
       const uint32_t idesc = make_idesc(128, 256, 0, 0);
+      const bool prof = p.prof != nullptr;
+      long long wa0 = 0, wa1 = 0, ww = 0;
+      const long long mt0 = prof ? clock64() : 0;
       for (int it = 0; it < iters; ++it) {
         for (int D = 0; D < 9; ++D) {
           const int nch = (D == 0) ? 2 : 4;
 #pragma unroll
           for (int t = 0; t < 2; ++t) {
+            const long long q0 = prof ? clock64() : 0;
             mbar_wait(bar2_act_ready(bar, t), n_act[t] & 1);
+            if (prof) { if (t == 0) wa0 += clock64() - q0; else wa1 += clock64() - q0; }
             ++n_act[t];
             tc_fence_after();
             for (int c = 0; c < nch; ++c) {
+              const long long q1 = prof ? clock64() : 0;
               mbar_wait(bar2_w_full(bar, ring.stage), ring.phase);
+              if (prof) ww += clock64() - q1;
               tc_fence_after();
               issue_chunk(tmem_base + t * 256, s_act + t * ACT_BYTES + c * SLAB_BYTES, s_w + ring.stage * WSTAGE, idesc, c == 0);
               umma_commit_multicast(bar2_w_empty(bar, ring.stage), (uint16_t)3);
@@ -849,6 +893,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) mlp_dgr
             umma_commit(bar2_acc_full(bar, t));
           }
         }
+      }
+      if (prof) {
+        long long *o = p.prof + blockIdx.x * 16;
+        o[0] = clock64() - mt0; o[1] = wa0; o[2] = wa1; o[3] = ww;
       }
     }
   } else {
@@ -864,6 +912,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) mlp_dgr
     const float *s_wa = s_head + 388;
     uint32_t n_acc = 0;
     bool store_pending = false;
+    const bool prof = p.prof != nullptr && (e & 7) == 0 && lane == 0;
+    long long e_acc = 0, e_st = 0, e_body = 0, e_tail = 0;
+    const long long et0 = prof ? clock64() : 0;
     for (int it = 0; it < iters; ++it) {
       const int pair_raw = (int)blockIdx.x + it * (int)gridDim.x;
       const bool live = pair_raw < p.n_pairs;
@@ -874,13 +925,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) mlp_dgr
       if (row < p.n) dr = reinterpret_cast<const float4 *>(p.draw)[row];
       const uint32_t *mask_base = p.stash_mask + (size_t)tile * 9 * 128 * 8 + (size_t)r * 8;
       for (int D = -1; D < 9; ++D) {
+        const long long q0 = prof ? clock64() : 0;
         if (D >= 0) {
           mbar_wait(bar2_acc_full(bar, t), n_acc & 1);
           ++n_acc;
           tc_fence_after();
         }
+        const long long q1 = prof ? clock64() : 0;
         if (elected && store_pending) bulk_wait_read0();
         named_bar_sync(1 + t, 256);
+        const long long q2 = prof ? clock64() : 0;
         const uint32_t *mk = (D != 0) ? mask_base + (size_t)((D < 0) ? 8 : 8 - D) * 128 * 8 : nullptr;
         if (D < 0) {
           const uint2 m2 = __ldg(reinterpret_cast<const uint2 *>(mk) + ch);
@@ -909,6 +963,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) mlp_dgr
         }
         tc_fence_before();
         fence_async_smem();
+        const long long q3 = prof ? clock64() : 0;
         named_bar_sync(1 + t, 256);
         if (elected && live) {
           int slot = (D < 0) ? 9 : 8 - D;
@@ -918,7 +973,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) mlp_dgr
         }
         __syncwarp();
         if (D < 8 && lane == 0) mbar_arrive(bar2_act_ready(bar, t));
+        if (prof) { e_acc += q1 - q0; e_st += q2 - q1; e_body += q3 - q2; e_tail += clock64() - q3; }
       }
+    }
+    if (prof) {
+      long long *o = p.prof + blockIdx.x * 16 + 6 + t * 5;
+      o[0] = clock64() - et0; o[1] = e_acc; o[2] = e_st; o[3] = e_body; o[4] = e_tail;
     }
     if (elected && store_pending) bulk_wait_all0();
   }
@@ -1362,6 +1422,34 @@ static int kernel_generation() {
 static bool g_tables_ready = false;
 static int g_wgrad_grid = 0;
 
+// FLNERF_TC_PROF=1: the gen-2 forward / dgrad kernels count, per role, the cycles spent waiting on each barrier; the
+// host prints CTA 0/1 and the grid mean for every launch of >= 1024 pairs (development aid, off by default)
+static long long *prof_buffer() {
+  static long long *buf = nullptr;
+  static int on = -1;
+  if (on < 0) {
+    on = getenv("FLNERF_TC_PROF") != nullptr;
+    if (on && cudaMalloc(&buf, sizeof(long long) * 16 * 1024) != cudaSuccess) buf = nullptr;
+  }
+  return buf;
+}
+static void prof_report(const char *name, int grid, int n_pairs, cudaStream_t st) {
+  if (n_pairs < 1024) return;
+  static long long h[16 * 1024];
+  cudaStreamSynchronize(st);
+  cudaMemcpy(h, prof_buffer(), sizeof(long long) * 16 * grid, cudaMemcpyDeviceToHost);
+  static const char *lbl[16] = {"mma_total", "mma_wait_act0", "mma_wait_act1", "mma_wait_wfull", "prod_wait_empty", "prod_total",
+                                "epi0_total", "epi0_wait_acc", "epi0_wait_store", "epi0_body", "epi0_tail",
+                                "epi1_total", "epi1_wait_acc", "epi1_wait_store", "epi1_body", "epi1_tail"};
+  fprintf(stderr, "tcprof %s grid %d pairs %d:", name, grid, n_pairs);
+  for (int k = 0; k < 16; ++k) {
+    double m = 0;
+    for (int i = 0; i < grid; ++i) m += (double)h[i * 16 + k];
+    fprintf(stderr, " %s=%.0f(cta0 %lld)", lbl[k], m / grid, h[k]);
+  }
+  fprintf(stderr, "\n");
+}
+
 static int setup_tables(int sm_count) {
   if (g_tables_ready) return 0;
   ChunkSrc ch[FWD_CHUNKS + DG_CHUNKS];
@@ -1479,9 +1567,11 @@ int mlp_tc_forward(flnerf_ctx *ctx, const float *params, const void *packed, int
   p.stagger_cycles = p.n_pairs >= 4 * grid ? tc::stagger_setting() : 0;   // only worth it for long launches
   FL_CHECK_CUDA(cudaMemsetAsync(raw, 0, (size_t)n * 4 * sizeof(float), st));  // column-half warps accumulate into it
   { const char *e = getenv("FLNERF_FWD_DBG"); p.dbg = e ? atoi(e) : 0; }
+  p.prof = tc::prof_buffer();
   if (tc::kernel_generation() >= 2 && p.n_pairs >= 2) {
     grid &= ~1;  // clusters of 2
     FL_LAUNCH(tc::mlp_fwd_tc2, grid, tc::kThreads, tc::SMEM_FWD, st, p);
+    if (p.prof) tc::prof_report("fwd", grid, p.n_pairs, st);
   } else {
     FL_LAUNCH(tc::mlp_fwd_tc, grid, tc::kThreads, tc::SMEM_FWD, st, p);
   }
@@ -1502,7 +1592,9 @@ int mlp_tc_backward(flnerf_ctx *ctx, const float *params, const void *packed, in
   d.stagger_cycles = d.n_pairs >= 4 * grid ? tc::stagger_setting() : 0;
   if (stages & 1) {
     if (tc::kernel_generation() >= 2 && d.n_pairs >= 2) {
+      d.prof = tc::prof_buffer();
       FL_LAUNCH(tc::mlp_dgrad_tc2, grid & ~1, tc::kThreads, tc::SMEM_FWD, st, d);
+      if (d.prof) tc::prof_report("dgrad", grid & ~1, d.n_pairs, st);
     } else {
       FL_LAUNCH(tc::mlp_dgrad_tc, grid, tc::kThreads, tc::SMEM_FWD, st, d);
     }
