@@ -238,6 +238,72 @@ __device__ __forceinline__ void dgrad_epilogue_half(uint32_t tmem_row, uint32_t 
   }
 }
 
+// views_linears.0 (N=128: 64 columns per warp) + rgb_linear on CUDA cores -> raw[row].rgb (accumulated by both halves)
+struct FwdParams;
+template <class Params>
+__device__ __forceinline__ void fwd_views_rgb(const Params &p, uint32_t tmem_row, uint32_t ch, uint8_t *act_tile, uint32_t r,
+                                              int64_t row, bool live, uint32_t *mask_dst, const float *s_head) {
+  const int64_t ray = (row < p.n ? row : p.n - 1) / p.S;
+  const float4 *vb4 = reinterpret_cast<const float4 *>(p.viewbias + ray * 128);
+  float c0 = 0.f, c1 = 0.f, c2 = 0.f;
+  uint32_t mk2[2];
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const uint32_t cb = ch * 2 + i;
+    uint32_t v[32], pk[16], m = 0;
+    tmem_ld32(tmem_row + cb * 32, v);
+    tmem_ld_wait(v);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const float4 b = __ldg(vb4 + cb * 8 + q);
+      const uint32_t w0 = pack_bf16_relu(__uint_as_float(v[4 * q]) + b.x, __uint_as_float(v[4 * q + 1]) + b.y);
+      const uint32_t w1 = pack_bf16_relu(__uint_as_float(v[4 * q + 2]) + b.z, __uint_as_float(v[4 * q + 3]) + b.w);
+      pk[2 * q] = w0;
+      pk[2 * q + 1] = w1;
+      m += nz_nibble(w0, w1) << (4 * q);
+      const float h[4] = {bf16_lo(w0), bf16_hi(w0), bf16_lo(w1), bf16_hi(w1)};
+      const int k = cb * 32 + 4 * q;
+#pragma unroll
+      for (int x = 0; x < 4; ++x) {
+        c0 = fmaf(h[x], s_head[k + x], c0);
+        c1 = fmaf(h[x], s_head[128 + k + x], c1);
+        c2 = fmaf(h[x], s_head[256 + k + x], c2);
+      }
+    }
+    mk2[i] = m;
+    store_cols32(act_tile, r, cb * 32, pk);
+  }
+  if (live && row < p.n) {
+    const float bsel = ch == 0 ? 1.f : 0.f;
+    atomicAdd(p.raw + row * 4 + 0, c0 + bsel * s_head[384]);
+    atomicAdd(p.raw + row * 4 + 1, c1 + bsel * s_head[385]);
+    atomicAdd(p.raw + row * 4 + 2, c2 + bsel * s_head[386]);
+  }
+  if (mask_dst) *reinterpret_cast<uint2 *>(mask_dst + ch * 2) = make_uint2(mk2[0], mk2[1]);
+}
+
+// backward stage -1: G9 = (d_rgb * W_rgb) masked by relu(h9) -> act slabs 0,1 (64 columns per warp)
+__device__ __forceinline__ void dgrad_g9(const float4 dr, const uint32_t *mk, uint32_t ch, const float *s_head,
+                                         uint8_t *act_tile, uint32_t r) {
+  const uint2 m2 = __ldg(reinterpret_cast<const uint2 *>(mk) + ch);
+  const uint32_t mw[2] = {m2.x, m2.y};
+#pragma unroll
+  for (int j = 0; j < 2; ++j) {
+    const uint32_t cb = ch * 2 + j;
+    uint32_t pk[16];
+#pragma unroll
+    for (int i = 0; i < 32; i += 2) {
+      const int k = cb * 32 + i;
+      float g0 = dr.x * s_head[k] + dr.y * s_head[128 + k] + dr.z * s_head[256 + k];
+      float g1 = dr.x * s_head[k + 1] + dr.y * s_head[128 + k + 1] + dr.z * s_head[256 + k + 1];
+      g0 = (mw[j] & (1u << i)) ? g0 : 0.f;
+      g1 = (mw[j] & (2u << i)) ? g1 : 0.f;
+      pk[i >> 1] = pack_bf16_fast(g0, g1);
+    }
+    store_cols32(act_tile, r, cb * 32, pk);
+  }
+}
+
 // =================================================================================================
 // forward
 // =================================================================================================
@@ -989,6 +1055,410 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) mlp_dgr
 }
 
 // =================================================================================================
+// generation 3: CTA PAIR.  One tcgen05.mma.cta_group::2 (M = 256 = 128 rows in each CTA of a 2-cluster, N = 256)
+// is issued by the leader CTA for both SMs; each CTA keeps its own two 128-row tiles and only HALF of every weight
+// chunk (16 KB instead of 32 KB), and a layer's chunks stay in the ring for BOTH tile sets (A then B).
+// Why: gen-2 is shared-memory-bandwidth bound.  Per 128-row tile-layer an SM moved 192 KB of operand reads
+// (4 KB A + 8 KB B per MMA) + 128 KB of weight-chunk writes + 64 KB of epilogue stores (+ 64 KB read back by the
+// stash bulk store) = 384..448 KB against 128 B/clk x 2048 clk (the MMA floor) = 256 KB.  The pair halves the B
+// reads (each SM reads its half and receives the other from its peer) and the chunk writes, sharing a chunk between
+// the tile sets halves them again: 128 + 32 + 64 (+ 64) = 224..288 KB.  The ring is 6 x 16 KB stages.
+//   producer (warp 0, both CTAs)  : fills the local stage (its half chunk / its PE slab)
+//   relay    (warp 1, follower)   : forwards "my stage is full" to the leader's full barrier (count 2 there)
+//   issuer   (warp 1, leader)     : waits for both halves, issues the pair MMAs, multicast-commits to both CTAs
+//   epilogue (16 warps, both CTAs): as in gen-2; "inputs ready / accumulator drained" arrives on the LEADER's barrier
+// =================================================================================================
+constexpr int NST3 = 6;
+constexpr uint32_t WSTAGE3 = 16384;
+static_assert(NST3 * WSTAGE3 == NSTAGE * WSTAGE, "gen-3 ring uses the same shared-memory region");
+__device__ __forceinline__ uint32_t bar3_w_full(uint32_t base, uint32_t i) { return base + 8u * i; }
+__device__ __forceinline__ uint32_t bar3_w_empty(uint32_t base, uint32_t i) { return base + 8u * (NST3 + i); }
+__device__ __forceinline__ uint32_t bar3_acc_full(uint32_t base, uint32_t t) { return base + 8u * (2 * NST3 + t); }
+__device__ __forceinline__ uint32_t bar3_act_ready(uint32_t base, uint32_t t) { return base + 8u * (2 * NST3 + 2 + t); }
+static_assert(8u * (2 * NST3 + 4) <= 128u, "barrier block: the TMEM slot sits at +128");
+
+struct Ring3 {
+  uint32_t stage = 0, phase = 0;
+  __device__ __forceinline__ void next() {
+    if (++stage == NST3) { stage = 0; phase ^= 1; }
+  }
+};
+__device__ __forceinline__ uint32_t item_stage(uint32_t q) { return q % NST3; }
+__device__ __forceinline__ uint32_t item_phase(uint32_t q) { return (q / NST3) & 1u; }
+
+// pair MMA over one 64-wide K chunk: A = this tile set's K-major slab (in both CTAs, same offset), B = half chunk
+__device__ __forceinline__ void issue_chunk2(uint32_t tmem_d, uint32_t a_smem, uint32_t b_smem, uint32_t idesc, bool first) {
+  uint64_t da = make_smem_desc(a_smem, 0, 1024), db = make_smem_desc(b_smem, 0, 1024);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) umma2_bf16(tmem_d, da + 2 * k, db + 2 * k, idesc, (first && k == 0) ? 0u : 1u);
+}
+
+// barrier / TMEM set-up shared by the two gen-3 kernels; returns the TMEM base
+__device__ __forceinline__ uint32_t pair_setup(uint8_t *smem, uint32_t bar, uint32_t cr, int warp, uint32_t lane,
+                                               const float *P) {
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + OFF_BAR + 128);
+  if ((smem_u32(smem) & 1023u) != 0) __trap();
+  float *head = reinterpret_cast<float *>(smem + OFF_HEAD);
+  for (int i = threadIdx.x; i < (int)HEAD_FLOATS; i += blockDim.x)
+    head[i] = i < 387 ? P[W_RGB + i] : (i == 387 ? P[B_ALPHA] : P[W_ALPHA + (i - 388)]);
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < NST3; ++i) {
+      mbar_init(bar3_w_full(bar, i), cr == 0 ? 2 : 1);  // leader: own producer + the follower's relay
+      mbar_init(bar3_w_empty(bar, i), 1);
+    }
+    for (int t = 0; t < 2; ++t) { mbar_init(bar3_acc_full(bar, t), 1); mbar_init(bar3_act_ready(bar, t), kEpiWarps); }
+    fence_mbar_init();
+  }
+  __syncthreads();
+  cluster_sync_all();  // barriers of both CTAs exist before any remote arrive / multicast commit
+  if (warp == 0) { tmem_alloc2(smem_u32(tmem_slot), 512); tmem_relinquish2(); }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();  // both halves of the pair allocation are in place before the leader's first MMA
+  tc_fence_after();
+  return *tmem_slot;
+}
+
+constexpr int FWD_ITEMS = 42;  // ring items of one iteration: L0 {PE_A, W, PE_B}, L5 {PE_A, W, PE_B, W x4}, 8 layers x 4
+constexpr int DG_ITEMS = 34;
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) mlp_fwd_tc3(FwdParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const int warp = threadIdx.x >> 5;
+  const uint32_t lane = lane_id();
+  const uint32_t bar = smem_u32(smem + OFF_BAR);
+  const uint32_t cr = cluster_ctarank();
+  const uint32_t tmem_base = pair_setup(smem, bar, cr, warp, lane, p.P);
+  const uint32_t s_act = smem_u32(smem + OFF_ACT), s_w = smem_u32(smem + OFF_W);
+  const int iters = (p.n_pairs + (int)gridDim.x - 1) / (int)gridDim.x;
+  const bool prof_on = p.prof != nullptr;
+
+  if (warp == 0) {
+    // ---------------------------------------------------------------- producer (both CTAs): local halves
+    if (lane == 0) {
+      Ring3 ring;
+      long long pw = 0;
+      const long long pt0 = prof_on ? clock64() : 0;
+      auto push = [&](const uint8_t *src, uint32_t bytes) {
+        const long long q0 = prof_on ? clock64() : 0;
+        mbar_wait(bar3_w_empty(bar, ring.stage), ring.phase ^ 1);
+        if (prof_on) pw += clock64() - q0;
+        mbar_arrive_expect_tx(bar3_w_full(bar, ring.stage), bytes);
+        bulk_g2s(s_w + ring.stage * WSTAGE3, src, bytes, bar3_w_full(bar, ring.stage));
+        ring.next();
+      };
+      auto push_w = [&](int cc) {  // this CTA's half (N/2 rows) of forward chunk cc
+        const uint32_t half = cc < 34 ? 16384u : 8192u;
+        const size_t off = cc < 34 ? (size_t)cc * 32768 : (size_t)34 * 32768 + (size_t)(cc - 34) * 16384;
+        push(p.packed + off + (size_t)cr * half, half);
+      };
+      for (int it = 0; it < iters; ++it) {
+        const int pair = min(p.n_pairs - 1, (int)blockIdx.x + it * (int)gridDim.x);
+        const uint8_t *pe = p.pe_tiles + (size_t)pair * 2 * PE_BYTES;
+        int ci = 0;
+        for (int L = 0; L < 10; ++L) {
+          if (L == 0) {
+            push(pe, PE_BYTES); push_w(0); push(pe + PE_BYTES, PE_BYTES);
+            ci = 1;
+          } else if (L == 5) {
+            push(pe, PE_BYTES); push_w(ci); push(pe + PE_BYTES, PE_BYTES);
+            for (int c = 1; c < 5; ++c) push_w(ci + c);
+            ci += 5;
+          } else {
+            for (int c = 0; c < 4; ++c) push_w(ci + c);
+            ci += 4;
+          }
+        }
+      }
+      if (prof_on) { p.prof[blockIdx.x * 16 + 4] = pw; p.prof[blockIdx.x * 16 + 5] = clock64() - pt0; }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && cr != 0) {
+      // -------------------------------------------------------------- relay (follower): local full -> leader's full
+      Ring3 ring;
+      const uint32_t remote_full = mapa_cluster(bar3_w_full(bar, 0), 0);
+      const int total = iters * FWD_ITEMS;
+      for (int q = 0; q < total; ++q) {
+        mbar_wait(bar3_w_full(bar, ring.stage), ring.phase);
+        mbar_arrive_cluster(remote_full + 8u * ring.stage);
+        ring.next();
+      }
+    } else if (lane == 0) {
+      // -------------------------------------------------------------- pair MMA issuer (leader)
+      uint32_t n_act[2] = {0u, 0u};
+      const uint32_t idesc256 = make_idesc(256, 256, 0, 0), idesc128 = make_idesc(256, 128, 0, 0);
+      long long wa0 = 0, wa1 = 0, ww = 0;
+      const long long mt0 = prof_on ? clock64() : 0;
+      uint32_t q0 = 0;  // ring index of the current layer's first item
+      for (int it = 0; it < iters; ++it) {
+        for (int L = 0; L < 10; ++L) {
+          const int nch = (L == 0) ? 1 : (L == 5 ? 5 : 4);
+          const uint32_t nitems = (L == 0) ? 3u : (L == 5 ? 7u : 4u);
+#pragma unroll
+          for (int t = 0; t < 2; ++t) {
+            if (!(it == 0 && L == 0)) {  // both CTAs' epilogue warps of tile set t: inputs written, accumulator drained
+              const long long c0 = prof_on ? clock64() : 0;
+              mbar_wait_cluster(bar3_act_ready(bar, t), n_act[t] & 1);
+              if (prof_on) { if (t == 0) wa0 += clock64() - c0; else wa1 += clock64() - c0; }
+              ++n_act[t];
+            }
+            tc_fence_after();
+            for (int c = 0; c < nch; ++c) {
+              const bool use_pe = (L == 0) || (L == 5 && c == 0);
+              const uint32_t wq = q0 + ((L == 0) ? 1u : (L == 5 ? (c == 0 ? 1u : 2u + (uint32_t)c) : (uint32_t)c));
+              const uint32_t pq = q0 + (t == 0 ? 0u : 2u);
+              const long long c1 = prof_on ? clock64() : 0;
+              if (use_pe) mbar_wait_cluster(bar3_w_full(bar, item_stage(pq)), item_phase(pq));
+              if (t == 0) mbar_wait_cluster(bar3_w_full(bar, item_stage(wq)), item_phase(wq));
+              if (prof_on) ww += clock64() - c1;
+              tc_fence_after();
+              const int slab = (L == 5) ? c - 1 : c;
+              const uint32_t a = use_pe ? s_w + item_stage(pq) * WSTAGE3 : s_act + t * ACT_BYTES + slab * SLAB_BYTES;
+              issue_chunk2(tmem_base + t * 256, a, s_w + item_stage(wq) * WSTAGE3, L == 9 ? idesc128 : idesc256, c == 0);
+              if (use_pe) umma2_commit_multicast(bar3_w_empty(bar, item_stage(pq)), (uint16_t)3);
+              if (t == 1) umma2_commit_multicast(bar3_w_empty(bar, item_stage(wq)), (uint16_t)3);  // both tile sets done
+            }
+            umma2_commit_multicast(bar3_acc_full(bar, t), (uint16_t)3);
+          }
+          q0 += nitems;
+        }
+      }
+      if (prof_on) {
+        long long *o = p.prof + blockIdx.x * 16;
+        o[0] = clock64() - mt0; o[1] = wa0; o[2] = wa1; o[3] = ww;
+      }
+    }
+  } else {
+    // ---------------------------------------------------------------- epilogue: 8 warps per tile (both CTAs)
+    const int e = warp - kEpiWarp0;
+    const int t = e >> 3;
+    const uint32_t ch = (uint32_t)(e >> 2) & 1u;
+    const uint32_t quarter = warp & 3;
+    const uint32_t r = quarter * 32 + lane;
+    uint8_t *act_tile = smem + OFF_ACT + t * ACT_BYTES;
+    const uint32_t tmem_row = tmem_base + ((quarter * 32) << 16) + t * 256;
+    const bool elected = (e & 7) == 0 && lane == 0;
+    const float *s_head = reinterpret_cast<const float *>(smem + OFF_HEAD);
+    const float *s_wa = s_head + 388;
+    const uint32_t ready_remote = mapa_cluster(bar3_act_ready(bar, t), 0);  // the leader's barrier
+    uint32_t n_acc = 0;
+    bool store_pending = false;
+    const bool prof = prof_on && (e & 7) == 0 && lane == 0;
+    long long e_acc = 0, e_st = 0, e_body = 0, e_tail = 0;
+    const long long et0 = prof ? clock64() : 0;
+    for (int it = 0; it < iters; ++it) {
+      const int pair_raw = (int)blockIdx.x + it * (int)gridDim.x;
+      const bool live = pair_raw < p.n_pairs;          // surplus iteration: compute, but write nothing
+      const int pair = live ? pair_raw : p.n_pairs - 1;
+      const int64_t tile = (int64_t)pair * 2 + t;
+      const int64_t row = tile * 128 + r;
+      uint8_t *stash_act = live ? p.stash_act : nullptr;
+      uint32_t *stash_mask = (live && !(p.dbg & 1)) ? p.stash_mask : nullptr;
+      for (int L = 0; L < 10; ++L) {
+        const long long c0 = prof ? clock64() : 0;
+        mbar_wait(bar3_acc_full(bar, t), n_acc & 1);
+        ++n_acc;
+        tc_fence_after();
+        const long long c1 = prof ? clock64() : 0;
+        if (p.stash_act) {
+          if (elected && store_pending) bulk_wait_read0();
+          named_bar_sync(1 + t, 256);
+        }
+        const long long c2 = prof ? clock64() : 0;
+        uint32_t *mask_dst = stash_mask ? stash_mask + ((size_t)tile * 9 + (L < 9 ? L : 8)) * 128 * 8 + (size_t)r * 8 : nullptr;
+        float alpha = 0.f;
+        if (L < 7) {
+          const float *bias = p.P + b_pts(L);
+          if (mask_dst) fwd_epilogue_half<0, true>(tmem_row, ch, bias, act_tile, r, mask_dst, s_wa, alpha);
+          else fwd_epilogue_half<0, false>(tmem_row, ch, bias, act_tile, r, nullptr, s_wa, alpha);
+        } else if (L == 7) {
+          if (mask_dst) fwd_epilogue_half<1, true>(tmem_row, ch, p.P + b_pts(7), act_tile, r, mask_dst, s_wa, alpha);
+          else fwd_epilogue_half<1, false>(tmem_row, ch, p.P + b_pts(7), act_tile, r, nullptr, s_wa, alpha);
+          if (live && row < p.n) atomicAdd(p.raw + row * 4 + 3, alpha + (ch == 0 ? s_head[387] : 0.f));
+        } else if (L == 8) {
+          fwd_epilogue_half<2, false>(tmem_row, ch, p.P + B_FEAT, act_tile, r, nullptr, s_wa, alpha);
+        } else {
+          fwd_views_rgb(p, tmem_row, ch, act_tile, r, row, live, mask_dst, s_head);
+        }
+        tc_fence_before();
+        fence_async_smem();
+        const long long c3 = prof ? clock64() : 0;
+        if (p.stash_act) {
+          named_bar_sync(1 + t, 256);
+          if (elected && stash_act && !(p.dbg & 2)) {
+            bulk_s2g(stash_act + (size_t)tile * TILE_ACT_BYTES + (size_t)L * 65536, smem_u32(act_tile), L == 9 ? 32768u : 65536u);
+            bulk_commit();
+            store_pending = true;
+          }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(ready_remote);
+        if (prof) { e_acc += c1 - c0; e_st += c2 - c1; e_body += c3 - c2; e_tail += clock64() - c3; }
+      }
+    }
+    if (prof) {
+      long long *o = p.prof + blockIdx.x * 16 + 6 + t * 5;
+      o[0] = clock64() - et0; o[1] = e_acc; o[2] = e_st; o[3] = e_body; o[4] = e_tail;
+    }
+    if (elected && store_pending) bulk_wait_all0();
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();  // nobody leaves (or frees TMEM) while the pair may still be working for it
+  if (warp == 0) tmem_dealloc2(tmem_base, 512);
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) mlp_dgrad_tc3(DgradParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const int warp = threadIdx.x >> 5;
+  const uint32_t lane = lane_id();
+  const uint32_t bar = smem_u32(smem + OFF_BAR);
+  const uint32_t cr = cluster_ctarank();
+  const uint32_t tmem_base = pair_setup(smem, bar, cr, warp, lane, p.P);
+  const uint32_t s_act = smem_u32(smem + OFF_ACT), s_w = smem_u32(smem + OFF_W);
+  const int iters = (p.n_pairs + (int)gridDim.x - 1) / (int)gridDim.x;
+  const bool prof_on = p.prof != nullptr;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      Ring3 ring;
+      long long pw = 0;
+      const long long pt0 = prof_on ? clock64() : 0;
+      for (int it = 0; it < iters; ++it)
+        for (int ci = 0; ci < DG_CHUNKS; ++ci) {
+          const long long q0 = prof_on ? clock64() : 0;
+          mbar_wait(bar3_w_empty(bar, ring.stage), ring.phase ^ 1);
+          if (prof_on) pw += clock64() - q0;
+          mbar_arrive_expect_tx(bar3_w_full(bar, ring.stage), 16384u);
+          bulk_g2s(s_w + ring.stage * WSTAGE3, p.packed_dg + (size_t)ci * 32768 + (size_t)cr * 16384, 16384u,
+                   bar3_w_full(bar, ring.stage));
+          ring.next();
+        }
+      if (prof_on) { p.prof[blockIdx.x * 16 + 4] = pw; p.prof[blockIdx.x * 16 + 5] = clock64() - pt0; }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && cr != 0) {
+      Ring3 ring;
+      const uint32_t remote_full = mapa_cluster(bar3_w_full(bar, 0), 0);
+      const int total = iters * DG_ITEMS;
+      for (int q = 0; q < total; ++q) {
+        mbar_wait(bar3_w_full(bar, ring.stage), ring.phase);
+        mbar_arrive_cluster(remote_full + 8u * ring.stage);
+        ring.next();
+      }
+    } else if (lane == 0) {
+      uint32_t n_act[2] = {0u, 0u};
+      const uint32_t idesc = make_idesc(256, 256, 0, 0);
+      long long wa0 = 0, wa1 = 0, ww = 0;
+      const long long mt0 = prof_on ? clock64() : 0;
+      uint32_t q0 = 0;
+      for (int it = 0; it < iters; ++it) {
+        for (int D = 0; D < 9; ++D) {  // D=0: dF = G9 * Wv (K=128); D>=1: K=256
+          const int nch = (D == 0) ? 2 : 4;
+#pragma unroll
+          for (int t = 0; t < 2; ++t) {
+            const long long c0 = prof_on ? clock64() : 0;
+            mbar_wait_cluster(bar3_act_ready(bar, t), n_act[t] & 1);
+            if (prof_on) { if (t == 0) wa0 += clock64() - c0; else wa1 += clock64() - c0; }
+            ++n_act[t];
+            tc_fence_after();
+            for (int c = 0; c < nch; ++c) {
+              const uint32_t wq = q0 + (uint32_t)c;
+              if (t == 0) {
+                const long long c1 = prof_on ? clock64() : 0;
+                mbar_wait_cluster(bar3_w_full(bar, item_stage(wq)), item_phase(wq));
+                if (prof_on) ww += clock64() - c1;
+                tc_fence_after();
+              }
+              issue_chunk2(tmem_base + t * 256, s_act + t * ACT_BYTES + c * SLAB_BYTES, s_w + item_stage(wq) * WSTAGE3, idesc,
+                           c == 0);
+              if (t == 1) umma2_commit_multicast(bar3_w_empty(bar, item_stage(wq)), (uint16_t)3);
+            }
+            umma2_commit_multicast(bar3_acc_full(bar, t), (uint16_t)3);
+          }
+          q0 += (uint32_t)nch;
+        }
+      }
+      if (prof_on) {
+        long long *o = p.prof + blockIdx.x * 16;
+        o[0] = clock64() - mt0; o[1] = wa0; o[2] = wa1; o[3] = ww;
+      }
+    }
+  } else {
+    const int e = warp - kEpiWarp0;
+    const int t = e >> 3;
+    const uint32_t ch = (uint32_t)(e >> 2) & 1u;
+    const uint32_t quarter = warp & 3;
+    const uint32_t r = quarter * 32 + lane;
+    uint8_t *act_tile = smem + OFF_ACT + t * ACT_BYTES;
+    const uint32_t tmem_row = tmem_base + ((quarter * 32) << 16) + t * 256;
+    const bool elected = (e & 7) == 0 && lane == 0;
+    const float *s_head = reinterpret_cast<const float *>(smem + OFF_HEAD);
+    const float *s_wa = s_head + 388;
+    const uint32_t ready_remote = mapa_cluster(bar3_act_ready(bar, t), 0);
+    uint32_t n_acc = 0;
+    bool store_pending = false;
+    const bool prof = prof_on && (e & 7) == 0 && lane == 0;
+    long long e_acc = 0, e_st = 0, e_body = 0, e_tail = 0;
+    const long long et0 = prof ? clock64() : 0;
+    for (int it = 0; it < iters; ++it) {
+      const int pair_raw = (int)blockIdx.x + it * (int)gridDim.x;
+      const bool live = pair_raw < p.n_pairs;
+      const int pair = live ? pair_raw : p.n_pairs - 1;
+      const int64_t tile = (int64_t)pair * 2 + t;
+      const int64_t row = tile * 128 + r;
+      float4 dr = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (row < p.n) dr = reinterpret_cast<const float4 *>(p.draw)[row];
+      const uint32_t *mask_base = p.stash_mask + (size_t)tile * 9 * 128 * 8 + (size_t)r * 8;
+      for (int D = -1; D < 9; ++D) {
+        const long long c0 = prof ? clock64() : 0;
+        if (D >= 0) {
+          mbar_wait(bar3_acc_full(bar, t), n_acc & 1);
+          ++n_acc;
+          tc_fence_after();
+        }
+        const long long c1 = prof ? clock64() : 0;
+        if (elected && store_pending) bulk_wait_read0();
+        named_bar_sync(1 + t, 256);
+        const long long c2 = prof ? clock64() : 0;
+        const uint32_t *mk = (D != 0) ? mask_base + (size_t)((D < 0) ? 8 : 8 - D) * 128 * 8 : nullptr;
+        if (D < 0) {
+          dgrad_g9(dr, mk, ch, s_head, act_tile, r);
+        } else if (D == 0) {
+          dgrad_epilogue_half<false, false>(tmem_row, ch, nullptr, 0.f, s_wa, act_tile, r);
+        } else if (D == 1) {
+          dgrad_epilogue_half<true, true>(tmem_row, ch, mk, dr.w, s_wa, act_tile, r);
+        } else {
+          dgrad_epilogue_half<false, true>(tmem_row, ch, mk, 0.f, s_wa, act_tile, r);
+        }
+        tc_fence_before();
+        fence_async_smem();
+        const long long c3 = prof ? clock64() : 0;
+        named_bar_sync(1 + t, 256);
+        if (elected && live) {
+          int slot = (D < 0) ? 9 : 8 - D;
+          bulk_s2g(p.dy + (size_t)tile * TILE_ACT_BYTES + (size_t)slot * 65536, smem_u32(act_tile), D < 0 ? 32768u : 65536u);
+          bulk_commit();
+          store_pending = true;
+        }
+        __syncwarp();
+        if (D < 8 && lane == 0) mbar_arrive_cluster(ready_remote);
+        if (prof) { e_acc += c1 - c0; e_st += c2 - c1; e_body += c3 - c2; e_tail += clock64() - c3; }
+      }
+    }
+    if (prof) {
+      long long *o = p.prof + blockIdx.x * 16 + 6 + t * 5;
+      o[0] = clock64() - et0; o[1] = e_acc; o[2] = e_st; o[3] = e_body; o[4] = e_tail;
+    }
+    if (elected && store_pending) bulk_wait_all0();
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 0) tmem_dealloc2(tmem_base, 512);
+}
+
+// =================================================================================================
 // backward, weight gradients:  dW[out][in] += sum_rows dY[row][out] * X[row][in]
 // Both operands are the stashed [rows x features] SWIZZLE_128B images read as MN-major UMMA operands
 // (LBO = distance between 64-feature slabs, SBO = 1024 = distance between 8-row groups).
@@ -1415,9 +1885,16 @@ static int kernel_generation() {
   static int v = -1;
   if (v < 0) {
     const char *e = getenv("FLNERF_TC_GEN");
-    v = e ? atoi(e) : 2;
+    v = e ? atoi(e) : 3;
   }
   return v;
+}
+// clusters of 2, one pair per CTA: even grid, at least 2 (a CTA without a pair of its own recomputes the last one)
+static int pair_grid(int n_pairs, int sm_count) {
+  int g = n_pairs < sm_count ? n_pairs : sm_count;
+  g = (g + 1) & ~1;
+  if (g > sm_count) g -= 2;
+  return g < 2 ? 2 : g;
 }
 static bool g_tables_ready = false;
 static int g_wgrad_grid = 0;
@@ -1520,6 +1997,8 @@ static int setup_tables(int sm_count) {
   if (cudaFuncSetAttribute(mlp_dgrad_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_FWD) != cudaSuccess) return 1;
   if (cudaFuncSetAttribute(mlp_fwd_tc2, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_FWD) != cudaSuccess) return 1;
   if (cudaFuncSetAttribute(mlp_dgrad_tc2, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_FWD) != cudaSuccess) return 1;
+  if (cudaFuncSetAttribute(mlp_fwd_tc3, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_FWD) != cudaSuccess) return 1;
+  if (cudaFuncSetAttribute(mlp_dgrad_tc3, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_FWD) != cudaSuccess) return 1;
   if (cudaFuncSetAttribute(mlp_wgrad_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_WG) != cudaSuccess) return 1;
   g_tables_ready = true;
   return 0;
@@ -1568,7 +2047,11 @@ int mlp_tc_forward(flnerf_ctx *ctx, const float *params, const void *packed, int
   FL_CHECK_CUDA(cudaMemsetAsync(raw, 0, (size_t)n * 4 * sizeof(float), st));  // column-half warps accumulate into it
   { const char *e = getenv("FLNERF_FWD_DBG"); p.dbg = e ? atoi(e) : 0; }
   p.prof = tc::prof_buffer();
-  if (tc::kernel_generation() >= 2 && p.n_pairs >= 2) {
+  if (tc::kernel_generation() >= 3) {
+    grid = tc::pair_grid(p.n_pairs, ctx->sm_count);
+    FL_LAUNCH(tc::mlp_fwd_tc3, grid, tc::kThreads, tc::SMEM_FWD, st, p);
+    if (p.prof) tc::prof_report("fwd3", grid, p.n_pairs, st);
+  } else if (tc::kernel_generation() >= 2 && p.n_pairs >= 2) {
     grid &= ~1;  // clusters of 2
     FL_LAUNCH(tc::mlp_fwd_tc2, grid, tc::kThreads, tc::SMEM_FWD, st, p);
     if (p.prof) tc::prof_report("fwd", grid, p.n_pairs, st);
@@ -1591,7 +2074,12 @@ int mlp_tc_backward(flnerf_ctx *ctx, const float *params, const void *packed, in
   int grid = d.n_pairs < ctx->sm_count ? d.n_pairs : ctx->sm_count;
   d.stagger_cycles = d.n_pairs >= 4 * grid ? tc::stagger_setting() : 0;
   if (stages & 1) {
-    if (tc::kernel_generation() >= 2 && d.n_pairs >= 2) {
+    if (tc::kernel_generation() >= 3) {
+      const int g3 = tc::pair_grid(d.n_pairs, ctx->sm_count);
+      d.prof = tc::prof_buffer();
+      FL_LAUNCH(tc::mlp_dgrad_tc3, g3, tc::kThreads, tc::SMEM_FWD, st, d);
+      if (d.prof) tc::prof_report("dgrad3", g3, d.n_pairs, st);
+    } else if (tc::kernel_generation() >= 2 && d.n_pairs >= 2) {
       d.prof = tc::prof_buffer();
       FL_LAUNCH(tc::mlp_dgrad_tc2, grid & ~1, tc::kThreads, tc::SMEM_FWD, st, d);
       if (d.prof) tc::prof_report("dgrad", grid & ~1, d.n_pairs, st);
