@@ -1,15 +1,19 @@
 // mlp_tc.cu -- FLNERF_MODE_BF16: the NeRF MLP (model.py:38-63) on the 5th-gen tensor cores.
 //
-//   * persistent, warp-specialised kernels: warp 0 = bulk-copy producer (UBLKCP into an mbarrier ring),
-//     warp 1 = single-thread tcgen05.mma issuer, warps 2..9 = epilogue (tcgen05.ld -> bias/ReLU/bf16 -> smem);
-//   * the activations of a 128-row tile never leave the SM between layers: the epilogue writes the next
-//     layer's A operand straight into shared memory in the SWIZZLE_128B K-major image the UMMA descriptor
-//     reads; every CTA carries TWO 128-row tiles so each 32 KB weight chunk fetched from L2 feeds 2x128 rows;
+//   * persistent, warp-specialised kernels on CTA PAIRS (clusters of 2, tcgen05.mma.cta_group::2, M = 256 = 128 rows
+//     in each CTA): warp 0 = bulk-copy producer (UBLKCP into an mbarrier ring), warp 1 = single-thread MMA issuer in
+//     the leader CTA / "stage full" relay in the follower, warps 2..17 = epilogue (tcgen05.ld -> bias/ReLU/bf16 -> smem);
+//   * the activations of a 128-row tile never leave the SM between layers: the epilogue writes the next layer's A
+//     operand straight into shared memory in the SWIZZLE_128B K-major image the UMMA descriptor reads; every CTA carries
+//     TWO 128-row tiles (tile sets A and B of the pair) half a period apart: A's MMAs overlap B's epilogue;
 //   * accumulators live in TMEM (2 tiles x 256 fp32 columns = all 512 columns);
-//   * weights are pre-packed once per optimiser step (flnerf_mlp_pack_weights) into the exact shared-memory
-//     image, so a chunk is ONE contiguous 32 KB bulk copy -- no tensor maps, no driver API;
-//   * for training the epilogue also bulk-stores every activation tile (and a ReLU bitmask) to HBM; the
-//     same image is read back as an MN-major operand by the weight-gradient kernel.
+//   * weights are pre-packed once per optimiser step (flnerf_mlp_pack_weights) into the exact shared-memory image; each
+//     CTA of a pair fetches only ITS half of a chunk (N/2 rows, 16 KB, one contiguous bulk copy -- no tensor maps, no
+//     driver API) and a layer's chunks stay in the 5 x 16 KB ring for both tile sets.  Shared-memory traffic per
+//     128-row tile-layer: 128 KB operand reads + 32 KB chunk writes + 64 KB epilogue stores (+ 64 KB read by the stash
+//     bulk stores) against 128 B/clk x 2048 clk = 256 KB at the MMA floor (a single-CTA M=128 design moves 384..448 KB);
+//   * for training every epilogue warp bulk-stores its own 4 KB pieces of the activation tile (and a ReLU bitmask) to
+//     HBM; the same image is read back as an MN-major operand by the weight-gradient kernel.
 //
 // Three kernels: mlp_fwd_tc (10 tensor layers + alpha/rgb heads on CUDA cores in the epilogue),
 // mlp_dgrad_tc (9 tensor layers, ReLU masks from the bitmask stash), mlp_wgrad_tc (per-layer dY^T X with the
@@ -23,17 +27,20 @@ namespace tc {
 
 using namespace mlp_layout;
 
-// CTA = 18 warps: warp 0 producer, warp 1 MMA issuer, warps 2..17 epilogue (2 tiles x 4 lane quarters x 2 column halves)
+// CTA = 18 warps: warp 0 producer, warp 1 MMA issuer / relay, warps 2..17 epilogue (2 tiles x 4 lane quarters x 2
+// column halves)
 constexpr int kEpiWarps = 16;
 constexpr int kThreads = (2 + kEpiWarps) * 32;  // 576
 constexpr int kEpiWarp0 = 2;
-constexpr uint32_t ACT_BYTES = 65536, SLAB_BYTES = 16384, PE_BYTES = 16384, WSTAGE = 32768;
-constexpr int NSTAGE = 3;  // 3 x 32 KB ring: weight chunks AND the PE slabs of the pair travel through it
-constexpr uint32_t OFF_ACT = 0, OFF_W = 2 * ACT_BYTES, OFF_BAR = OFF_W + NSTAGE * WSTAGE;
-// fp32 copies of the small heads: W_rgb[3][128], b_rgb[3], b_alpha[1], w_alpha[256]
-constexpr uint32_t OFF_HEAD = OFF_BAR + 256, HEAD_FLOATS = 384 + 4 + 256;
-constexpr uint32_t SMEM_FWD = OFF_HEAD + HEAD_FLOATS * 4;
-static_assert(SMEM_FWD <= 232448, "shared memory budget");
+constexpr uint32_t ACT_BYTES = 65536, SLAB_BYTES = 16384, PE_BYTES = 16384, WSTAGE = 16384;
+constexpr int NST = 5;  // 5 x 16 KB ring: half weight chunks AND the PE slabs travel through it
+// biases of pts_linears.0..7 + feature_linear, then fp32 copies of the small heads: W_rgb[3][128], b_rgb[3],
+// b_alpha[1], w_alpha[256]
+constexpr uint32_t BIAS_FLOATS = 9 * 256, HEAD_FLOATS = 384 + 4 + 256;
+constexpr uint32_t OFF_ACT = 0, OFF_W = 2 * ACT_BYTES, OFF_VEC = OFF_W + NST * WSTAGE;
+constexpr uint32_t OFF_HEAD = OFF_VEC + BIAS_FLOATS * 4, OFF_BAR = OFF_HEAD + HEAD_FLOATS * 4;
+constexpr uint32_t SMEM_FWD = OFF_BAR + 256;
+static_assert(OFF_BAR % 16 == 0 && SMEM_FWD <= 232448, "shared memory budget");
 
 // packed weight image of one net
 constexpr int FWD_CHUNKS = 38, DG_CHUNKS = 34;
@@ -41,7 +48,7 @@ constexpr size_t FWD_BYTES = (size_t)34 * 32768 + 4 * 16384;
 constexpr size_t DG_BYTES = (size_t)34 * 32768;
 constexpr size_t PACKED_BYTES = FWD_BYTES + DG_BYTES;
 
-// stash (bf16 mode): [viewbias B*128 fp32 (1 KB aligned)] [acts: tiles x 10 x 64 KB] [masks: tiles x 9 x 128 x 32 B]
+// stash (bf16 mode): [viewbias B*128 fp32 (1 KB aligned)] [acts: tiles x 10 x 64 KB] [masks: tiles x 9 x 2 x 128 x 16 B]
 constexpr size_t TILE_ACT_BYTES = 10 * 65536;
 constexpr size_t TILE_MASK_BYTES = 9 * 128 * 32;
 
@@ -91,54 +98,60 @@ __global__ void viewbias_kernel(int64_t B, const float *__restrict__ P, const fl
 
 // mbarrier addresses (bytes from the barrier block): no arrays, so nothing lands in local memory
 __device__ __forceinline__ uint32_t bar_w_full(uint32_t base, uint32_t i) { return base + 8u * i; }
-__device__ __forceinline__ uint32_t bar_w_empty(uint32_t base, uint32_t i) { return base + 8u * (NSTAGE + i); }
-__device__ __forceinline__ uint32_t bar_acc_full(uint32_t base) { return base + 8u * (2 * NSTAGE); }
-__device__ __forceinline__ uint32_t bar_act_ready(uint32_t base) { return base + 8u * (2 * NSTAGE + 1); }
-
-// All CTAs execute the same chunk sequence at the same speed; started together they would all pull the SAME 32 KB
-// weight chunk from the same few L2 slices at the same time.  CTA i therefore starts i * stagger cycles late.
-__device__ __forceinline__ void stagger_start(int cycles_per_cta) {
-  if (cycles_per_cta <= 0) return;
-  const long long t0 = clock64(), wait = (long long)blockIdx.x * cycles_per_cta;
-  while (clock64() - t0 < wait) __nanosleep(200);
-}
+__device__ __forceinline__ uint32_t bar_w_empty(uint32_t base, uint32_t i) { return base + 8u * (NST + i); }
+__device__ __forceinline__ uint32_t bar_acc_full(uint32_t base, uint32_t t) { return base + 8u * (2 * NST + t); }
+__device__ __forceinline__ uint32_t bar_act_ready(uint32_t base, uint32_t t) { return base + 8u * (2 * NST + 2 + t); }
+static_assert(8u * (2 * NST + 4) <= 128u, "barrier block: the TMEM slot sits at +128");
 
 struct Ring {
   uint32_t stage = 0, phase = 0;
   __device__ __forceinline__ void next() {
-    if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+    if (++stage == NST) { stage = 0; phase ^= 1; }
   }
 };
+// the issuer addresses ring items by their running index (a layer's items are used twice, by tile set A then B)
+__device__ __forceinline__ uint32_t item_stage(uint32_t q) { return q % NST; }
+__device__ __forceinline__ uint32_t item_phase(uint32_t q) { return (q / NST) & 1u; }
 
-// A operand: K-major SW128 slab [128 rows x 64]; B operand: K-major SW128 chunk [N rows x 64]; 4 k-steps of 16
-__device__ __forceinline__ void issue_chunk(uint32_t tmem_d, uint32_t a_smem, uint32_t b_smem, uint32_t idesc,
-                                            bool first) {
+// pair MMA over one 64-wide K chunk: A = this tile set's K-major SW128 slab [128 rows x 64] (same offset in both
+// CTAs), B = this CTA's half [N/2 rows x 64] of the weight chunk; 4 k-steps of 16
+__device__ __forceinline__ void issue_chunk(uint32_t tmem_d, uint32_t a_smem, uint32_t b_smem, uint32_t idesc, bool first) {
   uint64_t da = make_smem_desc(a_smem, 0, 1024), db = make_smem_desc(b_smem, 0, 1024);
 #pragma unroll
-  for (int k = 0; k < 4; ++k) umma_bf16(tmem_d, da + 2 * k, db + 2 * k, idesc, (first && k == 0) ? 0u : 1u);
+  for (int k = 0; k < 4; ++k) umma2_bf16(tmem_d, da + 2 * k, db + 2 * k, idesc, (first && k == 0) ? 0u : 1u);
 }
 
-__device__ __forceinline__ void common_setup(uint8_t *smem, uint32_t bar, uint32_t *tmem_slot, int warp, const float *P) {
-  if ((smem_u32(smem) & 1023u) != 0) {
-    if (threadIdx.x == 0) printf("flnerf: dynamic smem base not 1024-byte aligned\n");
-    __trap();
+// barrier / TMEM / constant-vector set-up shared by the two kernels; returns the TMEM base
+__device__ __forceinline__ uint32_t pair_setup(uint8_t *smem, uint32_t bar, uint32_t cr, int warp, uint32_t lane,
+                                               const float *P) {
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + OFF_BAR + 128);
+  if ((smem_u32(smem) & 1023u) != 0) __trap();
+  // biases of the 9 tensor layers that have one (pts 0..7, feature) and the small heads: resident for the whole
+  // launch, read as warp-uniform LDS (a global __ldg here costs an exposed L1/L2 latency per 4 columns)
+  float *bias = reinterpret_cast<float *>(smem + OFF_VEC);
+  for (int i = threadIdx.x; i < (int)BIAS_FLOATS; i += blockDim.x) {
+    const int l = i >> 8, c = i & 255;
+    bias[i] = P[(l < 8 ? b_pts(l) : B_FEAT) + c];
   }
   float *head = reinterpret_cast<float *>(smem + OFF_HEAD);
   for (int i = threadIdx.x; i < (int)HEAD_FLOATS; i += blockDim.x)
     head[i] = i < 387 ? P[W_RGB + i] : (i == 387 ? P[B_ALPHA] : P[W_ALPHA + (i - 388)]);
-  if (warp == 1 && lane_id() == 0) {
-    for (int i = 0; i < NSTAGE; ++i) { mbar_init(bar_w_full(bar, i), 1); mbar_init(bar_w_empty(bar, i), 1); }
-    mbar_init(bar_acc_full(bar), 1);
-    mbar_init(bar_act_ready(bar), kEpiWarps);
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < NST; ++i) {
+      mbar_init(bar_w_full(bar, i), cr == 0 ? 2 : 1);  // leader: own producer + the follower's relay
+      mbar_init(bar_w_empty(bar, i), 1);
+    }
+    for (int t = 0; t < 2; ++t) { mbar_init(bar_acc_full(bar, t), 1); mbar_init(bar_act_ready(bar, t), kEpiWarps); }
     fence_mbar_init();
   }
-  if (warp == 0) {
-    tmem_alloc(smem_u32(tmem_slot), 512);
-    tmem_relinquish();
-  }
+  __syncthreads();
+  cluster_sync_all();  // barriers of both CTAs exist before any remote arrive / multicast commit
+  if (warp == 0) { tmem_alloc2(smem_u32(tmem_slot), 512); tmem_relinquish2(); }
   tc_fence_before();
   __syncthreads();
+  cluster_sync_all();  // both halves of the pair allocation are in place before the leader's first MMA
   tc_fence_after();
+  return *tmem_slot;
 }
 
 // epilogue helper: store 32 consecutive bf16 columns [c0, c0+32) of row r (packed as 16 u32) into an act tile
@@ -152,16 +165,27 @@ __device__ __forceinline__ void store_cols32(uint8_t *act_tile, uint32_t r, uint
   }
 }
 
+// A warp owns rows [32*quarter, +32) x column half ch of its tile = a contiguous 4 KB piece of each of its slabs (in
+// shared memory and in the HBM image alike), so it ships its own pieces: no CTA-level barrier around the stash stores.
+__device__ __forceinline__ void warp_store_slabs(uint8_t *dst_tile_layer, const uint8_t *act_tile, uint32_t quarter,
+                                                 uint32_t slab0, uint32_t nslabs) {
+  for (uint32_t s = 0; s < nslabs; ++s) {
+    const uint32_t off = (slab0 + s) * SLAB_BYTES + quarter * 4096u;
+    bulk_s2g(dst_tile_layer + off, smem_u32(act_tile + off), 4096u);
+  }
+  bulk_commit();
+}
+
 // ---- epilogue building blocks ---------------------------------------------------------------------
 // forward: 32 accumulator columns [c0, c0+32) of row r -> +bias -> (relu) -> bf16 -> act tile; kType 0 relu,
 // 1 relu + alpha head, 2 linear.  Returns the non-zero mask of the 32 outputs (0 when not needed).
 template <int kType, bool kMask>
-__device__ __forceinline__ uint32_t fwd_block(const uint32_t v[32], const float4 bq[8], uint8_t *act_tile,
-                                              uint32_t r, uint32_t c0, const float *s_wa, float &alpha) {
+__device__ __forceinline__ uint32_t fwd_block(const uint32_t v[32], const float *s_b, uint8_t *act_tile, uint32_t r,
+                                              uint32_t c0, const float *s_wa, float &alpha) {
   uint32_t pk[16], m = 0;
 #pragma unroll
   for (int q = 0; q < 8; ++q) {
-    const float4 b = bq[q];
+    const float4 b = *reinterpret_cast<const float4 *>(s_b + c0 + 4 * q);
     const float x0 = __uint_as_float(v[4 * q]) + b.x, x1 = __uint_as_float(v[4 * q + 1]) + b.y;
     const float x2 = __uint_as_float(v[4 * q + 2]) + b.z, x3 = __uint_as_float(v[4 * q + 3]) + b.w;
     const uint32_t w0 = kType == 2 ? pack_bf16_fast(x0, x1) : pack_bf16_relu(x0, x1);
@@ -181,65 +205,29 @@ __device__ __forceinline__ uint32_t fwd_block(const uint32_t v[32], const float4
   return m;
 }
 
-// 128 columns [ch*128, ch*128+128) of one row (the other column half belongs to the partner warp)
+// 128 columns [ch*128, ch*128+128) of one row (the other column half belongs to the partner warp).  Two 32-column
+// TMEM loads are kept in flight: tcgen05.wait::ld waits for ALL outstanding loads, so block i+2 is issued right after
+// the wait that covers block i+1 and completes while block i+1 is being processed.
 template <int kType, bool kMask>
-__device__ __forceinline__ void fwd_epilogue_half(uint32_t tmem_row, uint32_t ch, const float *__restrict__ bias,
-                                                  uint8_t *act_tile, uint32_t r, uint32_t *mask_dst, const float *s_wa,
-                                                  float &alpha) {
-  uint32_t v[32], mk[4];
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const uint32_t cb = ch * 4 + i;
-    tmem_ld32(tmem_row + cb * 32, v);
-    float4 bq[8];  // bias loads are independent of the accumulator: issue them before waiting on TMEM
-#pragma unroll
-    for (int q = 0; q < 8; ++q) bq[q] = __ldg(reinterpret_cast<const float4 *>(bias + cb * 32) + q);
-    tmem_ld_wait(v);
-    mk[i] = fwd_block<kType, kMask>(v, bq, act_tile, r, cb * 32, s_wa, alpha);
-  }
-  if (kMask) *reinterpret_cast<uint4 *>(mask_dst + ch * 4) = make_uint4(mk[0], mk[1], mk[2], mk[3]);
-}
-
-// backward: gradient columns [c0, c0+32) -> (+ d_sigma * w_alpha) -> relu mask -> bf16 -> act tile
-template <bool kAlpha, bool kUseMask>
-__device__ __forceinline__ void dgrad_block(const uint32_t v[32], uint32_t m, float dsig, const float *s_wa,
-                                            uint8_t *act_tile, uint32_t r, uint32_t c0) {
-  uint32_t pk[16];
-#pragma unroll
-  for (int i = 0; i < 32; i += 2) {
-    float g0 = __uint_as_float(v[i]), g1 = __uint_as_float(v[i + 1]);
-    if (kAlpha) {
-      g0 = fmaf(dsig, s_wa[c0 + i], g0);
-      g1 = fmaf(dsig, s_wa[c0 + i + 1], g1);
-    }
-    if (kUseMask) {
-      g0 = (m & (1u << i)) ? g0 : 0.f;
-      g1 = (m & (2u << i)) ? g1 : 0.f;
-    }
-    pk[i >> 1] = pack_bf16_fast(g0, g1);
-  }
-  store_cols32(act_tile, r, c0, pk);
-}
-
-template <bool kAlpha, bool kUseMask>
-__device__ __forceinline__ void dgrad_epilogue_half(uint32_t tmem_row, uint32_t ch, const uint32_t *__restrict__ mask_row,
-                                                    float dsig, const float *s_wa, uint8_t *act_tile, uint32_t r) {
-  uint32_t v[32], mk[4] = {0u, 0u, 0u, 0u};
-  if (kUseMask) {
-    const uint4 a = __ldg(reinterpret_cast<const uint4 *>(mask_row) + ch);
-    mk[0] = a.x; mk[1] = a.y; mk[2] = a.z; mk[3] = a.w;
-  }
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const uint32_t cb = ch * 4 + i;
-    tmem_ld32(tmem_row + cb * 32, v);
-    tmem_ld_wait(v);
-    dgrad_block<kAlpha, kUseMask>(v, mk[i], dsig, s_wa, act_tile, r, cb * 32);
-  }
+__device__ __forceinline__ void fwd_epilogue_half(uint32_t tmem_row, uint32_t ch, const float *s_bias, uint8_t *act_tile,
+                                                  uint32_t r, uint32_t *mask_dst, const float *s_wa, float &alpha) {
+  uint32_t va[32], vb[32], mk[4];
+  const uint32_t c0 = ch * 128;
+  tmem_ld32(tmem_row + c0, va);
+  tmem_ld32(tmem_row + c0 + 32, vb);
+  tmem_ld_wait2(va, vb);
+  mk[0] = fwd_block<kType, kMask>(va, s_bias, act_tile, r, c0, s_wa, alpha);
+  tmem_ld32(tmem_row + c0 + 64, va);
+  mk[1] = fwd_block<kType, kMask>(vb, s_bias, act_tile, r, c0 + 32, s_wa, alpha);
+  tmem_ld_wait(va);
+  tmem_ld32(tmem_row + c0 + 96, vb);
+  mk[2] = fwd_block<kType, kMask>(va, s_bias, act_tile, r, c0 + 64, s_wa, alpha);
+  tmem_ld_wait(vb);
+  mk[3] = fwd_block<kType, kMask>(vb, s_bias, act_tile, r, c0 + 96, s_wa, alpha);
+  if (kMask) *reinterpret_cast<uint4 *>(mask_dst) = make_uint4(mk[0], mk[1], mk[2], mk[3]);
 }
 
 // views_linears.0 (N=128: 64 columns per warp) + rgb_linear on CUDA cores -> raw[row].rgb (accumulated by both halves)
-struct FwdParams;
 template <class Params>
 __device__ __forceinline__ void fwd_views_rgb(const Params &p, uint32_t tmem_row, uint32_t ch, uint8_t *act_tile, uint32_t r,
                                               int64_t row, bool live, uint32_t *mask_dst, const float *s_head) {
@@ -247,12 +235,15 @@ __device__ __forceinline__ void fwd_views_rgb(const Params &p, uint32_t tmem_row
   const float4 *vb4 = reinterpret_cast<const float4 *>(p.viewbias + ray * 128);
   float c0 = 0.f, c1 = 0.f, c2 = 0.f;
   uint32_t mk2[2];
+  uint32_t va[32], vb[32];
+  tmem_ld32(tmem_row + ch * 64, va);
+  tmem_ld32(tmem_row + ch * 64 + 32, vb);
+  tmem_ld_wait2(va, vb);
 #pragma unroll
   for (int i = 0; i < 2; ++i) {
     const uint32_t cb = ch * 2 + i;
-    uint32_t v[32], pk[16], m = 0;
-    tmem_ld32(tmem_row + cb * 32, v);
-    tmem_ld_wait(v);
+    const uint32_t *v = i == 0 ? va : vb;
+    uint32_t pk[16], m = 0;
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
       const float4 b = __ldg(vb4 + cb * 8 + q);
@@ -279,14 +270,53 @@ __device__ __forceinline__ void fwd_views_rgb(const Params &p, uint32_t tmem_row
     atomicAdd(p.raw + row * 4 + 1, c1 + bsel * s_head[385]);
     atomicAdd(p.raw + row * 4 + 2, c2 + bsel * s_head[386]);
   }
-  if (mask_dst) *reinterpret_cast<uint2 *>(mask_dst + ch * 2) = make_uint2(mk2[0], mk2[1]);
+  if (mask_dst) *reinterpret_cast<uint2 *>(mask_dst) = make_uint2(mk2[0], mk2[1]);
+}
+
+// backward: gradient columns [c0, c0+32) -> (+ d_sigma * w_alpha) -> relu mask -> bf16 -> act tile
+template <bool kAlpha, bool kUseMask>
+__device__ __forceinline__ void dgrad_block(const uint32_t v[32], uint32_t m, float dsig, const float *s_wa,
+                                            uint8_t *act_tile, uint32_t r, uint32_t c0) {
+  uint32_t pk[16];
+#pragma unroll
+  for (int i = 0; i < 32; i += 2) {
+    float g0 = __uint_as_float(v[i]), g1 = __uint_as_float(v[i + 1]);
+    if (kAlpha) {
+      g0 = fmaf(dsig, s_wa[c0 + i], g0);
+      g1 = fmaf(dsig, s_wa[c0 + i + 1], g1);
+    }
+    if (kUseMask) {
+      g0 = (m & (1u << i)) ? g0 : 0.f;
+      g1 = (m & (2u << i)) ? g1 : 0.f;
+    }
+    pk[i >> 1] = pack_bf16_fast(g0, g1);
+  }
+  store_cols32(act_tile, r, c0, pk);
+}
+
+// mk: this row's 128 ReLU mask bits of its column half (prefetched by the caller before the accumulator wait)
+template <bool kAlpha, bool kUseMask>
+__device__ __forceinline__ void dgrad_epilogue_half(uint32_t tmem_row, uint32_t ch, const uint4 mk, float dsig,
+                                                    const float *s_wa, uint8_t *act_tile, uint32_t r) {
+  uint32_t va[32], vb[32];
+  const uint32_t c0 = ch * 128;
+  tmem_ld32(tmem_row + c0, va);
+  tmem_ld32(tmem_row + c0 + 32, vb);
+  tmem_ld_wait2(va, vb);
+  dgrad_block<kAlpha, kUseMask>(va, mk.x, dsig, s_wa, act_tile, r, c0);
+  tmem_ld32(tmem_row + c0 + 64, va);
+  dgrad_block<kAlpha, kUseMask>(vb, mk.y, dsig, s_wa, act_tile, r, c0 + 32);
+  tmem_ld_wait(va);
+  tmem_ld32(tmem_row + c0 + 96, vb);
+  dgrad_block<kAlpha, kUseMask>(va, mk.z, dsig, s_wa, act_tile, r, c0 + 64);
+  tmem_ld_wait(vb);
+  dgrad_block<kAlpha, kUseMask>(vb, mk.w, dsig, s_wa, act_tile, r, c0 + 96);
 }
 
 // backward stage -1: G9 = (d_rgb * W_rgb) masked by relu(h9) -> act slabs 0,1 (64 columns per warp)
-__device__ __forceinline__ void dgrad_g9(const float4 dr, const uint32_t *mk, uint32_t ch, const float *s_head,
+__device__ __forceinline__ void dgrad_g9(const float4 dr, const uint4 mk, uint32_t ch, const float *s_head,
                                          uint8_t *act_tile, uint32_t r) {
-  const uint2 m2 = __ldg(reinterpret_cast<const uint2 *>(mk) + ch);
-  const uint32_t mw[2] = {m2.x, m2.y};
+  const uint32_t mw[2] = {mk.x, mk.y};
 #pragma unroll
   for (int j = 0; j < 2; ++j) {
     const uint32_t cb = ch * 2 + j;
@@ -304,6 +334,12 @@ __device__ __forceinline__ void dgrad_g9(const float4 dr, const uint32_t *mk, ui
   }
 }
 
+// ReLU bitmask stash: [tile][slot 0..8][column half][row][4 x u32] -- a warp's 32 rows are 512 contiguous bytes.
+// Slots 0..7 = H0..H7, slot 8 = h9 (views layer, 128 columns: 2 words per column half).
+__device__ __forceinline__ size_t mask_word_offset(int64_t tile, int slot, uint32_t ch, uint32_t r) {
+  return ((((size_t)tile * 9 + (size_t)slot) * 2 + ch) * 128 + r) * 4;
+}
+
 // =================================================================================================
 // forward
 // =================================================================================================
@@ -318,811 +354,21 @@ struct FwdParams {
   int64_t n;
   int S;
   int n_pairs;
-  int stagger_cycles;
   int dbg;   // profiling switches (bit 0: skip mask generation, bit 1: skip the activation bulk stores)
-  long long *prof;  // per-CTA cycle accounting of the three roles (16 slots per CTA) when FLNERF_TC_PROF is set, else null
+  long long *prof;  // per-CTA cycle accounting of the roles (PROF_SLOTS per CTA) when FLNERF_TC_PROF is set, else null
 };
+constexpr int PROF_SLOTS = 24;
 
-// ring items of one pair, in consumption order: PE(both tiles), W(L0), W(L1)x4 .. W(L4)x4, PE, W(L5)x5, W(L6)x4,
-// W(L7)x4, W(L8)x4, W(L9)x4  = 40 items
-__global__ void __launch_bounds__(kThreads, 1) mlp_fwd_tc(FwdParams p) {
-  extern __shared__ __align__(1024) uint8_t smem[];
-  const int warp = threadIdx.x >> 5;
-  const uint32_t lane = lane_id();
-  const uint32_t bar = smem_u32(smem + OFF_BAR);
-  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + OFF_BAR + 128);
-  common_setup(smem, bar, tmem_slot, warp, p.P);
-  const uint32_t tmem_base = *tmem_slot;
-  const uint32_t s_act = smem_u32(smem + OFF_ACT), s_w = smem_u32(smem + OFF_W);
-
-  if (warp == 0) {
-    // ---------------------------------------------------------------- producer
-    if (lane == 0) {
-      Ring ring;
-      stagger_start(p.stagger_cycles);
-      auto push = [&](const uint8_t *src, uint32_t bytes) {
-        mbar_wait(bar_w_empty(bar, ring.stage), ring.phase ^ 1);
-        mbar_arrive_expect_tx(bar_w_full(bar, ring.stage), bytes);
-        bulk_g2s(s_w + ring.stage * WSTAGE, src, bytes, bar_w_full(bar, ring.stage));
-        ring.next();
-      };
-      for (int pair = blockIdx.x; pair < p.n_pairs; pair += gridDim.x) {
-        const uint8_t *pe = p.pe_tiles + (size_t)pair * 2 * PE_BYTES;
-        for (int ci = 0; ci < FWD_CHUNKS; ++ci) {
-          if (ci == 0 || ci == 17) push(pe, 2 * PE_BYTES);  // layer 0 and the skip slab of layer 5
-          const uint32_t bytes = ci < 34 ? 32768u : 16384u;
-          const size_t off = ci < 34 ? (size_t)ci * 32768 : (size_t)34 * 32768 + (size_t)(ci - 34) * 16384;
-          push(p.packed + off, bytes);
-        }
-      }
-    }
-  } else if (warp == 1) {
-    // ---------------------------------------------------------------- MMA issuer
-    if (lane == 0) {
-      Ring ring;
-      uint32_t n_act = 0, it = 0;
-      const uint32_t idesc256 = make_idesc(128, 256, 0, 0), idesc128 = make_idesc(128, 128, 0, 0);
-      for (int pair = blockIdx.x; pair < p.n_pairs; pair += gridDim.x, ++it) {
-        for (int L = 0; L < 10; ++L) {
-          if (!(it == 0 && L == 0)) {  // inputs of this layer written / TMEM drained by the epilogue
-            mbar_wait(bar_act_ready(bar), n_act & 1);
-            ++n_act;
-          }
-          tc_fence_after();
-          const int nch = (L == 0) ? 1 : (L == 5 ? 5 : 4);
-          for (int c = 0; c < nch; ++c) {
-            const bool use_pe = (L == 0) || (L == 5 && c == 0);
-            uint32_t pe_stage = 0;
-            if (use_pe) {  // the PE slabs occupy the ring stage right before their weight chunk
-              mbar_wait(bar_w_full(bar, ring.stage), ring.phase);
-              pe_stage = ring.stage;
-              ring.next();
-            }
-            mbar_wait(bar_w_full(bar, ring.stage), ring.phase);
-            tc_fence_after();
-            const int slab = (L == 5) ? c - 1 : c;
-#pragma unroll
-            for (int t = 0; t < 2; ++t) {
-              uint32_t a = use_pe ? s_w + pe_stage * WSTAGE + t * PE_BYTES : s_act + t * ACT_BYTES + slab * SLAB_BYTES;
-              issue_chunk(tmem_base + t * 256, a, s_w + ring.stage * WSTAGE, L == 9 ? idesc128 : idesc256, c == 0);
-            }
-            if (use_pe) umma_commit(bar_w_empty(bar, pe_stage));
-            umma_commit(bar_w_empty(bar, ring.stage));
-            ring.next();
-          }
-          umma_commit(bar_acc_full(bar));
-        }
-      }
-    }
-  } else {
-    // ---------------------------------------------------------------- epilogue: 16 warps
-    const int e = warp - kEpiWarp0;
-    const int t = e >> 3;                         // tile of the pair
-    const uint32_t ch = (uint32_t)(e >> 2) & 1u;  // column half
-    const uint32_t quarter = warp & 3;            // TMEM lane quarter this warp may access
-    const uint32_t r = quarter * 32 + lane;       // row inside the tile == TMEM lane
-    uint8_t *act_tile = smem + OFF_ACT + t * ACT_BYTES;
-    const uint32_t tmem_row = tmem_base + ((quarter * 32) << 16) + t * 256;
-    const bool elected = (e & 7) == 0 && lane == 0;  // one thread per tile drives the bulk stores
-    const float *s_head = reinterpret_cast<const float *>(smem + OFF_HEAD);
-    const float *s_wa = s_head + 388;
-    uint32_t n_acc = 0;
-    bool store_pending = false;
-    for (int pair = blockIdx.x; pair < p.n_pairs; pair += gridDim.x) {
-      const int64_t tile = (int64_t)pair * 2 + t;
-      const int64_t row = tile * 128 + r;
-      for (int L = 0; L < 10; ++L) {
-        mbar_wait(bar_acc_full(bar), n_acc & 1);
-        ++n_acc;
-        tc_fence_after();
-        if (p.stash_act) {  // the previous layer's bulk store must have finished reading act_tile
-          if (elected && store_pending) bulk_wait_read0();
-          named_bar_sync(1 + t, 256);
-        }
-        uint32_t *mask_dst = p.stash_mask ? p.stash_mask + ((size_t)tile * 9 + (L < 9 ? L : 8)) * 128 * 8 + (size_t)r * 8
-                                          : nullptr;
-        float alpha = 0.f;
-        if (L < 7) {
-          const float *bias = p.P + b_pts(L);
-          if (mask_dst) fwd_epilogue_half<0, true>(tmem_row, ch, bias, act_tile, r, mask_dst, s_wa, alpha);
-          else fwd_epilogue_half<0, false>(tmem_row, ch, bias, act_tile, r, nullptr, s_wa, alpha);
-        } else if (L == 7) {
-          if (mask_dst) fwd_epilogue_half<1, true>(tmem_row, ch, p.P + b_pts(7), act_tile, r, mask_dst, s_wa, alpha);
-          else fwd_epilogue_half<1, false>(tmem_row, ch, p.P + b_pts(7), act_tile, r, nullptr, s_wa, alpha);
-          if (row < p.n) atomicAdd(p.raw + row * 4 + 3, alpha + (ch == 0 ? s_head[387] : 0.f));
-        } else if (L == 8) {
-          fwd_epilogue_half<2, false>(tmem_row, ch, p.P + B_FEAT, act_tile, r, nullptr, s_wa, alpha);
-        } else {
-          // views_linears.0 (N=128: 64 columns per warp) + rgb_linear on CUDA cores -> raw[row].rgb (accumulated)
-          const int64_t ray = (row < p.n ? row : p.n - 1) / p.S;
-          const float4 *vb4 = reinterpret_cast<const float4 *>(p.viewbias + ray * 128);
-          float c0 = 0.f, c1 = 0.f, c2 = 0.f;
-          uint32_t mk2[2];
-#pragma unroll
-          for (int i = 0; i < 2; ++i) {
-            const uint32_t cb = ch * 2 + i;
-            uint32_t v[32], pk[16], m = 0;
-            tmem_ld32(tmem_row + cb * 32, v);
-            tmem_ld_wait(v);
-#pragma unroll
-            for (int q = 0; q < 8; ++q) {
-              const float4 b = __ldg(vb4 + cb * 8 + q);
-              const uint32_t w0 = pack_bf16_relu(__uint_as_float(v[4 * q]) + b.x, __uint_as_float(v[4 * q + 1]) + b.y);
-              const uint32_t w1 = pack_bf16_relu(__uint_as_float(v[4 * q + 2]) + b.z, __uint_as_float(v[4 * q + 3]) + b.w);
-              pk[2 * q] = w0;
-              pk[2 * q + 1] = w1;
-              m += nz_nibble(w0, w1) << (4 * q);
-              const float h[4] = {bf16_lo(w0), bf16_hi(w0), bf16_lo(w1), bf16_hi(w1)};
-              const int k = cb * 32 + 4 * q;
-#pragma unroll
-              for (int x = 0; x < 4; ++x) {
-                c0 = fmaf(h[x], s_head[k + x], c0);
-                c1 = fmaf(h[x], s_head[128 + k + x], c1);
-                c2 = fmaf(h[x], s_head[256 + k + x], c2);
-              }
-            }
-            mk2[i] = m;
-            store_cols32(act_tile, r, cb * 32, pk);
-          }
-          if (row < p.n) {
-            const float bsel = ch == 0 ? 1.f : 0.f;
-            atomicAdd(p.raw + row * 4 + 0, c0 + bsel * s_head[384]);
-            atomicAdd(p.raw + row * 4 + 1, c1 + bsel * s_head[385]);
-            atomicAdd(p.raw + row * 4 + 2, c2 + bsel * s_head[386]);
-          }
-          if (mask_dst) *reinterpret_cast<uint2 *>(mask_dst + ch * 2) = make_uint2(mk2[0], mk2[1]);
-        }
-        tc_fence_before();
-        fence_async_smem();
-        if (p.stash_act) {
-          named_bar_sync(1 + t, 256);  // all 8 warps of this tile have written act_tile
-          if (elected) {
-            bulk_s2g(p.stash_act + (size_t)tile * TILE_ACT_BYTES + (size_t)L * 65536, smem_u32(act_tile),
-                     L == 9 ? 32768u : 65536u);
-            bulk_commit();
-          }
-          store_pending = true;
-        }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bar_act_ready(bar));
-      }
-    }
-    if (elected && store_pending) bulk_wait_all0();
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 0) tmem_dealloc(tmem_base, 512);
-}
-
-// =================================================================================================
-// forward, generation 2: 2-CTA cluster, weight chunks fetched ONCE per cluster and multicast into both rings
-// (each CTA requests one half), which halves the L2 traffic per SM and makes it affordable to run the two tiles
-// of a CTA half a period apart: tile A's MMAs overlap tile B's epilogue (cta_group::1 MMAs, per-tile barriers).
-// =================================================================================================
-__device__ __forceinline__ uint32_t bar2_w_full(uint32_t base, uint32_t i) { return base + 8u * i; }
-__device__ __forceinline__ uint32_t bar2_w_empty(uint32_t base, uint32_t i) { return base + 8u * (NSTAGE + i); }
-__device__ __forceinline__ uint32_t bar2_acc_full(uint32_t base, uint32_t t) { return base + 8u * (2 * NSTAGE + t); }
-__device__ __forceinline__ uint32_t bar2_act_ready(uint32_t base, uint32_t t) { return base + 8u * (2 * NSTAGE + 2 + t); }
-
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) mlp_fwd_tc2(FwdParams p) {
-  extern __shared__ __align__(1024) uint8_t smem[];
-  const int warp = threadIdx.x >> 5;
-  const uint32_t lane = lane_id();
-  const uint32_t bar = smem_u32(smem + OFF_BAR);
-  const uint32_t cr = cluster_ctarank();
-  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + OFF_BAR + 128);
-  if ((smem_u32(smem) & 1023u) != 0) __trap();
-  float *head = reinterpret_cast<float *>(smem + OFF_HEAD);
-  for (int i = threadIdx.x; i < (int)HEAD_FLOATS; i += blockDim.x)
-    head[i] = i < 387 ? p.P[W_RGB + i] : (i == 387 ? p.P[B_ALPHA] : p.P[W_ALPHA + (i - 388)]);
-  if (warp == 1 && lane == 0) {
-    for (int i = 0; i < NSTAGE; ++i) { mbar_init(bar2_w_full(bar, i), 1); mbar_init(bar2_w_empty(bar, i), 2); }
-    for (int t = 0; t < 2; ++t) { mbar_init(bar2_acc_full(bar, t), 1); mbar_init(bar2_act_ready(bar, t), kEpiWarps / 2); }
-    fence_mbar_init();
-  }
-  if (warp == 0) { tmem_alloc(smem_u32(tmem_slot), 512); tmem_relinquish(); }
-  tc_fence_before();
-  __syncthreads();
-  cluster_sync_all();  // the peer's barriers must be initialised before our multicast copies / commits reach them
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-  const uint32_t s_act = smem_u32(smem + OFF_ACT), s_w = smem_u32(smem + OFF_W);
-  // both CTAs of a cluster must walk the weight ring the same number of times: surplus iterations recompute the
-  // last pair without side effects
-  const int iters = (p.n_pairs + (int)gridDim.x - 1) / (int)gridDim.x;
-
-  if (warp == 0) {
-    // ---------------------------------------------------------------- producer
-    if (lane == 0) {
-      Ring ring;
-      const bool prof = p.prof != nullptr;
-      long long pw = 0;
-      const long long pt0 = prof ? clock64() : 0;
-      for (int it = 0; it < iters; ++it) {
-        const int pair = min(p.n_pairs - 1, (int)blockIdx.x + it * (int)gridDim.x);
-        const uint8_t *pe = p.pe_tiles + (size_t)pair * 2 * PE_BYTES;
-        int ci = 0;
-        for (int L = 0; L < 10; ++L) {
-          const int nch = (L == 0) ? 1 : (L == 5 ? 5 : 4);
-          for (int t = 0; t < 2; ++t) {
-            for (int c = 0; c < nch; ++c) {
-              if (c == 0 && (L == 0 || L == 5)) {  // this tile's PE slab: CTA-local item
-                mbar_wait(bar2_w_empty(bar, ring.stage), ring.phase ^ 1);
-                mbar_arrive_expect_tx(bar2_w_full(bar, ring.stage), PE_BYTES);
-                bulk_g2s(s_w + ring.stage * WSTAGE, pe + (size_t)t * PE_BYTES, PE_BYTES, bar2_w_full(bar, ring.stage));
-                ring.next();
-              }
-              const int cc = ci + c;
-              const uint32_t bytes = cc < 34 ? 32768u : 16384u, half = bytes / 2;
-              const size_t off = cc < 34 ? (size_t)cc * 32768 : (size_t)34 * 32768 + (size_t)(cc - 34) * 16384;
-              const long long q0 = prof ? clock64() : 0;
-              mbar_wait(bar2_w_empty(bar, ring.stage), ring.phase ^ 1);
-              if (prof) pw += clock64() - q0;
-              mbar_arrive_expect_tx(bar2_w_full(bar, ring.stage), bytes);   // my half + the peer's half
-              bulk_g2s_multicast(s_w + ring.stage * WSTAGE + cr * half, p.packed + off + (size_t)cr * half, half,
-                                 bar2_w_full(bar, ring.stage), (uint16_t)3);
-              ring.next();
-            }
-          }
-          ci += nch;
-        }
-      }
-      if (prof) { p.prof[blockIdx.x * 16 + 4] = pw; p.prof[blockIdx.x * 16 + 5] = clock64() - pt0; }
-    }
-  } else if (warp == 1) {
-    // ---------------------------------------------------------------- MMA issuer
-    if (lane == 0) {
-      Ring ring;
-      uint32_t n_act[2] = {0u, 0u};
-      const uint32_t idesc256 = make_idesc(128, 256, 0, 0), idesc128 = make_idesc(128, 128, 0, 0);
-      const bool prof = p.prof != nullptr;
-      long long wa0 = 0, wa1 = 0, ww = 0;
-      const long long mt0 = prof ? clock64() : 0;
-      for (int it = 0; it < iters; ++it) {
-        for (int L = 0; L < 10; ++L) {
-          const int nch = (L == 0) ? 1 : (L == 5 ? 5 : 4);
-#pragma unroll
-          for (int t = 0; t < 2; ++t) {
-            if (!(it == 0 && L == 0)) {  // this tile's inputs written / its accumulator drained by its epilogue warps
-              const long long q0 = prof ? clock64() : 0;
-              mbar_wait(bar2_act_ready(bar, t), n_act[t] & 1);
-              if (prof) { if (t == 0) wa0 += clock64() - q0; else wa1 += clock64() - q0; }
-              ++n_act[t];
-            }
-            tc_fence_after();
-            for (int c = 0; c < nch; ++c) {
-              const bool use_pe = (L == 0) || (L == 5 && c == 0);
-              uint32_t pe_stage = 0;
-              const long long q1 = prof ? clock64() : 0;
-              if (use_pe) {
-                mbar_wait(bar2_w_full(bar, ring.stage), ring.phase);
-                pe_stage = ring.stage;
-                ring.next();
-              }
-              mbar_wait(bar2_w_full(bar, ring.stage), ring.phase);
-              if (prof) ww += clock64() - q1;
-              tc_fence_after();
-              const int slab = (L == 5) ? c - 1 : c;
-              const uint32_t a = use_pe ? s_w + pe_stage * WSTAGE : s_act + t * ACT_BYTES + slab * SLAB_BYTES;
-              issue_chunk(tmem_base + t * 256, a, s_w + ring.stage * WSTAGE, L == 9 ? idesc128 : idesc256, c == 0);
-              if (use_pe) umma_commit_multicast(bar2_w_empty(bar, pe_stage), (uint16_t)3);
-              umma_commit_multicast(bar2_w_empty(bar, ring.stage), (uint16_t)3);
-              ring.next();
-            }
-            umma_commit(bar2_acc_full(bar, t));
-          }
-        }
-      }
-      if (prof) {
-        long long *o = p.prof + blockIdx.x * 16;
-        o[0] = clock64() - mt0; o[1] = wa0; o[2] = wa1; o[3] = ww;
-      }
-    }
-  } else {
-    // ---------------------------------------------------------------- epilogue: 8 warps per tile
-    const int e = warp - kEpiWarp0;
-    const int t = e >> 3;
-    const uint32_t ch = (uint32_t)(e >> 2) & 1u;
-    const uint32_t quarter = warp & 3;
-    const uint32_t r = quarter * 32 + lane;
-    uint8_t *act_tile = smem + OFF_ACT + t * ACT_BYTES;
-    const uint32_t tmem_row = tmem_base + ((quarter * 32) << 16) + t * 256;
-    const bool elected = (e & 7) == 0 && lane == 0;
-    const float *s_head = reinterpret_cast<const float *>(smem + OFF_HEAD);
-    const float *s_wa = s_head + 388;
-    uint32_t n_acc = 0;
-    bool store_pending = false;
-    const bool prof = p.prof != nullptr && (e & 7) == 0 && lane == 0;
-    long long e_acc = 0, e_st = 0, e_body = 0, e_tail = 0;
-    const long long et0 = prof ? clock64() : 0;
-    for (int it = 0; it < iters; ++it) {
-      const int pair_raw = (int)blockIdx.x + it * (int)gridDim.x;
-      const bool live = pair_raw < p.n_pairs;          // surplus iteration: compute, but write nothing
-      const int pair = live ? pair_raw : p.n_pairs - 1;
-      const int64_t tile = (int64_t)pair * 2 + t;
-      const int64_t row = tile * 128 + r;
-      uint8_t *stash_act = live ? p.stash_act : nullptr;
-      uint32_t *stash_mask = (live && !(p.dbg & 1)) ? p.stash_mask : nullptr;
-      for (int L = 0; L < 10; ++L) {
-        const long long q0 = prof ? clock64() : 0;
-        mbar_wait(bar2_acc_full(bar, t), n_acc & 1);
-        ++n_acc;
-        tc_fence_after();
-        const long long q1 = prof ? clock64() : 0;
-        if (p.stash_act) {
-          if (elected && store_pending) bulk_wait_read0();
-          named_bar_sync(1 + t, 256);
-        }
-        const long long q2 = prof ? clock64() : 0;
-        uint32_t *mask_dst = stash_mask ? stash_mask + ((size_t)tile * 9 + (L < 9 ? L : 8)) * 128 * 8 + (size_t)r * 8 : nullptr;
-        float alpha = 0.f;
-        if (L < 7) {
-          const float *bias = p.P + b_pts(L);
-          if (mask_dst) fwd_epilogue_half<0, true>(tmem_row, ch, bias, act_tile, r, mask_dst, s_wa, alpha);
-          else fwd_epilogue_half<0, false>(tmem_row, ch, bias, act_tile, r, nullptr, s_wa, alpha);
-        } else if (L == 7) {
-          if (mask_dst) fwd_epilogue_half<1, true>(tmem_row, ch, p.P + b_pts(7), act_tile, r, mask_dst, s_wa, alpha);
-          else fwd_epilogue_half<1, false>(tmem_row, ch, p.P + b_pts(7), act_tile, r, nullptr, s_wa, alpha);
-          if (live && row < p.n) atomicAdd(p.raw + row * 4 + 3, alpha + (ch == 0 ? s_head[387] : 0.f));
-        } else if (L == 8) {
-          fwd_epilogue_half<2, false>(tmem_row, ch, p.P + B_FEAT, act_tile, r, nullptr, s_wa, alpha);
-        } else {
-          const int64_t ray = (row < p.n ? row : p.n - 1) / p.S;
-          const float4 *vb4 = reinterpret_cast<const float4 *>(p.viewbias + ray * 128);
-          float c0 = 0.f, c1 = 0.f, c2 = 0.f;
-          uint32_t mk2[2];
-#pragma unroll
-          for (int i = 0; i < 2; ++i) {
-            const uint32_t cb = ch * 2 + i;
-            uint32_t v[32], pk[16], m = 0;
-            tmem_ld32(tmem_row + cb * 32, v);
-            tmem_ld_wait(v);
-#pragma unroll
-            for (int q = 0; q < 8; ++q) {
-              const float4 b = __ldg(vb4 + cb * 8 + q);
-              const uint32_t w0 = pack_bf16_relu(__uint_as_float(v[4 * q]) + b.x, __uint_as_float(v[4 * q + 1]) + b.y);
-              const uint32_t w1 = pack_bf16_relu(__uint_as_float(v[4 * q + 2]) + b.z, __uint_as_float(v[4 * q + 3]) + b.w);
-              pk[2 * q] = w0;
-              pk[2 * q + 1] = w1;
-              m += nz_nibble(w0, w1) << (4 * q);
-              const float h[4] = {bf16_lo(w0), bf16_hi(w0), bf16_lo(w1), bf16_hi(w1)};
-              const int k = cb * 32 + 4 * q;
-#pragma unroll
-              for (int x = 0; x < 4; ++x) {
-                c0 = fmaf(h[x], s_head[k + x], c0);
-                c1 = fmaf(h[x], s_head[128 + k + x], c1);
-                c2 = fmaf(h[x], s_head[256 + k + x], c2);
-              }
-            }
-            mk2[i] = m;
-            store_cols32(act_tile, r, cb * 32, pk);
-          }
-          if (live && row < p.n) {
-            const float bsel = ch == 0 ? 1.f : 0.f;
-            atomicAdd(p.raw + row * 4 + 0, c0 + bsel * s_head[384]);
-            atomicAdd(p.raw + row * 4 + 1, c1 + bsel * s_head[385]);
-            atomicAdd(p.raw + row * 4 + 2, c2 + bsel * s_head[386]);
-          }
-          if (mask_dst) *reinterpret_cast<uint2 *>(mask_dst + ch * 2) = make_uint2(mk2[0], mk2[1]);
-        }
-        tc_fence_before();
-        fence_async_smem();
-        const long long q3 = prof ? clock64() : 0;
-        if (p.stash_act) {
-          named_bar_sync(1 + t, 256);
-          if (elected && stash_act && !(p.dbg & 2)) {
-            bulk_s2g(stash_act + ((p.dbg & 4) ? (size_t)blockIdx.x * 131072 + t * 65536 : (size_t)tile * TILE_ACT_BYTES + (size_t)L * 65536), smem_u32(act_tile),
-                     L == 9 ? 32768u : 65536u);
-            bulk_commit();
-            store_pending = true;
-          }
-        }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bar2_act_ready(bar, t));
-        if (prof) { e_acc += q1 - q0; e_st += q2 - q1; e_body += q3 - q2; e_tail += clock64() - q3; }
-      }
-    }
-    if (prof) {
-      long long *o = p.prof + blockIdx.x * 16 + 6 + t * 5;
-      o[0] = clock64() - et0; o[1] = e_acc; o[2] = e_st; o[3] = e_body; o[4] = e_tail;
-    }
-    if (elected && store_pending) bulk_wait_all0();
-  }
-  tc_fence_before();
-  __syncthreads();
-  cluster_sync_all();  // nobody leaves while the peer may still multicast into this CTA
-  if (warp == 0) tmem_dealloc(tmem_base, 512);
-}
-
-// =================================================================================================
-// backward, data gradient chain:  G9 -> dF -> dH7 -> ... -> dH0   (pre-activation gradients, bf16)
-// =================================================================================================
-struct DgradParams {
-  const float *P;
-  const uint8_t *packed_dg;  // 34 chunks of 32 KB
-  const float *draw;         // [n][4]
-  const uint32_t *stash_mask;
-  uint8_t *dy;               // [tiles][10][64 KB]: slot l<8 = dH_l, slot 8 = dF, slot 9 = G9 (32 KB)
-  int64_t n;
-  int n_pairs;
-  int stagger_cycles;
-  long long *prof;
-};
-
-__global__ void __launch_bounds__(kThreads, 1) mlp_dgrad_tc(DgradParams p) {
-  extern __shared__ __align__(1024) uint8_t smem[];
-  const int warp = threadIdx.x >> 5;
-  const uint32_t lane = lane_id();
-  const uint32_t bar = smem_u32(smem + OFF_BAR);
-  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + OFF_BAR + 128);
-  common_setup(smem, bar, tmem_slot, warp, p.P);
-  const uint32_t tmem_base = *tmem_slot;
-  const uint32_t s_act = smem_u32(smem + OFF_ACT), s_w = smem_u32(smem + OFF_W);
-
-  if (warp == 0) {
-    if (lane == 0) {
-      Ring ring;
-      stagger_start(p.stagger_cycles);
-      for (int pair = blockIdx.x; pair < p.n_pairs; pair += gridDim.x) {
-        for (int ci = 0; ci < DG_CHUNKS; ++ci) {
-          mbar_wait(bar_w_empty(bar, ring.stage), ring.phase ^ 1);
-          mbar_arrive_expect_tx(bar_w_full(bar, ring.stage), 32768u);
-          bulk_g2s(s_w + ring.stage * WSTAGE, p.packed_dg + (size_t)ci * 32768, 32768u, bar_w_full(bar, ring.stage));
-          ring.next();
-        }
-      }
-    }
-  } else if (warp == 1) {
-    if (lane == 0) {
-      Ring ring;
-      uint32_t n_act = 0;
-      const uint32_t idesc = make_idesc(128, 256, 0, 0);
-      for (int pair = blockIdx.x; pair < p.n_pairs; pair += gridDim.x) {
-        for (int D = 0; D < 9; ++D) {  // D=0: dF = G9 * Wv (K=128); D>=1: K=256
-          mbar_wait(bar_act_ready(bar), n_act & 1);
-          ++n_act;
-          tc_fence_after();
-          const int nch = (D == 0) ? 2 : 4;
-          for (int c = 0; c < nch; ++c) {
-            mbar_wait(bar_w_full(bar, ring.stage), ring.phase);
-            tc_fence_after();
-#pragma unroll
-            for (int t = 0; t < 2; ++t)
-              issue_chunk(tmem_base + t * 256, s_act + t * ACT_BYTES + c * SLAB_BYTES, s_w + ring.stage * WSTAGE, idesc,
-                          c == 0);
-            umma_commit(bar_w_empty(bar, ring.stage));
-            ring.next();
-          }
-          umma_commit(bar_acc_full(bar));
-        }
-      }
-    }
-  } else {
-    const int e = warp - kEpiWarp0;
-    const int t = e >> 3;
-    const uint32_t ch = (uint32_t)(e >> 2) & 1u;
-    const uint32_t quarter = warp & 3;
-    const uint32_t r = quarter * 32 + lane;
-    uint8_t *act_tile = smem + OFF_ACT + t * ACT_BYTES;
-    const uint32_t tmem_row = tmem_base + ((quarter * 32) << 16) + t * 256;
-    const bool elected = (e & 7) == 0 && lane == 0;
-    const float *s_head = reinterpret_cast<const float *>(smem + OFF_HEAD);
-    const float *s_wa = s_head + 388;
-    uint32_t n_acc = 0;
-    bool store_pending = false;
-    for (int pair = blockIdx.x; pair < p.n_pairs; pair += gridDim.x) {
-      const int64_t tile = (int64_t)pair * 2 + t;
-      const int64_t row = tile * 128 + r;
-      float4 dr = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (row < p.n) dr = reinterpret_cast<const float4 *>(p.draw)[row];
-      const uint32_t *mask_base = p.stash_mask + (size_t)tile * 9 * 128 * 8 + (size_t)r * 8;
-      // stage -1: G9 = (d_rgb * W_rgb) masked by relu(h9) -> act slabs 0,1 ; stages 0..8 = tensor layers
-      for (int D = -1; D < 9; ++D) {
-        if (D >= 0) {
-          mbar_wait(bar_acc_full(bar), n_acc & 1);
-          ++n_acc;
-          tc_fence_after();
-        }
-        if (elected && store_pending) bulk_wait_read0();
-        named_bar_sync(1 + t, 256);
-        // ReLU mask of the activation this gradient flows into: D=-1 -> h9 (slot 8), D=0 -> none (feature is
-        // linear), D=1 -> H7, D=2 -> H6, ..., D=8 -> H0
-        const uint32_t *mk = (D != 0) ? mask_base + (size_t)((D < 0) ? 8 : 8 - D) * 128 * 8 : nullptr;
-        if (D < 0) {
-          const uint2 m2 = __ldg(reinterpret_cast<const uint2 *>(mk) + ch);
-          const uint32_t mw[2] = {m2.x, m2.y};
-#pragma unroll
-          for (int j = 0; j < 2; ++j) {
-            const uint32_t cb = ch * 2 + j;
-            uint32_t pk[16];
-#pragma unroll
-            for (int i = 0; i < 32; i += 2) {
-              const int k = cb * 32 + i;
-              float g0 = dr.x * s_head[k] + dr.y * s_head[128 + k] + dr.z * s_head[256 + k];
-              float g1 = dr.x * s_head[k + 1] + dr.y * s_head[128 + k + 1] + dr.z * s_head[256 + k + 1];
-              g0 = (mw[j] & (1u << i)) ? g0 : 0.f;
-              g1 = (mw[j] & (2u << i)) ? g1 : 0.f;
-              pk[i >> 1] = pack_bf16_fast(g0, g1);
-            }
-            store_cols32(act_tile, r, cb * 32, pk);
-          }
-        } else if (D == 0) {
-          dgrad_epilogue_half<false, false>(tmem_row, ch, nullptr, 0.f, s_wa, act_tile, r);
-        } else if (D == 1) {  // dH7 also receives d_sigma * w_alpha (alpha_linear reads H7)
-          dgrad_epilogue_half<true, true>(tmem_row, ch, mk, dr.w, s_wa, act_tile, r);
-        } else {
-          dgrad_epilogue_half<false, true>(tmem_row, ch, mk, 0.f, s_wa, act_tile, r);
-        }
-        tc_fence_before();
-        fence_async_smem();
-        named_bar_sync(1 + t, 256);
-        if (elected) {
-          int slot = (D < 0) ? 9 : 8 - D;  // D=0 -> dF (8), D=1 -> dH7 (7) ... D=8 -> dH0 (0)
-          bulk_s2g(p.dy + (size_t)tile * TILE_ACT_BYTES + (size_t)slot * 65536, smem_u32(act_tile),
-                   D < 0 ? 32768u : 65536u);
-          bulk_commit();
-        }
-        store_pending = true;
-        __syncwarp();
-        if (D < 8 && lane == 0) mbar_arrive(bar_act_ready(bar));  // the last stage feeds no further MMA
-      }
-    }
-    if (elected && store_pending) bulk_wait_all0();
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 0) tmem_dealloc(tmem_base, 512);
-}
-
-// =================================================================================================
-// data-gradient chain, generation 2 (same scheme as mlp_fwd_tc2: cluster of 2, multicast weight chunks, the two
-// tiles of a CTA half a period apart)
-// =================================================================================================
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) mlp_dgrad_tc2(DgradParams p) {
-  extern __shared__ __align__(1024) uint8_t smem[];
-  const int warp = threadIdx.x >> 5;
-  const uint32_t lane = lane_id();
-  const uint32_t bar = smem_u32(smem + OFF_BAR);
-  const uint32_t cr = cluster_ctarank();
-  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + OFF_BAR + 128);
-  if ((smem_u32(smem) & 1023u) != 0) __trap();
-  float *head = reinterpret_cast<float *>(smem + OFF_HEAD);
-  for (int i = threadIdx.x; i < (int)HEAD_FLOATS; i += blockDim.x)
-    head[i] = i < 387 ? p.P[W_RGB + i] : (i == 387 ? p.P[B_ALPHA] : p.P[W_ALPHA + (i - 388)]);
-  if (warp == 1 && lane == 0) {
-    for (int i = 0; i < NSTAGE; ++i) { mbar_init(bar2_w_full(bar, i), 1); mbar_init(bar2_w_empty(bar, i), 2); }
-    for (int t = 0; t < 2; ++t) { mbar_init(bar2_acc_full(bar, t), 1); mbar_init(bar2_act_ready(bar, t), kEpiWarps / 2); }
-    fence_mbar_init();
-  }
-  if (warp == 0) { tmem_alloc(smem_u32(tmem_slot), 512); tmem_relinquish(); }
-  tc_fence_before();
-  __syncthreads();
-  cluster_sync_all();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-  const uint32_t s_act = smem_u32(smem + OFF_ACT), s_w = smem_u32(smem + OFF_W);
-  const int iters = (p.n_pairs + (int)gridDim.x - 1) / (int)gridDim.x;
-
-  if (warp == 0) {
-    if (lane == 0) {
-      Ring ring;
-      const bool prof = p.prof != nullptr;
-      long long pw = 0;
-      const long long pt0 = prof ? clock64() : 0;
-      for (int it = 0; it < iters; ++it) {
-        int ci = 0;
-        for (int D = 0; D < 9; ++D) {
-          const int nch = (D == 0) ? 2 : 4;
-          for (int t = 0; t < 2; ++t)
-            for (int c = 0; c < nch; ++c) {
-              const long long q0 = prof ? clock64() : 0;
-              mbar_wait(bar2_w_empty(bar, ring.stage), ring.phase ^ 1);
-              if (prof) pw += clock64() - q0;
-              mbar_arrive_expect_tx(bar2_w_full(bar, ring.stage), 32768u);
-              bulk_g2s_multicast(s_w + ring.stage * WSTAGE + cr * 16384u,
-                                 p.packed_dg + (size_t)(ci + c) * 32768 + (size_t)cr * 16384, 16384u,
-                                 bar2_w_full(bar, ring.stage), (uint16_t)3);
-              ring.next();
-            }
-          ci += nch;
-        }
-      }
-      if (prof) { p.prof[blockIdx.x * 16 + 4] = pw; p.prof[blockIdx.x * 16 + 5] = clock64() - pt0; }
-    }
-  } else if (warp == 1) {
-    if (lane == 0) {
-      Ring ring;
-      uint32_t n_act[2] = {0u, 0u};
-      const uint32_t idesc = make_idesc(128, 256, 0, 0);
-      const bool prof = p.prof != nullptr;
-      long long wa0 = 0, wa1 = 0, ww = 0;
-      const long long mt0 = prof ? clock64() : 0;
-      for (int it = 0; it < iters; ++it) {
-        for (int D = 0; D < 9; ++D) {
-          const int nch = (D == 0) ? 2 : 4;
-#pragma unroll
-          for (int t = 0; t < 2; ++t) {
-            const long long q0 = prof ? clock64() : 0;
-            mbar_wait(bar2_act_ready(bar, t), n_act[t] & 1);
-            if (prof) { if (t == 0) wa0 += clock64() - q0; else wa1 += clock64() - q0; }
-            ++n_act[t];
-            tc_fence_after();
-            for (int c = 0; c < nch; ++c) {
-              const long long q1 = prof ? clock64() : 0;
-              mbar_wait(bar2_w_full(bar, ring.stage), ring.phase);
-              if (prof) ww += clock64() - q1;
-              tc_fence_after();
-              issue_chunk(tmem_base + t * 256, s_act + t * ACT_BYTES + c * SLAB_BYTES, s_w + ring.stage * WSTAGE, idesc, c == 0);
-              umma_commit_multicast(bar2_w_empty(bar, ring.stage), (uint16_t)3);
-              ring.next();
-            }
-            umma_commit(bar2_acc_full(bar, t));
-          }
-        }
-      }
-      if (prof) {
-        long long *o = p.prof + blockIdx.x * 16;
-        o[0] = clock64() - mt0; o[1] = wa0; o[2] = wa1; o[3] = ww;
-      }
-    }
-  } else {
-    const int e = warp - kEpiWarp0;
-    const int t = e >> 3;
-    const uint32_t ch = (uint32_t)(e >> 2) & 1u;
-    const uint32_t quarter = warp & 3;
-    const uint32_t r = quarter * 32 + lane;
-    uint8_t *act_tile = smem + OFF_ACT + t * ACT_BYTES;
-    const uint32_t tmem_row = tmem_base + ((quarter * 32) << 16) + t * 256;
-    const bool elected = (e & 7) == 0 && lane == 0;
-    const float *s_head = reinterpret_cast<const float *>(smem + OFF_HEAD);
-    const float *s_wa = s_head + 388;
-    uint32_t n_acc = 0;
-    bool store_pending = false;
-    const bool prof = p.prof != nullptr && (e & 7) == 0 && lane == 0;
-    long long e_acc = 0, e_st = 0, e_body = 0, e_tail = 0;
-    const long long et0 = prof ? clock64() : 0;
-    for (int it = 0; it < iters; ++it) {
-      const int pair_raw = (int)blockIdx.x + it * (int)gridDim.x;
-      const bool live = pair_raw < p.n_pairs;
-      const int pair = live ? pair_raw : p.n_pairs - 1;
-      const int64_t tile = (int64_t)pair * 2 + t;
-      const int64_t row = tile * 128 + r;
-      float4 dr = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (row < p.n) dr = reinterpret_cast<const float4 *>(p.draw)[row];
-      const uint32_t *mask_base = p.stash_mask + (size_t)tile * 9 * 128 * 8 + (size_t)r * 8;
-      for (int D = -1; D < 9; ++D) {
-        const long long q0 = prof ? clock64() : 0;
-        if (D >= 0) {
-          mbar_wait(bar2_acc_full(bar, t), n_acc & 1);
-          ++n_acc;
-          tc_fence_after();
-        }
-        const long long q1 = prof ? clock64() : 0;
-        if (elected && store_pending) bulk_wait_read0();
-        named_bar_sync(1 + t, 256);
-        const long long q2 = prof ? clock64() : 0;
-        const uint32_t *mk = (D != 0) ? mask_base + (size_t)((D < 0) ? 8 : 8 - D) * 128 * 8 : nullptr;
-        if (D < 0) {
-          const uint2 m2 = __ldg(reinterpret_cast<const uint2 *>(mk) + ch);
-          const uint32_t mw[2] = {m2.x, m2.y};
-#pragma unroll
-          for (int j = 0; j < 2; ++j) {
-            const uint32_t cb = ch * 2 + j;
-            uint32_t pk[16];
-#pragma unroll
-            for (int i = 0; i < 32; i += 2) {
-              const int k = cb * 32 + i;
-              float g0 = dr.x * s_head[k] + dr.y * s_head[128 + k] + dr.z * s_head[256 + k];
-              float g1 = dr.x * s_head[k + 1] + dr.y * s_head[128 + k + 1] + dr.z * s_head[256 + k + 1];
-              g0 = (mw[j] & (1u << i)) ? g0 : 0.f;
-              g1 = (mw[j] & (2u << i)) ? g1 : 0.f;
-              pk[i >> 1] = pack_bf16_fast(g0, g1);
-            }
-            store_cols32(act_tile, r, cb * 32, pk);
-          }
-        } else if (D == 0) {
-          dgrad_epilogue_half<false, false>(tmem_row, ch, nullptr, 0.f, s_wa, act_tile, r);
-        } else if (D == 1) {
-          dgrad_epilogue_half<true, true>(tmem_row, ch, mk, dr.w, s_wa, act_tile, r);
-        } else {
-          dgrad_epilogue_half<false, true>(tmem_row, ch, mk, 0.f, s_wa, act_tile, r);
-        }
-        tc_fence_before();
-        fence_async_smem();
-        const long long q3 = prof ? clock64() : 0;
-        named_bar_sync(1 + t, 256);
-        if (elected && live) {
-          int slot = (D < 0) ? 9 : 8 - D;
-          bulk_s2g(p.dy + (size_t)tile * TILE_ACT_BYTES + (size_t)slot * 65536, smem_u32(act_tile), D < 0 ? 32768u : 65536u);
-          bulk_commit();
-          store_pending = true;
-        }
-        __syncwarp();
-        if (D < 8 && lane == 0) mbar_arrive(bar2_act_ready(bar, t));
-        if (prof) { e_acc += q1 - q0; e_st += q2 - q1; e_body += q3 - q2; e_tail += clock64() - q3; }
-      }
-    }
-    if (prof) {
-      long long *o = p.prof + blockIdx.x * 16 + 6 + t * 5;
-      o[0] = clock64() - et0; o[1] = e_acc; o[2] = e_st; o[3] = e_body; o[4] = e_tail;
-    }
-    if (elected && store_pending) bulk_wait_all0();
-  }
-  tc_fence_before();
-  __syncthreads();
-  cluster_sync_all();
-  if (warp == 0) tmem_dealloc(tmem_base, 512);
-}
-
-// =================================================================================================
-// generation 3: CTA PAIR.  One tcgen05.mma.cta_group::2 (M = 256 = 128 rows in each CTA of a 2-cluster, N = 256)
-// is issued by the leader CTA for both SMs; each CTA keeps its own two 128-row tiles and only HALF of every weight
-// chunk (16 KB instead of 32 KB), and a layer's chunks stay in the ring for BOTH tile sets (A then B).
-// Why: gen-2 is shared-memory-bandwidth bound.  Per 128-row tile-layer an SM moved 192 KB of operand reads
-// (4 KB A + 8 KB B per MMA) + 128 KB of weight-chunk writes + 64 KB of epilogue stores (+ 64 KB read back by the
-// stash bulk store) = 384..448 KB against 128 B/clk x 2048 clk (the MMA floor) = 256 KB.  The pair halves the B
-// reads (each SM reads its half and receives the other from its peer) and the chunk writes, sharing a chunk between
-// the tile sets halves them again: 128 + 32 + 64 (+ 64) = 224..288 KB.  The ring is 6 x 16 KB stages.
-//   producer (warp 0, both CTAs)  : fills the local stage (its half chunk / its PE slab)
-//   relay    (warp 1, follower)   : forwards "my stage is full" to the leader's full barrier (count 2 there)
-//   issuer   (warp 1, leader)     : waits for both halves, issues the pair MMAs, multicast-commits to both CTAs
-//   epilogue (16 warps, both CTAs): as in gen-2; "inputs ready / accumulator drained" arrives on the LEADER's barrier
-// =================================================================================================
-constexpr int NST3 = 6;
-constexpr uint32_t WSTAGE3 = 16384;
-static_assert(NST3 * WSTAGE3 == NSTAGE * WSTAGE, "gen-3 ring uses the same shared-memory region");
-__device__ __forceinline__ uint32_t bar3_w_full(uint32_t base, uint32_t i) { return base + 8u * i; }
-__device__ __forceinline__ uint32_t bar3_w_empty(uint32_t base, uint32_t i) { return base + 8u * (NST3 + i); }
-__device__ __forceinline__ uint32_t bar3_acc_full(uint32_t base, uint32_t t) { return base + 8u * (2 * NST3 + t); }
-__device__ __forceinline__ uint32_t bar3_act_ready(uint32_t base, uint32_t t) { return base + 8u * (2 * NST3 + 2 + t); }
-static_assert(8u * (2 * NST3 + 4) <= 128u, "barrier block: the TMEM slot sits at +128");
-
-struct Ring3 {
-  uint32_t stage = 0, phase = 0;
-  __device__ __forceinline__ void next() {
-    if (++stage == NST3) { stage = 0; phase ^= 1; }
-  }
-};
-__device__ __forceinline__ uint32_t item_stage(uint32_t q) { return q % NST3; }
-__device__ __forceinline__ uint32_t item_phase(uint32_t q) { return (q / NST3) & 1u; }
-
-// pair MMA over one 64-wide K chunk: A = this tile set's K-major slab (in both CTAs, same offset), B = half chunk
-__device__ __forceinline__ void issue_chunk2(uint32_t tmem_d, uint32_t a_smem, uint32_t b_smem, uint32_t idesc, bool first) {
-  uint64_t da = make_smem_desc(a_smem, 0, 1024), db = make_smem_desc(b_smem, 0, 1024);
-#pragma unroll
-  for (int k = 0; k < 4; ++k) umma2_bf16(tmem_d, da + 2 * k, db + 2 * k, idesc, (first && k == 0) ? 0u : 1u);
-}
-
-// barrier / TMEM set-up shared by the two gen-3 kernels; returns the TMEM base
-__device__ __forceinline__ uint32_t pair_setup(uint8_t *smem, uint32_t bar, uint32_t cr, int warp, uint32_t lane,
-                                               const float *P) {
-  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + OFF_BAR + 128);
-  if ((smem_u32(smem) & 1023u) != 0) __trap();
-  float *head = reinterpret_cast<float *>(smem + OFF_HEAD);
-  for (int i = threadIdx.x; i < (int)HEAD_FLOATS; i += blockDim.x)
-    head[i] = i < 387 ? P[W_RGB + i] : (i == 387 ? P[B_ALPHA] : P[W_ALPHA + (i - 388)]);
-  if (warp == 1 && lane == 0) {
-    for (int i = 0; i < NST3; ++i) {
-      mbar_init(bar3_w_full(bar, i), cr == 0 ? 2 : 1);  // leader: own producer + the follower's relay
-      mbar_init(bar3_w_empty(bar, i), 1);
-    }
-    for (int t = 0; t < 2; ++t) { mbar_init(bar3_acc_full(bar, t), 1); mbar_init(bar3_act_ready(bar, t), kEpiWarps); }
-    fence_mbar_init();
-  }
-  __syncthreads();
-  cluster_sync_all();  // barriers of both CTAs exist before any remote arrive / multicast commit
-  if (warp == 0) { tmem_alloc2(smem_u32(tmem_slot), 512); tmem_relinquish2(); }
-  tc_fence_before();
-  __syncthreads();
-  cluster_sync_all();  // both halves of the pair allocation are in place before the leader's first MMA
-  tc_fence_after();
-  return *tmem_slot;
-}
-
-constexpr int FWD_ITEMS = 42;  // ring items of one iteration: L0 {PE_A, W, PE_B}, L5 {PE_A, W, PE_B, W x4}, 8 layers x 4
+// ring items of one iteration, in producer order (each = this CTA's half chunk or its own PE slab, <= 16 KB):
+//   L0     : PE_A, W0, PE_B                            (W0 feeds both tile sets)
+//   L1..L4 : 4 chunks each
+//   L5     : PE_A, Wpe, W1..W4, PE_B, Wpe, W1..W4      (PE + 5 chunks do not fit the five stages twice over: layer 5
+//            is fetched once per tile set and released chunk by chunk)
+//   L6..L9 : 4 chunks each
+constexpr int FWD_ITEMS = 3 + 16 + 12 + 16;
 constexpr int DG_ITEMS = 34;
 
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) mlp_fwd_tc3(FwdParams p) {
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) mlp_fwd_tc(FwdParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const int warp = threadIdx.x >> 5;
   const uint32_t lane = lane_id();
@@ -1136,15 +382,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) mlp_fwd
   if (warp == 0) {
     // ---------------------------------------------------------------- producer (both CTAs): local halves
     if (lane == 0) {
-      Ring3 ring;
+      Ring ring;
       long long pw = 0;
       const long long pt0 = prof_on ? clock64() : 0;
       auto push = [&](const uint8_t *src, uint32_t bytes) {
-        const long long q0 = prof_on ? clock64() : 0;
-        mbar_wait(bar3_w_empty(bar, ring.stage), ring.phase ^ 1);
-        if (prof_on) pw += clock64() - q0;
-        mbar_arrive_expect_tx(bar3_w_full(bar, ring.stage), bytes);
-        bulk_g2s(s_w + ring.stage * WSTAGE3, src, bytes, bar3_w_full(bar, ring.stage));
+        const long long c0 = prof_on ? clock64() : 0;
+        mbar_wait(bar_w_empty(bar, ring.stage), ring.phase ^ 1);
+        if (prof_on) pw += clock64() - c0;
+        mbar_arrive_expect_tx(bar_w_full(bar, ring.stage), bytes);
+        bulk_g2s(s_w + ring.stage * WSTAGE, src, bytes, bar_w_full(bar, ring.stage));
         ring.next();
       };
       auto push_w = [&](int cc) {  // this CTA's half (N/2 rows) of forward chunk cc
@@ -1161,8 +407,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) mlp_fwd
             push(pe, PE_BYTES); push_w(0); push(pe + PE_BYTES, PE_BYTES);
             ci = 1;
           } else if (L == 5) {
-            push(pe, PE_BYTES); push_w(ci); push(pe + PE_BYTES, PE_BYTES);
-            for (int c = 1; c < 5; ++c) push_w(ci + c);
+            for (int t = 0; t < 2; ++t) {
+              push(pe + (size_t)t * PE_BYTES, PE_BYTES);
+              for (int c = 0; c < 5; ++c) push_w(ci + c);
+            }
             ci += 5;
           } else {
             for (int c = 0; c < 4; ++c) push_w(ci + c);
@@ -1170,16 +418,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) mlp_fwd
           }
         }
       }
-      if (prof_on) { p.prof[blockIdx.x * 16 + 4] = pw; p.prof[blockIdx.x * 16 + 5] = clock64() - pt0; }
+      if (prof_on) { p.prof[blockIdx.x * PROF_SLOTS + 4] = pw; p.prof[blockIdx.x * PROF_SLOTS + 5] = clock64() - pt0; }
     }
   } else if (warp == 1) {
     if (lane == 0 && cr != 0) {
       // -------------------------------------------------------------- relay (follower): local full -> leader's full
-      Ring3 ring;
-      const uint32_t remote_full = mapa_cluster(bar3_w_full(bar, 0), 0);
+      Ring ring;
+      const uint32_t remote_full = mapa_cluster(bar_w_full(bar, 0), 0);
       const int total = iters * FWD_ITEMS;
       for (int q = 0; q < total; ++q) {
-        mbar_wait(bar3_w_full(bar, ring.stage), ring.phase);
+        mbar_wait(bar_w_full(bar, ring.stage), ring.phase);
         mbar_arrive_cluster(remote_full + 8u * ring.stage);
         ring.next();
       }
@@ -1187,45 +435,73 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) mlp_fwd
       // -------------------------------------------------------------- pair MMA issuer (leader)
       uint32_t n_act[2] = {0u, 0u};
       const uint32_t idesc256 = make_idesc(256, 256, 0, 0), idesc128 = make_idesc(256, 128, 0, 0);
-      long long wa0 = 0, wa1 = 0, ww = 0;
+      long long wa0 = 0, wa1 = 0, ww = 0, ww0 = 0, ww5 = 0;
       const long long mt0 = prof_on ? clock64() : 0;
       uint32_t q0 = 0;  // ring index of the current layer's first item
+      auto wait_full = [&](uint32_t q) { mbar_wait_cluster(bar_w_full(bar, item_stage(q)), item_phase(q)); };
+      auto release = [&](uint32_t q) { umma2_commit_multicast(bar_w_empty(bar, item_stage(q)), (uint16_t)3); };
+      auto st = [&](uint32_t q) { return s_w + item_stage(q) * WSTAGE; };
       for (int it = 0; it < iters; ++it) {
         for (int L = 0; L < 10; ++L) {
-          const int nch = (L == 0) ? 1 : (L == 5 ? 5 : 4);
-          const uint32_t nitems = (L == 0) ? 3u : (L == 5 ? 7u : 4u);
 #pragma unroll
           for (int t = 0; t < 2; ++t) {
             if (!(it == 0 && L == 0)) {  // both CTAs' epilogue warps of tile set t: inputs written, accumulator drained
               const long long c0 = prof_on ? clock64() : 0;
-              mbar_wait_cluster(bar3_act_ready(bar, t), n_act[t] & 1);
+              mbar_wait_cluster(bar_act_ready(bar, t), n_act[t] & 1);
               if (prof_on) { if (t == 0) wa0 += clock64() - c0; else wa1 += clock64() - c0; }
               ++n_act[t];
             }
             tc_fence_after();
-            for (int c = 0; c < nch; ++c) {
-              const bool use_pe = (L == 0) || (L == 5 && c == 0);
-              const uint32_t wq = q0 + ((L == 0) ? 1u : (L == 5 ? (c == 0 ? 1u : 2u + (uint32_t)c) : (uint32_t)c));
-              const uint32_t pq = q0 + (t == 0 ? 0u : 2u);
-              const long long c1 = prof_on ? clock64() : 0;
-              if (use_pe) mbar_wait_cluster(bar3_w_full(bar, item_stage(pq)), item_phase(pq));
-              if (t == 0) mbar_wait_cluster(bar3_w_full(bar, item_stage(wq)), item_phase(wq));
-              if (prof_on) ww += clock64() - c1;
+            const uint32_t d = tmem_base + t * 256, act = s_act + t * ACT_BYTES;
+            const long long c1 = prof_on ? clock64() : 0;
+            long long wsum = 0;
+            if (L == 0) {
+              const uint32_t pq = q0 + (t == 0 ? 0u : 2u), wq = q0 + 1;
+              wait_full(pq);
+              if (t == 0) wait_full(wq);
+              if (prof_on) wsum = clock64() - c1;
               tc_fence_after();
-              const int slab = (L == 5) ? c - 1 : c;
-              const uint32_t a = use_pe ? s_w + item_stage(pq) * WSTAGE3 : s_act + t * ACT_BYTES + slab * SLAB_BYTES;
-              issue_chunk2(tmem_base + t * 256, a, s_w + item_stage(wq) * WSTAGE3, L == 9 ? idesc128 : idesc256, c == 0);
-              if (use_pe) umma2_commit_multicast(bar3_w_empty(bar, item_stage(pq)), (uint16_t)3);
-              if (t == 1) umma2_commit_multicast(bar3_w_empty(bar, item_stage(wq)), (uint16_t)3);  // both tile sets done
+              issue_chunk(d, st(pq), st(wq), idesc256, true);
+              release(pq);
+              if (t == 1) release(wq);
+            } else if (L == 5) {
+              // the five-stage ring cannot hold PE + 5 chunks for two tile sets: layer 5 is fetched once per tile set,
+              // in the same chunk order (identical fp32 accumulation order keeps rows independent of their tile)
+              const uint32_t b = q0 + (t == 0 ? 0u : 6u);
+              wait_full(b); wait_full(b + 1);
+              if (prof_on) wsum = clock64() - c1;
+              tc_fence_after();
+              issue_chunk(d, st(b), st(b + 1), idesc256, true);
+              release(b); release(b + 1);
+              for (uint32_t c = 1; c < 5; ++c) {
+                const long long c2 = prof_on ? clock64() : 0;
+                wait_full(b + 1 + c);
+                if (prof_on) wsum += clock64() - c2;
+                tc_fence_after();
+                issue_chunk(d, act + (c - 1) * SLAB_BYTES, st(b + 1 + c), idesc256, false);
+                release(b + 1 + c);
+              }
+            } else {
+              for (uint32_t c = 0; c < 4; ++c) {
+                if (t == 0) {
+                  const long long c2 = prof_on ? clock64() : 0;
+                  wait_full(q0 + c);
+                  if (prof_on) wsum += clock64() - c2;
+                  tc_fence_after();
+                }
+                issue_chunk(d, act + c * SLAB_BYTES, st(q0 + c), L == 9 ? idesc128 : idesc256, c == 0);
+                if (t == 1) release(q0 + c);  // both tile sets are done with this chunk
+              }
             }
-            umma2_commit_multicast(bar3_acc_full(bar, t), (uint16_t)3);
+            if (prof_on) { if (L == 0) ww0 += wsum; else if (L == 5) ww5 += wsum; else ww += wsum; }
+            umma2_commit_multicast(bar_acc_full(bar, t), (uint16_t)3);
           }
-          q0 += nitems;
+          q0 += (L == 0) ? 3u : (L == 5 ? 12u : 4u);
         }
       }
       if (prof_on) {
-        long long *o = p.prof + blockIdx.x * 16;
-        o[0] = clock64() - mt0; o[1] = wa0; o[2] = wa1; o[3] = ww;
+        long long *o = p.prof + blockIdx.x * PROF_SLOTS;
+        o[0] = clock64() - mt0; o[1] = wa0; o[2] = wa1; o[3] = ww + ww0 + ww5; o[16] = ww0; o[17] = ww5;
       }
     }
   } else {
@@ -1237,10 +513,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) mlp_fwd
     const uint32_t r = quarter * 32 + lane;
     uint8_t *act_tile = smem + OFF_ACT + t * ACT_BYTES;
     const uint32_t tmem_row = tmem_base + ((quarter * 32) << 16) + t * 256;
-    const bool elected = (e & 7) == 0 && lane == 0;
+    const float *s_bias = reinterpret_cast<const float *>(smem + OFF_VEC);
     const float *s_head = reinterpret_cast<const float *>(smem + OFF_HEAD);
     const float *s_wa = s_head + 388;
-    const uint32_t ready_remote = mapa_cluster(bar3_act_ready(bar, t), 0);  // the leader's barrier
+    const uint32_t ready_remote = mapa_cluster(bar_act_ready(bar, t), 0);  // the leader's barrier
     uint32_t n_acc = 0;
     bool store_pending = false;
     const bool prof = prof_on && (e & 7) == 0 && lane == 0;
@@ -1252,55 +528,57 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) mlp_fwd
       const int pair = live ? pair_raw : p.n_pairs - 1;
       const int64_t tile = (int64_t)pair * 2 + t;
       const int64_t row = tile * 128 + r;
-      uint8_t *stash_act = live ? p.stash_act : nullptr;
+      uint8_t *stash_act = (live && !(p.dbg & 2)) ? p.stash_act : nullptr;
       uint32_t *stash_mask = (live && !(p.dbg & 1)) ? p.stash_mask : nullptr;
       for (int L = 0; L < 10; ++L) {
         const long long c0 = prof ? clock64() : 0;
-        mbar_wait(bar3_acc_full(bar, t), n_acc & 1);
+        mbar_wait(bar_acc_full(bar, t), n_acc & 1);
         ++n_acc;
         tc_fence_after();
         const long long c1 = prof ? clock64() : 0;
-        if (p.stash_act) {
-          if (elected && store_pending) bulk_wait_read0();
-          named_bar_sync(1 + t, 256);
+        if (p.stash_act) {  // the previous bulk store must have finished reading the part of act_tile I overwrite
+          if (lane == 0 && store_pending) bulk_wait_read0();
+          // a warp stores slabs {2ch, 2ch+1} of its rows, except after layer 9 (h9 = slabs 0,1: slab ch).  Entering
+          // layer 9 and layer 0 a warp therefore overwrites a piece its column-half partner stored: sync the two.
+          if (L == 9 || L == 0) named_bar_sync(1 + t * 4 + quarter, 64);
+          else __syncwarp();
         }
         const long long c2 = prof ? clock64() : 0;
-        uint32_t *mask_dst = stash_mask ? stash_mask + ((size_t)tile * 9 + (L < 9 ? L : 8)) * 128 * 8 + (size_t)r * 8 : nullptr;
+        uint32_t *mask_dst = stash_mask ? stash_mask + mask_word_offset(tile, L < 9 ? L : 8, ch, r) : nullptr;
         float alpha = 0.f;
         if (L < 7) {
-          const float *bias = p.P + b_pts(L);
-          if (mask_dst) fwd_epilogue_half<0, true>(tmem_row, ch, bias, act_tile, r, mask_dst, s_wa, alpha);
-          else fwd_epilogue_half<0, false>(tmem_row, ch, bias, act_tile, r, nullptr, s_wa, alpha);
+          if (mask_dst) fwd_epilogue_half<0, true>(tmem_row, ch, s_bias + L * 256, act_tile, r, mask_dst, s_wa, alpha);
+          else fwd_epilogue_half<0, false>(tmem_row, ch, s_bias + L * 256, act_tile, r, nullptr, s_wa, alpha);
         } else if (L == 7) {
-          if (mask_dst) fwd_epilogue_half<1, true>(tmem_row, ch, p.P + b_pts(7), act_tile, r, mask_dst, s_wa, alpha);
-          else fwd_epilogue_half<1, false>(tmem_row, ch, p.P + b_pts(7), act_tile, r, nullptr, s_wa, alpha);
+          if (mask_dst) fwd_epilogue_half<1, true>(tmem_row, ch, s_bias + 7 * 256, act_tile, r, mask_dst, s_wa, alpha);
+          else fwd_epilogue_half<1, false>(tmem_row, ch, s_bias + 7 * 256, act_tile, r, nullptr, s_wa, alpha);
           if (live && row < p.n) atomicAdd(p.raw + row * 4 + 3, alpha + (ch == 0 ? s_head[387] : 0.f));
         } else if (L == 8) {
-          fwd_epilogue_half<2, false>(tmem_row, ch, p.P + B_FEAT, act_tile, r, nullptr, s_wa, alpha);
+          fwd_epilogue_half<2, false>(tmem_row, ch, s_bias + 8 * 256, act_tile, r, nullptr, s_wa, alpha);
         } else {
           fwd_views_rgb(p, tmem_row, ch, act_tile, r, row, live, mask_dst, s_head);
         }
         tc_fence_before();
         fence_async_smem();
+        __syncwarp();
         const long long c3 = prof ? clock64() : 0;
-        if (p.stash_act) {
-          named_bar_sync(1 + t, 256);
-          if (elected && stash_act && !(p.dbg & 2)) {
-            bulk_s2g(stash_act + (size_t)tile * TILE_ACT_BYTES + (size_t)L * 65536, smem_u32(act_tile), L == 9 ? 32768u : 65536u);
-            bulk_commit();
+        if (lane == 0) {
+          if (stash_act) {
+            uint8_t *dst = stash_act + (size_t)tile * TILE_ACT_BYTES + (size_t)L * 65536;
+            if (L < 9) warp_store_slabs(dst, act_tile, quarter, 2 * ch, 2);
+            else warp_store_slabs(dst, act_tile, quarter, ch, 1);
             store_pending = true;
           }
+          mbar_arrive_cluster(ready_remote);
         }
-        __syncwarp();
-        if (lane == 0) mbar_arrive_cluster(ready_remote);
         if (prof) { e_acc += c1 - c0; e_st += c2 - c1; e_body += c3 - c2; e_tail += clock64() - c3; }
       }
     }
     if (prof) {
-      long long *o = p.prof + blockIdx.x * 16 + 6 + t * 5;
+      long long *o = p.prof + blockIdx.x * PROF_SLOTS + 6 + t * 5;
       o[0] = clock64() - et0; o[1] = e_acc; o[2] = e_st; o[3] = e_body; o[4] = e_tail;
     }
-    if (elected && store_pending) bulk_wait_all0();
+    if (lane == 0 && store_pending) bulk_wait_all0();
   }
   tc_fence_before();
   __syncthreads();
@@ -1308,7 +586,21 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) mlp_fwd
   if (warp == 0) tmem_dealloc2(tmem_base, 512);
 }
 
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) mlp_dgrad_tc3(DgradParams p) {
+// =================================================================================================
+// backward, data gradient chain:  G9 -> dF -> dH7 -> ... -> dH0   (pre-activation gradients, bf16)
+// =================================================================================================
+struct DgradParams {
+  const float *P;
+  const uint8_t *packed_dg;  // 34 chunks of 32 KB
+  const float *draw;         // [n][4]
+  const uint32_t *stash_mask;
+  uint8_t *dy;               // [tiles][10][64 KB]: slot l<8 = dH_l, slot 8 = dF, slot 9 = G9 (32 KB)
+  int64_t n;
+  int n_pairs;
+  long long *prof;
+};
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) mlp_dgrad_tc(DgradParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const int warp = threadIdx.x >> 5;
   const uint32_t lane = lane_id();
@@ -1321,28 +613,28 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) mlp_dgr
 
   if (warp == 0) {
     if (lane == 0) {
-      Ring3 ring;
+      Ring ring;
       long long pw = 0;
       const long long pt0 = prof_on ? clock64() : 0;
       for (int it = 0; it < iters; ++it)
         for (int ci = 0; ci < DG_CHUNKS; ++ci) {
-          const long long q0 = prof_on ? clock64() : 0;
-          mbar_wait(bar3_w_empty(bar, ring.stage), ring.phase ^ 1);
-          if (prof_on) pw += clock64() - q0;
-          mbar_arrive_expect_tx(bar3_w_full(bar, ring.stage), 16384u);
-          bulk_g2s(s_w + ring.stage * WSTAGE3, p.packed_dg + (size_t)ci * 32768 + (size_t)cr * 16384, 16384u,
-                   bar3_w_full(bar, ring.stage));
+          const long long c0 = prof_on ? clock64() : 0;
+          mbar_wait(bar_w_empty(bar, ring.stage), ring.phase ^ 1);
+          if (prof_on) pw += clock64() - c0;
+          mbar_arrive_expect_tx(bar_w_full(bar, ring.stage), 16384u);
+          bulk_g2s(s_w + ring.stage * WSTAGE, p.packed_dg + (size_t)ci * 32768 + (size_t)cr * 16384, 16384u,
+                   bar_w_full(bar, ring.stage));
           ring.next();
         }
-      if (prof_on) { p.prof[blockIdx.x * 16 + 4] = pw; p.prof[blockIdx.x * 16 + 5] = clock64() - pt0; }
+      if (prof_on) { p.prof[blockIdx.x * PROF_SLOTS + 4] = pw; p.prof[blockIdx.x * PROF_SLOTS + 5] = clock64() - pt0; }
     }
   } else if (warp == 1) {
     if (lane == 0 && cr != 0) {
-      Ring3 ring;
-      const uint32_t remote_full = mapa_cluster(bar3_w_full(bar, 0), 0);
+      Ring ring;
+      const uint32_t remote_full = mapa_cluster(bar_w_full(bar, 0), 0);
       const int total = iters * DG_ITEMS;
       for (int q = 0; q < total; ++q) {
-        mbar_wait(bar3_w_full(bar, ring.stage), ring.phase);
+        mbar_wait(bar_w_full(bar, ring.stage), ring.phase);
         mbar_arrive_cluster(remote_full + 8u * ring.stage);
         ring.next();
       }
@@ -1354,34 +646,34 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) mlp_dgr
       uint32_t q0 = 0;
       for (int it = 0; it < iters; ++it) {
         for (int D = 0; D < 9; ++D) {  // D=0: dF = G9 * Wv (K=128); D>=1: K=256
-          const int nch = (D == 0) ? 2 : 4;
+          const uint32_t nch = (D == 0) ? 2u : 4u;
 #pragma unroll
           for (int t = 0; t < 2; ++t) {
             const long long c0 = prof_on ? clock64() : 0;
-            mbar_wait_cluster(bar3_act_ready(bar, t), n_act[t] & 1);
+            mbar_wait_cluster(bar_act_ready(bar, t), n_act[t] & 1);
             if (prof_on) { if (t == 0) wa0 += clock64() - c0; else wa1 += clock64() - c0; }
             ++n_act[t];
             tc_fence_after();
-            for (int c = 0; c < nch; ++c) {
-              const uint32_t wq = q0 + (uint32_t)c;
+            for (uint32_t c = 0; c < nch; ++c) {
+              const uint32_t wq = q0 + c;
               if (t == 0) {
                 const long long c1 = prof_on ? clock64() : 0;
-                mbar_wait_cluster(bar3_w_full(bar, item_stage(wq)), item_phase(wq));
+                mbar_wait_cluster(bar_w_full(bar, item_stage(wq)), item_phase(wq));
                 if (prof_on) ww += clock64() - c1;
                 tc_fence_after();
               }
-              issue_chunk2(tmem_base + t * 256, s_act + t * ACT_BYTES + c * SLAB_BYTES, s_w + item_stage(wq) * WSTAGE3, idesc,
-                           c == 0);
-              if (t == 1) umma2_commit_multicast(bar3_w_empty(bar, item_stage(wq)), (uint16_t)3);
+              issue_chunk(tmem_base + t * 256, s_act + t * ACT_BYTES + c * SLAB_BYTES, s_w + item_stage(wq) * WSTAGE, idesc,
+                          c == 0);
+              if (t == 1) umma2_commit_multicast(bar_w_empty(bar, item_stage(wq)), (uint16_t)3);
             }
-            umma2_commit_multicast(bar3_acc_full(bar, t), (uint16_t)3);
+            umma2_commit_multicast(bar_acc_full(bar, t), (uint16_t)3);
           }
-          q0 += (uint32_t)nch;
+          q0 += nch;
         }
       }
       if (prof_on) {
-        long long *o = p.prof + blockIdx.x * 16;
-        o[0] = clock64() - mt0; o[1] = wa0; o[2] = wa1; o[3] = ww;
+        long long *o = p.prof + blockIdx.x * PROF_SLOTS;
+        o[0] = clock64() - mt0; o[1] = wa0; o[2] = wa1; o[3] = ww; o[16] = 0; o[17] = 0;
       }
     }
   } else {
@@ -1392,10 +684,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) mlp_dgr
     const uint32_t r = quarter * 32 + lane;
     uint8_t *act_tile = smem + OFF_ACT + t * ACT_BYTES;
     const uint32_t tmem_row = tmem_base + ((quarter * 32) << 16) + t * 256;
-    const bool elected = (e & 7) == 0 && lane == 0;
     const float *s_head = reinterpret_cast<const float *>(smem + OFF_HEAD);
     const float *s_wa = s_head + 388;
-    const uint32_t ready_remote = mapa_cluster(bar3_act_ready(bar, t), 0);
+    const uint32_t ready_remote = mapa_cluster(bar_act_ready(bar, t), 0);
     uint32_t n_acc = 0;
     bool store_pending = false;
     const bool prof = prof_on && (e & 7) == 0 && lane == 0;
@@ -1409,48 +700,61 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) mlp_dgr
       const int64_t row = tile * 128 + r;
       float4 dr = make_float4(0.f, 0.f, 0.f, 0.f);
       if (row < p.n) dr = reinterpret_cast<const float4 *>(p.draw)[row];
-      const uint32_t *mask_base = p.stash_mask + (size_t)tile * 9 * 128 * 8 + (size_t)r * 8;
+      // stage -1: G9 from d_rgb; stages 0..8 = tensor layers.  ReLU mask of the activation the gradient flows into:
+      // D=-1 -> h9 (slot 8), D=0 -> none (feature is linear), D=1 -> H7, D=2 -> H6, ..., D=8 -> H0
       for (int D = -1; D < 9; ++D) {
+        // the mask words come from HBM: fetch them BEFORE waiting for the accumulator
+        uint4 mk = make_uint4(0u, 0u, 0u, 0u);
+        if (D < 0) {
+          const uint2 m2 = __ldg(reinterpret_cast<const uint2 *>(p.stash_mask + mask_word_offset(tile, 8, ch, r)));
+          mk.x = m2.x; mk.y = m2.y;
+        } else if (D > 0) {
+          mk = __ldg(reinterpret_cast<const uint4 *>(p.stash_mask + mask_word_offset(tile, 8 - D, ch, r)));
+        }
         const long long c0 = prof ? clock64() : 0;
         if (D >= 0) {
-          mbar_wait(bar3_acc_full(bar, t), n_acc & 1);
+          mbar_wait(bar_acc_full(bar, t), n_acc & 1);
           ++n_acc;
           tc_fence_after();
         }
         const long long c1 = prof ? clock64() : 0;
-        if (elected && store_pending) bulk_wait_read0();
-        named_bar_sync(1 + t, 256);
+        if (lane == 0 && store_pending) bulk_wait_read0();
+        // G9 (stage -1) lives in slabs 0,1 (slab ch per warp), every other stage in slabs {2ch, 2ch+1}: entering stages
+        // -1 and 0 a warp overwrites a piece its column-half partner stored -- sync the two warps of a lane quarter
+        if (D <= 0) named_bar_sync(1 + t * 4 + quarter, 64);
+        else __syncwarp();
         const long long c2 = prof ? clock64() : 0;
-        const uint32_t *mk = (D != 0) ? mask_base + (size_t)((D < 0) ? 8 : 8 - D) * 128 * 8 : nullptr;
         if (D < 0) {
           dgrad_g9(dr, mk, ch, s_head, act_tile, r);
         } else if (D == 0) {
-          dgrad_epilogue_half<false, false>(tmem_row, ch, nullptr, 0.f, s_wa, act_tile, r);
-        } else if (D == 1) {
+          dgrad_epilogue_half<false, false>(tmem_row, ch, mk, 0.f, s_wa, act_tile, r);
+        } else if (D == 1) {  // dH7 also receives d_sigma * w_alpha (alpha_linear reads H7)
           dgrad_epilogue_half<true, true>(tmem_row, ch, mk, dr.w, s_wa, act_tile, r);
         } else {
           dgrad_epilogue_half<false, true>(tmem_row, ch, mk, 0.f, s_wa, act_tile, r);
         }
         tc_fence_before();
         fence_async_smem();
-        const long long c3 = prof ? clock64() : 0;
-        named_bar_sync(1 + t, 256);
-        if (elected && live) {
-          int slot = (D < 0) ? 9 : 8 - D;
-          bulk_s2g(p.dy + (size_t)tile * TILE_ACT_BYTES + (size_t)slot * 65536, smem_u32(act_tile), D < 0 ? 32768u : 65536u);
-          bulk_commit();
-          store_pending = true;
-        }
         __syncwarp();
-        if (D < 8 && lane == 0) mbar_arrive_cluster(ready_remote);
+        const long long c3 = prof ? clock64() : 0;
+        if (lane == 0) {
+          if (live) {
+            const int slot = (D < 0) ? 9 : 8 - D;  // D=0 -> dF (8), D=1 -> dH7 (7) ... D=8 -> dH0 (0)
+            uint8_t *dst = p.dy + (size_t)tile * TILE_ACT_BYTES + (size_t)slot * 65536;
+            if (D < 0) warp_store_slabs(dst, act_tile, quarter, ch, 1);
+            else warp_store_slabs(dst, act_tile, quarter, 2 * ch, 2);
+            store_pending = true;
+          }
+          if (D < 8) mbar_arrive_cluster(ready_remote);  // the last stage feeds no further MMA
+        }
         if (prof) { e_acc += c1 - c0; e_st += c2 - c1; e_body += c3 - c2; e_tail += clock64() - c3; }
       }
     }
     if (prof) {
-      long long *o = p.prof + blockIdx.x * 16 + 6 + t * 5;
+      long long *o = p.prof + blockIdx.x * PROF_SLOTS + 6 + t * 5;
       o[0] = clock64() - et0; o[1] = e_acc; o[2] = e_st; o[3] = e_body; o[4] = e_tail;
     }
-    if (elected && store_pending) bulk_wait_all0();
+    if (lane == 0 && store_pending) bulk_wait_all0();
   }
   tc_fence_before();
   __syncthreads();
@@ -1873,22 +1177,6 @@ __global__ void __launch_bounds__(512) wgrad_small_kernel(const uint8_t *__restr
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
-static int stagger_setting() {
-  static int v = -1;
-  if (v < 0) {
-    const char *e = getenv("FLNERF_STAGGER");
-    v = e ? atoi(e) : 600;
-  }
-  return v;
-}
-static int kernel_generation() {
-  static int v = -1;
-  if (v < 0) {
-    const char *e = getenv("FLNERF_TC_GEN");
-    v = e ? atoi(e) : 3;
-  }
-  return v;
-}
 // clusters of 2, one pair per CTA: even grid, at least 2 (a CTA without a pair of its own recomputes the last one)
 static int pair_grid(int n_pairs, int sm_count) {
   int g = n_pairs < sm_count ? n_pairs : sm_count;
@@ -1899,29 +1187,30 @@ static int pair_grid(int n_pairs, int sm_count) {
 static bool g_tables_ready = false;
 static int g_wgrad_grid = 0;
 
-// FLNERF_TC_PROF=1: the gen-2 forward / dgrad kernels count, per role, the cycles spent waiting on each barrier; the
-// host prints CTA 0/1 and the grid mean for every launch of >= 1024 pairs (development aid, off by default)
+// FLNERF_TC_PROF=1: the forward / dgrad kernels count, per role, the cycles spent waiting on each barrier; the host
+// prints the leader CTA 0 and the grid mean for every launch of >= 1024 pairs (development aid, off by default)
 static long long *prof_buffer() {
   static long long *buf = nullptr;
   static int on = -1;
   if (on < 0) {
     on = getenv("FLNERF_TC_PROF") != nullptr;
-    if (on && cudaMalloc(&buf, sizeof(long long) * 16 * 1024) != cudaSuccess) buf = nullptr;
+    if (on && cudaMalloc(&buf, sizeof(long long) * PROF_SLOTS * 1024) != cudaSuccess) buf = nullptr;
   }
   return buf;
 }
 static void prof_report(const char *name, int grid, int n_pairs, cudaStream_t st) {
   if (n_pairs < 1024) return;
-  static long long h[16 * 1024];
+  static long long h[PROF_SLOTS * 1024];
   cudaStreamSynchronize(st);
-  cudaMemcpy(h, prof_buffer(), sizeof(long long) * 16 * grid, cudaMemcpyDeviceToHost);
-  static const char *lbl[16] = {"mma_total", "mma_wait_act0", "mma_wait_act1", "mma_wait_wfull", "prod_wait_empty", "prod_total",
+  cudaMemcpy(h, prof_buffer(), sizeof(long long) * PROF_SLOTS * grid, cudaMemcpyDeviceToHost);
+  static const char *lbl[18] = {"mma_total", "mma_wait_act0", "mma_wait_act1", "mma_wait_wfull", "prod_wait_empty", "prod_total",
                                 "epi0_total", "epi0_wait_acc", "epi0_wait_store", "epi0_body", "epi0_tail",
-                                "epi1_total", "epi1_wait_acc", "epi1_wait_store", "epi1_body", "epi1_tail"};
+                                "epi1_total", "epi1_wait_acc", "epi1_wait_store", "epi1_body", "epi1_tail",
+                                "mma_wait_wfull_L0", "mma_wait_wfull_L5"};
   fprintf(stderr, "tcprof %s grid %d pairs %d:", name, grid, n_pairs);
-  for (int k = 0; k < 16; ++k) {
+  for (int k = 0; k < 18; ++k) {
     double m = 0;
-    for (int i = 0; i < grid; ++i) m += (double)h[i * 16 + k];
+    for (int i = 0; i < grid; ++i) m += (double)h[i * PROF_SLOTS + k];
     fprintf(stderr, " %s=%.0f(cta0 %lld)", lbl[k], m / grid, h[k]);
   }
   fprintf(stderr, "\n");
@@ -1995,10 +1284,6 @@ static int setup_tables(int sm_count) {
   if (cudaMemcpyToSymbol(c_units, un, sizeof(un)) != cudaSuccess) return 1;
   if (cudaFuncSetAttribute(mlp_fwd_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_FWD) != cudaSuccess) return 1;
   if (cudaFuncSetAttribute(mlp_dgrad_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_FWD) != cudaSuccess) return 1;
-  if (cudaFuncSetAttribute(mlp_fwd_tc2, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_FWD) != cudaSuccess) return 1;
-  if (cudaFuncSetAttribute(mlp_dgrad_tc2, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_FWD) != cudaSuccess) return 1;
-  if (cudaFuncSetAttribute(mlp_fwd_tc3, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_FWD) != cudaSuccess) return 1;
-  if (cudaFuncSetAttribute(mlp_dgrad_tc3, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_FWD) != cudaSuccess) return 1;
   if (cudaFuncSetAttribute(mlp_wgrad_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_WG) != cudaSuccess) return 1;
   g_tables_ready = true;
   return 0;
@@ -2042,22 +1327,12 @@ int mlp_tc_forward(flnerf_ctx *ctx, const float *params, const void *packed, int
     p.stash_act = (uint8_t *)stash + tc_vb_bytes(n, S);
     p.stash_mask = (uint32_t *)(p.stash_act + (size_t)(n_pad / 128) * tc::TILE_ACT_BYTES);
   }
-  int grid = p.n_pairs < ctx->sm_count ? p.n_pairs : ctx->sm_count;
-  p.stagger_cycles = p.n_pairs >= 4 * grid ? tc::stagger_setting() : 0;   // only worth it for long launches
   FL_CHECK_CUDA(cudaMemsetAsync(raw, 0, (size_t)n * 4 * sizeof(float), st));  // column-half warps accumulate into it
   { const char *e = getenv("FLNERF_FWD_DBG"); p.dbg = e ? atoi(e) : 0; }
   p.prof = tc::prof_buffer();
-  if (tc::kernel_generation() >= 3) {
-    grid = tc::pair_grid(p.n_pairs, ctx->sm_count);
-    FL_LAUNCH(tc::mlp_fwd_tc3, grid, tc::kThreads, tc::SMEM_FWD, st, p);
-    if (p.prof) tc::prof_report("fwd3", grid, p.n_pairs, st);
-  } else if (tc::kernel_generation() >= 2 && p.n_pairs >= 2) {
-    grid &= ~1;  // clusters of 2
-    FL_LAUNCH(tc::mlp_fwd_tc2, grid, tc::kThreads, tc::SMEM_FWD, st, p);
-    if (p.prof) tc::prof_report("fwd", grid, p.n_pairs, st);
-  } else {
-    FL_LAUNCH(tc::mlp_fwd_tc, grid, tc::kThreads, tc::SMEM_FWD, st, p);
-  }
+  const int grid = tc::pair_grid(p.n_pairs, ctx->sm_count);
+  FL_LAUNCH(tc::mlp_fwd_tc, grid, tc::kThreads, tc::SMEM_FWD, st, p);
+  if (p.prof) tc::prof_report("fwd", grid, p.n_pairs, st);
   return 0;
 }
 
@@ -2071,21 +1346,11 @@ int mlp_tc_backward(flnerf_ctx *ctx, const float *params, const void *packed, in
   tc::DgradParams d{};
   d.P = params; d.packed_dg = (const uint8_t *)packed + tc::FWD_BYTES; d.draw = draw; d.stash_mask = stash_mask;
   d.dy = (uint8_t *)ws; d.n = n; d.n_pairs = (int)(n_pad / 256);
-  int grid = d.n_pairs < ctx->sm_count ? d.n_pairs : ctx->sm_count;
-  d.stagger_cycles = d.n_pairs >= 4 * grid ? tc::stagger_setting() : 0;
   if (stages & 1) {
-    if (tc::kernel_generation() >= 3) {
-      const int g3 = tc::pair_grid(d.n_pairs, ctx->sm_count);
-      d.prof = tc::prof_buffer();
-      FL_LAUNCH(tc::mlp_dgrad_tc3, g3, tc::kThreads, tc::SMEM_FWD, st, d);
-      if (d.prof) tc::prof_report("dgrad3", g3, d.n_pairs, st);
-    } else if (tc::kernel_generation() >= 2 && d.n_pairs >= 2) {
-      d.prof = tc::prof_buffer();
-      FL_LAUNCH(tc::mlp_dgrad_tc2, grid & ~1, tc::kThreads, tc::SMEM_FWD, st, d);
-      if (d.prof) tc::prof_report("dgrad", grid & ~1, d.n_pairs, st);
-    } else {
-      FL_LAUNCH(tc::mlp_dgrad_tc, grid, tc::kThreads, tc::SMEM_FWD, st, d);
-    }
+    const int grid = tc::pair_grid(d.n_pairs, ctx->sm_count);
+    d.prof = tc::prof_buffer();
+    FL_LAUNCH(tc::mlp_dgrad_tc, grid, tc::kThreads, tc::SMEM_FWD, st, d);
+    if (d.prof) tc::prof_report("dgrad", grid, d.n_pairs, st);
   }
   tc::WgradParams w{};
   w.dy = (const uint8_t *)ws; w.stash_act = stash_act; w.pe_tiles = (const uint8_t *)pe_tiles; w.draw = draw;
