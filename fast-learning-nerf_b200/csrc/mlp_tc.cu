@@ -27,8 +27,8 @@ namespace tc {
 
 using namespace mlp_layout;
 
-// CTA = 18 warps: warp 0 producer, warp 1 MMA issuer / relay, warps 2..17 epilogue (2 tiles x 4 lane quarters x 2
-// column halves)
+// CTA = 18 warps: warp 0 producer, warp 1 MMA issuer / relay, warps 2..17 epilogue (4 lane quarters x 4 column
+// quarters, each warp serving both tiles)
 constexpr int kEpiWarps = 16;
 constexpr int kThreads = (2 + kEpiWarps) * 32;  // 576
 constexpr int kEpiWarp0 = 2;
@@ -39,7 +39,8 @@ constexpr int NST = 5;  // 5 x 16 KB ring: half weight chunks AND the PE slabs t
 constexpr uint32_t BIAS_FLOATS = 9 * 256, HEAD_FLOATS = 384 + 4 + 256;
 constexpr uint32_t OFF_ACT = 0, OFF_W = 2 * ACT_BYTES, OFF_VEC = OFF_W + NST * WSTAGE;
 constexpr uint32_t OFF_HEAD = OFF_VEC + BIAS_FLOATS * 4, OFF_BAR = OFF_HEAD + HEAD_FLOATS * 4;
-constexpr uint32_t SMEM_FWD = OFF_BAR + 256;
+constexpr uint32_t OFF_ALPHA = OFF_BAR + 256;  // [2 tiles][4 column quarters][128 rows] fp32 partial alpha sums
+constexpr uint32_t SMEM_FWD = OFF_ALPHA + 2 * 4 * 128 * 4;
 static_assert(OFF_BAR % 16 == 0 && SMEM_FWD <= 232448, "shared memory budget");
 
 // packed weight image of one net
@@ -48,7 +49,7 @@ constexpr size_t FWD_BYTES = (size_t)34 * 32768 + 4 * 16384;
 constexpr size_t DG_BYTES = (size_t)34 * 32768;
 constexpr size_t PACKED_BYTES = FWD_BYTES + DG_BYTES;
 
-// stash (bf16 mode): [viewbias B*128 fp32 (1 KB aligned)] [acts: tiles x 10 x 64 KB] [masks: tiles x 9 x 2 x 128 x 16 B]
+// stash (bf16 mode): [viewbias B*128 fp32 (1 KB aligned)] [acts: tiles x 10 x 64 KB] [masks: tiles x 9 x 4 x 128 x 8 B]
 constexpr size_t TILE_ACT_BYTES = 10 * 65536;
 constexpr size_t TILE_MASK_BYTES = 9 * 128 * 32;
 
@@ -141,7 +142,7 @@ __device__ __forceinline__ uint32_t pair_setup(uint8_t *smem, uint32_t bar, uint
       mbar_init(bar_w_full(bar, i), cr == 0 ? 2 : 1);  // leader: own producer + the follower's relay
       mbar_init(bar_w_empty(bar, i), 1);
     }
-    for (int t = 0; t < 2; ++t) { mbar_init(bar_acc_full(bar, t), 1); mbar_init(bar_act_ready(bar, t), kEpiWarps); }
+    for (int t = 0; t < 2; ++t) { mbar_init(bar_acc_full(bar, t), 1); mbar_init(bar_act_ready(bar, t), 2 * kEpiWarps); }
     fence_mbar_init();
   }
   __syncthreads();
@@ -205,32 +206,26 @@ __device__ __forceinline__ uint32_t fwd_block(const uint32_t v[32], const float 
   return m;
 }
 
-// 128 columns [ch*128, ch*128+128) of one row (the other column half belongs to the partner warp).  Two 32-column
-// TMEM loads are kept in flight: tcgen05.wait::ld waits for ALL outstanding loads, so block i+2 is issued right after
-// the wait that covers block i+1 and completes while block i+1 is being processed.
+// 64 columns [cq*64, cq*64+64) of one row: every epilogue warp owns one lane quarter x one column quarter of BOTH
+// tiles of its CTA.  Both 32-column TMEM loads are issued before the single wait.
 template <int kType, bool kMask>
-__device__ __forceinline__ void fwd_epilogue_half(uint32_t tmem_row, uint32_t ch, const float *s_bias, uint8_t *act_tile,
-                                                  uint32_t r, uint32_t *mask_dst, const float *s_wa, float &alpha) {
-  uint32_t va[32], vb[32], mk[4];
-  const uint32_t c0 = ch * 128;
-  tmem_ld32(tmem_row + c0, va);
-  tmem_ld32(tmem_row + c0 + 32, vb);
+__device__ __forceinline__ uint2 fwd_epilogue_q(uint32_t tmem_rc, uint32_t cq, const float *s_bias, uint8_t *act_tile,
+                                                uint32_t r, const float *s_wa, float &alpha) {
+  uint32_t va[32], vb[32];
+  const uint32_t c0 = cq * 64;
+  tmem_ld32(tmem_rc, va);
+  tmem_ld32(tmem_rc + 32, vb);
   tmem_ld_wait2(va, vb);
-  mk[0] = fwd_block<kType, kMask>(va, s_bias, act_tile, r, c0, s_wa, alpha);
-  tmem_ld32(tmem_row + c0 + 64, va);
-  mk[1] = fwd_block<kType, kMask>(vb, s_bias, act_tile, r, c0 + 32, s_wa, alpha);
-  tmem_ld_wait(va);
-  tmem_ld32(tmem_row + c0 + 96, vb);
-  mk[2] = fwd_block<kType, kMask>(va, s_bias, act_tile, r, c0 + 64, s_wa, alpha);
-  tmem_ld_wait(vb);
-  mk[3] = fwd_block<kType, kMask>(vb, s_bias, act_tile, r, c0 + 96, s_wa, alpha);
-  if (kMask) *reinterpret_cast<uint4 *>(mask_dst) = make_uint4(mk[0], mk[1], mk[2], mk[3]);
+  uint2 mk;
+  mk.x = fwd_block<kType, kMask>(va, s_bias, act_tile, r, c0, s_wa, alpha);
+  mk.y = fwd_block<kType, kMask>(vb, s_bias, act_tile, r, c0 + 32, s_wa, alpha);
+  return mk;
 }
 
 // views_linears.0 (N=128: 64 columns per warp) + rgb_linear on CUDA cores -> raw[row].rgb (accumulated by both halves)
 template <class Params>
-__device__ __forceinline__ void fwd_views_rgb(const Params &p, uint32_t tmem_row, uint32_t ch, uint8_t *act_tile, uint32_t r,
-                                              int64_t row, bool live, uint32_t *mask_dst, const float *s_head) {
+__device__ __forceinline__ uint2 fwd_views_rgb(const Params &p, uint32_t tmem_row, uint32_t ch, uint8_t *act_tile, uint32_t r,
+                                               int64_t row, bool live, const float *s_head) {
   const int64_t ray = (row < p.n ? row : p.n - 1) / p.S;
   const float4 *vb4 = reinterpret_cast<const float4 *>(p.viewbias + ray * 128);
   float c0 = 0.f, c1 = 0.f, c2 = 0.f;
@@ -270,7 +265,7 @@ __device__ __forceinline__ void fwd_views_rgb(const Params &p, uint32_t tmem_row
     atomicAdd(p.raw + row * 4 + 1, c1 + bsel * s_head[385]);
     atomicAdd(p.raw + row * 4 + 2, c2 + bsel * s_head[386]);
   }
-  if (mask_dst) *reinterpret_cast<uint2 *>(mask_dst) = make_uint2(mk2[0], mk2[1]);
+  return make_uint2(mk2[0], mk2[1]);
 }
 
 // backward: gradient columns [c0, c0+32) -> (+ d_sigma * w_alpha) -> relu mask -> bf16 -> act tile
@@ -294,27 +289,21 @@ __device__ __forceinline__ void dgrad_block(const uint32_t v[32], uint32_t m, fl
   store_cols32(act_tile, r, c0, pk);
 }
 
-// mk: this row's 128 ReLU mask bits of its column half (prefetched by the caller before the accumulator wait)
+// mk: this row's 64 ReLU mask bits of its column quarter (prefetched by the caller before the accumulator wait)
 template <bool kAlpha, bool kUseMask>
-__device__ __forceinline__ void dgrad_epilogue_half(uint32_t tmem_row, uint32_t ch, const uint4 mk, float dsig,
-                                                    const float *s_wa, uint8_t *act_tile, uint32_t r) {
+__device__ __forceinline__ void dgrad_epilogue_q(uint32_t tmem_rc, uint32_t cq, const uint2 mk, float dsig, const float *s_wa,
+                                                 uint8_t *act_tile, uint32_t r) {
   uint32_t va[32], vb[32];
-  const uint32_t c0 = ch * 128;
-  tmem_ld32(tmem_row + c0, va);
-  tmem_ld32(tmem_row + c0 + 32, vb);
+  const uint32_t c0 = cq * 64;
+  tmem_ld32(tmem_rc, va);
+  tmem_ld32(tmem_rc + 32, vb);
   tmem_ld_wait2(va, vb);
   dgrad_block<kAlpha, kUseMask>(va, mk.x, dsig, s_wa, act_tile, r, c0);
-  tmem_ld32(tmem_row + c0 + 64, va);
   dgrad_block<kAlpha, kUseMask>(vb, mk.y, dsig, s_wa, act_tile, r, c0 + 32);
-  tmem_ld_wait(va);
-  tmem_ld32(tmem_row + c0 + 96, vb);
-  dgrad_block<kAlpha, kUseMask>(va, mk.z, dsig, s_wa, act_tile, r, c0 + 64);
-  tmem_ld_wait(vb);
-  dgrad_block<kAlpha, kUseMask>(vb, mk.w, dsig, s_wa, act_tile, r, c0 + 96);
 }
 
 // backward stage -1: G9 = (d_rgb * W_rgb) masked by relu(h9) -> act slabs 0,1 (64 columns per warp)
-__device__ __forceinline__ void dgrad_g9(const float4 dr, const uint4 mk, uint32_t ch, const float *s_head,
+__device__ __forceinline__ void dgrad_g9(const float4 dr, const uint2 mk, uint32_t ch, const float *s_head,
                                          uint8_t *act_tile, uint32_t r) {
   const uint32_t mw[2] = {mk.x, mk.y};
 #pragma unroll
@@ -334,10 +323,10 @@ __device__ __forceinline__ void dgrad_g9(const float4 dr, const uint4 mk, uint32
   }
 }
 
-// ReLU bitmask stash: [tile][slot 0..8][column half][row][4 x u32] -- a warp's 32 rows are 512 contiguous bytes.
-// Slots 0..7 = H0..H7, slot 8 = h9 (views layer, 128 columns: 2 words per column half).
-__device__ __forceinline__ size_t mask_word_offset(int64_t tile, int slot, uint32_t ch, uint32_t r) {
-  return ((((size_t)tile * 9 + (size_t)slot) * 2 + ch) * 128 + r) * 4;
+// ReLU bitmask stash: [tile][slot 0..8][column quarter][row][2 x u32] -- a warp's 32 rows are 256 contiguous bytes.
+// Slots 0..7 = H0..H7, slot 8 = h9 (views layer, 128 columns: column quarters 0,1 only).
+__device__ __forceinline__ size_t mask_word_offset(int64_t tile, int slot, uint32_t cq, uint32_t r) {
+  return ((((size_t)tile * 9 + (size_t)slot) * 4 + cq) * 128 + r) * 2;
 }
 
 // =================================================================================================
@@ -505,78 +494,89 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) mlp_fwd
       }
     }
   } else {
-    // ---------------------------------------------------------------- epilogue: 8 warps per tile (both CTAs)
+    // ---------------------------------------------------------------- epilogue: 16 warps (both CTAs)
+    // Every warp owns one lane quarter x one 64-column quarter of BOTH tiles and serves them alternately: a tile's
+    // accumulator is drained by all 16 warps at once (half the latency of 8 warps per tile working side by side), so
+    // tile A's next MMAs start while the same warps drain tile B.
     const int e = warp - kEpiWarp0;
-    const int t = e >> 3;
-    const uint32_t ch = (uint32_t)(e >> 2) & 1u;
-    const uint32_t quarter = warp & 3;
-    const uint32_t r = quarter * 32 + lane;
-    uint8_t *act_tile = smem + OFF_ACT + t * ACT_BYTES;
-    const uint32_t tmem_row = tmem_base + ((quarter * 32) << 16) + t * 256;
+    const uint32_t cq = (uint32_t)e >> 2;    // column quarter: columns [64 cq, 64 cq + 64) = slab cq
+    const uint32_t quarter = warp & 3;       // TMEM lane quarter this warp may access
+    const uint32_t r = quarter * 32 + lane;  // row inside the tile == TMEM lane
     const float *s_bias = reinterpret_cast<const float *>(smem + OFF_VEC);
     const float *s_head = reinterpret_cast<const float *>(smem + OFF_HEAD);
     const float *s_wa = s_head + 388;
-    const uint32_t ready_remote = mapa_cluster(bar_act_ready(bar, t), 0);  // the leader's barrier
-    uint32_t n_acc = 0;
+    float *s_alpha = reinterpret_cast<float *>(smem + OFF_ALPHA);  // [tile][cq][row] partial alpha sums (layer 7)
+    uint32_t n_layer = 0;  // both tiles' accumulator barriers flip once per layer, in order
     bool store_pending = false;
-    const bool prof = prof_on && (e & 7) == 0 && lane == 0;
+    const bool prof = prof_on && e == 0 && lane == 0;
     long long e_acc = 0, e_st = 0, e_body = 0, e_tail = 0;
     const long long et0 = prof ? clock64() : 0;
     for (int it = 0; it < iters; ++it) {
       const int pair_raw = (int)blockIdx.x + it * (int)gridDim.x;
       const bool live = pair_raw < p.n_pairs;          // surplus iteration: compute, but write nothing
       const int pair = live ? pair_raw : p.n_pairs - 1;
-      const int64_t tile = (int64_t)pair * 2 + t;
-      const int64_t row = tile * 128 + r;
       uint8_t *stash_act = (live && !(p.dbg & 2)) ? p.stash_act : nullptr;
       uint32_t *stash_mask = (live && !(p.dbg & 1)) ? p.stash_mask : nullptr;
-      for (int L = 0; L < 10; ++L) {
-        const long long c0 = prof ? clock64() : 0;
-        mbar_wait(bar_acc_full(bar, t), n_acc & 1);
-        ++n_acc;
-        tc_fence_after();
-        const long long c1 = prof ? clock64() : 0;
-        if (p.stash_act) {  // the previous bulk store must have finished reading the part of act_tile I overwrite
-          if (lane == 0 && store_pending) bulk_wait_read0();
-          // a warp stores slabs {2ch, 2ch+1} of its rows, except after layer 9 (h9 = slabs 0,1: slab ch).  Entering
-          // layer 9 and layer 0 a warp therefore overwrites a piece its column-half partner stored: sync the two.
-          if (L == 9 || L == 0) named_bar_sync(1 + t * 4 + quarter, 64);
-          else __syncwarp();
-        }
-        const long long c2 = prof ? clock64() : 0;
-        uint32_t *mask_dst = stash_mask ? stash_mask + mask_word_offset(tile, L < 9 ? L : 8, ch, r) : nullptr;
-        float alpha = 0.f;
-        if (L < 7) {
-          if (mask_dst) fwd_epilogue_half<0, true>(tmem_row, ch, s_bias + L * 256, act_tile, r, mask_dst, s_wa, alpha);
-          else fwd_epilogue_half<0, false>(tmem_row, ch, s_bias + L * 256, act_tile, r, nullptr, s_wa, alpha);
-        } else if (L == 7) {
-          if (mask_dst) fwd_epilogue_half<1, true>(tmem_row, ch, s_bias + 7 * 256, act_tile, r, mask_dst, s_wa, alpha);
-          else fwd_epilogue_half<1, false>(tmem_row, ch, s_bias + 7 * 256, act_tile, r, nullptr, s_wa, alpha);
-          if (live && row < p.n) atomicAdd(p.raw + row * 4 + 3, alpha + (ch == 0 ? s_head[387] : 0.f));
-        } else if (L == 8) {
-          fwd_epilogue_half<2, false>(tmem_row, ch, s_bias + 8 * 256, act_tile, r, nullptr, s_wa, alpha);
-        } else {
-          fwd_views_rgb(p, tmem_row, ch, act_tile, r, row, live, mask_dst, s_head);
-        }
-        tc_fence_before();
-        fence_async_smem();
-        __syncwarp();
-        const long long c3 = prof ? clock64() : 0;
-        if (lane == 0) {
-          if (stash_act) {
-            uint8_t *dst = stash_act + (size_t)tile * TILE_ACT_BYTES + (size_t)L * 65536;
-            if (L < 9) warp_store_slabs(dst, act_tile, quarter, 2 * ch, 2);
-            else warp_store_slabs(dst, act_tile, quarter, ch, 1);
-            store_pending = true;
+      for (int L = 0; L < 10; ++L, ++n_layer) {
+#pragma unroll 1
+        for (int t = 0; t < 2; ++t) {
+          const int64_t tile = (int64_t)pair * 2 + t;
+          const int64_t row = tile * 128 + r;
+          uint8_t *act_tile = smem + OFF_ACT + t * ACT_BYTES;
+          const uint32_t tmem_rc = tmem_base + ((quarter * 32) << 16) + t * 256 + cq * 64;
+          const bool has_cols = L < 9 || cq < 2;   // the views layer has 128 outputs: column quarters 0,1 only
+          const long long c0 = prof ? clock64() : 0;
+          mbar_wait(bar_acc_full(bar, t), n_layer & 1);
+          tc_fence_after();
+          const long long c1 = prof ? clock64() : 0;
+          if (p.stash_act) {  // my previous store of THIS tile's piece (two groups ago) must have finished reading it
+            if (lane == 0 && store_pending) bulk_wait_read1();
+            __syncwarp();
           }
-          mbar_arrive_cluster(ready_remote);
+          const long long c2 = prof ? clock64() : 0;
+          float alpha = 0.f;
+          uint2 mk = make_uint2(0u, 0u);
+          const bool want_mask = stash_mask != nullptr;
+          if (L < 7) {
+            if (want_mask) mk = fwd_epilogue_q<0, true>(tmem_rc, cq, s_bias + L * 256, act_tile, r, s_wa, alpha);
+            else fwd_epilogue_q<0, false>(tmem_rc, cq, s_bias + L * 256, act_tile, r, s_wa, alpha);
+          } else if (L == 7) {
+            if (want_mask) mk = fwd_epilogue_q<1, true>(tmem_rc, cq, s_bias + 7 * 256, act_tile, r, s_wa, alpha);
+            else fwd_epilogue_q<1, false>(tmem_rc, cq, s_bias + 7 * 256, act_tile, r, s_wa, alpha);
+            // alpha_linear: the four column quarters of a row are summed in a fixed order (bit-reproducible)
+            s_alpha[(t * 4 + cq) * 128 + r] = alpha;
+            named_bar_sync(1 + quarter, 128);
+            if (cq == 0 && live && row < p.n) {
+              const float *pa = s_alpha + t * 512 + r;
+              p.raw[row * 4 + 3] = ((pa[0] + pa[128]) + (pa[256] + pa[384])) + s_head[387];
+            }
+          } else if (L == 8) {
+            fwd_epilogue_q<2, false>(tmem_rc, cq, s_bias + 8 * 256, act_tile, r, s_wa, alpha);
+          } else if (has_cols) {
+            mk = fwd_views_rgb(p, tmem_rc - cq * 64, cq, act_tile, r, row, live, s_head);  // adds its own column offset
+          }
+          tc_fence_before();
+          fence_async_smem();
+          __syncwarp();
+          const long long c3 = prof ? clock64() : 0;
+          if (lane == 0) {
+            if (stash_act && has_cols) {
+              warp_store_slabs(stash_act + (size_t)tile * TILE_ACT_BYTES + (size_t)L * 65536, act_tile, quarter, cq, 1);
+              store_pending = true;
+            }
+            mbar_arrive_cluster(mapa_cluster(bar_act_ready(bar, t), 0));  // the leader's barrier
+          }
+          // the mask words leave AFTER the arrive: its release would otherwise wait for these global stores
+          if (want_mask && L != 8 && has_cols)
+            *reinterpret_cast<uint2 *>(stash_mask + mask_word_offset(tile, L < 9 ? L : 8, cq, r)) = mk;
+          if (prof) { e_acc += c1 - c0; e_st += c2 - c1; e_body += c3 - c2; e_tail += clock64() - c3; }
         }
-        if (prof) { e_acc += c1 - c0; e_st += c2 - c1; e_body += c3 - c2; e_tail += clock64() - c3; }
       }
     }
     if (prof) {
-      long long *o = p.prof + blockIdx.x * PROF_SLOTS + 6 + t * 5;
+      long long *o = p.prof + blockIdx.x * PROF_SLOTS + 6;
       o[0] = clock64() - et0; o[1] = e_acc; o[2] = e_st; o[3] = e_body; o[4] = e_tail;
+      for (int k = 5; k < 10; ++k) o[k] = 0;
     }
     if (lane == 0 && store_pending) bulk_wait_all0();
   }
@@ -677,82 +677,80 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) mlp_dgr
       }
     }
   } else {
+    // epilogue: 16 warps, each one lane quarter x one 64-column quarter of BOTH tiles (see mlp_fwd_tc)
     const int e = warp - kEpiWarp0;
-    const int t = e >> 3;
-    const uint32_t ch = (uint32_t)(e >> 2) & 1u;
+    const uint32_t cq = (uint32_t)e >> 2;
     const uint32_t quarter = warp & 3;
     const uint32_t r = quarter * 32 + lane;
-    uint8_t *act_tile = smem + OFF_ACT + t * ACT_BYTES;
-    const uint32_t tmem_row = tmem_base + ((quarter * 32) << 16) + t * 256;
     const float *s_head = reinterpret_cast<const float *>(smem + OFF_HEAD);
     const float *s_wa = s_head + 388;
-    const uint32_t ready_remote = mapa_cluster(bar_act_ready(bar, t), 0);
-    uint32_t n_acc = 0;
+    uint32_t n_layer = 0;
     bool store_pending = false;
-    const bool prof = prof_on && (e & 7) == 0 && lane == 0;
+    const bool prof = prof_on && e == 0 && lane == 0;
     long long e_acc = 0, e_st = 0, e_body = 0, e_tail = 0;
     const long long et0 = prof ? clock64() : 0;
     for (int it = 0; it < iters; ++it) {
       const int pair_raw = (int)blockIdx.x + it * (int)gridDim.x;
       const bool live = pair_raw < p.n_pairs;
       const int pair = live ? pair_raw : p.n_pairs - 1;
-      const int64_t tile = (int64_t)pair * 2 + t;
-      const int64_t row = tile * 128 + r;
-      float4 dr = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (row < p.n) dr = reinterpret_cast<const float4 *>(p.draw)[row];
+      float4 dr[2];
+#pragma unroll
+      for (int t = 0; t < 2; ++t) {
+        const int64_t row = ((int64_t)pair * 2 + t) * 128 + r;
+        dr[t] = row < p.n ? reinterpret_cast<const float4 *>(p.draw)[row] : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
       // stage -1: G9 from d_rgb; stages 0..8 = tensor layers.  ReLU mask of the activation the gradient flows into:
       // D=-1 -> h9 (slot 8), D=0 -> none (feature is linear), D=1 -> H7, D=2 -> H6, ..., D=8 -> H0
       for (int D = -1; D < 9; ++D) {
-        // the mask words come from HBM: fetch them BEFORE waiting for the accumulator
-        uint4 mk = make_uint4(0u, 0u, 0u, 0u);
-        if (D < 0) {
-          const uint2 m2 = __ldg(reinterpret_cast<const uint2 *>(p.stash_mask + mask_word_offset(tile, 8, ch, r)));
-          mk.x = m2.x; mk.y = m2.y;
-        } else if (D > 0) {
-          mk = __ldg(reinterpret_cast<const uint4 *>(p.stash_mask + mask_word_offset(tile, 8 - D, ch, r)));
-        }
-        const long long c0 = prof ? clock64() : 0;
-        if (D >= 0) {
-          mbar_wait(bar_acc_full(bar, t), n_acc & 1);
-          ++n_acc;
-          tc_fence_after();
-        }
-        const long long c1 = prof ? clock64() : 0;
-        if (lane == 0 && store_pending) bulk_wait_read0();
-        // G9 (stage -1) lives in slabs 0,1 (slab ch per warp), every other stage in slabs {2ch, 2ch+1}: entering stages
-        // -1 and 0 a warp overwrites a piece its column-half partner stored -- sync the two warps of a lane quarter
-        if (D <= 0) named_bar_sync(1 + t * 4 + quarter, 64);
-        else __syncwarp();
-        const long long c2 = prof ? clock64() : 0;
-        if (D < 0) {
-          dgrad_g9(dr, mk, ch, s_head, act_tile, r);
-        } else if (D == 0) {
-          dgrad_epilogue_half<false, false>(tmem_row, ch, mk, 0.f, s_wa, act_tile, r);
-        } else if (D == 1) {  // dH7 also receives d_sigma * w_alpha (alpha_linear reads H7)
-          dgrad_epilogue_half<true, true>(tmem_row, ch, mk, dr.w, s_wa, act_tile, r);
-        } else {
-          dgrad_epilogue_half<false, true>(tmem_row, ch, mk, 0.f, s_wa, act_tile, r);
-        }
-        tc_fence_before();
-        fence_async_smem();
-        __syncwarp();
-        const long long c3 = prof ? clock64() : 0;
-        if (lane == 0) {
-          if (live) {
-            const int slot = (D < 0) ? 9 : 8 - D;  // D=0 -> dF (8), D=1 -> dH7 (7) ... D=8 -> dH0 (0)
-            uint8_t *dst = p.dy + (size_t)tile * TILE_ACT_BYTES + (size_t)slot * 65536;
-            if (D < 0) warp_store_slabs(dst, act_tile, quarter, ch, 1);
-            else warp_store_slabs(dst, act_tile, quarter, 2 * ch, 2);
-            store_pending = true;
+#pragma unroll 1
+        for (int t = 0; t < 2; ++t) {
+          const int64_t tile = (int64_t)pair * 2 + t;
+          uint8_t *act_tile = smem + OFF_ACT + t * ACT_BYTES;
+          const uint32_t tmem_rc = tmem_base + ((quarter * 32) << 16) + t * 256 + cq * 64;
+          const bool has_cols = D >= 0 || cq < 2;  // G9 has 128 columns: column quarters 0,1 only
+          // the mask words come from HBM: fetch them BEFORE waiting for the accumulator
+          uint2 mk = make_uint2(0u, 0u);
+          if (D != 0 && has_cols)
+            mk = __ldg(reinterpret_cast<const uint2 *>(p.stash_mask + mask_word_offset(tile, D < 0 ? 8 : 8 - D, cq, r)));
+          const long long c0 = prof ? clock64() : 0;
+          if (D >= 0) {
+            mbar_wait(bar_acc_full(bar, t), n_layer & 1);
+            tc_fence_after();
           }
-          if (D < 8) mbar_arrive_cluster(ready_remote);  // the last stage feeds no further MMA
+          const long long c1 = prof ? clock64() : 0;
+          if (lane == 0 && store_pending) bulk_wait_read1();  // my store of THIS tile's piece is two groups back
+          __syncwarp();
+          const long long c2 = prof ? clock64() : 0;
+          if (D < 0) {
+            if (has_cols) dgrad_g9(t ? dr[1] : dr[0], mk, cq, s_head, act_tile, r);
+          } else if (D == 0) {
+            dgrad_epilogue_q<false, false>(tmem_rc, cq, mk, 0.f, s_wa, act_tile, r);
+          } else if (D == 1) {  // dH7 also receives d_sigma * w_alpha (alpha_linear reads H7)
+            dgrad_epilogue_q<true, true>(tmem_rc, cq, mk, t ? dr[1].w : dr[0].w, s_wa, act_tile, r);
+          } else {
+            dgrad_epilogue_q<false, true>(tmem_rc, cq, mk, 0.f, s_wa, act_tile, r);
+          }
+          tc_fence_before();
+          fence_async_smem();
+          __syncwarp();
+          const long long c3 = prof ? clock64() : 0;
+          if (lane == 0) {
+            if (live && has_cols) {
+              const int slot = (D < 0) ? 9 : 8 - D;  // D=0 -> dF (8), D=1 -> dH7 (7) ... D=8 -> dH0 (0)
+              warp_store_slabs(p.dy + (size_t)tile * TILE_ACT_BYTES + (size_t)slot * 65536, act_tile, quarter, cq, 1);
+              store_pending = true;
+            }
+            if (D < 8) mbar_arrive_cluster(mapa_cluster(bar_act_ready(bar, t), 0));  // the last stage feeds no further MMA
+          }
+          if (prof) { e_acc += c1 - c0; e_st += c2 - c1; e_body += c3 - c2; e_tail += clock64() - c3; }
         }
-        if (prof) { e_acc += c1 - c0; e_st += c2 - c1; e_body += c3 - c2; e_tail += clock64() - c3; }
+        if (D >= 0) ++n_layer;
       }
     }
     if (prof) {
-      long long *o = p.prof + blockIdx.x * PROF_SLOTS + 6 + t * 5;
+      long long *o = p.prof + blockIdx.x * PROF_SLOTS + 6;
       o[0] = clock64() - et0; o[1] = e_acc; o[2] = e_st; o[3] = e_body; o[4] = e_tail;
+      for (int k = 5; k < 10; ++k) o[k] = 0;
     }
     if (lane == 0 && store_pending) bulk_wait_all0();
   }
