@@ -179,7 +179,8 @@ __device__ __forceinline__ void warp_store_slabs(uint8_t *dst_tile_layer, const 
 
 // ---- epilogue building blocks ---------------------------------------------------------------------
 // forward: 32 accumulator columns [c0, c0+32) of row r -> +bias -> (relu) -> bf16 -> act tile; kType 0 relu,
-// 1 relu + alpha head, 2 linear.  Returns the non-zero mask of the 32 outputs (0 when not needed).
+// 1 relu + alpha head, 2 linear.  Returns the ReLU mask word of the 32 outputs (bit 31-i set = output i inactive,
+// i.e. pre-activation negative; 0 when not needed).
 template <int kType, bool kMask>
 __device__ __forceinline__ uint32_t fwd_block(const uint32_t v[32], const float *s_b, uint8_t *act_tile, uint32_t r,
                                               uint32_t c0, const float *s_wa, float &alpha) {
@@ -187,13 +188,19 @@ __device__ __forceinline__ uint32_t fwd_block(const uint32_t v[32], const float 
 #pragma unroll
   for (int q = 0; q < 8; ++q) {
     const float4 b = *reinterpret_cast<const float4 *>(s_b + c0 + 4 * q);
-    const float x0 = __uint_as_float(v[4 * q]) + b.x, x1 = __uint_as_float(v[4 * q + 1]) + b.y;
-    const float x2 = __uint_as_float(v[4 * q + 2]) + b.z, x3 = __uint_as_float(v[4 * q + 3]) + b.w;
-    const uint32_t w0 = kType == 2 ? pack_bf16_fast(x0, x1) : pack_bf16_relu(x0, x1);
-    const uint32_t w1 = kType == 2 ? pack_bf16_fast(x2, x3) : pack_bf16_relu(x2, x3);
+    // packed fp32x2 adds (FADD2): half the issue slots of 4 scalar adds
+    const float2 x01 = __fadd2_rn(make_float2(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1])), make_float2(b.x, b.y));
+    const float2 x23 = __fadd2_rn(make_float2(__uint_as_float(v[4 * q + 2]), __uint_as_float(v[4 * q + 3])), make_float2(b.z, b.w));
+    const uint32_t w0 = kType == 2 ? pack_bf16_fast(x01.x, x01.y) : pack_bf16_relu(x01.x, x01.y);
+    const uint32_t w1 = kType == 2 ? pack_bf16_fast(x23.x, x23.y) : pack_bf16_relu(x23.x, x23.y);
     pk[2 * q] = w0;
     pk[2 * q + 1] = w1;
-    if (kMask) m += nz_nibble(w0, w1) << (4 * q);
+    if (kMask) {  // one funnel shift per output collects the SIGN bits: element i ends up at bit 31 - i, 1 = inactive
+      m = __funnelshift_l(__float_as_uint(x01.x), m, 1);
+      m = __funnelshift_l(__float_as_uint(x01.y), m, 1);
+      m = __funnelshift_l(__float_as_uint(x23.x), m, 1);
+      m = __funnelshift_l(__float_as_uint(x23.y), m, 1);
+    }
     if (kType == 1) {  // alpha_linear on the bf16-rounded activations the next layers also see
       const float4 a = *reinterpret_cast<const float4 *>(s_wa + c0 + 4 * q);
       alpha = fmaf(bf16_lo(w0), a.x, alpha);
@@ -242,11 +249,16 @@ __device__ __forceinline__ uint2 fwd_views_rgb(const Params &p, uint32_t tmem_ro
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
       const float4 b = __ldg(vb4 + cb * 8 + q);
-      const uint32_t w0 = pack_bf16_relu(__uint_as_float(v[4 * q]) + b.x, __uint_as_float(v[4 * q + 1]) + b.y);
-      const uint32_t w1 = pack_bf16_relu(__uint_as_float(v[4 * q + 2]) + b.z, __uint_as_float(v[4 * q + 3]) + b.w);
+      const float x0 = __uint_as_float(v[4 * q]) + b.x, x1 = __uint_as_float(v[4 * q + 1]) + b.y;
+      const float x2 = __uint_as_float(v[4 * q + 2]) + b.z, x3 = __uint_as_float(v[4 * q + 3]) + b.w;
+      const uint32_t w0 = pack_bf16_relu(x0, x1);
+      const uint32_t w1 = pack_bf16_relu(x2, x3);
       pk[2 * q] = w0;
       pk[2 * q + 1] = w1;
-      m += nz_nibble(w0, w1) << (4 * q);
+      m = __funnelshift_l(__float_as_uint(x0), m, 1);
+      m = __funnelshift_l(__float_as_uint(x1), m, 1);
+      m = __funnelshift_l(__float_as_uint(x2), m, 1);
+      m = __funnelshift_l(__float_as_uint(x3), m, 1);
       const float h[4] = {bf16_lo(w0), bf16_hi(w0), bf16_lo(w1), bf16_hi(w1)};
       const int k = cb * 32 + 4 * q;
 #pragma unroll
@@ -280,9 +292,9 @@ __device__ __forceinline__ void dgrad_block(const uint32_t v[32], uint32_t m, fl
       g0 = fmaf(dsig, s_wa[c0 + i], g0);
       g1 = fmaf(dsig, s_wa[c0 + i + 1], g1);
     }
-    if (kUseMask) {
-      g0 = (m & (1u << i)) ? g0 : 0.f;
-      g1 = (m & (2u << i)) ? g1 : 0.f;
+    if (kUseMask) {  // mask bit 31 - i set = output i of the forward layer was inactive
+      g0 = (m & (0x80000000u >> i)) ? 0.f : g0;
+      g1 = (m & (0x40000000u >> i)) ? 0.f : g1;
     }
     pk[i >> 1] = pack_bf16_fast(g0, g1);
   }
@@ -315,15 +327,16 @@ __device__ __forceinline__ void dgrad_g9(const float4 dr, const uint2 mk, uint32
       const int k = cb * 32 + i;
       float g0 = dr.x * s_head[k] + dr.y * s_head[128 + k] + dr.z * s_head[256 + k];
       float g1 = dr.x * s_head[k + 1] + dr.y * s_head[128 + k + 1] + dr.z * s_head[256 + k + 1];
-      g0 = (mw[j] & (1u << i)) ? g0 : 0.f;
-      g1 = (mw[j] & (2u << i)) ? g1 : 0.f;
+      g0 = (mw[j] & (0x80000000u >> i)) ? 0.f : g0;
+      g1 = (mw[j] & (0x40000000u >> i)) ? 0.f : g1;
       pk[i >> 1] = pack_bf16_fast(g0, g1);
     }
     store_cols32(act_tile, r, cb * 32, pk);
   }
 }
 
-// ReLU bitmask stash: [tile][slot 0..8][column quarter][row][2 x u32] -- a warp's 32 rows are 256 contiguous bytes.
+// ReLU bitmask stash: [tile][slot 0..8][column quarter][row][2 x u32] -- a warp's 32 rows are 256 contiguous bytes;
+// word w covers columns 64 cq + 32 w + i at bit 31 - i, set = inactive (sign bit of the pre-activation).
 // Slots 0..7 = H0..H7, slot 8 = h9 (views layer, 128 columns: column quarters 0,1 only).
 __device__ __forceinline__ size_t mask_word_offset(int64_t tile, int slot, uint32_t cq, uint32_t r) {
   return ((((size_t)tile * 9 + (size_t)slot) * 4 + cq) * 128 + r) * 2;
@@ -351,8 +364,8 @@ constexpr int PROF_SLOTS = 24;
 // ring items of one iteration, in producer order (each = this CTA's half chunk or its own PE slab, <= 16 KB):
 //   L0     : PE_A, W0, PE_B                            (W0 feeds both tile sets)
 //   L1..L4 : 4 chunks each
-//   L5     : PE_A, Wpe, W1..W4, PE_B, Wpe, W1..W4      (PE + 5 chunks do not fit the five stages twice over: layer 5
-//            is fetched once per tile set and released chunk by chunk)
+//   L5     : W1..W4, Wpe, PE_A, W1..W4, Wpe, PE_B      (PE + 5 chunks do not fit the five stages twice over: layer 5
+//            is fetched once per tile set and released chunk by chunk, the PE chunk last)
 //   L6..L9 : 4 chunks each
 constexpr int FWD_ITEMS = 3 + 16 + 12 + 16;
 constexpr int DG_ITEMS = 34;
@@ -397,8 +410,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) mlp_fwd
             ci = 1;
           } else if (L == 5) {
             for (int t = 0; t < 2; ++t) {
+              for (int c = 1; c < 5; ++c) push_w(ci + c);
+              push_w(ci);
               push(pe + (size_t)t * PE_BYTES, PE_BYTES);
-              for (int c = 0; c < 5; ++c) push_w(ci + c);
             }
             ci += 5;
           } else {
@@ -454,22 +468,25 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) mlp_fwd
               release(pq);
               if (t == 1) release(wq);
             } else if (L == 5) {
-              // the five-stage ring cannot hold PE + 5 chunks for two tile sets: layer 5 is fetched once per tile set,
-              // in the same chunk order (identical fp32 accumulation order keeps rows independent of their tile)
+              // the five-stage ring cannot hold PE + 5 chunks for two tile sets: layer 5 is fetched once per tile set
+              // and released chunk by chunk, in the same order for both (identical fp32 accumulation order keeps a row's
+              // result independent of its tile).  The short-lived PE item comes last: every refill then has four
+              // chunk-times of cover.
               const uint32_t b = q0 + (t == 0 ? 0u : 6u);
-              wait_full(b); wait_full(b + 1);
-              if (prof_on) wsum = clock64() - c1;
-              tc_fence_after();
-              issue_chunk(d, st(b), st(b + 1), idesc256, true);
-              release(b); release(b + 1);
               for (uint32_t c = 1; c < 5; ++c) {
                 const long long c2 = prof_on ? clock64() : 0;
-                wait_full(b + 1 + c);
+                wait_full(b + c - 1);
                 if (prof_on) wsum += clock64() - c2;
                 tc_fence_after();
-                issue_chunk(d, act + (c - 1) * SLAB_BYTES, st(b + 1 + c), idesc256, false);
-                release(b + 1 + c);
+                issue_chunk(d, act + (c - 1) * SLAB_BYTES, st(b + c - 1), idesc256, c == 1);
+                release(b + c - 1);
               }
+              const long long c2 = prof_on ? clock64() : 0;
+              wait_full(b + 4); wait_full(b + 5);
+              if (prof_on) wsum += clock64() - c2;
+              tc_fence_after();
+              issue_chunk(d, st(b + 5), st(b + 4), idesc256, false);
+              release(b + 4); release(b + 5);
             } else {
               for (uint32_t c = 0; c < 4; ++c) {
                 if (t == 0) {

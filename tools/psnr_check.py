@@ -52,6 +52,7 @@ for seed in SEEDS:
                     break
             mgr.refine(0.001)
         res["%s.seed%d" % (prec, seed)] = {"train": psnr_on(nc, nf, poses[::10], imgs[::10]), "test": psnr_on(nc, nf, test_poses, test_imgs)}
+        print("partial", prec, seed, res["%s.seed%d" % (prec, seed)], file=sys.stderr, flush=True)
 for k in ("train", "test"):
     d = [res["bf16.seed%d" % s][k] - res["fp32.seed%d" % s][k] for s in SEEDS]
     res["delta_%s_db" % k] = d
