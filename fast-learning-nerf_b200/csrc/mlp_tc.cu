@@ -83,18 +83,24 @@ __global__ void pack_weights_kernel(const float *__restrict__ P, uint8_t *__rest
 
 // viewbias[ray][c] = b_v[c] + sum_j W_v[c][256+j] * PE4(viewdir)[j]  -- the 27 view-direction inputs of
 // views_linears.0 are constant along a ray, so their contribution is a per-ray bias (fp32, exact)
-__global__ void viewbias_kernel(int64_t B, const float *__restrict__ P, const float *__restrict__ dirpe,
-                                float *__restrict__ vb) {
-  int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= B * 128) return;
-  int64_t ray = idx >> 7;
-  int c = (int)(idx & 127);
-  const float *w = P + W_VIEWS + c * 283 + 256;
-  const float *pe = dirpe + ray * 32;
-  float s = P[B_VIEWS + c];
+__global__ void __launch_bounds__(128) viewbias_kernel(int64_t B, const float *__restrict__ P, const float *__restrict__ dirpe,
+                                                       float *__restrict__ vb) {
+  // thread = output channel c: its 27 view-direction weights stay in registers for kRays rays (the strided weight reads
+  // are paid once per block); the ray's PE values are warp-uniform loads, the stores are coalesced
+  constexpr int kRays = 16;
+  const int c = threadIdx.x;
+  float w[27];
 #pragma unroll
-  for (int j = 0; j < 27; ++j) s = fmaf(w[j], pe[j], s);
-  vb[idx] = s;
+  for (int j = 0; j < 27; ++j) w[j] = P[W_VIEWS + c * 283 + 256 + j];
+  const float b = P[B_VIEWS + c];
+  const int64_t r0 = (int64_t)blockIdx.x * kRays;
+  for (int64_t ray = r0; ray < r0 + kRays && ray < B; ++ray) {
+    const float *pe = dirpe + ray * 32;
+    float s = b;
+#pragma unroll
+    for (int j = 0; j < 27; ++j) s = fmaf(w[j], __ldg(pe + j), s);
+    vb[ray * 128 + c] = s;
+  }
 }
 
 // mbarrier addresses (bytes from the barrier block): no arrays, so nothing lands in local memory
@@ -1332,7 +1338,7 @@ int mlp_tc_forward(flnerf_ctx *ctx, const float *params, const void *packed, int
   FL_REQUIRE(n % S == 0, "mlp_tc_forward: n=%lld is not a multiple of S=%d", (long long)n, S);
   int64_t B = n / S;
   float *vb = (float *)stash;
-  FL_LAUNCH(tc::viewbias_kernel, (unsigned)ceil_div64(B * 128, 256), 256, 0, st, B, params, dirpe, vb);
+  FL_LAUNCH(tc::viewbias_kernel, (unsigned)ceil_div64(B, 16), 128, 0, st, B, params, dirpe, vb);
   tc::FwdParams p{};
   p.P = params; p.packed = (const uint8_t *)packed; p.pe_tiles = (const uint8_t *)pe_tiles; p.viewbias = vb;
   p.raw = raw; p.n = n; p.S = S;

@@ -254,6 +254,180 @@ __global__ void qt_emit_kernel(int n_images, int cap, int W, const double *__res
   ray_gid[pos] = (int32_t)lo;
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// probability-guided pixel sampling (prob=True): image_process.py:26-96 + tree.py:583-595
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ int reflect101(int i, int n) {  // cv2 BORDER_REFLECT_101 (the cv2.blur default)
+  if (i < 0) i = -i;
+  if (i >= n) i = 2 * n - 2 - i;
+  return i < 0 ? 0 : i;
+}
+
+// get_sharp_img (image_process.py:26-39): per channel sqrt|blur3x3(x^2) - blur3x3(x)^2|, then the BGR2GRAY weights
+// on the channel-reversed image = 0.299 R + 0.587 G + 0.114 B.  cv2.blur sums a float image in double.
+__global__ void sharp_map_kernel(int n_images, int H, int W, const float *__restrict__ images, float *__restrict__ sharp) {
+  int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t total = (int64_t)n_images * H * W;
+  if (idx >= total) return;
+  int img = (int)(idx / ((int64_t)H * W));
+  int rem = (int)(idx % ((int64_t)H * W));
+  int r = rem / W, c = rem % W;
+  const float *im = images + (int64_t)img * H * W * 3;
+  double s1[3] = {0, 0, 0}, s2[3] = {0, 0, 0};
+  for (int dr = -1; dr <= 1; ++dr)
+    for (int dc = -1; dc <= 1; ++dc) {
+      const float *px = im + ((int64_t)reflect101(r + dr, H) * W + reflect101(c + dc, W)) * 3;
+#pragma unroll
+      for (int ch = 0; ch < 3; ++ch) {
+        float v = px[ch];
+        s1[ch] += (double)v;
+        s2[ch] += (double)__fmul_rn(v, v);  // img ** 2 is a float32 array
+      }
+    }
+  float g[3];
+#pragma unroll
+  for (int ch = 0; ch < 3; ++ch) {
+    float e2 = (float)(s2[ch] * (1.0 / 9.0)), e1 = (float)(s1[ch] * (1.0 / 9.0));
+    g[ch] = sqrtf(fabsf(__fsub_rn(e2, __fmul_rn(e1, e1))));
+  }
+  sharp[idx] = g[2] * 0.114f + g[1] * 0.587f + g[0] * 0.299f;
+}
+
+// per-slot block heights int(x1) - int(x0) (tree.py:587: sharp[int(x0):int(x1), int(y0):int(y1)]) -> exclusive scan
+__global__ void __launch_bounds__(256)
+qt_prob_rows_kernel(int n_images, int cap, const double *__restrict__ boxes, const int32_t *__restrict__ count,
+                    int64_t *__restrict__ row_offset) {
+  __shared__ int s_warp[33];
+  int64_t running = 0;
+  int64_t slots = (int64_t)n_images * cap;
+  for (int64_t base = 0; base < slots; base += blockDim.x) {
+    int64_t s = base + threadIdx.x;
+    int c = 0;
+    if (s < slots && (int)(s % cap) < count[s / cap]) {
+      const double *b = boxes + s * 4;
+      c = max(0, (int)b[2] - (int)b[0]);
+    }
+    int total;
+    int ex = block_excl_scan(c, &total, s_warp);
+    if (s < slots) row_offset[s] = running + ex;
+    running += total;
+  }
+  if (threadIdx.x == 0) row_offset[slots] = running;
+}
+
+// to_prob_v2 (image_process.py:59-74) of one leaf block: g = gray + 1e-6 (float64); the weights are
+// clip(g, 0.01*mean(g), max(g)) / max(g) / sum -- the common scale cancels in sampling, so w = max(g, 0.01*mean(g)).
+// One CTA per leaf: thr, then the inclusive prefix of the per-row weight sums (float64).
+__global__ void __launch_bounds__(256)
+qt_prob_prepare_kernel(int cap, int H, int W, const double *__restrict__ boxes, const int32_t *__restrict__ count,
+                       const float *__restrict__ sharp, const int64_t *__restrict__ row_offset,
+                       double *__restrict__ row_cdf, double *__restrict__ leaf_thr) {
+  const int64_t s = blockIdx.x;
+  const int img = (int)(s / cap), j = (int)(s % cap);
+  if (j >= count[img]) return;
+  const double *b = boxes + s * 4;
+  const int X0 = (int)b[0], X1 = (int)b[2], Y0 = (int)b[1], Y1 = (int)b[3];
+  const int h = X1 - X0, w = Y1 - Y0;
+  if (h <= 0 || w <= 0) { if (threadIdx.x == 0) leaf_thr[s] = 0.0; return; }
+  const float *g = sharp + (int64_t)img * H * W;
+  __shared__ double s_red[256];
+  double acc = 0.0;
+  for (int i = threadIdx.x; i < h * w; i += blockDim.x) acc += (double)g[(int64_t)(X0 + i / w) * W + Y0 + i % w] + 1e-6;
+  s_red[threadIdx.x] = acc;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) s_red[threadIdx.x] += s_red[threadIdx.x + o];
+    __syncthreads();
+  }
+  const double thr = 0.01 * (s_red[0] / (double)(h * w));
+  __syncthreads();
+  double *cdf = row_cdf + row_offset[s];
+  // row sums: one warp per row (lanes stride the columns), then a serial prefix by thread 0 (h <= a few hundred)
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int r = warp; r < h; r += 8) {
+    double rs = 0.0;
+    for (int c = lane; c < w; c += 32) rs += fmax((double)g[(int64_t)(X0 + r) * W + Y0 + c] + 1e-6, thr);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) rs += __shfl_xor_sync(0xffffffffu, rs, o);
+    if (lane == 0) cdf[r] = rs;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double run = 0.0;
+    for (int r = 0; r < h; ++r) { run += cdf[r]; cdf[r] = run; }
+    leaf_thr[s] = thr;
+  }
+}
+
+// tree.py:583-599 with prob=True: of a leaf's ray_num rays the first int(ray_num*(1-rand_frac)) are drawn from the
+// sharpness distribution of its block (np.random.choice(p): inverse CDF over the row-major flattened block, offset
+// (int(x0), int(y0))), the rest uniformly as in the prob=False path.  u (optional, [N][2]) replaces Philox.
+__global__ void qt_emit_prob_kernel(int n_images, int cap, int H, int W, const double *__restrict__ boxes,
+                                    const int64_t *__restrict__ ray_offset, int64_t N, int half, uint64_t seed,
+                                    double rand_frac, const float *__restrict__ sharp,
+                                    const int64_t *__restrict__ row_offset, const double *__restrict__ row_cdf,
+                                    const double *__restrict__ leaf_thr, const float *__restrict__ u, int shuffle,
+                                    int32_t *__restrict__ ray_pix, int32_t *__restrict__ ray_gid) {
+  int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= N) return;
+  int64_t lo = 0, hi = (int64_t)n_images * cap;
+  while (hi - lo > 1) {
+    int64_t mid = (lo + hi) >> 1;
+    if (ray_offset[mid] <= j) lo = mid; else hi = mid;
+  }
+  const double *b = boxes + lo * 4;
+  const int ray_num = (int)(ray_offset[lo + 1] - ray_offset[lo]);
+  const int ray_num1 = (int)((double)ray_num * (1.0 - rand_frac));  // int(ray_num * (1 - randSamp_proc))
+  const int k = (int)(j - ray_offset[lo]);
+  double u0, u1;
+  if (u) {
+    u0 = (double)u[j * 2]; u1 = (double)u[j * 2 + 1];
+  } else {
+    uint32_t r[4];
+    philox4x32(seed, (uint64_t)j, 0x9E17ull, r);
+    u0 = ((double)r[0] * 4294967296.0 + (double)r[1]) * (1.0 / 18446744073709551616.0);  // 64-bit uniform, like numpy
+    u1 = (double)u32_to_unit(r[2]);
+  }
+  int row, col;
+  const int X0 = (int)b[0], X1 = (int)b[2], Y0 = (int)b[1], Y1 = (int)b[3];
+  const int h = X1 - X0, w = Y1 - Y0;
+  if (k < ray_num1 && h > 0 && w > 0) {
+    const double *cdf = row_cdf + row_offset[lo];
+    const double thr = leaf_thr[lo];
+    const double target = u0 * cdf[h - 1];
+    int a = 0, e = h - 1;   // first row whose inclusive prefix exceeds the target (searchsorted side='right')
+    while (a < e) {
+      int m = (a + e) >> 1;
+      if (cdf[m] > target) e = m; else a = m + 1;
+    }
+    double run = a > 0 ? cdf[a - 1] : 0.0;
+    const float *g = sharp + ((int64_t)(lo / cap) * H + X0 + a) * W + Y0;
+    int c = 0;
+    for (; c < w - 1; ++c) {
+      run += fmax((double)g[c] + 1e-6, thr);
+      if (run > target) break;
+    }
+    row = X0 + a;
+    col = Y0 + c;
+  } else {
+    int x_lo = (int)ceil(b[0]), x_hi = (int)ceil(b[2]);
+    int y_lo = (int)ceil(b[1]), y_hi = (int)ceil(b[3] - 0.01);
+    if (u) {
+      row = x_lo + min(max(1, x_hi - x_lo) - 1, (int)(u0 * (double)max(1, x_hi - x_lo)));
+      col = y_lo + min(max(1, y_hi - y_lo) - 1, (int)(u1 * (double)max(1, y_hi - y_lo)));
+    } else {
+      uint32_t r[4];
+      philox4x32(seed, (uint64_t)j, 0x9E18ull, r);
+      row = x_lo + (int)(r[0] % (uint32_t)max(1, x_hi - x_lo));
+      col = y_lo + (int)(r[1] % (uint32_t)max(1, y_hi - y_lo));
+    }
+  }
+  int64_t pos = shuffle ? (int64_t)feistel_perm((uint64_t)j, (uint64_t)N, half, seed ^ 0xA5A5A5A55A5A5A5Aull) : j;
+  ray_pix[pos] = row * W + col;
+  ray_gid[pos] = (int32_t)lo;
+}
+
 }  // namespace
 
 extern "C" {
@@ -318,6 +492,46 @@ int flnerf_qt_emit(flnerf_ctx *ctx, int n_images, int cap, int W, const double *
   int half = (bits + 1) / 2;
   FL_LAUNCH(qt_emit_kernel, (unsigned)ceil_div64(n_rays, 256), 256, 0, stream, n_images, cap, W, boxes, ray_offset,
             n_rays, half, seed, ray_pix, ray_gid);
+  return 0;
+}
+
+int flnerf_sharp_map(flnerf_ctx *ctx, int n_images, int H, int W, const float *images, float *sharp, void *stream) {
+  FL_REQUIRE(ctx && images && sharp && n_images > 0 && H > 1 && W > 1, "flnerf_sharp_map: bad arguments");
+  FL_LAUNCH(sharp_map_kernel, (unsigned)ceil_div64((int64_t)n_images * H * W, 256), 256, 0, stream, n_images, H, W, images,
+            sharp);
+  return 0;
+}
+
+int flnerf_qt_prob_rows(flnerf_ctx *ctx, int n_images, int cap, const double *boxes, const int32_t *count,
+                        int64_t *row_offset, void *stream) {
+  FL_REQUIRE(ctx && boxes && count && row_offset, "flnerf_qt_prob_rows: bad arguments");
+  FL_LAUNCH(qt_prob_rows_kernel, 1, 256, 0, stream, n_images, cap, boxes, count, row_offset);
+  return 0;
+}
+
+int flnerf_qt_prob_prepare(flnerf_ctx *ctx, int n_images, int cap, int H, int W, const double *boxes,
+                           const int32_t *count, const float *sharp, const int64_t *row_offset, double *row_cdf,
+                           double *leaf_thr, void *stream) {
+  FL_REQUIRE(ctx && boxes && count && sharp && row_offset && row_cdf && leaf_thr, "flnerf_qt_prob_prepare: bad arguments");
+  FL_LAUNCH(qt_prob_prepare_kernel, (unsigned)((int64_t)n_images * cap), 256, 0, stream, cap, H, W, boxes, count, sharp,
+            row_offset, row_cdf, leaf_thr);
+  return 0;
+}
+
+int flnerf_qt_emit_prob(flnerf_ctx *ctx, int n_images, int cap, int H, int W, const double *boxes, const int32_t *count,
+                        const int64_t *ray_offset, int64_t n_rays, uint64_t seed, double rand_frac, const float *sharp,
+                        const int64_t *row_offset, const double *row_cdf, const double *leaf_thr, const float *u,
+                        int shuffle, int32_t *ray_pix, int32_t *ray_gid, void *stream) {
+  (void)count;
+  FL_REQUIRE(ctx && boxes && ray_offset && ray_pix && ray_gid && sharp && row_offset && row_cdf && leaf_thr && n_rays >= 0 &&
+                 rand_frac >= 0.0 && rand_frac <= 1.0,
+             "flnerf_qt_emit_prob: bad arguments");
+  if (n_rays == 0) return 0;
+  int bits = 2;
+  while ((1ull << bits) < (uint64_t)n_rays) ++bits;
+  int half = (bits + 1) / 2;
+  FL_LAUNCH(qt_emit_prob_kernel, (unsigned)ceil_div64(n_rays, 256), 256, 0, stream, n_images, cap, H, W, boxes, ray_offset,
+            n_rays, half, seed, rand_frac, sharp, row_offset, row_cdf, leaf_thr, u, shuffle, ray_pix, ray_gid);
   return 0;
 }
 

@@ -48,6 +48,11 @@ SIGNATURES = {
     "flnerf_qt_refine": (_i, [_vp, _i, _i, _vp, _vp, _vp, _vp, _f, _vp, _vp, _vp]),
     "flnerf_qt_count": (_i, [_vp, _i, _i, _vp, _vp, _vp, _d, _vp, _vp]),
     "flnerf_qt_emit": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp, _i64, _u64, _vp, _vp, _vp]),
+    "flnerf_sharp_map": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp]),
+    "flnerf_qt_prob_rows": (_i, [_vp, _i, _i, _vp, _vp, _vp, _vp]),
+    "flnerf_qt_prob_prepare": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "flnerf_qt_emit_prob": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp, _i64, _u64, _d, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp,
+                                 _vp]),
     "flnerf_gather_batch": (_i, [_vp, _i64, _i64, _i64, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "flnerf_launch_count": (_i64, [_i]),
 }

@@ -262,6 +262,39 @@ def qt_emit(n_images, cap, W, boxes, count, ray_offset, n_rays, seed, ray_pix, r
                                     int(n_rays), int(seed), _ptr(ray_pix), _ptr(ray_gid), _stream()), "flnerf_qt_emit")
 
 
+def sharp_map(images):
+    """image_process.py:26-39 for every image: [n,H,W,3] fp32 -> [n,H,W] fp32 sharpness (gray local std)."""
+    n, H, W, _ = images.shape
+    out = torch.empty(n, H, W, dtype=torch.float32, device=images.device)
+    L.check(L.load().flnerf_sharp_map(_ctx(images), int(n), int(H), int(W), _ptr(images), _ptr(out), _stream()),
+            "flnerf_sharp_map")
+    return out
+
+
+def qt_prob_prepare(n_images, cap, H, W, boxes, count, sharp):
+    """Per-leaf to_prob_v2 tables (image_process.py:59-74): returns (row_offset, row_cdf, leaf_thr)."""
+    dev = boxes.device
+    row_offset = torch.empty(n_images * cap + 1, dtype=torch.int64, device=dev)
+    L.check(L.load().flnerf_qt_prob_rows(_ctx(boxes), n_images, cap, _ptr(boxes), _ptr(count), _ptr(row_offset), _stream()),
+            "flnerf_qt_prob_rows")
+    rows = int(row_offset[-1].item())
+    row_cdf = torch.empty(max(rows, 1), dtype=torch.float64, device=dev)
+    leaf_thr = torch.zeros(n_images * cap, dtype=torch.float64, device=dev)
+    L.check(L.load().flnerf_qt_prob_prepare(_ctx(boxes), n_images, cap, int(H), int(W), _ptr(boxes), _ptr(count), _ptr(sharp),
+                                            _ptr(row_offset), _ptr(row_cdf), _ptr(leaf_thr), _stream()),
+            "flnerf_qt_prob_prepare")
+    return row_offset, row_cdf, leaf_thr
+
+
+def qt_emit_prob(n_images, cap, H, W, boxes, count, ray_offset, n_rays, seed, rand_frac, sharp, tables, ray_pix, ray_gid,
+                 u=None, shuffle=True):
+    row_offset, row_cdf, leaf_thr = tables
+    L.check(L.load().flnerf_qt_emit_prob(_ctx(boxes), n_images, cap, int(H), int(W), _ptr(boxes), _ptr(count),
+                                         _ptr(ray_offset), int(n_rays), int(seed), float(rand_frac), _ptr(sharp),
+                                         _ptr(row_offset), _ptr(row_cdf), _ptr(leaf_thr), _ptr(u), 1 if shuffle else 0,
+                                         _ptr(ray_pix), _ptr(ray_gid), _stream()), "flnerf_qt_emit_prob")
+
+
 def gather_batch(B, first, stride, ray_pix, ray_gid, cap, H, W, K, poses, images, want_gid=True):
     dev = images.device
     o = torch.empty(B, 3, dtype=torch.float32, device=dev)

@@ -104,7 +104,8 @@ class QuadTreeManager:
         self.K = np.asarray(K, dtype=np.float64)
         self.images = images
         self.epoch_size = self.n_images * self.h * self.w
-        self.processor = None           # ImageProcessor sharpness maps are only used with prob=True (tree.py:583-595)
+        self.processor = None           # the reference's ImageProcessor; here the sharpness maps live on the GPU and are
+        self._sharp = None              # computed on first use (only prob=True reads them: tree.py:583-595)
         self._images_dev = torch.as_tensor(images, dtype=torch.float32).to(self.device).contiguous()
         self._poses_dev = torch.as_tensor(poses, dtype=torch.float32)[:, :3, :4].to(self.device).contiguous()
         self.max_level = int(max_level) if max_level is not None else int(max_depth) + 6
@@ -187,8 +188,16 @@ class QuadTreeManager:
         return torch.stack([g // self.cap, g % self.cap], 1).float()
 
     # ------------------------------------------------------------------ emission
-    def emit_epoch(self, down_scale=1, last_epoch=False, seed=None):
-        """Builds the epoch's shuffled ray index buffer on the GPU; returns the number of rays."""
+    @property
+    def sharp_imgs(self):
+        """ImageProcessor.sharp_imgs (image_process.py:24-39) as one [n,H,W] GPU tensor."""
+        if self._sharp is None:
+            self._sharp = ops.sharp_map(self._images_dev)
+        return self._sharp
+
+    def emit_epoch(self, down_scale=1, last_epoch=False, seed=None, prob=False, randSamp_proc=0.95, u=None, shuffle=True):
+        """Builds the epoch's shuffled ray index buffer on the GPU; returns the number of rays.  prob=True draws
+        int(ray_num*(1-randSamp_proc)) rays of every leaf from its sharpness distribution (tree.py:583-595)."""
         rpp = self.epoch_size / self.n_images / down_scale / self.h / self.w      # tree.py:381-382
         n = self.n_images
         if last_epoch:   # throw-away depth-1 trees: H*W uniform draws per image (tree.py:390-400)
@@ -204,7 +213,12 @@ class QuadTreeManager:
         self.ray_gid = torch.empty(self.n_rays, dtype=torch.int32, device=self.device)
         self._epoch += 1
         s = self.seed * 1000003 + self._epoch if seed is None else int(seed)
-        ops.qt_emit(n, self.cap, self.w, boxes, count, self._ray_offset, self.n_rays, s, self.ray_pix, self.ray_gid)
+        if prob:
+            tables = ops.qt_prob_prepare(n, self.cap, self.h, self.w, boxes, count, self.sharp_imgs)
+            ops.qt_emit_prob(n, self.cap, self.h, self.w, boxes, count, self._ray_offset, self.n_rays, s, float(randSamp_proc),
+                             self.sharp_imgs, tables, self.ray_pix, self.ray_gid, u=u, shuffle=shuffle)
+        else:
+            ops.qt_emit(n, self.cap, self.w, boxes, count, self._ray_offset, self.n_rays, s, self.ray_pix, self.ray_gid)
         self._emitted_last = bool(last_epoch)
         return self.n_rays
 
@@ -215,10 +229,7 @@ class QuadTreeManager:
 
     def gen_rays_v3_multiThread(self, down_scale=16, prob=True, randSamp_proc=0.95, debug=False, last_epoch=False):
         """tree.py:377-428 -> (origins[N,3], dirs[N,3], rgb[N,3]) (GPU tensors, already shuffled)."""
-        if prob:
-            raise FlnerfError("probability-guided pixel sampling (prob=True, image_process.py) is not implemented; "
-                              "nerf-ours/run_nerf.py always passes prob=False (run_nerf.py:440,452)")
-        n = self.emit_epoch(down_scale, last_epoch)
+        n = self.emit_epoch(down_scale, last_epoch, prob=bool(prob), randSamp_proc=randSamp_proc)
         o, d, rgb, _ = ops.gather_batch(n, 0, 1, self.ray_pix, self.ray_gid, self.cap, self.h, self.w, self.K,
                                         self._poses_dev, self._images_dev, want_gid=False)
         return o, d, rgb

@@ -146,6 +146,26 @@ int flnerf_qt_count(flnerf_ctx *, int n_images, int cap, const double *boxes, co
 int flnerf_qt_emit(flnerf_ctx *, int n_images, int cap, int W, const double *boxes, const int32_t *count,
                    const int64_t *ray_offset, int64_t n_rays, uint64_t seed, int32_t *ray_pix, int32_t *ray_gid,
                    void *stream);
+/* ---- probability-guided pixel sampling (prob=True; image_process.py:9-96, tree.py:583-595) ------------------------
+ * sharp[n,H,W] = get_sharp_img(images[n,H,W,3]): 3x3 box-blur variance per channel -> sqrt|.| -> luminance
+ * (image_process.py:26-39; cv2.blur border = BORDER_REFLECT_101, sums in double). */
+int flnerf_sharp_map(flnerf_ctx *, int n_images, int H, int W, const float *images, float *sharp, void *stream);
+/* row_offset[n_images*cap+1] = exclusive scan of the block heights int(x1)-int(x0) of every leaf (the slice
+ * sharp[int(x0):int(x1), int(y0):int(y1)] of tree.py:587); total rows = row_offset[n_images*cap]. */
+int flnerf_qt_prob_rows(flnerf_ctx *, int n_images, int cap, const double *boxes, const int32_t *count,
+                        int64_t *row_offset, void *stream);
+/* to_prob_v2 (image_process.py:59-74) per leaf: leaf_thr = 0.01*mean(gray+1e-6) and row_cdf[row_offset[s]+r] = inclusive
+ * prefix over rows of sum_c max(gray+1e-6, leaf_thr) (float64).  row_cdf holds row_offset[n_images*cap] doubles. */
+int flnerf_qt_prob_prepare(flnerf_ctx *, int n_images, int cap, int H, int W, const double *boxes,
+                           const int32_t *count, const float *sharp, const int64_t *row_offset, double *row_cdf,
+                           double *leaf_thr, void *stream);
+/* gen_rays_v3_1 with prob=True: of a leaf's rays the first int(ray_num*(1-rand_frac)) follow np.random.choice(p) over
+ * its block (inverse CDF, row-major, searchsorted side='right'), the rest the uniform rule of flnerf_qt_emit.
+ * u [n_rays][2] fp32 (optional) replaces the Philox draws; shuffle=0 keeps emission order (parity tests). */
+int flnerf_qt_emit_prob(flnerf_ctx *, int n_images, int cap, int H, int W, const double *boxes, const int32_t *count,
+                        const int64_t *ray_offset, int64_t n_rays, uint64_t seed, double rand_frac, const float *sharp,
+                        const int64_t *row_offset, const double *row_cdf, const double *leaf_thr, const float *u,
+                        int shuffle, int32_t *ray_pix, int32_t *ray_gid, void *stream);
 /* gathers a batch: for k in [0,B): ray = first + k*stride; target rgb from images (fp32 [n,H,W,3]) and the ray
  * (o,d) regenerated from pose/intrinsics (== get_rays at that pixel).  poses fp32 [n_images,12]. */
 int flnerf_gather_batch(flnerf_ctx *, int64_t B, int64_t first, int64_t stride, const int32_t *ray_pix,

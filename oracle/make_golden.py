@@ -53,9 +53,60 @@ def close(a, b, tol=0.0, what=""):
     return err
 
 
+def prob_sampling_golden(ref):
+    """prob=True fixtures (image_process.py + tree.py:583-595) from the reference's own ImageProcessor and
+    gen_rays_v3_1_subThread: sharpness maps, per-leaf probabilities and the pixels np.random.choice returns for seeded
+    uniforms.  25x25 images give half-pixel leaf boxes (12.5) so int() and ceil() bounds differ."""
+    T, IP = ref.tree, ref.image_process.ImageProcessor
+    Hq = Wq = 25
+    n_img = 2
+    rs = np.random.RandomState(21)
+    imgs = rs.uniform(0, 1, (n_img, Hq, Wq, 3)).astype(np.float32)
+    imgs[1, 3:11, 2:12] = 0.75                                   # flat patch (zero variance)
+    proc = IP(torch.from_numpy(imgs), scale=0)
+    g = {"images": imgs, "H": Hq, "W": Wq, "n_img": n_img, "rand_frac": 0.25, "max_depth": 3}
+    for i in range(n_img):
+        close(O.sharp_img(imgs[i]), proc.sharp_imgs[i], 1e-6, "sharp_img")
+        g["sharp%d" % i] = proc.sharp_imgs[i]
+    tree = T.QuadTree(imgs[0], 0.0, 3)                           # uniform depth-3 tree: 16 leaves of 6.25 x 6.25
+    leaves = T.get_children(tree.root)
+    boxes = np.array([(n.x0, n.y0, n.x1, n.y1) for n in leaves], np.float64)
+    g["boxes"], g["min_area"] = boxes, tree.minArea
+    rpp = 1.0
+    counts = [O.leaf_ray_count(tuple(b), tree.minArea, rpp) for b in boxes]
+    g["counts"] = np.array(counts)
+    for i in range(n_img):
+        us, want = [], []
+        for j, b in enumerate(boxes):
+            n1 = int(counts[j] * (1 - 0.25))
+            u = np.random.RandomState(1000 * i + j).random_sample((counts[j], 2))
+            block = proc.sharp_imgs[i][int(b[0]):int(b[2]), int(b[1]):int(b[3])]
+            pix = proc.to_prob_v2(block)                             # the reference's own probabilities
+            cdf = np.cumsum(pix.reshape(-1)); cdf /= cdf[-1]
+            ref_idx = cdf.searchsorted(u[:n1, 0], side="right")      # what np.random.choice does with these uniforms
+            ref_pix = np.stack([np.floor(ref_idx / block.shape[1]), ref_idx - np.floor(ref_idx / block.shape[1]) * block.shape[1]], 1)
+            ref_pix = ref_pix.astype(np.int64) + np.array([int(b[0]), int(b[1])])
+            mine = O.emit_leaf_prob(tuple(b), tree.minArea, rpp, 0.25, proc.sharp_imgs[i], u)
+            assert np.array_equal(mine[:n1], ref_pix), (i, j)
+            us.append(u.astype(np.float32)); want.append(O.emit_leaf_prob(tuple(b), tree.minArea, rpp, 0.25, proc.sharp_imgs[i], u.astype(np.float32)))
+        g["u%d" % i] = np.concatenate(us, 0)
+        g["pix%d" % i] = np.concatenate(want, 0)
+    # end-to-end against sample_pixels itself (seeded global numpy state)
+    block = proc.sharp_imgs[1][0:12, 0:12]
+    np.random.seed(5)
+    want = proc.sample_pixels(block, 300).numpy()
+    np.random.seed(5)
+    assert np.array_equal(O.sample_pixels(block, np.random.random_sample(300)), want)
+    np.savez_compressed(os.path.join(OUT, "prob_sampling.npz"), **g)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     ref = ref_shim.load()
+    if os.environ.get("GOLDEN_ONLY") == "prob":
+        prob_sampling_golden(ref)
+        print("wrote prob_sampling.npz")
+        return
     H = ref.helpers
     torch.manual_seed(0)
     np.random.seed(0)
@@ -268,6 +319,7 @@ def main():
     assert np.array_equal(np.array(ob), q["tie.newboxes"]) and om == t_one.minArea
     q["H"] = Hq; q["W"] = Wq; q["n_img"] = n_img; q["leaf_hist"] = np.array(hist)
     np.savez_compressed(os.path.join(OUT, "quadtree.npz"), **q)
+    prob_sampling_golden(ref)
     print("golden fixtures written to", OUT)
     for f in sorted(os.listdir(OUT)):
         print("  %-20s %8d bytes" % (f, os.path.getsize(os.path.join(OUT, f))))

@@ -74,6 +74,7 @@ def load():
         ns.model = importlib.import_module("model")
         ns.render = importlib.import_module("render")
         ns.tree = importlib.import_module("tree")
+        ns.image_process = importlib.import_module("image_process")
     finally:
         sys.path[:] = saved_path
         # keep the reference modules out of the global namespace so that the product's

@@ -125,3 +125,41 @@ def test_two_rank_data_parallel_step_matches_single_process():
     assert np.linalg.norm(g2 - g1) <= 1e-4 * np.linalg.norm(g1)          # one all-reduce reproduces the full-batch gradient
     w1 = torch.cat([nc.flat_parameters(), nf.flat_parameters()]).cpu().numpy()
     assert float(np.abs(w2 - w1).mean()) < 1e-5
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_baseline_config1_coarse_only_step(precision):
+    """BASELINE.json configs[0]: 400x400 camera, 32 coarse samples, no fine network, N_rand=256 -- render() + img2mse +
+    backward + Adam through the reference-facing API, against the oracle on the same rays (the reference's train()
+    itself needs N_importance > 0: SURVEY 8a quirk 4, so this is the render()+loss+backward micro-configuration)."""
+    import render as R, run_nerf, run_nerf_helpers as H
+    from flnerf_b200.engine import FusedAdam
+    B, Nc = 256, 32
+    nc = make_net(1, precision)
+    q = run_nerf.NetworkQuery(H.get_embedder(10)[0], H.get_embedder(4)[0], 65536)
+    o, d, tgt = rays(B, seed=5)
+    K = np.array([[555.56, 0, 200.0], [0, 555.56, 200.0], [0, 0, 1]])
+    rgb, disp, acc, ex = R.render(400, 400, K, rays=torch.stack([o, d], 0), ndc=False, near=2.0, far=6.0, use_viewdirs=True,
+                                  network_query_fn=q, network_fn=nc, network_fine=None, N_samples=Nc, N_importance=0,
+                                  white_bkgd=True, perturb=0.0, retraw=True)
+    assert "rgb0" not in ex and ex["raw"].shape == (B, Nc, 4)
+    pc = O.init_params(1)
+    r11 = O.pack_rays(400, 400, K, o.cpu(), d.cpu(), 2.0, 6.0, ndc=False)
+    for t in pc.values():
+        t.requires_grad_(True)
+    ref = O.render_rays(r11, pc, None, Nc, 0, white_bkgd=True)
+    tol = 2e-5 if precision == "fp32" else 3e-2
+    np.testing.assert_allclose(rgb.detach().cpu().numpy(), ref["rgb_map"].detach().numpy(), atol=tol)
+    loss = H.img2mse(rgb, tgt)
+    loss_ref = O.mse(ref["rgb_map"], tgt.cpu())
+    np.testing.assert_allclose(float(loss), float(loss_ref), rtol=1e-4 if precision == "fp32" else 2e-2)
+    loss.backward()
+    loss_ref.backward()
+    g = nc._grad_bucket().cpu()
+    gref = torch.cat([t.grad.reshape(-1) for t in pc.values()])
+    rel = float((g - gref).norm() / gref.norm())
+    assert rel < (2e-4 if precision == "fp32" else 3e-2), rel
+    opt = FusedAdam(list(nc.parameters()), [nc], lr=5e-4)
+    before = nc.flat_parameters().clone()
+    opt.step()
+    assert float((nc.flat_parameters() - before).abs().max()) > 0

@@ -280,3 +280,48 @@ def test_feistel_emit_is_a_permutation(ops):
     a = gid.copy()
     mgr.emit_epoch()
     assert not np.array_equal(a, mgr.ray_gid.cpu().numpy())                 # a new permutation every epoch
+
+
+def test_prob_guided_sampling(golden, ops):
+    """prob=True emission (image_process.py + tree.py:583-595): sharpness maps vs the reference's cv2 result, the
+    inverse-CDF pixel choice bit-exact on the fixture's uniforms, and the Philox path's counts / bounds / distribution."""
+    import tree
+    g = golden("prob_sampling")
+    H, W, n_img, rf = int(g["H"]), int(g["W"]), int(g["n_img"]), float(g["rand_frac"])
+    imgs = T(g["images"])
+    sharp = ops.sharp_map(imgs)
+    for i in range(n_img):
+        np.testing.assert_allclose(sharp[i].cpu().numpy(), g["sharp%d" % i], atol=2e-6, rtol=0)
+    K = np.array([[30.0, 0, W / 2], [0, 30.0, H / 2], [0, 0, 1]])
+    poses = torch.eye(4)[None, :3, :4].repeat(n_img, 1, 1)
+    mgr = tree.QuadTreeManager(H, W, K, g["images"], poses, mseThres=0.0, max_depth=int(g["max_depth"]), max_level=5)
+    np.testing.assert_array_equal(mgr.leaf_lists()[0][0], g["boxes"])
+    mgr._sharp = torch.stack([T(g["sharp%d" % i]) for i in range(n_img)], 0).contiguous()   # teacher-forced maps
+    u = torch.cat([T(g["u%d" % i]) for i in range(n_img)], 0).contiguous()
+    n = mgr.emit_epoch(down_scale=1, prob=True, randSamp_proc=rf, u=u, shuffle=False)
+    want = np.concatenate([g["pix%d" % i] for i in range(n_img)], 0)
+    assert n == len(want)
+    pix = mgr.ray_pix.cpu().numpy()
+    assert np.array_equal(np.stack([pix // W, pix % W], 1), want)                               # index work: bit-exact
+    gid = mgr.ray_gid.cpu().numpy()
+    counts = g["counts"]
+    assert np.array_equal(np.bincount(gid, minlength=n_img * mgr.cap).reshape(n_img, mgr.cap)[:, :len(counts)],
+                          np.tile(counts, (n_img, 1)))
+    # Philox path on one big leaf per image (depth-1 tree): the prob share follows to_prob_v2, the rest is uniform
+    big = tree.QuadTreeManager(H, W, K, g["images"], poses, mseThres=0.0, max_depth=1, max_level=3, seed=3)
+    big._sharp = mgr._sharp
+    n = big.emit_epoch(down_scale=1.0 / 64, prob=True, randSamp_proc=0.5, shuffle=False)       # 64 rays per pixel
+    per = H * W * 64
+    assert n == n_img * per
+    pix = big.ray_pix.cpu().numpy().reshape(n_img, per)
+    n1 = int(per * 0.5)
+    for i in range(n_img):
+        p = O.to_prob_v2(g["sharp%d" % i][0:H, 0:W]).reshape(-1)
+        freq = np.bincount(pix[i, :n1], minlength=H * W) / n1
+        chi2 = float((n1 * (freq - p) ** 2 / p).sum())
+        assert chi2 < H * W + 6 * np.sqrt(2 * H * W), chi2                                      # ~ chi^2(H*W - 1)
+        rest = np.bincount(pix[i, n1:], minlength=H * W) / (per - n1)
+        assert abs(rest - 1.0 / (H * W)).max() < 6 * np.sqrt(1.0 / (H * W) / (per - n1))
+    # reference-facing entry point
+    o, d, rgb = big.gen_rays_v3_multiThread(down_scale=1, prob=True, randSamp_proc=0.95)
+    assert o.shape == (n_img * H * W, 3) and rgb.shape == o.shape and bool(torch.isfinite(d).all())

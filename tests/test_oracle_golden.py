@@ -142,3 +142,25 @@ def test_leaf_pixel_ranges():
     assert O.leaf_pixel_range((12.5, 12.5, 25.0, 25.0)) == (13, 25, 13, 25)
     assert O.leaf_ray_count((0, 0, 12.5, 12.5), 156.25, 1.0) == 156
     assert O.leaf_ray_count((0, 0, 25.0, 25.0), 156.25, 1.0) == 10
+
+
+def test_prob_sampling(golden):
+    """prob=True (image_process.py, tree.py:583-595): sharpness maps and the pixels np.random.choice picks for the
+    fixture's uniforms -- index work, exact."""
+    g = golden("prob_sampling")
+    boxes, ma, rf = g["boxes"], float(g["min_area"]), float(g["rand_frac"])
+    for i in range(int(g["n_img"])):
+        np.testing.assert_allclose(O.sharp_img(g["images"][i]), g["sharp%d" % i], atol=1e-6, rtol=0)
+        u, pix, k = g["u%d" % i], g["pix%d" % i], 0
+        for j, b in enumerate(boxes):
+            n = int(g["counts"][j])
+            got = O.emit_leaf_prob(tuple(b), ma, 1.0, rf, g["sharp%d" % i], u[k:k + n])
+            assert np.array_equal(got, pix[k:k + n])
+            n1 = int(n * (1 - rf))
+            # prob part inside the int() block, uniform part inside the ceil() bounds
+            assert (got[:n1, 0] >= int(b[0])).all() and (got[:n1, 0] < int(b[2])).all()
+            assert (got[n1:, 0] >= np.ceil(b[0])).all() and (got[n1:, 0] < np.ceil(b[2])).all()
+            k += n
+        assert k == len(pix)
+    p = O.to_prob_v2(g["sharp1"][3:11, 2:12])
+    assert abs(p.sum() - 1) < 1e-12 and p.min() > 0

@@ -53,3 +53,22 @@ def test_adam_matches_torch():
         mine.step(gs)
     for a, b in zip(mine.params, ref_w):
         np.testing.assert_allclose(a.numpy(), b.detach().numpy(), rtol=1e-6, atol=1e-8)
+
+
+def test_prob_sampling_matches_image_processor(ref):
+    """image_process.py (real cv2.blur / cvtColor, np.random.choice) against the oracle's restatement."""
+    IP = ref.image_process.ImageProcessor
+    rs = np.random.RandomState(3)
+    imgs = rs.uniform(0, 1, (2, 37, 29, 3)).astype(np.float32)
+    imgs[1, 5:20, 3:17] = 1.0                                   # a flat patch: variance 0 -> the 0.01*mean floor matters
+    proc = IP(torch.from_numpy(imgs), scale=0)
+    for i in range(2):
+        np.testing.assert_allclose(O.sharp_img(imgs[i]), proc.sharp_imgs[i], atol=1e-6, rtol=0)
+        for (a, b, c, d) in [(0, 0, 37, 29), (5, 3, 20, 17), (18, 14, 37, 29)]:
+            block = proc.sharp_imgs[i][a:c, b:d]
+            np.testing.assert_allclose(O.to_prob_v2(block), proc.to_prob_v2(block), rtol=1e-12, atol=0)
+            np.random.seed(11 + i)
+            want = proc.sample_pixels(block, 500).numpy()
+            np.random.seed(11 + i)
+            u = np.random.random_sample(500)
+            assert np.array_equal(O.sample_pixels(block, u), want)

@@ -35,10 +35,20 @@ def psnr_on(nc, nf, ps, gts):
 
 res = {}
 for seed in SEEDS:
-    for prec in ("fp32", "bf16"):
+    # "fp32p" = the fp32 run again with every initial weight perturbed by 1e-6 relative: its distance from "fp32" is the
+    # noise floor of the comparison (training trajectories are chaotic), the yardstick for the bf16 - fp32 difference
+    for prec in ("fp32", "bf16") + (("fp32p",) if os.environ.get("PC_NOISE_FLOOR", "1") == "1" else ()):
         torch.manual_seed(seed)
-        nc = model.NeRF(8, 256, 63, 27, 5, [4], True, precision=prec).to(dev)
-        nf = model.NeRF(8, 256, 63, 27, 5, [4], True, precision=prec).to(dev)
+        nc = model.NeRF(8, 256, 63, 27, 5, [4], True, precision=prec[:4]).to(dev)
+        nf = model.NeRF(8, 256, 63, 27, 5, [4], True, precision=prec[:4]).to(dev)
+        if prec == "fp32p":
+            with torch.no_grad():
+                g = torch.Generator(device=dev).manual_seed(1234 + seed)
+                for net in (nc, nf):
+                    for prm in net.parameters():
+                        prm.mul_(1 + 1e-6 * torch.randn(prm.shape, device=dev, generator=g))
+                    if hasattr(net, "weights_version"):
+                        net.weights_version += 1
         opt = FusedAdam(list(nc.parameters()) + list(nf.parameters()), [nc, nf], lr=5e-4)
         tr = Trainer(nc, nf, opt, RES, RES, K, 2.0, 6.0, 64, 128, white_bkgd=True, perturb=1.0, seed=seed)
         mgr = tree.QuadTreeManager(RES, RES, K, imgs, torch.as_tensor(poses[:, :3, :4]), mseThres=0.0, max_depth=2, max_level=5, seed=seed)
@@ -57,5 +67,10 @@ for k in ("train", "test"):
     d = [res["bf16.seed%d" % s][k] - res["fp32.seed%d" % s][k] for s in SEEDS]
     res["delta_%s_db" % k] = d
     res["mean_delta_%s_db" % k] = float(np.mean(d))
+    if "fp32p.seed%d" % SEEDS[0] in res:
+        f = [res["fp32p.seed%d" % s][k] - res["fp32.seed%d" % s][k] for s in SEEDS]
+        res["noise_floor_%s_db" % k] = f
+        res["mean_abs_noise_floor_%s_db" % k] = float(np.mean(np.abs(f)))
+        res["mean_abs_delta_%s_db" % k] = float(np.mean(np.abs(d)))
 res["config"] = dict(res=RES, views=VIEWS, iters=ITERS, n_rand=NRAND)
 print(json.dumps(res))
