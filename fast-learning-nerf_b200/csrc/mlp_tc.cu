@@ -220,18 +220,20 @@ __device__ __forceinline__ uint32_t fwd_block(const uint32_t v[32], const float 
 }
 
 // 64 columns [cq*64, cq*64+64) of one row: every epilogue warp owns one lane quarter x one column quarter of BOTH
-// tiles of its CTA.  Both 32-column TMEM loads are issued before the single wait.
+// tiles of its CTA.  One 32-column TMEM load at a time: a tcgen05.ld costs ~40 cycles (tools/ub/tmem_bw.cu), while a
+// second register block in flight costs spills at the 96-register cap (5 warps per scheduler) -- measured: -11 % dgrad.
 template <int kType, bool kMask>
 __device__ __forceinline__ uint2 fwd_epilogue_q(uint32_t tmem_rc, uint32_t cq, const float *s_bias, uint8_t *act_tile,
                                                 uint32_t r, const float *s_wa, float &alpha) {
-  uint32_t va[32], vb[32];
+  uint32_t va[32];
   const uint32_t c0 = cq * 64;
-  tmem_ld32(tmem_rc, va);
-  tmem_ld32(tmem_rc + 32, vb);
-  tmem_ld_wait2(va, vb);
   uint2 mk;
+  tmem_ld32(tmem_rc, va);
+  tmem_ld_wait(va);
   mk.x = fwd_block<kType, kMask>(va, s_bias, act_tile, r, c0, s_wa, alpha);
-  mk.y = fwd_block<kType, kMask>(vb, s_bias, act_tile, r, c0 + 32, s_wa, alpha);
+  tmem_ld32(tmem_rc + 32, va);
+  tmem_ld_wait(va);
+  mk.y = fwd_block<kType, kMask>(va, s_bias, act_tile, r, c0 + 32, s_wa, alpha);
   return mk;
 }
 
@@ -311,13 +313,14 @@ __device__ __forceinline__ void dgrad_block(const uint32_t v[32], uint32_t m, fl
 template <bool kAlpha, bool kUseMask>
 __device__ __forceinline__ void dgrad_epilogue_q(uint32_t tmem_rc, uint32_t cq, const uint2 mk, float dsig, const float *s_wa,
                                                  uint8_t *act_tile, uint32_t r) {
-  uint32_t va[32], vb[32];
+  uint32_t va[32];
   const uint32_t c0 = cq * 64;
   tmem_ld32(tmem_rc, va);
-  tmem_ld32(tmem_rc + 32, vb);
-  tmem_ld_wait2(va, vb);
+  tmem_ld_wait(va);
   dgrad_block<kAlpha, kUseMask>(va, mk.x, dsig, s_wa, act_tile, r, c0);
-  dgrad_block<kAlpha, kUseMask>(vb, mk.y, dsig, s_wa, act_tile, r, c0 + 32);
+  tmem_ld32(tmem_rc + 32, va);
+  tmem_ld_wait(va);
+  dgrad_block<kAlpha, kUseMask>(va, mk.y, dsig, s_wa, act_tile, r, c0 + 32);
 }
 
 // backward stage -1: G9 = (d_rgb * W_rgb) masked by relu(h9) -> act slabs 0,1 (64 columns per warp)
@@ -376,6 +379,7 @@ constexpr int PROF_SLOTS = 24;
 constexpr int FWD_ITEMS = 3 + 16 + 12 + 16;
 constexpr int DG_ITEMS = 34;
 
+template <bool kProf>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) mlp_fwd_tc(FwdParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const int warp = threadIdx.x >> 5;
@@ -385,7 +389,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) mlp_fwd
   const uint32_t tmem_base = pair_setup(smem, bar, cr, warp, lane, p.P);
   const uint32_t s_act = smem_u32(smem + OFF_ACT), s_w = smem_u32(smem + OFF_W);
   const int iters = (p.n_pairs + (int)gridDim.x - 1) / (int)gridDim.x;
-  const bool prof_on = p.prof != nullptr;
+  const bool prof_on = kProf && p.prof != nullptr;  // the accounting is compiled out of the production instantiation
 
   if (warp == 0) {
     // ---------------------------------------------------------------- producer (both CTAs): local halves
@@ -447,7 +451,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) mlp_fwd
       long long wa0 = 0, wa1 = 0, ww = 0, ww0 = 0, ww5 = 0;
       const long long mt0 = prof_on ? clock64() : 0;
       uint32_t q0 = 0;  // ring index of the current layer's first item
-      auto wait_full = [&](uint32_t q) { mbar_wait_cluster(bar_w_full(bar, item_stage(q)), item_phase(q)); };
+      auto wait_full = [&](uint32_t q) { mbar_wait(bar_w_full(bar, item_stage(q)), item_phase(q)); };
       auto release = [&](uint32_t q) { umma2_commit_multicast(bar_w_empty(bar, item_stage(q)), (uint16_t)3); };
       auto st = [&](uint32_t q) { return s_w + item_stage(q) * WSTAGE; };
       for (int it = 0; it < iters; ++it) {
@@ -456,7 +460,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) mlp_fwd
           for (int t = 0; t < 2; ++t) {
             if (!(it == 0 && L == 0)) {  // both CTAs' epilogue warps of tile set t: inputs written, accumulator drained
               const long long c0 = prof_on ? clock64() : 0;
-              mbar_wait_cluster(bar_act_ready(bar, t), n_act[t] & 1);
+              mbar_wait(bar_act_ready(bar, t), n_act[t] & 1);
               if (prof_on) { if (t == 0) wa0 += clock64() - c0; else wa1 += clock64() - c0; }
               ++n_act[t];
             }
@@ -583,11 +587,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) mlp_fwd
           __syncwarp();
           const long long c3 = prof ? clock64() : 0;
           if (lane == 0) {
+            // arrive FIRST: the issuer waits for it, while the stash store only has to leave before this warp rewrites
+            // its piece one layer later (bulk_wait_read1 above); both only read the tile
+            mbar_arrive_cluster(mapa_cluster(bar_act_ready(bar, t), 0));  // the leader's barrier
             if (stash_act && has_cols) {
               warp_store_slabs(stash_act + (size_t)tile * TILE_ACT_BYTES + (size_t)L * 65536, act_tile, quarter, cq, 1);
               store_pending = true;
             }
-            mbar_arrive_cluster(mapa_cluster(bar_act_ready(bar, t), 0));  // the leader's barrier
           }
           // the mask words leave AFTER the arrive: its release would otherwise wait for these global stores
           if (want_mask && L != 8 && has_cols)
@@ -623,6 +629,7 @@ struct DgradParams {
   long long *prof;
 };
 
+template <bool kProf>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) mlp_dgrad_tc(DgradParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const int warp = threadIdx.x >> 5;
@@ -632,7 +639,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) mlp_dgr
   const uint32_t tmem_base = pair_setup(smem, bar, cr, warp, lane, p.P);
   const uint32_t s_act = smem_u32(smem + OFF_ACT), s_w = smem_u32(smem + OFF_W);
   const int iters = (p.n_pairs + (int)gridDim.x - 1) / (int)gridDim.x;
-  const bool prof_on = p.prof != nullptr;
+  const bool prof_on = kProf && p.prof != nullptr;  // the accounting is compiled out of the production instantiation
 
   if (warp == 0) {
     if (lane == 0) {
@@ -673,7 +680,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) mlp_dgr
 #pragma unroll
           for (int t = 0; t < 2; ++t) {
             const long long c0 = prof_on ? clock64() : 0;
-            mbar_wait_cluster(bar_act_ready(bar, t), n_act[t] & 1);
+            mbar_wait(bar_act_ready(bar, t), n_act[t] & 1);
             if (prof_on) { if (t == 0) wa0 += clock64() - c0; else wa1 += clock64() - c0; }
             ++n_act[t];
             tc_fence_after();
@@ -681,7 +688,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) mlp_dgr
               const uint32_t wq = q0 + c;
               if (t == 0) {
                 const long long c1 = prof_on ? clock64() : 0;
-                mbar_wait_cluster(bar_w_full(bar, item_stage(wq)), item_phase(wq));
+                mbar_wait(bar_w_full(bar, item_stage(wq)), item_phase(wq));
                 if (prof_on) ww += clock64() - c1;
                 tc_fence_after();
               }
@@ -758,12 +765,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) mlp_dgr
           __syncwarp();
           const long long c3 = prof ? clock64() : 0;
           if (lane == 0) {
+            if (D < 8) mbar_arrive_cluster(mapa_cluster(bar_act_ready(bar, t), 0));  // the last stage feeds no further MMA
             if (live && has_cols) {
               const int slot = (D < 0) ? 9 : 8 - D;  // D=0 -> dF (8), D=1 -> dH7 (7) ... D=8 -> dH0 (0)
               warp_store_slabs(p.dy + (size_t)tile * TILE_ACT_BYTES + (size_t)slot * 65536, act_tile, quarter, cq, 1);
               store_pending = true;
             }
-            if (D < 8) mbar_arrive_cluster(mapa_cluster(bar_act_ready(bar, t), 0));  // the last stage feeds no further MMA
           }
           if (prof) { e_acc += c1 - c0; e_st += c2 - c1; e_body += c3 - c2; e_tail += clock64() - c3; }
         }
@@ -1303,8 +1310,10 @@ static int setup_tables(int sm_count) {
   }
   g_wgrad_grid = used;
   if (cudaMemcpyToSymbol(c_units, un, sizeof(un)) != cudaSuccess) return 1;
-  if (cudaFuncSetAttribute(mlp_fwd_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_FWD) != cudaSuccess) return 1;
-  if (cudaFuncSetAttribute(mlp_dgrad_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_FWD) != cudaSuccess) return 1;
+  if (cudaFuncSetAttribute(mlp_fwd_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_FWD) != cudaSuccess) return 1;
+  if (cudaFuncSetAttribute(mlp_fwd_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_FWD) != cudaSuccess) return 1;
+  if (cudaFuncSetAttribute(mlp_dgrad_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_FWD) != cudaSuccess) return 1;
+  if (cudaFuncSetAttribute(mlp_dgrad_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_FWD) != cudaSuccess) return 1;
   if (cudaFuncSetAttribute(mlp_wgrad_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_WG) != cudaSuccess) return 1;
   g_tables_ready = true;
   return 0;
@@ -1352,8 +1361,12 @@ int mlp_tc_forward(flnerf_ctx *ctx, const float *params, const void *packed, int
   { const char *e = getenv("FLNERF_FWD_DBG"); p.dbg = e ? atoi(e) : 0; }
   p.prof = tc::prof_buffer();
   const int grid = tc::pair_grid(p.n_pairs, ctx->sm_count);
-  FL_LAUNCH(tc::mlp_fwd_tc, grid, tc::kThreads, tc::SMEM_FWD, st, p);
-  if (p.prof) tc::prof_report("fwd", grid, p.n_pairs, st);
+  if (p.prof) {
+    FL_LAUNCH(tc::mlp_fwd_tc<true>, grid, tc::kThreads, tc::SMEM_FWD, st, p);
+    tc::prof_report("fwd", grid, p.n_pairs, st);
+  } else {
+    FL_LAUNCH(tc::mlp_fwd_tc<false>, grid, tc::kThreads, tc::SMEM_FWD, st, p);
+  }
   return 0;
 }
 
@@ -1370,8 +1383,12 @@ int mlp_tc_backward(flnerf_ctx *ctx, const float *params, const void *packed, in
   if (stages & 1) {
     const int grid = tc::pair_grid(d.n_pairs, ctx->sm_count);
     d.prof = tc::prof_buffer();
-    FL_LAUNCH(tc::mlp_dgrad_tc, grid, tc::kThreads, tc::SMEM_FWD, st, d);
-    if (d.prof) tc::prof_report("dgrad", grid, d.n_pairs, st);
+    if (d.prof) {
+      FL_LAUNCH(tc::mlp_dgrad_tc<true>, grid, tc::kThreads, tc::SMEM_FWD, st, d);
+      tc::prof_report("dgrad", grid, d.n_pairs, st);
+    } else {
+      FL_LAUNCH(tc::mlp_dgrad_tc<false>, grid, tc::kThreads, tc::SMEM_FWD, st, d);
+    }
   }
   tc::WgradParams w{};
   w.dy = (const uint8_t *)ws; w.stash_act = stash_act; w.pe_tiles = (const uint8_t *)pe_tiles; w.draw = draw;

@@ -148,31 +148,14 @@ __device__ __forceinline__ uint32_t mapa_cluster(uint32_t smem_addr, uint32_t ra
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(rank));
   return r;
 }
-// arrive on an mbarrier anywhere in the cluster.  Default semantics (release at CTA scope), as CUTLASS's
+// arrive on an mbarrier anywhere in the cluster; the (local) waiter uses the plain mbar_wait, as CUTLASS's
+// ClusterBarrier does.  Default semantics (release at CTA scope), as CUTLASS's
 // ClusterBarrier::arrive(cta_id): what the arrive publishes never leaves this SM (shared-memory operand tiles made
 // visible to the async proxy by fence.proxy.async, TMEM reads ordered by tcgen05.fence::before_thread_sync) -- a
 // cluster-scope release would also wait for every outstanding GLOBAL store of the thread (masks, atomics): measured
 // at 1500..5000 cycles per arrive.
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
   asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
-}
-__device__ __forceinline__ uint32_t mbar_try_wait_cluster(uint32_t bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2, %3;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(ok)
-      : "r"(bar), "r"(parity), "r"(20000u)
-      : "memory");
-  return ok;
-}
-// wait on a LOCAL mbarrier whose arrivals may come from the other CTA of the cluster (acquire at cluster scope)
-__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
-  uint32_t spins = 0;
-  while (!mbar_try_wait_cluster(bar, parity)) {
-    if (++spins > (1u << 17)) mbar_timeout(bar, parity);
-  }
 }
 // 32 lanes x 32 consecutive fp32 columns -> 32 registers per thread (thread i <-> TMEM lane base+i)
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t v[32]) {
