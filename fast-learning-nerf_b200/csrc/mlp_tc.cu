@@ -723,12 +723,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) mlp_dgr
       const int pair_raw = (int)blockIdx.x + it * (int)gridDim.x;
       const bool live = pair_raw < p.n_pairs;
       const int pair = live ? pair_raw : p.n_pairs - 1;
-      float4 dr[2];
-#pragma unroll
-      for (int t = 0; t < 2; ++t) {
-        const int64_t row = ((int64_t)pair * 2 + t) * 128 + r;
-        dr[t] = row < p.n ? reinterpret_cast<const float4 *>(p.draw)[row] : make_float4(0.f, 0.f, 0.f, 0.f);
-      }
       // stage -1: G9 from d_rgb; stages 0..8 = tensor layers.  ReLU mask of the activation the gradient flows into:
       // D=-1 -> h9 (slot 8), D=0 -> none (feature is linear), D=1 -> H7, D=2 -> H6, ..., D=8 -> H0
       for (int D = -1; D < 9; ++D) {
@@ -738,7 +732,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) mlp_dgr
           uint8_t *act_tile = smem + OFF_ACT + t * ACT_BYTES;
           const uint32_t tmem_rc = tmem_base + ((quarter * 32) << 16) + t * 256 + cq * 64;
           const bool has_cols = D >= 0 || cq < 2;  // G9 has 128 columns: column quarters 0,1 only
-          // the mask words come from HBM: fetch them BEFORE waiting for the accumulator
+          // the mask words (and, for the two stages that use it, the row's d_raw) come from HBM / L2: fetch them BEFORE
+          // waiting for the accumulator; d_raw is not kept in registers across the stage loop
+          float4 dr = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (D <= 1 && D != 0) {
+            const int64_t row = tile * 128 + r;
+            if (row < p.n) dr = __ldg(reinterpret_cast<const float4 *>(p.draw) + row);
+          }
           uint2 mk = make_uint2(0u, 0u);
           if (D != 0 && has_cols)
             mk = __ldg(reinterpret_cast<const uint2 *>(p.stash_mask + mask_word_offset(tile, D < 0 ? 8 : 8 - D, cq, r)));
@@ -752,11 +752,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) mlp_dgr
           __syncwarp();
           const long long c2 = prof ? clock64() : 0;
           if (D < 0) {
-            if (has_cols) dgrad_g9(t ? dr[1] : dr[0], mk, cq, s_head, act_tile, r);
+            if (has_cols) dgrad_g9(dr, mk, cq, s_head, act_tile, r);
           } else if (D == 0) {
             dgrad_epilogue_q<false, false>(tmem_rc, cq, mk, 0.f, s_wa, act_tile, r);
           } else if (D == 1) {  // dH7 also receives d_sigma * w_alpha (alpha_linear reads H7)
-            dgrad_epilogue_q<true, true>(tmem_rc, cq, mk, t ? dr[1].w : dr[0].w, s_wa, act_tile, r);
+            dgrad_epilogue_q<true, true>(tmem_rc, cq, mk, dr.w, s_wa, act_tile, r);
           } else {
             dgrad_epilogue_q<false, true>(tmem_rc, cq, mk, 0.f, s_wa, act_tile, r);
           }
