@@ -46,7 +46,8 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    """nvidia-smi clocks / throttle reasons sampled every 20 ms from before the warm-up until after the e2e loop; every
+    row is stamped on arrival and ``window(t0, t1)`` reports the rows that fell inside the timed region."""
 
     def __init__(self, index):
         self.index, self.rows, self.proc = index, [], None
@@ -57,26 +58,33 @@ class ClockSampler:
              "clocks_event_reasons.sw_power_cap")
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE, text=True)
+                                          "--format=csv,noheader,nounits", "-lms", "20"], stdout=subprocess.PIPE, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
             self.proc = None
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+            self.rows.append((time.perf_counter(), [x.strip() for x in line.split(",")]))
 
     def stop(self):
+        if self.proc is not None:
+            time.sleep(0.05)
+            self.proc.terminate()
+
+    def window(self, t0, t1):
         if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        sm = sorted(float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit())
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"], "samples": 0}
+        rows = [r for (t, r) in self.rows if t0 <= t <= t1 and len(r) >= 7]
+        note = "timed region"
+        if not rows:   # a region shorter than the sampling period: fall back to every row taken under load
+            rows, note = [r for (_, r) in self.rows if len(r) >= 7], "warm-up + timed + e2e (no sample fell inside the timed region)"
+        sm = sorted(float(r[0]) for r in rows if r[0].replace(".", "").isdigit())
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(len(r) >= 7 and r[3 + i].lower().startswith("active") for r in self.rows)]
-        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        reasons = [n for i, n in enumerate(names) if any(r[3 + i].lower().startswith("active") for r in rows)]
+        mx = [float(r[1]) for r in rows if r[1].replace(".", "").isdigit()]
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx[0] if mx else None, "reasons": reasons,
-                "samples": len(sm)}
+                "samples": len(sm), "window": note}
 
 
 # ------------------------------------------------------------------------------------------------- reference arm
@@ -176,21 +184,22 @@ def run_ours(args):
 
     # ---------------- value: device-resident inputs
     first = 0
+    clocks = ClockSampler(local)
+    clocks.start()
     for _ in range(args.warmup):
         tr.step_from_tree(mgr, first, gb); first += gb
     barrier()
     lib.launch_count(reset=True)
-    clocks = ClockSampler(local)
-    clocks.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    w0 = time.perf_counter()
     e0.record()
     for _ in range(args.steps):
         loss = tr.step_from_tree(mgr, first, gb); first += gb
     e1.record()
     barrier()
+    w1 = time.perf_counter()
     ms = e0.elapsed_time(e1)
     launches = lib.launch_count()
-    clk = clocks.stop()
     t = torch.tensor([ms], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -234,6 +243,8 @@ def run_ours(args):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_value = gb * args.steps / (float(t.item()) * 1e-3)
+    clocks.stop()
+    clk = clocks.window(w0, w1)
 
     if world > 1:
         dist.barrier()
