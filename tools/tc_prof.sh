@@ -1,5 +1,5 @@
 #!/bin/bash
-# On the GPU box: role-level cycle accounting of the gen-2 forward / dgrad kernels (FLNERF_TC_PROF) next to their
+# On the GPU box: role-level cycle accounting of the forward / dgrad kernels (FLNERF_TC_PROF) next to their
 # CUDA-event timings, with and without the activation stores / mask generation.
 mkdir -p gpurun_out
 {
