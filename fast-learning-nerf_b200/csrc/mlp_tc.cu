@@ -33,15 +33,40 @@ constexpr int kEpiWarps = 16;
 constexpr int kThreads = (2 + kEpiWarps) * 32;  // 576
 constexpr int kEpiWarp0 = 2;
 constexpr uint32_t ACT_BYTES = 65536, SLAB_BYTES = 16384, PE_BYTES = 16384, WSTAGE = 16384;
-constexpr int NST = 5;  // 5 x 16 KB ring: half weight chunks AND the PE slabs travel through it
 // biases of pts_linears.0..7 + feature_linear, then fp32 copies of the small heads: W_rgb[3][128], b_rgb[3],
 // b_alpha[1], w_alpha[256]
 constexpr uint32_t BIAS_FLOATS = 9 * 256, HEAD_FLOATS = 384 + 4 + 256;
-constexpr uint32_t OFF_ACT = 0, OFF_W = 2 * ACT_BYTES, OFF_VEC = OFF_W + NST * WSTAGE;
-constexpr uint32_t OFF_HEAD = OFF_VEC + BIAS_FLOATS * 4, OFF_BAR = OFF_HEAD + HEAD_FLOATS * 4;
-constexpr uint32_t OFF_ALPHA = OFF_BAR + 256;  // [2 tiles][4 column quarters][128 rows] fp32 partial alpha sums
-constexpr uint32_t SMEM_FWD = OFF_ALPHA + 2 * 4 * 128 * 4;
-static_assert(OFF_BAR % 16 == 0 && SMEM_FWD <= 232448, "shared memory budget");
+constexpr uint32_t OFF_ACT = 0, OFF_W = 2 * ACT_BYTES;
+// shared-memory layout after the two activation tiles: ring of kNst x 16 KB stages (half weight chunks AND the PE slabs
+// travel through it), [bias table], heads, barrier block, [alpha partial sums].  The forward kernel trades one ring
+// stage for its resident bias table (5 stages); dgrad needs neither biases nor alpha sums and runs 6 stages.
+template <int kNst, bool kFwd>
+struct Lay {
+  static constexpr int NST = kNst;
+  static constexpr uint32_t OFF_VEC = OFF_W + kNst * WSTAGE;
+  static constexpr uint32_t OFF_HEAD = OFF_VEC + (kFwd ? BIAS_FLOATS * 4 : 0);
+  static constexpr uint32_t OFF_BAR = OFF_HEAD + HEAD_FLOATS * 4;
+  static constexpr uint32_t OFF_ALPHA = OFF_BAR + 256;  // [2 tiles][4 column quarters][128 rows] fp32 partial alpha sums
+  static constexpr uint32_t SMEM = OFF_ALPHA + (kFwd ? 2 * 4 * 128 * 4 : 0);
+  static_assert(OFF_BAR % 16 == 0 && SMEM <= 232448, "shared memory budget");
+  static_assert(8u * (2 * kNst + 4) <= 128u, "barrier block: the TMEM slot sits at +128");
+  // mbarrier addresses (bytes from the barrier block): no arrays, so nothing lands in local memory
+  __device__ static __forceinline__ uint32_t w_full(uint32_t base, uint32_t i) { return base + 8u * i; }
+  __device__ static __forceinline__ uint32_t w_empty(uint32_t base, uint32_t i) { return base + 8u * (kNst + i); }
+  __device__ static __forceinline__ uint32_t acc_full(uint32_t base, uint32_t t) { return base + 8u * (2 * kNst + t); }
+  __device__ static __forceinline__ uint32_t act_ready(uint32_t base, uint32_t t) { return base + 8u * (2 * kNst + 2 + t); }
+  // the issuer addresses ring items by their running index (a layer's items are used twice, by tile set A then B)
+  __device__ static __forceinline__ uint32_t item_stage(uint32_t q) { return q % kNst; }
+  __device__ static __forceinline__ uint32_t item_phase(uint32_t q) { return (q / kNst) & 1u; }
+  struct Ring {
+    uint32_t stage = 0, phase = 0;
+    __device__ __forceinline__ void next() {
+      if (++stage == (uint32_t)kNst) { stage = 0; phase ^= 1; }
+    }
+  };
+};
+using LayF = Lay<5, true>;
+using LayD = Lay<6, false>;
 
 // packed weight image of one net
 constexpr int FWD_CHUNKS = 38, DG_CHUNKS = 34;
@@ -103,23 +128,6 @@ __global__ void __launch_bounds__(128) viewbias_kernel(int64_t B, const float *_
   }
 }
 
-// mbarrier addresses (bytes from the barrier block): no arrays, so nothing lands in local memory
-__device__ __forceinline__ uint32_t bar_w_full(uint32_t base, uint32_t i) { return base + 8u * i; }
-__device__ __forceinline__ uint32_t bar_w_empty(uint32_t base, uint32_t i) { return base + 8u * (NST + i); }
-__device__ __forceinline__ uint32_t bar_acc_full(uint32_t base, uint32_t t) { return base + 8u * (2 * NST + t); }
-__device__ __forceinline__ uint32_t bar_act_ready(uint32_t base, uint32_t t) { return base + 8u * (2 * NST + 2 + t); }
-static_assert(8u * (2 * NST + 4) <= 128u, "barrier block: the TMEM slot sits at +128");
-
-struct Ring {
-  uint32_t stage = 0, phase = 0;
-  __device__ __forceinline__ void next() {
-    if (++stage == NST) { stage = 0; phase ^= 1; }
-  }
-};
-// the issuer addresses ring items by their running index (a layer's items are used twice, by tile set A then B)
-__device__ __forceinline__ uint32_t item_stage(uint32_t q) { return q % NST; }
-__device__ __forceinline__ uint32_t item_phase(uint32_t q) { return (q / NST) & 1u; }
-
 // pair MMA over one 64-wide K chunk: A = this tile set's K-major SW128 slab [128 rows x 64] (same offset in both
 // CTAs), B = this CTA's half [N/2 rows x 64] of the weight chunk; 4 k-steps of 16
 __device__ __forceinline__ void issue_chunk(uint32_t tmem_d, uint32_t a_smem, uint32_t b_smem, uint32_t idesc, bool first) {
@@ -129,26 +137,29 @@ __device__ __forceinline__ void issue_chunk(uint32_t tmem_d, uint32_t a_smem, ui
 }
 
 // barrier / TMEM / constant-vector set-up shared by the two kernels; returns the TMEM base
+template <class L>
 __device__ __forceinline__ uint32_t pair_setup(uint8_t *smem, uint32_t bar, uint32_t cr, int warp, uint32_t lane,
                                                const float *P) {
-  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + OFF_BAR + 128);
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + L::OFF_BAR + 128);
   if ((smem_u32(smem) & 1023u) != 0) __trap();
   // biases of the 9 tensor layers that have one (pts 0..7, feature) and the small heads: resident for the whole
   // launch, read as warp-uniform LDS (a global __ldg here costs an exposed L1/L2 latency per 4 columns)
-  float *bias = reinterpret_cast<float *>(smem + OFF_VEC);
-  for (int i = threadIdx.x; i < (int)BIAS_FLOATS; i += blockDim.x) {
-    const int l = i >> 8, c = i & 255;
-    bias[i] = P[(l < 8 ? b_pts(l) : B_FEAT) + c];
+  if (L::OFF_HEAD != L::OFF_VEC) {
+    float *bias = reinterpret_cast<float *>(smem + L::OFF_VEC);
+    for (int i = threadIdx.x; i < (int)BIAS_FLOATS; i += blockDim.x) {
+      const int l = i >> 8, c = i & 255;
+      bias[i] = P[(l < 8 ? b_pts(l) : B_FEAT) + c];
+    }
   }
-  float *head = reinterpret_cast<float *>(smem + OFF_HEAD);
+  float *head = reinterpret_cast<float *>(smem + L::OFF_HEAD);
   for (int i = threadIdx.x; i < (int)HEAD_FLOATS; i += blockDim.x)
     head[i] = i < 387 ? P[W_RGB + i] : (i == 387 ? P[B_ALPHA] : P[W_ALPHA + (i - 388)]);
   if (warp == 1 && lane == 0) {
-    for (int i = 0; i < NST; ++i) {
-      mbar_init(bar_w_full(bar, i), cr == 0 ? 2 : 1);  // leader: own producer + the follower's relay
-      mbar_init(bar_w_empty(bar, i), 1);
+    for (int i = 0; i < L::NST; ++i) {
+      mbar_init(L::w_full(bar, i), cr == 0 ? 2 : 1);  // leader: own producer + the follower's relay
+      mbar_init(L::w_empty(bar, i), 1);
     }
-    for (int t = 0; t < 2; ++t) { mbar_init(bar_acc_full(bar, t), 1); mbar_init(bar_act_ready(bar, t), 2 * kEpiWarps); }
+    for (int t = 0; t < 2; ++t) { mbar_init(L::acc_full(bar, t), 1); mbar_init(L::act_ready(bar, t), 2 * kEpiWarps); }
     fence_mbar_init();
   }
   __syncthreads();
@@ -384,9 +395,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) mlp_fwd
   extern __shared__ __align__(1024) uint8_t smem[];
   const int warp = threadIdx.x >> 5;
   const uint32_t lane = lane_id();
-  const uint32_t bar = smem_u32(smem + OFF_BAR);
+  const uint32_t bar = smem_u32(smem + LayF::OFF_BAR);
   const uint32_t cr = cluster_ctarank();
-  const uint32_t tmem_base = pair_setup(smem, bar, cr, warp, lane, p.P);
+  const uint32_t tmem_base = pair_setup<LayF>(smem, bar, cr, warp, lane, p.P);
   const uint32_t s_act = smem_u32(smem + OFF_ACT), s_w = smem_u32(smem + OFF_W);
   const int iters = (p.n_pairs + (int)gridDim.x - 1) / (int)gridDim.x;
   const bool prof_on = kProf && p.prof != nullptr;  // the accounting is compiled out of the production instantiation
@@ -394,15 +405,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) mlp_fwd
   if (warp == 0) {
     // ---------------------------------------------------------------- producer (both CTAs): local halves
     if (lane == 0) {
-      Ring ring;
+      LayF::Ring ring;
       long long pw = 0;
       const long long pt0 = prof_on ? clock64() : 0;
       auto push = [&](const uint8_t *src, uint32_t bytes) {
         const long long c0 = prof_on ? clock64() : 0;
-        mbar_wait(bar_w_empty(bar, ring.stage), ring.phase ^ 1);
+        mbar_wait(LayF::w_empty(bar, ring.stage), ring.phase ^ 1);
         if (prof_on) pw += clock64() - c0;
-        mbar_arrive_expect_tx(bar_w_full(bar, ring.stage), bytes);
-        bulk_g2s(s_w + ring.stage * WSTAGE, src, bytes, bar_w_full(bar, ring.stage));
+        mbar_arrive_expect_tx(LayF::w_full(bar, ring.stage), bytes);
+        bulk_g2s(s_w + ring.stage * WSTAGE, src, bytes, LayF::w_full(bar, ring.stage));
         ring.next();
       };
       auto push_w = [&](int cc) {  // this CTA's half (N/2 rows) of forward chunk cc
@@ -436,11 +447,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) mlp_fwd
   } else if (warp == 1) {
     if (lane == 0 && cr != 0) {
       // -------------------------------------------------------------- relay (follower): local full -> leader's full
-      Ring ring;
-      const uint32_t remote_full = mapa_cluster(bar_w_full(bar, 0), 0);
+      LayF::Ring ring;
+      const uint32_t remote_full = mapa_cluster(LayF::w_full(bar, 0), 0);
       const int total = iters * FWD_ITEMS;
       for (int q = 0; q < total; ++q) {
-        mbar_wait(bar_w_full(bar, ring.stage), ring.phase);
+        mbar_wait(LayF::w_full(bar, ring.stage), ring.phase);
         mbar_arrive_cluster(remote_full + 8u * ring.stage);
         ring.next();
       }
@@ -451,16 +462,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) mlp_fwd
       long long wa0 = 0, wa1 = 0, ww = 0, ww0 = 0, ww5 = 0;
       const long long mt0 = prof_on ? clock64() : 0;
       uint32_t q0 = 0;  // ring index of the current layer's first item
-      auto wait_full = [&](uint32_t q) { mbar_wait(bar_w_full(bar, item_stage(q)), item_phase(q)); };
-      auto release = [&](uint32_t q) { umma2_commit_multicast(bar_w_empty(bar, item_stage(q)), (uint16_t)3); };
-      auto st = [&](uint32_t q) { return s_w + item_stage(q) * WSTAGE; };
+      auto wait_full = [&](uint32_t q) { mbar_wait(LayF::w_full(bar, LayF::item_stage(q)), LayF::item_phase(q)); };
+      auto release = [&](uint32_t q) { umma2_commit_multicast(LayF::w_empty(bar, LayF::item_stage(q)), (uint16_t)3); };
+      auto st = [&](uint32_t q) { return s_w + LayF::item_stage(q) * WSTAGE; };
       for (int it = 0; it < iters; ++it) {
         for (int L = 0; L < 10; ++L) {
 #pragma unroll
           for (int t = 0; t < 2; ++t) {
             if (!(it == 0 && L == 0)) {  // both CTAs' epilogue warps of tile set t: inputs written, accumulator drained
               const long long c0 = prof_on ? clock64() : 0;
-              mbar_wait(bar_act_ready(bar, t), n_act[t] & 1);
+              mbar_wait(LayF::act_ready(bar, t), n_act[t] & 1);
               if (prof_on) { if (t == 0) wa0 += clock64() - c0; else wa1 += clock64() - c0; }
               ++n_act[t];
             }
@@ -510,7 +521,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) mlp_fwd
               }
             }
             if (prof_on) { if (L == 0) ww0 += wsum; else if (L == 5) ww5 += wsum; else ww += wsum; }
-            umma2_commit_multicast(bar_acc_full(bar, t), (uint16_t)3);
+            umma2_commit_multicast(LayF::acc_full(bar, t), (uint16_t)3);
           }
           q0 += (L == 0) ? 3u : (L == 5 ? 12u : 4u);
         }
@@ -529,10 +540,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) mlp_fwd
     const uint32_t cq = (uint32_t)e >> 2;    // column quarter: columns [64 cq, 64 cq + 64) = slab cq
     const uint32_t quarter = warp & 3;       // TMEM lane quarter this warp may access
     const uint32_t r = quarter * 32 + lane;  // row inside the tile == TMEM lane
-    const float *s_bias = reinterpret_cast<const float *>(smem + OFF_VEC);
-    const float *s_head = reinterpret_cast<const float *>(smem + OFF_HEAD);
+    const float *s_bias = reinterpret_cast<const float *>(smem + LayF::OFF_VEC);
+    const float *s_head = reinterpret_cast<const float *>(smem + LayF::OFF_HEAD);
     const float *s_wa = s_head + 388;
-    float *s_alpha = reinterpret_cast<float *>(smem + OFF_ALPHA);  // [tile][cq][row] partial alpha sums (layer 7)
+    float *s_alpha = reinterpret_cast<float *>(smem + LayF::OFF_ALPHA);  // [tile][cq][row] partial alpha sums (layer 7)
     uint32_t n_layer = 0;  // both tiles' accumulator barriers flip once per layer, in order
     bool store_pending = false;
     const bool prof = prof_on && e == 0 && lane == 0;
@@ -553,7 +564,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) mlp_fwd
           const uint32_t tmem_rc = tmem_base + ((quarter * 32) << 16) + t * 256 + cq * 64;
           const bool has_cols = L < 9 || cq < 2;   // the views layer has 128 outputs: column quarters 0,1 only
           const long long c0 = prof ? clock64() : 0;
-          mbar_wait(bar_acc_full(bar, t), n_layer & 1);
+          mbar_wait(LayF::acc_full(bar, t), n_layer & 1);
           tc_fence_after();
           const long long c1 = prof ? clock64() : 0;
           if (p.stash_act) {  // my previous store of THIS tile's piece (two groups ago) must have finished reading it
@@ -589,7 +600,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) mlp_fwd
           if (lane == 0) {
             // arrive FIRST: the issuer waits for it, while the stash store only has to leave before this warp rewrites
             // its piece one layer later (bulk_wait_read1 above); both only read the tile
-            mbar_arrive_cluster(mapa_cluster(bar_act_ready(bar, t), 0));  // the leader's barrier
+            mbar_arrive_cluster(mapa_cluster(LayF::act_ready(bar, t), 0));  // the leader's barrier
             if (stash_act && has_cols) {
               warp_store_slabs(stash_act + (size_t)tile * TILE_ACT_BYTES + (size_t)L * 65536, act_tile, quarter, cq, 1);
               store_pending = true;
@@ -634,37 +645,37 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) mlp_dgr
   extern __shared__ __align__(1024) uint8_t smem[];
   const int warp = threadIdx.x >> 5;
   const uint32_t lane = lane_id();
-  const uint32_t bar = smem_u32(smem + OFF_BAR);
+  const uint32_t bar = smem_u32(smem + LayD::OFF_BAR);
   const uint32_t cr = cluster_ctarank();
-  const uint32_t tmem_base = pair_setup(smem, bar, cr, warp, lane, p.P);
+  const uint32_t tmem_base = pair_setup<LayD>(smem, bar, cr, warp, lane, p.P);
   const uint32_t s_act = smem_u32(smem + OFF_ACT), s_w = smem_u32(smem + OFF_W);
   const int iters = (p.n_pairs + (int)gridDim.x - 1) / (int)gridDim.x;
   const bool prof_on = kProf && p.prof != nullptr;  // the accounting is compiled out of the production instantiation
 
   if (warp == 0) {
     if (lane == 0) {
-      Ring ring;
+      LayD::Ring ring;
       long long pw = 0;
       const long long pt0 = prof_on ? clock64() : 0;
       for (int it = 0; it < iters; ++it)
         for (int ci = 0; ci < DG_CHUNKS; ++ci) {
           const long long c0 = prof_on ? clock64() : 0;
-          mbar_wait(bar_w_empty(bar, ring.stage), ring.phase ^ 1);
+          mbar_wait(LayD::w_empty(bar, ring.stage), ring.phase ^ 1);
           if (prof_on) pw += clock64() - c0;
-          mbar_arrive_expect_tx(bar_w_full(bar, ring.stage), 16384u);
+          mbar_arrive_expect_tx(LayD::w_full(bar, ring.stage), 16384u);
           bulk_g2s(s_w + ring.stage * WSTAGE, p.packed_dg + (size_t)ci * 32768 + (size_t)cr * 16384, 16384u,
-                   bar_w_full(bar, ring.stage));
+                   LayD::w_full(bar, ring.stage));
           ring.next();
         }
       if (prof_on) { p.prof[blockIdx.x * PROF_SLOTS + 4] = pw; p.prof[blockIdx.x * PROF_SLOTS + 5] = clock64() - pt0; }
     }
   } else if (warp == 1) {
     if (lane == 0 && cr != 0) {
-      Ring ring;
-      const uint32_t remote_full = mapa_cluster(bar_w_full(bar, 0), 0);
+      LayD::Ring ring;
+      const uint32_t remote_full = mapa_cluster(LayD::w_full(bar, 0), 0);
       const int total = iters * DG_ITEMS;
       for (int q = 0; q < total; ++q) {
-        mbar_wait(bar_w_full(bar, ring.stage), ring.phase);
+        mbar_wait(LayD::w_full(bar, ring.stage), ring.phase);
         mbar_arrive_cluster(remote_full + 8u * ring.stage);
         ring.next();
       }
@@ -680,7 +691,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) mlp_dgr
 #pragma unroll
           for (int t = 0; t < 2; ++t) {
             const long long c0 = prof_on ? clock64() : 0;
-            mbar_wait(bar_act_ready(bar, t), n_act[t] & 1);
+            mbar_wait(LayD::act_ready(bar, t), n_act[t] & 1);
             if (prof_on) { if (t == 0) wa0 += clock64() - c0; else wa1 += clock64() - c0; }
             ++n_act[t];
             tc_fence_after();
@@ -688,15 +699,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) mlp_dgr
               const uint32_t wq = q0 + c;
               if (t == 0) {
                 const long long c1 = prof_on ? clock64() : 0;
-                mbar_wait(bar_w_full(bar, item_stage(wq)), item_phase(wq));
+                mbar_wait(LayD::w_full(bar, LayD::item_stage(wq)), LayD::item_phase(wq));
                 if (prof_on) ww += clock64() - c1;
                 tc_fence_after();
               }
-              issue_chunk(tmem_base + t * 256, s_act + t * ACT_BYTES + c * SLAB_BYTES, s_w + item_stage(wq) * WSTAGE, idesc,
+              issue_chunk(tmem_base + t * 256, s_act + t * ACT_BYTES + c * SLAB_BYTES, s_w + LayD::item_stage(wq) * WSTAGE, idesc,
                           c == 0);
-              if (t == 1) umma2_commit_multicast(bar_w_empty(bar, item_stage(wq)), (uint16_t)3);
+              if (t == 1) umma2_commit_multicast(LayD::w_empty(bar, LayD::item_stage(wq)), (uint16_t)3);
             }
-            umma2_commit_multicast(bar_acc_full(bar, t), (uint16_t)3);
+            umma2_commit_multicast(LayD::acc_full(bar, t), (uint16_t)3);
           }
           q0 += nch;
         }
@@ -712,7 +723,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) mlp_dgr
     const uint32_t cq = (uint32_t)e >> 2;
     const uint32_t quarter = warp & 3;
     const uint32_t r = quarter * 32 + lane;
-    const float *s_head = reinterpret_cast<const float *>(smem + OFF_HEAD);
+    const float *s_head = reinterpret_cast<const float *>(smem + LayD::OFF_HEAD);
     const float *s_wa = s_head + 388;
     uint32_t n_layer = 0;
     bool store_pending = false;
@@ -744,7 +755,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) mlp_dgr
             mk = __ldg(reinterpret_cast<const uint2 *>(p.stash_mask + mask_word_offset(tile, D < 0 ? 8 : 8 - D, cq, r)));
           const long long c0 = prof ? clock64() : 0;
           if (D >= 0) {
-            mbar_wait(bar_acc_full(bar, t), n_layer & 1);
+            mbar_wait(LayD::acc_full(bar, t), n_layer & 1);
             tc_fence_after();
           }
           const long long c1 = prof ? clock64() : 0;
@@ -765,7 +776,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) mlp_dgr
           __syncwarp();
           const long long c3 = prof ? clock64() : 0;
           if (lane == 0) {
-            if (D < 8) mbar_arrive_cluster(mapa_cluster(bar_act_ready(bar, t), 0));  // the last stage feeds no further MMA
+            if (D < 8) mbar_arrive_cluster(mapa_cluster(LayD::act_ready(bar, t), 0));  // the last stage feeds no further MMA
             if (live && has_cols) {
               const int slot = (D < 0) ? 9 : 8 - D;  // D=0 -> dF (8), D=1 -> dH7 (7) ... D=8 -> dH0 (0)
               warp_store_slabs(p.dy + (size_t)tile * TILE_ACT_BYTES + (size_t)slot * 65536, act_tile, quarter, cq, 1);
@@ -1310,10 +1321,10 @@ static int setup_tables(int sm_count) {
   }
   g_wgrad_grid = used;
   if (cudaMemcpyToSymbol(c_units, un, sizeof(un)) != cudaSuccess) return 1;
-  if (cudaFuncSetAttribute(mlp_fwd_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_FWD) != cudaSuccess) return 1;
-  if (cudaFuncSetAttribute(mlp_fwd_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_FWD) != cudaSuccess) return 1;
-  if (cudaFuncSetAttribute(mlp_dgrad_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_FWD) != cudaSuccess) return 1;
-  if (cudaFuncSetAttribute(mlp_dgrad_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_FWD) != cudaSuccess) return 1;
+  if (cudaFuncSetAttribute(mlp_fwd_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, LayF::SMEM) != cudaSuccess) return 1;
+  if (cudaFuncSetAttribute(mlp_fwd_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, LayF::SMEM) != cudaSuccess) return 1;
+  if (cudaFuncSetAttribute(mlp_dgrad_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, LayD::SMEM) != cudaSuccess) return 1;
+  if (cudaFuncSetAttribute(mlp_dgrad_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, LayD::SMEM) != cudaSuccess) return 1;
   if (cudaFuncSetAttribute(mlp_wgrad_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_WG) != cudaSuccess) return 1;
   g_tables_ready = true;
   return 0;
@@ -1362,10 +1373,10 @@ int mlp_tc_forward(flnerf_ctx *ctx, const float *params, const void *packed, int
   p.prof = tc::prof_buffer();
   const int grid = tc::pair_grid(p.n_pairs, ctx->sm_count);
   if (p.prof) {
-    FL_LAUNCH(tc::mlp_fwd_tc<true>, grid, tc::kThreads, tc::SMEM_FWD, st, p);
+    FL_LAUNCH(tc::mlp_fwd_tc<true>, grid, tc::kThreads, tc::LayF::SMEM, st, p);
     tc::prof_report("fwd", grid, p.n_pairs, st);
   } else {
-    FL_LAUNCH(tc::mlp_fwd_tc<false>, grid, tc::kThreads, tc::SMEM_FWD, st, p);
+    FL_LAUNCH(tc::mlp_fwd_tc<false>, grid, tc::kThreads, tc::LayF::SMEM, st, p);
   }
   return 0;
 }
@@ -1384,10 +1395,10 @@ int mlp_tc_backward(flnerf_ctx *ctx, const float *params, const void *packed, in
     const int grid = tc::pair_grid(d.n_pairs, ctx->sm_count);
     d.prof = tc::prof_buffer();
     if (d.prof) {
-      FL_LAUNCH(tc::mlp_dgrad_tc<true>, grid, tc::kThreads, tc::SMEM_FWD, st, d);
+      FL_LAUNCH(tc::mlp_dgrad_tc<true>, grid, tc::kThreads, tc::LayD::SMEM, st, d);
       tc::prof_report("dgrad", grid, d.n_pairs, st);
     } else {
-      FL_LAUNCH(tc::mlp_dgrad_tc<false>, grid, tc::kThreads, tc::SMEM_FWD, st, d);
+      FL_LAUNCH(tc::mlp_dgrad_tc<false>, grid, tc::kThreads, tc::LayD::SMEM, st, d);
     }
   }
   tc::WgradParams w{};
