@@ -96,9 +96,6 @@ class QuadTreeManager:
     """GPU-resident replacement of tree.py:159-566 (constructor and the two methods run_nerf.py calls)."""
 
     def __init__(self, H, W, K, images, poses, mseThres=0.1, max_depth=5, max_level=None, device=None, seed=0):
-        if mseThres > 0:
-            raise FlnerfError("flnerf QuadTreeManager builds the uniform initial tree (mseThres<=0, what run_nerf.py "
-                              "passes, run_nerf.py:337); variance-driven initial splits are not implemented")
         self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
         self.n_images, self.h, self.w = int(poses.shape[0]), int(H), int(W)
         self.K = np.asarray(K, dtype=np.float64)
@@ -115,7 +112,14 @@ class QuadTreeManager:
         self._count = [torch.zeros(n, dtype=torch.int32, device=self.device) for _ in range(2)]
         self._min_area = torch.zeros(n, dtype=torch.float64, device=self.device)
         self._cur = 0
-        ops.qt_init(n, self.cap, self.h, self.w, int(max_depth), self._boxes[0], self._count[0], self._min_area)
+        self._mirror = None
+        if mseThres > 0:
+            # variance-driven initial trees (tree.py:84-100,655-676): a one-off host recursion per image, uploaded into
+            # the SoA.  Leaves coarser than minArea stay frozen at 10 rays per epoch (tree.py:578-581, 642).
+            imgs = images.detach().cpu().numpy() if torch.is_tensor(images) else np.asarray(images)
+            self.quadTrees = [QuadTree(imgs[i], float(mseThres), int(max_depth)) for i in range(n)]
+        else:
+            ops.qt_init(n, self.cap, self.h, self.w, int(max_depth), self._boxes[0], self._count[0], self._min_area)
         self.cur_level = max_depth
         self.leaf_max = torch.full((n * self.cap,), -1.0, dtype=torch.float32, device=self.device)
         self._ray_offset = torch.zeros(n * self.cap + 1, dtype=torch.int64, device=self.device)
@@ -123,7 +127,6 @@ class QuadTreeManager:
         self.n_rays = 0
         self._epoch = 0
         self.seed = int(seed)
-        self._mirror = None
 
     # ------------------------------------------------------------------ GPU state
     @property

@@ -100,9 +100,31 @@ def prob_sampling_golden(ref):
     np.savez_compressed(os.path.join(OUT, "prob_sampling.npz"), **g)
 
 
+def variance_tree_golden(ref):
+    """mseThres > 0 initial trees (tree.py:28-56,84-100,655-676): leaf boxes of the reference's QuadTree on images with
+    flat and busy regions, at several thresholds."""
+    T = ref.tree
+    rs = np.random.RandomState(33)
+    Hq = Wq = 48
+    img = np.full((Hq, Wq, 3), 0.5, np.float32)
+    img[4:20, 6:30] = rs.uniform(0, 1, (16, 24, 3)).astype(np.float32)          # a busy patch in a flat image
+    img[30:44, 30:46] += rs.normal(0, 0.02, (14, 16, 3)).astype(np.float32)     # a faint texture
+    g = {"image": img, "max_depth": 5, "thres": np.array([1e-4, 3e-3, 5e-2])}
+    for k, th in enumerate(g["thres"]):
+        t = T.QuadTree(img, float(th), 5)
+        g["boxes%d" % k] = np.array([(n.x0, n.y0, n.x1, n.y1) for n in T.get_children(t.root)], np.float64)
+        g["minarea%d" % k] = t.minArea
+    assert len(g["boxes0"]) > len(g["boxes1"]) > len(g["boxes2"]) >= 1
+    np.savez_compressed(os.path.join(OUT, "variance_tree.npz"), **g)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     ref = ref_shim.load()
+    if os.environ.get("GOLDEN_ONLY") == "vartree":
+        variance_tree_golden(ref)
+        print("wrote variance_tree.npz")
+        return
     if os.environ.get("GOLDEN_ONLY") == "prob":
         prob_sampling_golden(ref)
         print("wrote prob_sampling.npz")
@@ -320,6 +342,7 @@ def main():
     q["H"] = Hq; q["W"] = Wq; q["n_img"] = n_img; q["leaf_hist"] = np.array(hist)
     np.savez_compressed(os.path.join(OUT, "quadtree.npz"), **q)
     prob_sampling_golden(ref)
+    variance_tree_golden(ref)
     print("golden fixtures written to", OUT)
     for f in sorted(os.listdir(OUT)):
         print("  %-20s %8d bytes" % (f, os.path.getsize(os.path.join(OUT, f))))

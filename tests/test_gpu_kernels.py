@@ -325,3 +325,24 @@ def test_prob_guided_sampling(golden, ops):
     # reference-facing entry point
     o, d, rgb = big.gen_rays_v3_multiThread(down_scale=1, prob=True, randSamp_proc=0.95)
     assert o.shape == (n_img * H * W, 3) and rgb.shape == o.shape and bool(torch.isfinite(d).all())
+
+
+def test_variance_driven_initial_trees_on_device(golden, ops):
+    """QuadTreeManager(mseThres > 0): the uploaded SoA equals the reference's leaf lists; leaves coarser than minArea
+    get 10 rays per epoch, the finest int(area) (tree.py:578-581)."""
+    import tree
+    g = golden("variance_tree")
+    img = g["image"]
+    K = np.array([[50.0, 0, 24], [0, 50.0, 24], [0, 0, 1]])
+    poses = torch.eye(4)[None, :3, :4].repeat(2, 1, 1)
+    mgr = tree.QuadTreeManager(48, 48, K, np.stack([img, img]), poses, mseThres=float(g["thres"][1]),
+                               max_depth=int(g["max_depth"]), max_level=6)
+    want = g["boxes1"]
+    for boxes, ma in mgr.leaf_lists():
+        assert np.array_equal(boxes, want) and ma == float(g["minarea1"])
+    n = mgr.emit_epoch(down_scale=1, shuffle=True)
+    area = (want[:, 2] - want[:, 0]) * (want[:, 3] - want[:, 1])
+    exp = np.where(area > float(g["minarea1"]) + 0.01, 10, area.astype(np.int64))
+    assert n == 2 * int(exp.sum())
+    cnt = np.bincount(mgr.ray_gid.cpu().numpy(), minlength=2 * mgr.cap).reshape(2, mgr.cap)[:, :len(want)]
+    assert np.array_equal(cnt, np.stack([exp, exp]))

@@ -78,3 +78,16 @@ def test_lr_schedule_and_feistel_free_logic():
     from flnerf_b200.engine import lr_at
     assert abs(lr_at(5e-4, 500, 0) - 5e-4) < 1e-12
     assert abs(lr_at(5e-4, 500, 500000) - 5e-5) < 1e-12
+
+
+def test_variance_driven_initial_tree_matches_reference(golden):
+    """mseThres > 0 (tree.py:28-56,655-676): the host recursion that seeds the GPU SoA -- leaf lists bit-exact."""
+    import tree
+    g = golden("variance_tree")
+    for k, th in enumerate(g["thres"]):
+        t = tree.QuadTree(g["image"], float(th), int(g["max_depth"]))
+        boxes = np.array([n.box() for n in tree.get_children(t.root)], np.float64)
+        assert np.array_equal(boxes, g["boxes%d" % k]) and t.minArea == float(g["minarea%d" % k])
+        # DFS leaf order survives the SoA round trip used by QuadTreeManager.quadTrees
+        t2 = tree.QuadTree((48, 48), 0.0, 1, _boxes=boxes, _min_area=t.minArea)
+        assert [n.box() for n in tree.get_children(t2.root)] == [tuple(b) for b in boxes]
