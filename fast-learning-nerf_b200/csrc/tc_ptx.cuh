@@ -48,21 +48,11 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void *src, uin
                "l"(src), "r"(bytes), "r"(bar)
                : "memory");
 }
-// same, but the bytes (and the complete_tx on the mbarrier at the same offset) land in every CTA of cta_mask
-__device__ __forceinline__ void bulk_g2s_multicast(uint32_t dst_smem, const void *src, uint32_t bytes, uint32_t bar,
-                                                   uint16_t cta_mask) {
-  asm volatile(
-      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;" ::"r"(
-          dst_smem),
-      "l"(src), "r"(bytes), "r"(bar), "h"(cta_mask)
-      : "memory");
-}
 __device__ __forceinline__ void bulk_s2g(void *dst, uint32_t src_smem, uint32_t bytes) {
   asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src_smem), "r"(bytes)
                : "memory");
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 // all but the most recent group have finished reading their shared-memory source
 __device__ __forceinline__ void bulk_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_all0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
@@ -99,13 +89,6 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint
 // arrives on the mbarrier when all previously issued tcgen05.mma of this thread have completed
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-// commit that arrives on the mbarrier at this offset in every CTA of cta_mask (ring stages filled by multicast
-// copies may only be refilled once BOTH CTAs' MMAs have consumed them)
-__device__ __forceinline__ void umma_commit_multicast(uint32_t bar, uint16_t cta_mask) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
-               "h"(cta_mask)
-               : "memory");
 }
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
@@ -224,21 +207,6 @@ __device__ __forceinline__ uint32_t pack_bf16_fast(float a, float b) {
   uint32_t d;
   asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(b), "f"(a));
   return d;
-}
-// bits e and e+1 of a 32-bit row mask from a packed pair of NON-NEGATIVE bf16 (halfword != 0); e is a constant
-__device__ __forceinline__ uint32_t nz_bits(uint32_t w, int e) {
-  uint32_t t = w + 0x7FFF7FFFu;  // bit 15 / bit 31 set iff the low / high halfword is non-zero (no carry: h <= 0x7F80)
-  uint32_t lo = (e <= 15) ? (t >> (15 - e)) : (t << (e - 15));
-  uint32_t hi = t >> (30 - e);
-  return (lo & (1u << e)) | (hi & (2u << e));
-}
-// 4 mask bits (bit i = element i != 0) from two packed pairs of NON-NEGATIVE bf16: w + 0x7FFF7FFF puts the "non-zero"
-// flags into bits 15/31 (IMAD, fma pipe); PRMT gathers the four flag bytes; (u & 0x80808080) * 0x00204081 moves the
-// flags at bits 7,15,23,31 to bits 28..31 without carries (all 16 partial products land on distinct bits)
-__device__ __forceinline__ uint32_t nz_nibble(uint32_t w0, uint32_t w1) {
-  const uint32_t t0 = w0 + 0x7FFF7FFFu, t1 = w1 + 0x7FFF7FFFu;
-  const uint32_t u = __byte_perm(t0, t1, 0x7531);
-  return ((u & 0x80808080u) * 0x00204081u) >> 28;
 }
 __device__ __forceinline__ float bf16_lo(uint32_t p) { return __uint_as_float(p << 16); }
 __device__ __forceinline__ float bf16_hi(uint32_t p) { return __uint_as_float(p & 0xFFFF0000u); }
