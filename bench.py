@@ -252,6 +252,23 @@ def run_ours(args):
         if world > 1:
             dist.destroy_process_group()
         return
+    # ---------------- eval path (informational): one full 800x800 frame through render() without gradients
+    eval_info = None
+    if args.precision == "bf16":
+        with torch.no_grad():
+            pose = mgr._poses_dev[0]
+            kw = dict(chunk=32768, c2w=pose, ndc=False, near=2.0, far=6.0, use_viewdirs=True, network_query_fn=q, network_fn=nc,
+                      network_fine=nf, N_samples=64, N_importance=128, white_bkgd=True, perturb=0.0, raw_noise_std=0.0)
+            R.render(H, W, K, **kw)
+            torch.cuda.synchronize()
+            g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            g0.record()
+            R.render(H, W, K, **kw)
+            g1.record()
+            torch.cuda.synchronize()
+            ems = g0.elapsed_time(g1)
+        eval_info = {"rays_per_s": H * W / (ems * 1e-3), "ms_per_frame": ems, "frame": "%dx%d, 64+128 samples, render() under no_grad" % (H, W),
+                     "tflops": H * W * 256 * FLOP_FWD_PER_SAMPLE / (ems * 1e-3) / 1e12}
     # ---------------- per-kernel roofline (rank 0, fine pass: 4096 x 192 rows), CUDA events on the launch stream
     peaks = measured_peaks()
     roof, kernels = None, {}
@@ -326,7 +343,7 @@ def run_ours(args):
                    "epoch_rays": n_rays},
         "e2e": {"value": e2e_value, "unit": "rays/s", "h2d_bytes_per_step": bytes_in, "d2h_bytes_per_step": 8},
         "gpu_launches": int(launches), "clocks": clk, "roofline": roof, "cpu_baseline": cpu,
-        "loss": loss_host}))
+        "eval_render": eval_info, "loss": loss_host}))
     if world > 1:
         dist.destroy_process_group()
 

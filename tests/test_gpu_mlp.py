@@ -213,6 +213,30 @@ def test_fused_trainer_matches_autograd_path_and_oracle(golden, precision):
     assert rel_l2(tr.bucket.cpu(), g_or) < (2e-3 if precision == "fp32" else 1e-1)
 
 
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_fused_trainer_ndc_config3(golden, precision):
+    """BASELINE.json configs[2] (llff fern, NDC, 64+128): one fused training step on forward-facing rays against one full
+    reference iteration of the oracle (same rays, perturb=0 / deterministic fine sampling)."""
+    from flnerf_b200.engine import FusedAdam, Trainer
+    g = golden("render_ndc")
+    ro, rd = T(g["rays_o"]), T(g["rays_d"])
+    tgt = torch.rand(ro.shape[0], 3, generator=torch.Generator().manual_seed(3)).cuda()
+    K, Hh, Ww = g["K"], int(g["H"]), int(g["W"])
+    nc, nf = make_net(int(g["seed_c"]), precision), make_net(int(g["seed_f"]), precision)
+    opt = FusedAdam(list(nc.parameters()) + list(nf.parameters()), [nc, nf], lr=5e-4)
+    tr = Trainer(nc, nf, opt, Hh, Ww, K, 0.0, 1.0, 64, 128, white_bkgd=False, perturb=0.0, ndc=True)
+    loss = tr.step(ro, rd, tgt)
+    np.testing.assert_allclose(tr.last["rgb"].cpu().numpy(), g["rgb"], atol=2e-5 if precision == "fp32" else 3e-2)
+    np.testing.assert_allclose(tr.last["rgb0"].cpu().numpy(), g["rgb0"], atol=2e-5 if precision == "fp32" else 3e-2)
+    pc, pf = O.init_params(int(g["seed_c"])), O.init_params(int(g["seed_f"]))
+    o_opt = O.AdamState(list(pc.values()) + list(pf.values()))
+    rays11 = O.pack_rays(Hh, Ww, K, ro.cpu(), rd.cpu(), 0.0, 1.0, ndc=True)
+    res = O.train_step(rays11, tgt.cpu(), pc, pf, o_opt, 64, 128, white_bkgd=False)
+    np.testing.assert_allclose(float(loss.sum()), res["loss"], rtol=1e-4 if precision == "fp32" else 5e-2)
+    g_or = torch.cat([x.reshape(-1) for x in res["grads"]])
+    assert rel_l2(tr.bucket.cpu(), g_or) < (2e-3 if precision == "fp32" else 1e-1)
+
+
 def test_fused_adam_state_dict_is_stock_adam_compatible(tmp_path):
     from flnerf_b200.engine import FusedAdam
     import run_nerf
