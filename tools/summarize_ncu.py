@@ -4,6 +4,7 @@ usage: python tools/summarize_ncu.py <tag>      e.g. r01a"""
 import collections
 import csv
 import json
+import re
 import os
 import subprocess
 import sys
@@ -71,7 +72,8 @@ if os.path.isfile(rep):
             rd, wr = float(r[hdr.index("dram__bytes_read.sum")]), float(r[hdr.index("dram__bytes_write.sum")])
             scale = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1}
             ur, uw = units[hdr.index("dram__bytes_read.sum")], units[hdr.index("dram__bytes_write.sum")]
-            traffic[r[hdr.index("Kernel Name")].split("(")[0].replace("tc::", "")] = rd * scale[ur] + wr * scale[uw]
+            name = r[hdr.index("Kernel Name")].split("(")[0].replace("tc::", "").replace("void ", "")
+            traffic[re.sub(r"<.*>", "", name)] = rd * scale[ur] + wr * scale[uw]     # template arguments dropped
         except Exception:
             pass
     json.dump(traffic, open(os.path.join(out, "roofline_traffic.json"), "w"), indent=1)
