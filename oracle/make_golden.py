@@ -118,8 +118,50 @@ def variance_tree_golden(ref):
     np.savez_compressed(os.path.join(OUT, "variance_tree.npz"), **g)
 
 
+def nerfpp_golden():
+    """nerf++-ours fixtures produced by the reference's own nerf_network / ddp_model / ddp_train_nerf
+    functions; the oracle (oracle/nerfpp_oracle.py) is asserted against them on the way."""
+    import nerfpp_oracle as P
+    ref = ref_shim.load_nerfpp()
+    g0 = torch.Generator().manual_seed(41)
+    o = torch.randn(6, 3, generator=g0) * 0.25
+    d = torch.nn.functional.normalize(torch.randn(6, 3, generator=g0), dim=-1) * (0.5 + torch.rand(6, 1, generator=g0))
+    g = {"ray_o": o, "ray_d": d, "seed_fg": 21, "seed_bg": 22}
+    g["fg_far"] = ref.train.intersect_sphere(o, d)
+    close(P.intersect_sphere(o, d), g["fg_far"], 0.0, "intersect_sphere")
+    probe = torch.sort(torch.rand(6, 5, generator=g0), -1)[0]
+    pts, dr = ref.model.depth2pts_outside(o[:, None].expand(-1, 5, -1), d[:, None].expand(-1, 5, -1), probe)
+    g["bg_probe"], g["bg_pts"], g["bg_depth_real"] = probe, pts, dr
+    bins = torch.sort(torch.rand(6, 11, generator=g0), -1)[0]
+    w = torch.rand(6, 10, generator=g0) ** 4
+    torch.manual_seed(8)
+    u = torch.rand(6, 16)
+    torch.manual_seed(8)
+    g["bins"], g["weights"], g["u"] = bins, w, u
+    g["samples"] = ref.train.sample_pdf(bins, w, 16, det=False)
+    g["samples_det"] = ref.train.sample_pdf(bins, w, 16, det=True)
+    close(P.sample_pdf(bins, w, 16, u), g["samples"], 0.0, "sample_pdf")
+    args = type("A", (), dict(max_freq_log2=10, max_freq_log2_viewdirs=4, netdepth=8, netwidth=256, use_viewdirs=True))()
+    net = ref.model.NerfNet(args)
+    net.fg_net.load_state_dict(P.init_mlp_params(21, 63))
+    net.bg_net.load_state_dict(P.init_mlp_params(22, 84))
+    _, fg_z, bg_z = P.cascade_depths(o, d, 16, 0, t_fg=torch.rand(6, 16, generator=g0), t_bg=torch.rand(6, 16, generator=g0))
+    with torch.no_grad():
+        ret = net(o, d, g["fg_far"], fg_z, bg_z)
+    mine = P.nerfnet_forward(P.init_mlp_params(21, 63), P.init_mlp_params(22, 84), o, d, g["fg_far"], fg_z, bg_z)
+    for k, v in ret.items():
+        close(mine[k], v, 2e-6, "NerfNet." + k)
+        g["ret." + k] = v
+    g["fg_z"], g["bg_z"] = fg_z, bg_z
+    np.savez_compressed(os.path.join(OUT, "nerfpp.npz"), **t2n(g))
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
+    if os.environ.get("GOLDEN_ONLY") == "nerfpp":
+        nerfpp_golden()
+        print("wrote nerfpp.npz")
+        return
     ref = ref_shim.load()
     if os.environ.get("GOLDEN_ONLY") == "vartree":
         variance_tree_golden(ref)
@@ -343,6 +385,7 @@ def main():
     np.savez_compressed(os.path.join(OUT, "quadtree.npz"), **q)
     prob_sampling_golden(ref)
     variance_tree_golden(ref)
+    nerfpp_golden()
     print("golden fixtures written to", OUT)
     for f in sorted(os.listdir(OUT)):
         print("  %-20s %8d bytes" % (f, os.path.getsize(os.path.join(OUT, f))))

@@ -99,3 +99,43 @@ def ref_run_network(ns, inputs, viewdirs, fn, embed_fn, embeddirs_fn, netchunk=1
         emb = torch.cat([emb, embeddirs_fn(dirs)], -1)
     out = torch.cat([fn(emb[i:i + netchunk]) for i in range(0, emb.shape[0], netchunk)], 0)
     return out.reshape(list(inputs.shape[:-1]) + [out.shape[-1]])
+
+
+REF_NERFPP = os.path.join(os.path.dirname(REF_NERF), "nerf++-ours")
+
+
+def load_nerfpp():
+    """The reference's nerf++ fork: nerf_network (Embedder, MLPNet), ddp_model (depth2pts_outside,
+    NerfNet) and the sampling helpers of ddp_train_nerf (intersect_sphere, perturb_samples, sample_pdf), imported
+    unmodified behind the same kind of stubs as load()."""
+    if not os.path.isdir(REF_NERFPP):
+        raise RuntimeError("reference tree not present at %s" % REF_NERFPP)
+    load()      # installs the imageio / matplotlib / colour / cv2.cv2 / threadpool stubs
+    mpl = sys.modules["matplotlib"]
+    mpl.__path__ = []           # make the stub a package so that its sub-modules can be stubbed too
+    for name, attrs in [("matplotlib.backends", {}), ("matplotlib.backends.backend_agg", {"FigureCanvasAgg": object}),
+                        ("matplotlib.figure", {"Figure": object}), ("matplotlib.cm", {})]:
+        m = sys.modules.get(name) or types.ModuleType(name)
+        for k, v in attrs.items():
+            setattr(m, k, v)
+        sys.modules[name] = m
+    mpl.cm = sys.modules["matplotlib.cm"]
+    names = ["utils", "nerf_network", "ddp_model", "nerf_sample_ray_split", "data_loader_split", "image_process", "tree",
+             "tree_utils", "ddp_train_nerf"]
+    saved_path = list(sys.path)
+    saved_mods = {k: sys.modules.get(k) for k in names}
+    for k in names:
+        sys.modules.pop(k, None)
+    sys.path.insert(0, REF_NERFPP)
+    try:
+        ns = types.SimpleNamespace()
+        ns.network = importlib.import_module("nerf_network")
+        ns.model = importlib.import_module("ddp_model")
+        ns.train = importlib.import_module("ddp_train_nerf")
+    finally:
+        sys.path[:] = saved_path
+        for k, v in saved_mods.items():
+            sys.modules.pop(k, None)
+            if v is not None:
+                sys.modules[k] = v
+    return ns

@@ -1,0 +1,99 @@
+"""CPU: the nerf++ oracle (oracle/nerfpp_oracle.py -- the checker for SURVEY 8f rank 1, the next row) against the live,
+unmodified reference (build container only) and against the committed fixture tests/golden/nerfpp.npz."""
+import numpy as np
+import pytest
+import torch
+
+import nerfpp_oracle as P
+import ref_shim
+
+
+def T(a):
+    return torch.from_numpy(np.asarray(a))
+
+
+def _rays(n, seed):
+    g = torch.Generator().manual_seed(seed)
+    o = torch.randn(n, 3, generator=g) * 0.25                     # cameras inside the unit sphere
+    d = torch.nn.functional.normalize(torch.randn(n, 3, generator=g), dim=-1) * (0.5 + torch.rand(n, 1, generator=g))
+    return o, d
+
+
+def test_golden_fixture(golden):
+    g = golden("nerfpp")
+    o, d = T(g["ray_o"]), T(g["ray_d"])
+    fg_far = P.intersect_sphere(o, d)
+    np.testing.assert_allclose(fg_far.numpy(), g["fg_far"], rtol=0, atol=1e-6)
+    pts, depth_real = P.depth2pts_outside(o[:, None].expand(-1, 5, -1), d[:, None].expand(-1, 5, -1), T(g["bg_probe"]))
+    np.testing.assert_allclose(pts.numpy(), g["bg_pts"], rtol=0, atol=2e-6)
+    np.testing.assert_allclose(depth_real.numpy(), g["bg_depth_real"], rtol=2e-6, atol=2e-6)
+    assert torch.equal(P.sample_pdf(T(g["bins"]), T(g["weights"]), 16, T(g["u"])), T(g["samples"]))
+    assert torch.equal(P.sample_pdf(T(g["bins"]), T(g["weights"]), 16, None), T(g["samples_det"]))
+    p_fg, p_bg = P.init_mlp_params(int(g["seed_fg"]), 63), P.init_mlp_params(int(g["seed_bg"]), 84)
+    ret = P.nerfnet_forward(p_fg, p_bg, o, d, fg_far, T(g["fg_z"]), T(g["bg_z"]))
+    for k in ("rgb", "fg_weights", "bg_weights", "bg_lambda", "fg_depth", "bg_depth"):
+        np.testing.assert_allclose(ret[k].numpy(), g["ret." + k], rtol=0, atol=3e-6)
+
+
+def test_fg_net_maps_onto_the_nerf_kernel_layout():
+    """MLPNet (fg) == nerf-ours NeRF on the renamed parameters, up to the output activations: the existing MLP kernels can
+    serve the foreground network of this row unchanged."""
+    import nerf_oracle as O
+    p = P.init_mlp_params(3, 63)
+    q = P.mlp_params_to_nerf_layout(p)
+    ref = O.init_params(0)
+    assert list(q.keys()) != [] and set(q.keys()) == set(ref.keys())
+    assert all(q[k].shape == ref[k].shape for k in ref)
+    x = torch.randn(40, 90)
+    rgb, sigma = P.mlp_forward(p, x, 63)
+    raw = O.mlp_forward({k: q[k] for k in ref}, x)            # nerf-ours forward: [rgb(3) pre-sigmoid, alpha(1) pre-relu]
+    np.testing.assert_allclose(torch.sigmoid(raw[:, :3]).numpy(), rgb.numpy(), atol=2e-6)
+    np.testing.assert_allclose(torch.abs(raw[:, 3]).numpy(), sigma.numpy(), atol=2e-6)
+
+
+@pytest.mark.skipif(not ref_shim.available(), reason="reference tree not present")
+def test_against_live_reference():
+    ref = ref_shim.load_nerfpp()
+    o, d = _rays(9, 1)
+    assert torch.equal(P.intersect_sphere(o, d), ref.train.intersect_sphere(o, d))
+    z = torch.sort(torch.rand(9, 12), -1)[0]
+    a = P.depth2pts_outside(o[:, None].expand(-1, 12, -1), d[:, None].expand(-1, 12, -1), z)
+    b = ref.model.depth2pts_outside(o[:, None].expand(-1, 12, -1), d[:, None].expand(-1, 12, -1), z)
+    assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
+    torch.manual_seed(5)
+    t = torch.rand_like(z)
+    torch.manual_seed(5)
+    assert torch.equal(P.perturb_samples(z, t), ref.train.perturb_samples(z))
+    bins, w = torch.sort(torch.rand(9, 11), -1)[0], torch.rand(9, 10) ** 4
+    assert torch.equal(P.sample_pdf(bins, w, 16, None), ref.train.sample_pdf(bins, w, 16, det=True))
+    torch.manual_seed(6)
+    u = torch.rand(9, 16)
+    torch.manual_seed(6)
+    assert torch.equal(P.sample_pdf(bins, w, 16, u), ref.train.sample_pdf(bins, w, 16, det=False))
+    for dim, L in ((3, 10), (4, 10), (3, 4)):
+        x = torch.randn(7, dim)
+        e = ref.network.Embedder(input_dim=dim, max_freq_log2=L - 1, N_freqs=L)
+        assert torch.equal(P.embed(x, L), e(x)) and e.out_dim == dim * (1 + 2 * L)
+    # MLPNet with 63 / 84 input channels and the whole NerfNet.forward
+    args = type("A", (), dict(max_freq_log2=10, max_freq_log2_viewdirs=4, netdepth=8, netwidth=256, use_viewdirs=True))()
+    net = ref.model.NerfNet(args)
+    p_fg, p_bg = P.init_mlp_params(11, 63), P.init_mlp_params(12, 84)
+    assert list(net.fg_net.state_dict().keys()) == list(p_fg.keys())
+    net.fg_net.load_state_dict(p_fg)
+    net.bg_net.load_state_dict(p_bg)
+    fg_far = P.intersect_sphere(o, d)
+    _, fg_z, bg_z = P.cascade_depths(o, d, 16, 0, t_fg=torch.rand(9, 16), t_bg=torch.rand(9, 16))
+    mine = P.nerfnet_forward(p_fg, p_bg, o, d, fg_far, fg_z, bg_z)
+    with torch.no_grad():
+        want = net(o, d, fg_far, fg_z, bg_z)
+    for k in want:
+        np.testing.assert_allclose(mine[k].numpy(), want[k].numpy(), rtol=0, atol=2e-6, err_msg=k)
+    # level-1 sample placement (ddp_train_nerf.py:369-382), restated with the reference's own sample_pdf
+    torch.manual_seed(9)
+    u_fg, u_bg = torch.rand(9, 8), torch.rand(9, 8)
+    torch.manual_seed(9)
+    fg_s = ref.train.sample_pdf(bins=0.5 * (fg_z[..., 1:] + fg_z[..., :-1]), weights=want["fg_weights"][..., 1:-1], N_samples=8, det=False)
+    bg_s = ref.train.sample_pdf(bins=0.5 * (bg_z[..., 1:] + bg_z[..., :-1]), weights=want["bg_weights"][..., 1:-1], N_samples=8, det=False)
+    fg1, bg1 = torch.sort(torch.cat((fg_z, fg_s), -1))[0], torch.sort(torch.cat((bg_z, bg_s), -1))[0]
+    _, a1, b1 = P.cascade_depths(o, d, 16, 8, ret0={k: v for k, v in want.items()}, fg_prev=fg_z, bg_prev=bg_z, u_fg=u_fg, u_bg=u_bg)
+    assert torch.equal(a1, fg1) and torch.equal(b1, bg1)
