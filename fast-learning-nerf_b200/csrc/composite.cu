@@ -201,7 +201,9 @@ composite_bwd_kernel(int64_t B, int S, const float4 *__restrict__ raw, const flo
 // kBins = false: z = coarse depths [B,Nc], wts = compositing weights [B,Nc]; bins are the mid-points and the
 //                 weights are wts[1:-1] (render.py:279-280); output merged + sorted with z.
 // kBins = true : z = bins [B,Nc-1] and wts = weights [B,Nc-2] taken as they are (the generic sample_pdf API).
-template <bool kBins>
+// kPP = 1: the nerf++ variant of the resampler (nerf++-ours/ddp_train_nerf.py:84-133): 1e-6 instead of 1e-5 floors, the
+// inverse CDF counts u >= cdf[:M] (no clamp of the upper index), and the bin width carries a +1e-6
+template <bool kBins, int kPP>
 __global__ void __launch_bounds__(kRaysPerBlock * 32)
 sample_pdf_merge_kernel(int64_t B, int Nc, int Nf, int P2, const float *__restrict__ z, const float *__restrict__ wts,
                         const float *__restrict__ u_in, int det, uint64_t seed, uint64_t offset,
@@ -219,7 +221,8 @@ sample_pdf_merge_kernel(int64_t B, int Nc, int Nf, int P2, const float *__restri
   __syncwarp();
   // pdf = (w[1:-1] + 1e-5) / sum ; cdf = [0, cumsum(pdf)]      (helpers:114-117)
   float part = 0.f;
-  for (int k = lane; k < M; k += 32) part += __fadd_rn(ww[k + 1], 1e-5f);
+  const float eps = kPP ? 1e-6f : 1e-5f;
+  for (int k = lane; k < M; k += 32) part += __fadd_rn(ww[k + 1], eps);
   float total = warp_sum(part);
   // torch.cumsum on the CPU accumulates fp32 inputs in double and rounds every prefix once; do the same so that the
   // searchsorted / den<1e-5 decisions below see the reference's cdf
@@ -227,7 +230,7 @@ sample_pdf_merge_kernel(int64_t B, int Nc, int Nf, int P2, const float *__restri
   if (lane == 0) cdf[0] = 0.f;
   for (int base = 0; base < M; base += 32) {
     int k = base + lane;
-    double incl = (k < M) ? (double)__fdiv_rn(__fadd_rn(ww[k + 1], 1e-5f), total) : 0.0;
+    double incl = (k < M) ? (double)__fdiv_rn(__fadd_rn(ww[k + 1], eps), total) : 0.0;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
       double t = __shfl_up_sync(0xffffffffu, incl, o);
@@ -251,7 +254,7 @@ sample_pdf_merge_kernel(int64_t B, int Nc, int Nf, int P2, const float *__restri
       philox4x32(seed, offset + (uint64_t)(ray * Nf + j), 0x5D0Full, r);
       u = u32_to_unit(r[0]);
     }
-    int lo = 0, hi = ncdf;  // searchsorted(right=True): count of cdf entries <= u
+    int lo = 0, hi = kPP ? M : ncdf;  // searchsorted(right=True): count of cdf entries <= u (nerf++: among cdf[:M])
     while (lo < hi) {
       int mid = (lo + hi) >> 1;
       if (cdf[mid] <= u) lo = mid + 1; else hi = mid;
@@ -261,9 +264,9 @@ sample_pdf_merge_kernel(int64_t B, int Nc, int Nf, int P2, const float *__restri
     float bb = kBins ? buf[below] : __fmul_rn(0.5f, __fadd_rn(buf[below + 1], buf[below]));
     float ba = kBins ? buf[above] : __fmul_rn(0.5f, __fadd_rn(buf[above + 1], buf[above]));
     float den = __fsub_rn(ca, cb);
-    if (den < 1e-5f) den = 1.0f;
+    if (den < eps) den = 1.0f;
     float t = __fdiv_rn(__fsub_rn(u, cb), den);
-    float smp = __fadd_rn(bb, __fmul_rn(t, __fsub_rn(ba, bb)));
+    float smp = __fadd_rn(bb, __fmul_rn(t, kPP ? __fadd_rn(__fsub_rn(ba, bb), 1e-6f) : __fsub_rn(ba, bb)));
     if (!kBins) buf[Nc + j] = smp;
     if (z_samples) z_samples[ray * Nf + j] = smp;
     s1 += smp;
@@ -300,6 +303,11 @@ sample_pdf_merge_kernel(int64_t B, int Nc, int Nf, int P2, const float *__restri
   float *out = z_merged + ray * (Nc + Nf);
   for (int i = lane; i < Nc + Nf; i += 32) out[i] = buf[i];
 }
+
+// template instantiations behind plain names (a comma inside FL_LAUNCH's first argument would split it)
+constexpr auto k_merge = sample_pdf_merge_kernel<false, 0>;
+constexpr auto k_bins = sample_pdf_merge_kernel<true, 0>;
+constexpr auto k_merge_pp = sample_pdf_merge_kernel<false, 1>;
 
 }  // namespace
 
@@ -340,7 +348,7 @@ int flnerf_sample_pdf_merge(flnerf_ctx *ctx, int64_t B, int Nc, int Nf, const fl
   while (P2 < Nc + Nf) P2 <<= 1;
   size_t smem = (size_t)kRaysPerBlock * (Nc - 1 + P2) * sizeof(float);
   FL_REQUIRE(smem <= 48 * 1024, "flnerf_sample_pdf_merge: Nc+Nf=%d too large", Nc + Nf);
-  FL_LAUNCH(sample_pdf_merge_kernel<false>, (unsigned)ceil_div64(B, kRaysPerBlock), kRaysPerBlock * 32, smem, stream, B,
+  FL_LAUNCH(k_merge, (unsigned)ceil_div64(B, kRaysPerBlock), kRaysPerBlock * 32, smem, stream, B,
             Nc, Nf, P2, z, weights, u, det, seed, offset, z_merged, z_samples, z_std);
   return 0;
 }
@@ -352,8 +360,24 @@ int flnerf_sample_pdf(flnerf_ctx *ctx, int64_t B, int n_bins, int Nf, const floa
   int Nc = n_bins + 1;
   size_t smem = (size_t)kRaysPerBlock * (Nc - 1 + Nc) * sizeof(float);
   FL_REQUIRE(smem <= 48 * 1024, "flnerf_sample_pdf: too many bins (%d)", n_bins);
-  FL_LAUNCH(sample_pdf_merge_kernel<true>, (unsigned)ceil_div64(B, kRaysPerBlock), kRaysPerBlock * 32, smem, stream, B,
+  FL_LAUNCH(k_bins, (unsigned)ceil_div64(B, kRaysPerBlock), kRaysPerBlock * 32, smem, stream, B,
             Nc, Nf, Nc, bins, weights, u, det, seed, offset, nullptr, z_samples, nullptr);
+  return 0;
+}
+
+/* nerf++ level-1 sample placement (nerf++-ours/ddp_train_nerf.py:369-382): resample Nf depths from the previous level's
+ * weights[..., 1:-1] over the mid-point bins with the nerf++ sample_pdf, then sort-merge with the previous depths. */
+int flnerf_pp_sample_pdf_merge(flnerf_ctx *ctx, int64_t B, int Nc, int Nf, const float *z, const float *weights,
+                               const float *u, int det, uint64_t seed, uint64_t offset, float *z_merged,
+                               float *z_samples, void *stream) {
+  FL_REQUIRE(ctx && z && weights && z_merged && Nc >= 3 && Nf >= 2 && B >= 0, "flnerf_pp_sample_pdf_merge: bad arguments");
+  if (B == 0) return 0;
+  int P2 = 1;
+  while (P2 < Nc + Nf) P2 <<= 1;
+  size_t smem = (size_t)kRaysPerBlock * (Nc - 1 + P2) * sizeof(float);
+  FL_REQUIRE(smem <= 48 * 1024, "flnerf_pp_sample_pdf_merge: Nc+Nf=%d too large", Nc + Nf);
+  FL_LAUNCH(k_merge_pp, (unsigned)ceil_div64(B, kRaysPerBlock), kRaysPerBlock * 32, smem, stream, B,
+            Nc, Nf, P2, z, weights, u, det, seed, offset, z_merged, z_samples, nullptr);
   return 0;
 }
 

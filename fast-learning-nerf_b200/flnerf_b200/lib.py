@@ -54,6 +54,11 @@ SIGNATURES = {
     "flnerf_qt_emit_prob": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp, _i64, _u64, _d, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp,
                                  _vp]),
     "flnerf_gather_batch": (_i, [_vp, _i64, _i64, _i64, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "flnerf_pp_depths0": (_i, [_vp, _i64, _i, _vp, _vp, _vp, _vp, _i, _u64, _u64, _vp, _vp, _vp, _vp]),
+    "flnerf_pp_bg_encode": (_i, [_vp, _i64, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "flnerf_pp_composite_forward": (_i, [_vp, _i64, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "flnerf_pp_composite_backward": (_i, [_vp, _i64, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "flnerf_pp_sample_pdf_merge": (_i, [_vp, _i64, _i, _i, _vp, _vp, _vp, _i, _u64, _u64, _vp, _vp, _vp]),
     "flnerf_launch_count": (_i64, [_i]),
 }
 

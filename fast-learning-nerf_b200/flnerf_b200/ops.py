@@ -306,3 +306,67 @@ def gather_batch(B, first, stride, ray_pix, ray_gid, cap, H, W, K, poses, images
                                          int(cap), int(H), int(W), Kh, _ptr(poses), _ptr(images), _ptr(o), _ptr(d),
                                          _ptr(t), _ptr(gid), _stream()), "flnerf_gather_batch")
     return o, d, t, gid
+
+
+# ------------------------------------------------------------------------------------------ nerf++ building blocks
+# (the next row: parity-tested kernels, no complete path yet -- see DESIGN.md section 8)
+def pp_depths0(rays_o, rays_d, N, perturb, t_fg=None, t_bg=None, seed=0, offset=0):
+    """ddp_train_nerf.py:352-366 -> (fg_far[B], fg_z[B,N], bg_z[B,N])."""
+    B, dev = rays_o.shape[0], rays_o.device
+    fg_far = torch.empty(B, dtype=torch.float32, device=dev)
+    fg_z = torch.empty(B, N, dtype=torch.float32, device=dev)
+    bg_z = torch.empty(B, N, dtype=torch.float32, device=dev)
+    L.check(L.load().flnerf_pp_depths0(_ctx(rays_o), B, int(N), _ptr(_f32c(rays_o)), _ptr(_f32c(rays_d)), _ptr(t_fg), _ptr(t_bg),
+                                       int(bool(perturb)), int(seed), int(offset), _ptr(fg_far), _ptr(fg_z), _ptr(bg_z),
+                                       _stream()), "flnerf_pp_depths0")
+    return fg_far, fg_z, bg_z
+
+
+def pp_bg_encode(rays_o, rays_d, bg_z, want_pts=False):
+    """ddp_model.py:16-45,109-117 -> (x111[B,N,111] flipped, bg_z_flip[B,N], pts4[B,N,4] or None)."""
+    B, N = bg_z.shape
+    dev = bg_z.device
+    x = torch.empty(B, N, 111, dtype=torch.float32, device=dev)
+    zf = torch.empty(B, N, dtype=torch.float32, device=dev)
+    pts = torch.empty(B, N, 4, dtype=torch.float32, device=dev) if want_pts else None
+    L.check(L.load().flnerf_pp_bg_encode(_ctx(bg_z), B, N, _ptr(_f32c(rays_o)), _ptr(_f32c(rays_d)), _ptr(_f32c(bg_z)), _ptr(x),
+                                         _ptr(zf), _ptr(pts), _stream()), "flnerf_pp_bg_encode")
+    return x, zf, pts
+
+
+def pp_composite_forward(raw_fg, fg_z, fg_far, raw_bg, bg_z_flip, rays_d):
+    """ddp_model.py:93-133 on raw network outputs -> (rgb[B,3], fg_weights, bg_weights, aux9[B,9])."""
+    B, Sf = fg_z.shape
+    Sb = bg_z_flip.shape[1]
+    dev = fg_z.device
+    rgb = torch.empty(B, 3, dtype=torch.float32, device=dev)
+    fw = torch.empty(B, Sf, dtype=torch.float32, device=dev)
+    bw = torch.empty(B, Sb, dtype=torch.float32, device=dev)
+    aux = torch.empty(B, 9, dtype=torch.float32, device=dev)
+    L.check(L.load().flnerf_pp_composite_forward(_ctx(fg_z), B, Sf, Sb, _ptr(_f32c(raw_fg)), _ptr(_f32c(fg_z)), _ptr(_f32c(fg_far)),
+                                                 _ptr(_f32c(raw_bg)), _ptr(_f32c(bg_z_flip)), _ptr(_f32c(rays_d)), _ptr(rgb),
+                                                 _ptr(fw), _ptr(bw), _ptr(aux), _stream()), "flnerf_pp_composite_forward")
+    return rgb, fw, bw, aux
+
+
+def pp_composite_backward(raw_fg, fg_z, fg_far, raw_bg, bg_z_flip, rays_d, g_rgb):
+    B, Sf = fg_z.shape
+    Sb = bg_z_flip.shape[1]
+    dfg, dbg = torch.empty_like(raw_fg, dtype=torch.float32), torch.empty_like(raw_bg, dtype=torch.float32)
+    L.check(L.load().flnerf_pp_composite_backward(_ctx(fg_z), B, Sf, Sb, _ptr(_f32c(raw_fg)), _ptr(_f32c(fg_z)), _ptr(_f32c(fg_far)),
+                                                  _ptr(_f32c(raw_bg)), _ptr(_f32c(bg_z_flip)), _ptr(_f32c(rays_d)),
+                                                  _ptr(_f32c(g_rgb)), _ptr(dfg), _ptr(dbg), _stream()),
+            "flnerf_pp_composite_backward")
+    return dfg, dbg
+
+
+def pp_sample_pdf_merge(z, weights, Nf, det, u=None, seed=0, offset=0):
+    """ddp_train_nerf.py:369-382 -> (z_merged[B,Nc+Nf], z_samples[B,Nf])."""
+    B, Nc = z.shape
+    dev = z.device
+    zm = torch.empty(B, Nc + Nf, dtype=torch.float32, device=dev)
+    zs = torch.empty(B, Nf, dtype=torch.float32, device=dev)
+    L.check(L.load().flnerf_pp_sample_pdf_merge(_ctx(z), B, Nc, int(Nf), _ptr(_f32c(z)), _ptr(_f32c(weights)), _ptr(u),
+                                                int(bool(det)), int(seed), int(offset), _ptr(zm), _ptr(zs), _stream()),
+            "flnerf_pp_sample_pdf_merge")
+    return zm, zs

@@ -173,6 +173,34 @@ int flnerf_gather_batch(flnerf_ctx *, int64_t B, int64_t first, int64_t stride, 
                         const float *images, float *rays_o, float *rays_d, float *target, int32_t *leaf_gid,
                         void *stream);
 
+/* ---- next row: nerf++-ours dual-MLP path -- parity-tested building blocks, no complete path yet.
+ * Level-0 sample placement (ddp_train_nerf.py:54-81,352-366): fg_far[B] = unit-sphere exit depth, fg_z[B,N] linear in
+ * [1e-4, fg_far], bg_z[B,N] = linspace(0,1) inverse depths; perturb != 0 jitters both inside their mid-point intervals with
+ * the caller's uniforms t_fg/t_bg [B,N] (both or neither) or Philox(seed, offset). */
+int flnerf_pp_depths0(flnerf_ctx *, int64_t B, int N, const float *rays_o, const float *rays_d, const float *t_fg,
+                      const float *t_bg, int perturb, uint64_t seed, uint64_t offset, float *fg_far, float *fg_z, float *bg_z,
+                      void *stream);
+/* depth2pts_outside (ddp_model.py:16-45) + Embedder(4 -> 84) + Embedder(viewdir -> 27) in the FLIPPED sample order
+ * NerfNet.forward feeds its background network (ddp_model.py:113-117): x111[B,N,111], bg_z_flip[B,N]; pts4[B,N,4]
+ * (optional) = the un-flipped (unit direction, 1/r) points. */
+int flnerf_pp_bg_encode(flnerf_ctx *, int64_t B, int N, const float *rays_o, const float *rays_d, const float *bg_z,
+                        float *x111, float *bg_z_flip, float *pts4, void *stream);
+/* NerfNet.forward compositing (ddp_model.py:93-133) from the two networks' raw outputs [.,4] = (rgb before the sigmoid,
+ * sigma before |.|): rgb[B,3] = fg + bg_lambda*bg; fg_weights[B,Sf], bg_weights[B,Sb] (optional); aux9[B,9] (optional) =
+ * fg_rgb(3), fg_depth, bg_rgb(3), bg_depth, bg_lambda.  bg_z_flip runs 1 -> 0 as produced by flnerf_pp_bg_encode. */
+int flnerf_pp_composite_forward(flnerf_ctx *, int64_t B, int Sf, int Sb, const float *raw_fg, const float *fg_z,
+                                const float *fg_far, const float *raw_bg, const float *bg_z_flip, const float *rays_d,
+                                float *rgb, float *fg_weights, float *bg_weights, float *aux9, void *stream);
+/* its backward for a loss on rgb: draw_fg[B,Sf,4], draw_bg[B,Sb,4] */
+int flnerf_pp_composite_backward(flnerf_ctx *, int64_t B, int Sf, int Sb, const float *raw_fg, const float *fg_z,
+                                 const float *fg_far, const float *raw_bg, const float *bg_z_flip, const float *rays_d,
+                                 const float *g_rgb, float *draw_fg, float *draw_bg, void *stream);
+/* level-1 sample placement (ddp_train_nerf.py:84-133,369-382): Nf depths resampled from weights[...,1:-1] over the
+ * mid-point bins with the nerf++ sample_pdf (1e-6 floors, count-based inverse CDF), sort-merged with z[B,Nc]. */
+int flnerf_pp_sample_pdf_merge(flnerf_ctx *, int64_t B, int Nc, int Nf, const float *z, const float *weights,
+                               const float *u, int det, uint64_t seed, uint64_t offset, float *z_merged,
+                               float *z_samples, void *stream);
+
 /* ---- diagnostics: number of kernels this library launched since the counter was last reset */
 int64_t flnerf_launch_count(int reset);
 

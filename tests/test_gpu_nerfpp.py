@@ -1,0 +1,110 @@
+"""GPU (-m gpu): the first kernels of the nerf++ row through the C ABI against the oracle
+(oracle/nerfpp_oracle.py, itself pinned against the unmodified reference) and the golden fixture.
+Tolerances: pointwise geometry / encodings <= 3e-6 abs (libm vs torch transcendentals); compositing <= 2e-5 abs (parallel
+scans); resampled depths <= 2e-5 (inverse CDF through tiny bins); gradients 1e-4 relative-L2 against torch autograd of
+the oracle; sort order / merge exact."""
+import numpy as np
+import pytest
+import torch
+
+import nerfpp_oracle as P
+
+pytestmark = pytest.mark.gpu
+
+
+def T(a):
+    return torch.from_numpy(np.asarray(a)).cuda()
+
+
+def _rays(n, seed):
+    g = torch.Generator().manual_seed(seed)
+    o = torch.randn(n, 3, generator=g) * 0.25
+    d = torch.nn.functional.normalize(torch.randn(n, 3, generator=g), dim=-1) * (0.5 + torch.rand(n, 1, generator=g))
+    return o, d
+
+
+def test_sample_placement_and_background_points(golden):
+    from flnerf_b200 import ops
+    g = golden("nerfpp")
+    o, d = torch.from_numpy(g["ray_o"]), torch.from_numpy(g["ray_d"])
+    # level 0 without jitter == the oracle's linear / linspace depths; fg_far == the fixture
+    fg_far, fg_z, bg_z = ops.pp_depths0(o.cuda(), d.cuda(), 16, False)
+    np.testing.assert_allclose(fg_far.cpu().numpy(), g["fg_far"], atol=2e-6)
+    _, f0, b0 = P.cascade_depths(o, d, 16, 0)
+    np.testing.assert_allclose(fg_z.cpu().numpy(), f0.numpy(), atol=2e-6)
+    np.testing.assert_allclose(bg_z.cpu().numpy(), b0.numpy(), atol=1e-7)
+    # with the caller's uniforms == perturb_samples
+    o2, d2 = _rays(33, 4)
+    t_fg, t_bg = torch.rand(33, 64), torch.rand(33, 64)
+    _, f1, b1 = P.cascade_depths(o2, d2, 64, 0, t_fg=t_fg, t_bg=t_bg)
+    _, fg1, bg1 = ops.pp_depths0(o2.cuda(), d2.cuda(), 64, True, t_fg.cuda(), t_bg.cuda())
+    np.testing.assert_allclose(fg1.cpu().numpy(), f1.numpy(), atol=3e-6)
+    np.testing.assert_allclose(bg1.cpu().numpy(), b1.numpy(), atol=2e-7)
+    # Philox jitter: every sample stays inside its own mid-point interval, depths stay sorted
+    _, fg2, bg2 = ops.pp_depths0(o2.cuda(), d2.cuda(), 64, True, None, None, 7, 0)
+    assert bool((fg2[:, 1:] >= fg2[:, :-1]).all()) and bool((bg2[:, 1:] >= bg2[:, :-1]).all())
+    assert float(bg2.min()) >= 0 and float(bg2.max()) <= 1 and not torch.equal(fg2, fg1)
+    # inverted-sphere points (fixture) and the flipped 111-channel encoding (oracle)
+    x, zf, pts = ops.pp_bg_encode(T(g["ray_o"]), T(g["ray_d"]), T(g["bg_probe"]), want_pts=True)
+    np.testing.assert_allclose(pts.cpu().numpy(), g["bg_pts"], atol=3e-6)
+    assert torch.equal(zf.cpu(), torch.flip(torch.from_numpy(g["bg_probe"]), dims=[-1]))
+    v = torch.nn.functional.normalize(d, dim=-1)[:, None].expand(-1, 5, -1)
+    # the encoding is checked on the kernel's own points (sin(512 p) turns a 3e-6 point difference into 1.5e-3)
+    want = torch.flip(torch.cat((P.embed(pts.cpu(), 10), P.embed(v, 4)), -1), dims=[-2])
+    np.testing.assert_allclose(x.cpu().numpy(), want.numpy(), atol=2e-6)
+
+
+def test_composite_forward_backward_vs_oracle(golden):
+    from flnerf_b200 import ops
+    o, d = _rays(41, 9)
+    Sf, Sb = 70, 45                                   # > 32 and not multiples of the warp: exercises the chunk carries
+    fg_far, fg_z, bg_z = P.cascade_depths(o, d, Sf, 0, t_fg=torch.rand(41, Sf), t_bg=torch.rand(41, Sf))
+    bg_z = bg_z[:, :Sb].contiguous()
+    bg_flip = torch.flip(bg_z, dims=[-1]).contiguous()
+    raw_fg = (torch.randn(41, Sf, 4) * torch.tensor([1.0, 1.0, 1.0, 8.0])).requires_grad_(True)
+    raw_bg = (torch.randn(41, Sb, 4) * torch.tensor([1.0, 1.0, 1.0, 3.0])).requires_grad_(True)
+
+    def oracle(rf, rb):   # ddp_model.py:93-133 on raw outputs (rgb sigmoid, sigma abs), via the pinned oracle's own ops
+        nrm = torch.norm(d, dim=-1, keepdim=True)
+        fd = nrm * torch.cat((fg_z[..., 1:] - fg_z[..., :-1], fg_far.unsqueeze(-1) - fg_z[..., -1:]), -1)
+        fa = 1.0 - torch.exp(-torch.abs(rf[..., 3]) * fd)
+        Tt = torch.cumprod(1.0 - fa + P.TINY_NUMBER, -1)
+        lam = Tt[..., -1]
+        fw = fa * torch.cat((torch.ones_like(Tt[..., :1]), Tt[..., :-1]), -1)
+        bd = torch.cat((bg_flip[..., :-1] - bg_flip[..., 1:], P.HUGE_NUMBER * torch.ones_like(bg_flip[..., :1])), -1)
+        ba = 1.0 - torch.exp(-torch.abs(rb[..., 3]) * bd)
+        Tb = torch.cat((torch.ones_like(ba[..., :1]), torch.cumprod(1.0 - ba + P.TINY_NUMBER, -1)[..., :-1]), -1)
+        bw = ba * Tb
+        frgb = torch.sum(fw.unsqueeze(-1) * torch.sigmoid(rf[..., :3]), -2)
+        brgb = lam.unsqueeze(-1) * torch.sum(bw.unsqueeze(-1) * torch.sigmoid(rb[..., :3]), -2)
+        return frgb + brgb, fw, bw, lam
+
+    rgb_o, fw_o, bw_o, lam_o = oracle(raw_fg, raw_bg)
+    c = lambda t: t.detach().cuda().contiguous()
+    rgb, fw, bw, aux = ops.pp_composite_forward(c(raw_fg), c(fg_z), c(fg_far), c(raw_bg), c(bg_flip), c(d))
+    np.testing.assert_allclose(rgb.cpu().numpy(), rgb_o.detach().numpy(), atol=2e-5)
+    np.testing.assert_allclose(fw.cpu().numpy(), fw_o.detach().numpy(), atol=2e-5)
+    np.testing.assert_allclose(bw.cpu().numpy(), bw_o.detach().numpy(), atol=2e-5)
+    np.testing.assert_allclose(aux[:, 8].cpu().numpy(), lam_o.detach().numpy(), atol=2e-5)
+    g_rgb = torch.randn(41, 3)
+    (rgb_o * g_rgb).sum().backward()
+    dfg, dbg = ops.pp_composite_backward(c(raw_fg), c(fg_z), c(fg_far), c(raw_bg), c(bg_flip), c(d), g_rgb.cuda())
+    rel = lambda a, b: float((a - b).norm() / b.norm())
+    assert rel(dfg.cpu(), raw_fg.grad) < 1e-4 and rel(dbg.cpu(), raw_bg.grad) < 1e-4
+
+
+def test_level1_resampling_matches_oracle(golden):
+    from flnerf_b200 import ops
+    g = golden("nerfpp")
+    # the fixture's bins / weights are exactly the (mid-points, weights[1:-1]) interface of sample_pdf: rebuild a z whose
+    # mid-points are those bins is not possible in general, so drive the merged kernel with z and weights directly
+    z = torch.sort(torch.rand(29, 16), -1)[0] * 2 + 0.1
+    w = torch.rand(29, 16) ** 3
+    u = torch.rand(29, 24)
+    mid = 0.5 * (z[:, 1:] + z[:, :-1])
+    for uu in (u, None):
+        s = P.sample_pdf(mid, w[:, 1:-1], 24, uu)
+        zm, zs = ops.pp_sample_pdf_merge(z.cuda(), w.cuda(), 24, uu is None, None if uu is None else uu.cuda())
+        # t = (u - cdf_b) / den amplifies the last-bit differences of the cdf where a bin's mass is tiny (den ~ 1e-5)
+        np.testing.assert_allclose(zs.cpu().numpy(), s.numpy(), atol=2e-5)
+        assert torch.equal(zm.cpu(), torch.sort(torch.cat((z, zs.cpu()), -1), -1)[0])          # merge: exact
