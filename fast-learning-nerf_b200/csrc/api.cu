@@ -18,6 +18,12 @@ size_t mlp_simt_bwd_workspace_bytes(int64_t n);
 int mlp_simt_forward(const float *P, int64_t n, const float *x90, float *raw, float *stash, cudaStream_t st);
 int mlp_simt_backward(const float *P, int64_t n, const float *x90, const float *stash, const float *draw, float *G,
                       float *ws, cudaStream_t st);
+int64_t mlp_simt_param_count(int in_pts, int in_views);
+int mlp_simt_forward_g(int in_pts, int in_views, const float *P, int64_t n, const float *x, float *raw, float *stash,
+                       cudaStream_t st);
+int mlp_simt_backward_g(int in_pts, int in_views, const float *P, int64_t n, const float *x, const float *stash,
+                        const float *draw, float *G, float *ws, cudaStream_t st);
+int mlp_simt_layout_selfcheck();
 // mlp_tc.cu
 size_t mlp_tc_packed_bytes();
 size_t mlp_tc_stash_bytes(int64_t n, int S, int training);
@@ -124,6 +130,29 @@ int flnerf_mlp_backward_stages(flnerf_ctx *ctx, int mode, const float *params, c
              "flnerf_mlp_backward: packed / pe_tiles / stash / workspace must be 1024-byte aligned");
   return mlp_tc_backward(ctx, params, packed, n, S, x, dirpe, stash, draw, grads, workspace, stages,
                          (cudaStream_t)stream);
+}
+
+int64_t flnerf_mlp_param_count_g(int in_pts, int in_views) {
+  if (in_pts < 1 || in_views < 1) return -1;
+  return mlp_simt_param_count(in_pts, in_views);
+}
+
+int flnerf_mlp_fp32_forward_g(flnerf_ctx *ctx, int in_pts, int in_views, const float *params, int64_t n, const float *x,
+                              float *raw_out, void *stash, void *stream) {
+  FL_REQUIRE(ctx && params && x && raw_out && stash && n > 0 && in_pts > 0 && in_views > 0, "flnerf_mlp_fp32_forward_g: bad arguments");
+  FL_REQUIRE(((uintptr_t)raw_out & 15) == 0, "flnerf_mlp_fp32_forward_g: raw_out must be 16-byte aligned");
+  FL_REQUIRE(mlp_simt_layout_selfcheck() == 0, "flnerf: generic parameter layout disagrees with mlp_layout.h");
+  return mlp_simt_forward_g(in_pts, in_views, params, n, x, raw_out, (float *)stash, (cudaStream_t)stream);
+}
+
+int flnerf_mlp_fp32_backward_g(flnerf_ctx *ctx, int in_pts, int in_views, const float *params, int64_t n, const float *x,
+                               const void *stash, const float *draw, float *grads, void *workspace, size_t workspace_bytes,
+                               void *stream) {
+  FL_REQUIRE(ctx && params && x && stash && draw && grads && workspace && n > 0 && in_pts > 0 && in_views > 0,
+             "flnerf_mlp_fp32_backward_g: bad arguments");
+  FL_REQUIRE(workspace_bytes >= mlp_simt_bwd_workspace_bytes(n), "flnerf_mlp_fp32_backward_g: workspace too small");
+  return mlp_simt_backward_g(in_pts, in_views, params, n, x, (const float *)stash, draw, grads, (float *)workspace,
+                             (cudaStream_t)stream);
 }
 
 }  // extern "C"

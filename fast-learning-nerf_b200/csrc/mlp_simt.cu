@@ -164,73 +164,129 @@ GemmArgs wgrad_args(const float *dY, int64_t ldy, const float *X, int64_t ldx, f
 
 }  // namespace
 
+// Parameter offsets (floats) for D=8, W=256, skip after layer 4, with in_pts position channels and in_views view
+// channels, in the flat order of mlp_layout.h (pts_linears.0..7 {weight,bias}, views_linears.0, feature_linear,
+// alpha_linear, rgb_linear).  in_pts = 63, in_views = 27 reproduces mlp_layout.h; in_pts = 84 is the nerf++ background
+// network (nerf++-ours/nerf_network.py:70-118 has the same chain, see oracle/nerfpp_oracle.py).
+struct SimtLayout {
+  int in_pts, in_views;
+  int w_pts[8], b_pts[8], k_pts[8];
+  int w_views, b_views, w_feat, b_feat, w_alpha, b_alpha, w_rgb, b_rgb, total;
+};
+
+static SimtLayout make_layout(int in_pts, int in_views) {
+  SimtLayout L{};
+  L.in_pts = in_pts; L.in_views = in_views;
+  int off = 0;
+  for (int l = 0; l < 8; ++l) {
+    L.k_pts[l] = (l == 0) ? in_pts : (l == 5 ? in_pts + 256 : 256);
+    L.w_pts[l] = off; off += 256 * L.k_pts[l];
+    L.b_pts[l] = off; off += 256;
+  }
+  L.w_views = off; off += 128 * (256 + in_views);
+  L.b_views = off; off += 128;
+  L.w_feat = off; off += 256 * 256;
+  L.b_feat = off; off += 256;
+  L.w_alpha = off; off += 256;
+  L.b_alpha = off; off += 1;
+  L.w_rgb = off; off += 3 * 128;
+  L.b_rgb = off; off += 3;
+  L.total = off;
+  return L;
+}
+
+int64_t mlp_simt_param_count(int in_pts, int in_views) { return make_layout(in_pts, in_views).total; }
+
 size_t mlp_simt_stash_bytes(int64_t n) { return (size_t)n * (8 * 256 + 256 + 128) * sizeof(float); }
 size_t mlp_simt_bwd_workspace_bytes(int64_t n) { return (size_t)n * 2 * 256 * sizeof(float); }
 
-int mlp_simt_forward(const float *P, int64_t n, const float *x90, float *raw, float *stash, cudaStream_t st) {
+// x: fp32 [n, in_pts + in_views] (the reference's embedded layout)
+int mlp_simt_forward_g(int in_pts, int in_views, const float *P, int64_t n, const float *x, float *raw, float *stash,
+                       cudaStream_t st) {
+  const SimtLayout L = make_layout(in_pts, in_views);
+  const int ldx = in_pts + in_views, kv = 256 + in_views;
   float *H[8];
   for (int l = 0; l < 8; ++l) H[l] = stash + (size_t)l * n * 256;
   float *F = stash + (size_t)8 * n * 256;
   float *H9 = F + (size_t)n * 256;
-  using namespace mlp_layout;
-  RUN(launch_gemm(fwd_args(x90, 90, P + W_PTS[0], 63, H[0], 256, n, 256, 63, P + B_PTS[0], 1, 0), st));
+  RUN(launch_gemm(fwd_args(x, ldx, P + L.w_pts[0], in_pts, H[0], 256, n, 256, in_pts, P + L.b_pts[0], 1, 0), st));
   for (int l = 1; l < 8; ++l) {
-    if (l == 5) {  // skip: input = [x_pts(63), h(256)] (model.py:47)
-      RUN(launch_gemm(fwd_args(x90, 90, P + W_PTS[5], 319, H[5], 256, n, 256, 63, nullptr, 0, 0), st));
-      RUN(launch_gemm(fwd_args(H[4], 256, P + W_PTS[5] + 63, 319, H[5], 256, n, 256, 256, P + B_PTS[5], 1, 1), st));
+    if (l == 5) {  // skip: input = [x_pts, h(256)] (model.py:47)
+      RUN(launch_gemm(fwd_args(x, ldx, P + L.w_pts[5], L.k_pts[5], H[5], 256, n, 256, in_pts, nullptr, 0, 0), st));
+      RUN(launch_gemm(fwd_args(H[4], 256, P + L.w_pts[5] + in_pts, L.k_pts[5], H[5], 256, n, 256, 256, P + L.b_pts[5], 1, 1), st));
     } else {
-      RUN(launch_gemm(fwd_args(H[l - 1], 256, P + W_PTS[l], 256, H[l], 256, n, 256, 256, P + B_PTS[l], 1, 0), st));
+      RUN(launch_gemm(fwd_args(H[l - 1], 256, P + L.w_pts[l], 256, H[l], 256, n, 256, 256, P + L.b_pts[l], 1, 0), st));
     }
   }
-  RUN(launch_gemm(fwd_args(H[7], 256, P + W_ALPHA, 256, raw + 3, 4, n, 1, 256, P + B_ALPHA, 0, 0), st));
-  RUN(launch_gemm(fwd_args(H[7], 256, P + W_FEAT, 256, F, 256, n, 256, 256, P + B_FEAT, 0, 0), st));
-  RUN(launch_gemm(fwd_args(F, 256, P + W_VIEWS, 283, H9, 128, n, 128, 256, nullptr, 0, 0), st));
-  RUN(launch_gemm(fwd_args(x90 + 63, 90, P + W_VIEWS + 256, 283, H9, 128, n, 128, 27, P + B_VIEWS, 1, 1), st));
-  RUN(launch_gemm(fwd_args(H9, 128, P + W_RGB, 128, raw, 4, n, 3, 128, P + B_RGB, 0, 0), st));
+  RUN(launch_gemm(fwd_args(H[7], 256, P + L.w_alpha, 256, raw + 3, 4, n, 1, 256, P + L.b_alpha, 0, 0), st));
+  RUN(launch_gemm(fwd_args(H[7], 256, P + L.w_feat, 256, F, 256, n, 256, 256, P + L.b_feat, 0, 0), st));
+  RUN(launch_gemm(fwd_args(F, 256, P + L.w_views, kv, H9, 128, n, 128, 256, nullptr, 0, 0), st));
+  RUN(launch_gemm(fwd_args(x + in_pts, ldx, P + L.w_views + 256, kv, H9, 128, n, 128, in_views, P + L.b_views, 1, 1), st));
+  RUN(launch_gemm(fwd_args(H9, 128, P + L.w_rgb, 128, raw, 4, n, 3, 128, P + L.b_rgb, 0, 0), st));
   return 0;
 }
 
-int mlp_simt_backward(const float *P, int64_t n, const float *x90, const float *stash, const float *draw, float *G,
-                      float *ws, cudaStream_t st) {
+int mlp_simt_backward_g(int in_pts, int in_views, const float *P, int64_t n, const float *x, const float *stash,
+                        const float *draw, float *G, float *ws, cudaStream_t st) {
+  const SimtLayout L = make_layout(in_pts, in_views);
+  const int ldx = in_pts + in_views, kv = 256 + in_views;
   const float *H[8];
   for (int l = 0; l < 8; ++l) H[l] = stash + (size_t)l * n * 256;
   const float *F = stash + (size_t)8 * n * 256;
   const float *H9 = F + (size_t)n * 256;
   float *bufA = ws, *bufB = ws + (size_t)n * 256;
-  using namespace mlp_layout;
   // rgb head
-  RUN(launch_gemm(wgrad_args(draw, 4, H9, 128, G + W_RGB, 128, n, 3, 128), st));
-  RUN(launch_colsum(draw, n, 4, 3, G + B_RGB, st));
-  RUN(launch_colsum(draw + 3, n, 4, 1, G + B_ALPHA, st));
+  RUN(launch_gemm(wgrad_args(draw, 4, H9, 128, G + L.w_rgb, 128, n, 3, 128), st));
+  RUN(launch_colsum(draw, n, 4, 3, G + L.b_rgb, st));
+  RUN(launch_colsum(draw + 3, n, 4, 1, G + L.b_alpha, st));
   float *G9 = bufA;  // [n,128]
-  RUN(launch_gemm(dgrad_args(draw, 4, P + W_RGB, 128, G9, 128, n, 3, 128, H9, 128, 0), st));
+  RUN(launch_gemm(dgrad_args(draw, 4, P + L.w_rgb, 128, G9, 128, n, 3, 128, H9, 128, 0), st));
   // views layer
-  RUN(launch_gemm(wgrad_args(G9, 128, F, 256, G + W_VIEWS, 283, n, 128, 256), st));
-  RUN(launch_gemm(wgrad_args(G9, 128, x90 + 63, 90, G + W_VIEWS + 256, 283, n, 128, 27), st));
-  RUN(launch_colsum(G9, n, 128, 128, G + B_VIEWS, st));
+  RUN(launch_gemm(wgrad_args(G9, 128, F, 256, G + L.w_views, kv, n, 128, 256), st));
+  RUN(launch_gemm(wgrad_args(G9, 128, x + in_pts, ldx, G + L.w_views + 256, kv, n, 128, in_views), st));
+  RUN(launch_colsum(G9, n, 128, 128, G + L.b_views, st));
   float *GF = bufB;  // d feature [n,256]
-  RUN(launch_gemm(dgrad_args(G9, 128, P + W_VIEWS, 283, GF, 256, n, 128, 256, nullptr, 0, 0), st));
+  RUN(launch_gemm(dgrad_args(G9, 128, P + L.w_views, kv, GF, 256, n, 128, 256, nullptr, 0, 0), st));
   // feature + alpha
-  RUN(launch_gemm(wgrad_args(GF, 256, H[7], 256, G + W_FEAT, 256, n, 256, 256), st));
-  RUN(launch_colsum(GF, n, 256, 256, G + B_FEAT, st));
-  RUN(launch_gemm(wgrad_args(draw + 3, 4, H[7], 256, G + W_ALPHA, 256, n, 1, 256), st));
+  RUN(launch_gemm(wgrad_args(GF, 256, H[7], 256, G + L.w_feat, 256, n, 256, 256), st));
+  RUN(launch_colsum(GF, n, 256, 256, G + L.b_feat, st));
+  RUN(launch_gemm(wgrad_args(draw + 3, 4, H[7], 256, G + L.w_alpha, 256, n, 1, 256), st));
   float *cur = bufA;  // dH7 (pre-activation gradient of layer 7)
-  RUN(launch_gemm(dgrad_args(GF, 256, P + W_FEAT, 256, cur, 256, n, 256, 256, nullptr, 0, 0), st));
-  RUN(launch_gemm(dgrad_args(draw + 3, 4, P + W_ALPHA, 256, cur, 256, n, 1, 256, H[7], 256, 1), st));
+  RUN(launch_gemm(dgrad_args(GF, 256, P + L.w_feat, 256, cur, 256, n, 256, 256, nullptr, 0, 0), st));
+  RUN(launch_gemm(dgrad_args(draw + 3, 4, P + L.w_alpha, 256, cur, 256, n, 1, 256, H[7], 256, 1), st));
   float *other = bufB;
   for (int l = 7; l >= 1; --l) {
-    RUN(launch_colsum(cur, n, 256, 256, G + B_PTS[l], st));
+    RUN(launch_colsum(cur, n, 256, 256, G + L.b_pts[l], st));
     if (l == 5) {
-      RUN(launch_gemm(wgrad_args(cur, 256, x90, 90, G + W_PTS[5], 319, n, 256, 63), st));
-      RUN(launch_gemm(wgrad_args(cur, 256, H[4], 256, G + W_PTS[5] + 63, 319, n, 256, 256), st));
-      RUN(launch_gemm(dgrad_args(cur, 256, P + W_PTS[5] + 63, 319, other, 256, n, 256, 256, H[4], 256, 0), st));
+      RUN(launch_gemm(wgrad_args(cur, 256, x, ldx, G + L.w_pts[5], L.k_pts[5], n, 256, in_pts), st));
+      RUN(launch_gemm(wgrad_args(cur, 256, H[4], 256, G + L.w_pts[5] + in_pts, L.k_pts[5], n, 256, 256), st));
+      RUN(launch_gemm(dgrad_args(cur, 256, P + L.w_pts[5] + in_pts, L.k_pts[5], other, 256, n, 256, 256, H[4], 256, 0), st));
     } else {
-      RUN(launch_gemm(wgrad_args(cur, 256, H[l - 1], 256, G + W_PTS[l], 256, n, 256, 256), st));
-      RUN(launch_gemm(dgrad_args(cur, 256, P + W_PTS[l], 256, other, 256, n, 256, 256, H[l - 1], 256, 0), st));
+      RUN(launch_gemm(wgrad_args(cur, 256, H[l - 1], 256, G + L.w_pts[l], 256, n, 256, 256), st));
+      RUN(launch_gemm(dgrad_args(cur, 256, P + L.w_pts[l], 256, other, 256, n, 256, 256, H[l - 1], 256, 0), st));
     }
     float *t = cur; cur = other; other = t;
   }
-  RUN(launch_colsum(cur, n, 256, 256, G + B_PTS[0], st));
-  RUN(launch_gemm(wgrad_args(cur, 256, x90, 90, G + W_PTS[0], 63, n, 256, 63), st));
+  RUN(launch_colsum(cur, n, 256, 256, G + L.b_pts[0], st));
+  RUN(launch_gemm(wgrad_args(cur, 256, x, ldx, G + L.w_pts[0], in_pts, n, 256, in_pts), st));
   return 0;
+}
+
+// the nerf-ours network: 63 position + 27 view channels (offsets identical to mlp_layout.h, checked once)
+int mlp_simt_forward(const float *P, int64_t n, const float *x90, float *raw, float *stash, cudaStream_t st) {
+  return mlp_simt_forward_g(63, 27, P, n, x90, raw, stash, st);
+}
+
+int mlp_simt_backward(const float *P, int64_t n, const float *x90, const float *stash, const float *draw, float *G,
+                      float *ws, cudaStream_t st) {
+  return mlp_simt_backward_g(63, 27, P, n, x90, stash, draw, G, ws, st);
+}
+
+int mlp_simt_layout_selfcheck() {
+  using namespace mlp_layout;
+  const SimtLayout L = make_layout(63, 27);
+  bool ok = L.total == TOTAL && L.w_views == W_VIEWS && L.b_views == B_VIEWS && L.w_feat == W_FEAT && L.b_feat == B_FEAT &&
+            L.w_alpha == W_ALPHA && L.b_alpha == B_ALPHA && L.w_rgb == W_RGB && L.b_rgb == B_RGB;
+  for (int l = 0; l < 8; ++l) ok = ok && L.w_pts[l] == W_PTS[l] && L.b_pts[l] == B_PTS[l] && L.k_pts[l] == K_PTS[l];
+  return ok ? 0 : 1;
 }

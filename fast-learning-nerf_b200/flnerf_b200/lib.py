@@ -54,6 +54,9 @@ SIGNATURES = {
     "flnerf_qt_emit_prob": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp, _i64, _u64, _d, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp,
                                  _vp]),
     "flnerf_gather_batch": (_i, [_vp, _i64, _i64, _i64, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "flnerf_mlp_param_count_g": (_i64, [_i, _i]),
+    "flnerf_mlp_fp32_forward_g": (_i, [_vp, _i, _i, _vp, _i64, _vp, _vp, _vp, _vp]),
+    "flnerf_mlp_fp32_backward_g": (_i, [_vp, _i, _i, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "flnerf_pp_depths0": (_i, [_vp, _i64, _i, _vp, _vp, _vp, _vp, _i, _u64, _u64, _vp, _vp, _vp, _vp]),
     "flnerf_pp_bg_encode": (_i, [_vp, _i64, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "flnerf_pp_composite_forward": (_i, [_vp, _i64, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),

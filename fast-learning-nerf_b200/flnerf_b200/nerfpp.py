@@ -1,0 +1,71 @@
+"""First complete CUDA path of the nerf++ row, FP32 parity mode: NerfNet.forward (nerf++-ours/
+ddp_model.py:74-143) and its backward as a sequence of libflnerf.so kernels -- foreground network on the nerf-ours
+encode + MLP kernels, background network through ``flnerf_pp_bg_encode`` + the generic-width fp32 MLP, both composited by
+``flnerf_pp_composite_forward/backward``.  The tensor-core (bf16) path for the 84-channel background network, the cascade
+training loop and the reference-facing module API are still to come."""
+from typing import Dict
+
+import torch
+
+from . import ops
+from .lib import FlnerfError
+
+_ORDER = [("base_layers.%d.0" % i, "pts_linears.%d" % i) for i in range(8)] + \
+         [("rgb_layers.0", "views_linears.0"), ("base_remap_layers.0", "feature_linear"), ("sigma_layers.0", "alpha_linear"),
+          ("rgb_layers.2", "rgb_linear")]
+
+
+def flat_from_mlpnet(state: Dict[str, torch.Tensor], device) -> torch.Tensor:
+    """MLPNet.state_dict() (nerf_network.py:86-118) -> the flat fp32 parameter buffer of the flnerf kernels (nerf-ours
+    parameters() order: pts_linears.0..7, views_linears.0, feature_linear, alpha_linear, rgb_linear)."""
+    return torch.cat([state[a + s].reshape(-1).float() for a, _ in _ORDER for s in (".weight", ".bias")]).to(device).contiguous()
+
+
+def mlpnet_from_flat(flat: torch.Tensor, like: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
+    """Inverse of flat_from_mlpnet (used to hand gradients back under the reference's parameter names)."""
+    out, off = {}, 0
+    for a, _ in _ORDER:
+        for s in (".weight", ".bias"):
+            n = like[a + s].numel()
+            out[a + s] = flat[off:off + n].view(like[a + s].shape)
+            off += n
+    if off != flat.numel():
+        raise FlnerfError("parameter buffer has %d floats, the MLPNet needs %d" % (flat.numel(), off))
+    return out
+
+
+class NerfNetFP32:
+    """NerfNet.forward + backward without autograd (fp32 parity path)."""
+
+    def __init__(self, flat_fg: torch.Tensor, flat_bg: torch.Tensor, in_pts_bg: int = 84, in_views: int = 27):
+        self.fg, self.bg, self.in_bg, self.in_views = flat_fg, flat_bg, int(in_pts_bg), int(in_views)
+        self.grad_fg, self.grad_bg = torch.zeros_like(flat_fg), torch.zeros_like(flat_bg)
+        self._saved = None
+
+    @torch.no_grad()
+    def forward(self, ray_o, ray_d, fg_z_max, fg_z_vals, bg_z_vals):
+        B, Sf = fg_z_vals.shape
+        Sb = bg_z_vals.shape[1]
+        rays11 = ops.pack_rays(ray_o, ray_d, 0.0, 1.0, False, 1, 1, 1.0)       # o, d, -, -, viewdir = d/|d|
+        x_fg = ops.encode_f32(rays11, fg_z_vals)
+        raw_fg, st_fg = ops.mlp_forward(ops.MODE_FP32, self.fg, None, x_fg, None, B * Sf, Sf, True)
+        x_bg, bg_flip, _ = ops.pp_bg_encode(ray_o, ray_d, bg_z_vals)
+        raw_bg, st_bg = ops.mlp_fp32_forward_g(self.in_bg, self.in_views, self.bg, x_bg.view(B * Sb, -1), B * Sb)
+        rgb, fw, bw, aux = ops.pp_composite_forward(raw_fg.view(B, Sf, 4), fg_z_vals, fg_z_max, raw_bg.view(B, Sb, 4), bg_flip,
+                                                    ray_d)
+        self._saved = (B, Sf, Sb, x_fg, st_fg, raw_fg, x_bg, st_bg, raw_bg, fg_z_vals, fg_z_max, bg_flip, ray_d)
+        return {"rgb": rgb, "fg_weights": fw, "bg_weights": bw, "fg_rgb": aux[:, 0:3], "fg_depth": aux[:, 3],
+                "bg_rgb": aux[:, 4:7], "bg_depth": aux[:, 7], "bg_lambda": aux[:, 8]}
+
+    @torch.no_grad()
+    def backward(self, g_rgb):
+        """Accumulates d(loss)/d(params) into grad_fg / grad_bg for a loss whose gradient w.r.t. ret['rgb'] is g_rgb."""
+        if self._saved is None:
+            raise FlnerfError("NerfNetFP32.backward() without a forward()")
+        B, Sf, Sb, x_fg, st_fg, raw_fg, x_bg, st_bg, raw_bg, fg_z, fg_far, bg_flip, ray_d = self._saved
+        d_fg, d_bg = ops.pp_composite_backward(raw_fg.view(B, Sf, 4), fg_z, fg_far, raw_bg.view(B, Sb, 4), bg_flip, ray_d, g_rgb)
+        ops.mlp_backward(ops.MODE_FP32, self.fg, None, x_fg, None, st_fg, d_fg.view(B * Sf, 4), self.grad_fg, B * Sf, Sf)
+        ops.mlp_fp32_backward_g(self.in_bg, self.in_views, self.bg, x_bg.view(B * Sb, -1), st_bg, d_bg.view(B * Sb, 4),
+                                self.grad_bg, B * Sb)
+        self._saved = None
+        return self.grad_fg, self.grad_bg

@@ -370,3 +370,21 @@ def pp_sample_pdf_merge(z, weights, Nf, det, u=None, seed=0, offset=0):
                                                 int(bool(det)), int(seed), int(offset), _ptr(zm), _ptr(zs), _stream()),
             "flnerf_pp_sample_pdf_merge")
     return zm, zs
+
+
+def mlp_fp32_forward_g(in_pts, in_views, flat_params, x, n):
+    """The fp32 MLP with in_pts position / in_views view channels (84 / 27 = the nerf++ background network)."""
+    dev = flat_params.device
+    raw = torch.empty(n, 4, dtype=torch.float32, device=dev)
+    stash = _alloc_bytes(L.load().flnerf_mlp_stash_bytes(MODE_FP32, n, 1, 1), dev)
+    L.check(L.load().flnerf_mlp_fp32_forward_g(_ctx(flat_params), int(in_pts), int(in_views), _ptr(flat_params), int(n),
+                                               _ptr(_f32c(x)), _ptr(raw), _ptr(stash), _stream()), "flnerf_mlp_fp32_forward_g")
+    return raw, stash
+
+
+def mlp_fp32_backward_g(in_pts, in_views, flat_params, x, stash, draw, grads, n):
+    nbytes = L.load().flnerf_mlp_bwd_workspace_bytes(MODE_FP32, n)
+    ws = _alloc_bytes(nbytes, flat_params.device)
+    L.check(L.load().flnerf_mlp_fp32_backward_g(_ctx(flat_params), int(in_pts), int(in_views), _ptr(flat_params), int(n),
+                                                _ptr(_f32c(x)), _ptr(stash), _ptr(_f32c(draw)), _ptr(grads), _ptr(ws),
+                                                int(nbytes), _stream()), "flnerf_mlp_fp32_backward_g")

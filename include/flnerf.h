@@ -85,6 +85,17 @@ int flnerf_mlp_backward(flnerf_ctx *, int mode, const float *params, const void 
                         const void *x, const float *dirpe, const void *stash, const float *draw, float *grads,
                         void *workspace, size_t workspace_bytes, void *stream);
 
+/* ---- the same MLP with a caller-chosen number of position / view channels, FP32 (CUDA-core) path only: in_pts = 63,
+ * in_views = 27 is the nerf-ours network; in_pts = 84 is the nerf++ background network (nerf++-ours/nerf_network.py:70-142,
+ * PE of (x,y,z,1/r)).  params / grads: flat fp32[flnerf_mlp_param_count_g()] in the order above; x fp32 [n, in_pts+in_views];
+ * stash / workspace sizes are those of FLNERF_MODE_FP32. */
+int64_t flnerf_mlp_param_count_g(int in_pts, int in_views);
+int flnerf_mlp_fp32_forward_g(flnerf_ctx *, int in_pts, int in_views, const float *params, int64_t n, const float *x,
+                              float *raw_out, void *stash, void *stream);
+int flnerf_mlp_fp32_backward_g(flnerf_ctx *, int in_pts, int in_views, const float *params, int64_t n, const float *x,
+                               const void *stash, const float *draw, float *grads, void *workspace, size_t workspace_bytes,
+                               void *stream);
+
 /* same, running only the selected backward kernels (bit 0: data-gradient chain, bit 1: weight gradients, bit 2:
  * rgb/view-direction heads) -- used by bench.py to time each kernel with CUDA events; FP32 mode ignores it */
 int flnerf_mlp_backward_stages(flnerf_ctx *, int mode, const float *params, const void *packed, int64_t n, int S,

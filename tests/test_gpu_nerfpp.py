@@ -108,3 +108,29 @@ def test_level1_resampling_matches_oracle(golden):
         # t = (u - cdf_b) / den amplifies the last-bit differences of the cdf where a bin's mass is tiny (den ~ 1e-5)
         np.testing.assert_allclose(zs.cpu().numpy(), s.numpy(), atol=2e-5)
         assert torch.equal(zm.cpu(), torch.sort(torch.cat((z, zs.cpu()), -1), -1)[0])          # merge: exact
+
+
+def test_nerfnet_fp32_forward_backward_vs_oracle():
+    """The first complete CUDA path of this row: NerfNet.forward + backward (fp32 kernels, no autograd) against the pinned
+    oracle and torch autograd of it -- rgb / weights / bg_lambda <= 3e-5 abs, parameter gradients <= 2e-3 relative-L2 (the
+    bar the nerf-ours fp32 path is held to)."""
+    from flnerf_b200 import nerfpp
+    p_fg = {k: v.clone().requires_grad_(True) for k, v in P.init_mlp_params(21, 63).items()}
+    p_bg = {k: v.clone().requires_grad_(True) for k, v in P.init_mlp_params(22, 84).items()}
+    o, d = _rays(19, 3)
+    N = 24
+    fg_far, fg_z, bg_z = P.cascade_depths(o, d, N, 0, t_fg=torch.rand(19, N), t_bg=torch.rand(19, N))
+    ret = P.nerfnet_forward(p_fg, p_bg, o, d, fg_far, fg_z, bg_z)
+    g = torch.randn(19, 3)
+    (ret["rgb"] * g).sum().backward()
+    net = nerfpp.NerfNetFP32(nerfpp.flat_from_mlpnet({k: v.detach() for k, v in p_fg.items()}, "cuda"),
+                             nerfpp.flat_from_mlpnet({k: v.detach() for k, v in p_bg.items()}, "cuda"))
+    out = net.forward(o.cuda(), d.cuda(), fg_far.cuda(), fg_z.cuda(), bg_z.cuda())
+    for k in ("rgb", "fg_weights", "bg_weights", "bg_lambda", "fg_rgb", "bg_rgb", "fg_depth", "bg_depth"):
+        np.testing.assert_allclose(out[k].cpu().numpy(), ret[k].detach().numpy(), atol=3e-5, err_msg=k)
+    gf, gb = net.backward(g.cuda())
+    want_f = nerfpp.flat_from_mlpnet({k: v.grad for k, v in p_fg.items()}, "cpu")
+    want_b = nerfpp.flat_from_mlpnet({k: v.grad for k, v in p_bg.items()}, "cpu")
+    rel = lambda a, b: float((a - b).norm() / b.norm())
+    assert rel(gf.cpu(), want_f) < 2e-3 and rel(gb.cpu(), want_b) < 2e-3, (rel(gf.cpu(), want_f), rel(gb.cpu(), want_b))
+    assert gb.numel() == 595844 + 21 * 256 * 2 and gf.numel() == 595844      # 84 instead of 63 channels at layers 0 and 5

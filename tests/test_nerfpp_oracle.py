@@ -97,3 +97,20 @@ def test_against_live_reference():
     fg1, bg1 = torch.sort(torch.cat((fg_z, fg_s), -1))[0], torch.sort(torch.cat((bg_z, bg_s), -1))[0]
     _, a1, b1 = P.cascade_depths(o, d, 16, 8, ret0={k: v for k, v in want.items()}, fg_prev=fg_z, bg_prev=bg_z, u_fg=u_fg, u_bg=u_bg)
     assert torch.equal(a1, fg1) and torch.equal(b1, bg1)
+
+
+def test_flat_parameter_mapping_roundtrip():
+    """flnerf_b200.nerfpp: MLPNet.state_dict() <-> the flat parameter order of the kernels (host logic, no device)."""
+    from flnerf_b200 import nerfpp
+    import nerf_oracle as O
+    for seed, ch in ((5, 63), (6, 84)):
+        p = P.init_mlp_params(seed, ch)
+        flat = nerfpp.flat_from_mlpnet(p, "cpu")
+        assert flat.numel() == 595844 + (ch - 63) * 256 * 2
+        back = nerfpp.mlpnet_from_flat(flat, p)
+        assert all(torch.equal(back[k], p[k]) for k in p)
+    # for 63 channels the flat buffer IS the nerf-ours parameter vector of the renamed state dict
+    p = P.init_mlp_params(5, 63)
+    q = P.mlp_params_to_nerf_layout(p)
+    ref_order = list(O.init_params(0).keys())
+    assert torch.equal(nerfpp.flat_from_mlpnet(p, "cpu"), torch.cat([q[k].reshape(-1) for k in ref_order]))
