@@ -69,3 +69,42 @@ class NerfNetFP32:
                                 self.grad_bg, B * Sb)
         self._saved = None
         return self.grad_fg, self.grad_bg
+
+
+class FlatAdam:
+    """torch.optim.Adam(lr, betas=(0.9, 0.999), eps=1e-8) over flat parameter buffers (one fused kernel per buffer)."""
+
+    def __init__(self, flats, lr=5e-4, betas=(0.9, 0.999), eps=1e-8):
+        self.flats, self.lr, self.betas, self.eps, self.t = list(flats), float(lr), betas, float(eps), 0
+        self.m = [torch.zeros_like(f) for f in self.flats]
+        self.v = [torch.zeros_like(f) for f in self.flats]
+
+    def step(self, grads):
+        self.t += 1
+        for f, m, v, g in zip(self.flats, self.m, self.v, grads):
+            ops.adam_step(f, m, v, g, self.lr, self.betas[0], self.betas[1], self.eps, self.t)
+
+
+@torch.no_grad()
+def cascade_train_step(nets, adams, ray_o, ray_d, rgb_gt, samples=(64, 128), t_fg=None, t_bg=None, u_fg=None, u_bg=None,
+                       seed=0, offset=0):
+    """One iteration of the nerf++ training loop for one batch (ddp_train_nerf.py:346-404, auto-exposure off): two cascade
+    levels, each a NerfNetFP32 with its own FlatAdam; level 1 resamples the fg and bg depths from level 0's weights
+    (bg_weights un-flipped, as the fork does).  Uniforms are the caller's (parity) or Philox(seed, offset).  Returns the two
+    losses as DEVICE tensors and the last rgb."""
+    B = ray_o.shape[0]
+    losses, ret, fg_z, bg_z, fg_far = [], None, None, None, None
+    for m, net in enumerate(nets):
+        if m == 0:
+            fg_far, fg_z, bg_z = ops.pp_depths0(ray_o, ray_d, samples[0], True, t_fg, t_bg, seed, offset)
+        else:
+            fg_z, _ = ops.pp_sample_pdf_merge(fg_z, ret["fg_weights"], samples[1], False, u_fg, seed + 1, offset)
+            bg_z, _ = ops.pp_sample_pdf_merge(bg_z, ret["bg_weights"], samples[1], False, u_bg, seed + 2, offset)
+        net.grad_fg.zero_()
+        net.grad_bg.zero_()
+        ret = net.forward(ray_o, ray_d, fg_far, fg_z, bg_z)
+        loss, d_rgb, _ = ops.mse_leafmax(ret["rgb"], None, rgb_gt, B)
+        net.backward(d_rgb)
+        adams[m].step([net.grad_fg, net.grad_bg])
+        losses.append(loss[0:1])
+    return torch.cat(losses), ret["rgb"]

@@ -226,3 +226,32 @@ def cascade_depths(ray_o, ray_d, n0: int, n1: int, ret0=None, fg_prev=None, bg_p
     bg_s = sample_pdf(bg_mid, bg_w[..., 1:-1], n1, u_bg).detach()
     bg, _ = torch.sort(torch.cat((bg_prev, bg_s), dim=-1))
     return fg_far, fg, bg
+
+
+def train_step(levels, adams, ray_o, ray_d, rgb_gt, samples=(64, 128), t_fg=None, t_bg=None, u_fg=None, u_bg=None):
+    """One iteration of nerf++-ours train_step for ONE batch (ddp_train_nerf.py:346-404, auto-exposure off): cascade level
+    m has its own NerfNet ``levels[m] = (p_fg, p_bg)`` and its own Adam ``adams[m]`` (nerf_oracle.AdamState over
+    list(p_fg.values()) + list(p_bg.values())); level 1 resamples both depth sets from level 0's weights (with the fork's
+    un-flipped bg_weights, see cascade_depths).  Explicit uniforms replace torch.rand.  Returns per-level loss / gradients."""
+    out, ret, fg_z, bg_z = [], None, None, None
+    for m, (p_fg, p_bg) in enumerate(levels):
+        params = list(p_fg.values()) + list(p_bg.values())
+        for q in params:
+            q.requires_grad_(True)
+            q.grad = None
+        if m == 0:
+            fg_far, fg_z, bg_z = cascade_depths(ray_o, ray_d, samples[0], 0, t_fg=t_fg, t_bg=t_bg)
+        else:
+            fg_far, fg_z, bg_z = cascade_depths(ray_o, ray_d, samples[0], samples[1], ret0=ret, fg_prev=fg_z, bg_prev=bg_z,
+                                                u_fg=u_fg, u_bg=u_bg)
+        ret = nerfnet_forward(p_fg, p_bg, ray_o, ray_d, fg_far, fg_z, bg_z)
+        loss = torch.mean((ret["rgb"] - rgb_gt) * (ret["rgb"] - rgb_gt))          # utils.img2mse (utils.py:12-14)
+        loss.backward()
+        grads = [q.grad.clone() for q in params]
+        with torch.no_grad():
+            adams[m].step(grads)
+        for q in params:
+            q.requires_grad_(False)
+        ret = {k: v.detach() for k, v in ret.items()}
+        out.append({"loss": float(loss.detach()), "grads": grads, "rgb": ret["rgb"], "fg_z": fg_z, "bg_z": bg_z})
+    return out
