@@ -72,3 +72,19 @@ def test_prob_sampling_matches_image_processor(ref):
             np.random.seed(11 + i)
             u = np.random.random_sample(500)
             assert np.array_equal(O.sample_pixels(block, u), want)
+
+
+def test_compute_ssim_matches_reference(ref):
+    """run_nerf_helpers.compute_ssim (run_nerf_helpers.py:158-234, the metric render_path reports) -- pure torch on both
+    sides, so the product function is compared directly (it needs no device)."""
+    import importlib
+    ours = importlib.import_module("run_nerf_helpers")          # fast-learning-nerf_b200/run_nerf_helpers.py (conftest path)
+    rs = np.random.RandomState(2)
+    a = torch.from_numpy(rs.uniform(0, 1, (40, 36, 3)).astype(np.float32))
+    b = (a + torch.from_numpy(rs.normal(0, 0.05, (40, 36, 3)).astype(np.float32))).clamp(0, 1)
+    want = ref.helpers.compute_ssim(a, b)
+    got = ours.compute_ssim(a, b)
+    np.testing.assert_allclose(float(got), float(want), rtol=1e-5)
+    np.testing.assert_allclose(ours.compute_ssim(a, b, return_map=True).numpy(), ref.helpers.compute_ssim(a, b, return_map=True).numpy(),
+                               atol=2e-5)
+    assert abs(float(ours.compute_ssim(a, a)) - 1.0) < 1e-6
