@@ -91,3 +91,23 @@ def test_variance_driven_initial_tree_matches_reference(golden):
         # DFS leaf order survives the SoA round trip used by QuadTreeManager.quadTrees
         t2 = tree.QuadTree((48, 48), 0.0, 1, _boxes=boxes, _min_area=t.minArea)
         assert [n.box() for n in tree.get_children(t2.root)] == [tuple(b) for b in boxes]
+
+
+def test_bench_clock_sampler_window():
+    """bench.py's nvidia-smi sampler: rows are windowed by arrival time; a timed region shorter than the sampling period
+    falls back to every row taken under load and says so."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(os.path.dirname(PKG), "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    cs = bench.ClockSampler(0)
+    cs.proc = object()                       # pretend nvidia-smi is running
+    row = lambda mhz, cap: [str(mhz), "1965", "700.0", "Not Active", "Not Active", "Not Active", cap]
+    cs.rows = [(1.0, row(1900, "Not Active")), (2.0, row(1950, "Active")), (2.5, row(1930, "Active")), (9.0, row(600, "Not Active"))]
+    w = cs.window(1.5, 3.0)
+    assert w["samples"] == 2 and w["sm_mhz"] == 1950.0 and w["sm_max_mhz"] == 1965.0 and w["reasons"] == ["sw_power_cap"]
+    assert w["window"] == "timed region"
+    w = cs.window(3.1, 3.2)                  # nothing inside: fall back to all rows
+    assert w["samples"] == 4 and "no sample fell inside" in w["window"]
+    none = bench.ClockSampler(0)
+    assert none.window(0, 1)["reasons"] == ["nvidia-smi unavailable"]
