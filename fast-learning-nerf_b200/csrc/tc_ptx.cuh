@@ -38,7 +38,7 @@ __device__ __noinline__ void mbar_timeout(uint32_t bar, uint32_t parity) {
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins > (1u << 17)) mbar_timeout(bar, parity);
+    if (++spins > (1u << 20)) mbar_timeout(bar, parity);
   }
 }
 
