@@ -132,6 +132,7 @@ def load_nerfpp():
         ns.network = importlib.import_module("nerf_network")
         ns.model = importlib.import_module("ddp_model")
         ns.train = importlib.import_module("ddp_train_nerf")
+        ns.tree = sys.modules["tree"]              # nerf++-ours/tree.py (the .mean() refinement variant)
     finally:
         sys.path[:] = saved_path
         for k, v in saved_mods.items():

@@ -114,3 +114,30 @@ def test_flat_parameter_mapping_roundtrip():
     q = P.mlp_params_to_nerf_layout(p)
     ref_order = list(O.init_params(0).keys())
     assert torch.equal(nerfpp.flat_from_mlpnet(p, "cpu"), torch.cat([q[k].reshape(-1) for k in ref_order]))
+
+
+@pytest.mark.skipif(not ref_shim.available(), reason="reference tree not present")
+def test_mean_refinement_variant_matches_nerfpp_tree():
+    """nerf++-ours/tree.py:610-632 splits on leaf_loss.mean() > thres: the oracle's leaf_mean_table + refine reproduce its
+    leaf lists (incl. leaves without rays, whose NaN mean never splits)."""
+    import nerf_oracle as O
+    T = ref_shim.load_nerfpp().tree
+    rs = np.random.RandomState(4)
+    img = rs.uniform(0, 1, (32, 32, 3)).astype(np.float32)
+    t = T.QuadTree(img, 0.0, 3)
+    ch = T.get_children(t.root)
+    boxes = [(n.x0, n.y0, n.x1, n.y1) for n in ch]
+    n_rays = 400
+    lid = np.stack([np.zeros(n_rays), rs.randint(0, len(ch) - 2, n_rays)], 1).astype(np.float32)   # the last two leaves get no rays
+    gt = rs.uniform(0, 1, (n_rays, 3)).astype(np.float32)
+    pred = (gt + rs.normal(0, 0.02, gt.shape) * (rs.rand(n_rays, 1) > 0.5)).astype(np.float32)
+    thres = 0.008
+
+    class M:
+        childrens = [ch]
+    T.adjust_tree_subThread(M, 0, torch.from_numpy(lid), torch.abs(torch.from_numpy(gt) - torch.from_numpy(pred)), ch, thres, t)
+    want = [(n.x0, n.y0, n.x1, n.y1) for n in M.childrens[0]]
+    table = O.leaf_mean_table(lid, gt, pred, 1, [len(boxes)])
+    assert np.isnan(table[0][-1]) and np.isnan(table[0][-2])
+    got, new_min = O.refine(boxes, 32 * 32 / 16, table[0], thres)
+    assert got == want and new_min == t.minArea and len(got) > len(boxes)
