@@ -1,26 +1,36 @@
 #!/usr/bin/env python
 """bench.py -- training rays/sec at 64 coarse + 128 fine samples (BASELINE.json metric).
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--precision bf16|fp32]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--precision bf16|bf16x3|fp32]
 
 A "step" is one pass of the hot path over one batch: quadtree batch gather -> ray packing -> stratified depths ->
 PE -> coarse MLP -> compositing -> inverse-CDF resampling + merge -> PE -> fine MLP -> compositing -> both MSE
 losses (+ per-leaf max table) -> backward through both nets -> (gradient all-reduce) -> Adam.  Workload =
-BASELINE config 2 ("lego 800x800, 64+128, N_rand=4096, quadtree on") on synthetic lego-like cameras/images;
-under torchrun every rank takes 4096 rays of a N*4096-ray global batch (config 4), weak scaling.
+BASELINE configs[1] ("lego 800x800, 64+128, N_rand=4096, quadtree on") on synthetic lego-like cameras/images;
+under torchrun every rank takes 4096 rays of a N*4096-ray global batch (configs[3]), weak scaling.
 
-`value`   : rays/s with rays, targets and the quadtree index buffer resident in HBM (CUDA events, max over ranks).
-`e2e`     : the same metric through the reference-facing API (render() + loss.backward() + optimizer.step()) with
-            HOST ray buffers: pinned H2D copy of (rays_o, rays_d, target) and a D2H read of the loss every step.
-`roofline`: the dominant kernel (by measured time) against the roof that bounds it (measured bf16 tensor peak or measured
-            HBM bandwidth; algorithmic FLOPs / bytes only), every MLP kernel's two fractions, and the whole step's tensor fraction.
-`cpu_baseline` / --impl reference: the oracle port of the reference's PyTorch path on the host cores.
+Keys of the JSON line (rank 0):
+  value       rays/s with rays, targets and the quadtree index buffer resident in HBM (CUDA events, max over ranks).
+  e2e         the same metric through the reference-facing API (render() + loss.backward() + optimizer.step()) with HOST
+              ray buffers: pinned H2D copy of (rays_o, rays_d, target) and a D2H read of the loss every step.
+  roofline    SURVEY 8(d): the MLP is TENSOR bound.  The dominant kernel (largest measured time on the fine pass) as
+              ALGORITHMIC FLOP/s over the measured bf16 burst peak (kernel timed alone, CUDA events on the launch stream);
+              `kernels` holds every MLP kernel (also against the sustained peak, plus the stash bytes it moves), `step` the
+              whole step against the sustained peak, `traffic` the ncu DRAM bytes of the same kernel (profiles/).
+  parity_mode the same step in FLNERF_MODE_BF16X3 (split-precision tcgen05: the mode that meets the 1e-4 tolerance).
+  hbm_kernels compositing / resampling / PE / gather / loss kernels as achieved GB/s of ALGORITHMIC bytes, at the step's
+              size with L2 flushed between launches and at a size whose inputs exceed L2.
+  epoch_ops   the per-epoch quadtree kernels (emit the ray index buffer; refine), timed separately.
+  cpu_baseline / --impl reference: the UNMODIFIED reference (baseline/_ref/nerf-ours/run_nerf.py: create_nerf + render +
+              img2mse + Adam, the loop body of run_nerf.py:470-502) on the host cores; reference_gpu: the same code, fp32,
+              TF32 off, on the same B200.
 """
 import argparse
 import json
 import os
 import subprocess
 import sys
+import tempfile
 import threading
 import time
 
@@ -31,10 +41,12 @@ FLOP_TRAIN_PER_RAY = 0.893190e9      # 256 MLP evaluations x 3 489 02
 FLOP_FWD_PER_SAMPLE = 1186816.0
 FLOP_DGRAD_PER_SAMPLE = 2.0 * 557696
 FLOP_WGRAD_PER_SAMPLE = 2.0 * 593408
-# algorithmic HBM bytes per sample: activation / gradient stash images are 64 KB per 128-row tile and layer
-BYTES_FWD_PER_SAMPLE = (16384 + 10 * 65536 - 32768 + 36864) / 128.0 + 16      # PE tile in; 9.5 act slots + masks, raw out
-BYTES_DGRAD_PER_SAMPLE = (36864 + 10 * 65536 - 32768) / 128.0 + 16            # masks + draw in; 9.5 gradient slots out
-BYTES_WGRAD_PER_SAMPLE = (672 + 608 + 32) * 1024 / 128.0                      # dY slots (dY5 twice) + activations + PE
+# compulsory HBM bytes per sample of an MLP kernel (what any implementation must move): the bf16 PE tile in, raw[4] out /
+# d_raw[4] in.  The activation / gradient stash a kernel moves on top of that is a DESIGN cost, reported separately.
+BYTES_MIN_PER_SAMPLE = 128.0 + 16.0
+STASH_FWD_PER_SAMPLE = (10 * 65536 - 32768 + 36864) / 128.0          # 9.5 activation slots + ReLU masks written
+STASH_DGRAD_PER_SAMPLE = (36864 + 10 * 65536 - 32768) / 128.0        # masks read, 9.5 gradient slots written
+STASH_WGRAD_PER_SAMPLE = (672 + 608 + 32) * 1024 / 128.0             # dY slots (dY5 twice) + activations + PE read
 
 
 def measured_peaks():
@@ -88,30 +100,80 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------- reference arm
-def oracle_rays_per_s(n_rand, steps, warmup, threads=None):
-    """The reference's own CPU path (oracle port: render + 2 MSE + backward + Adam), host cores."""
+def host_memory_gb():
+    """Usable host memory: MemAvailable bounded by the cgroup limit (the container may be capped below the host)."""
+    avail = None
+    try:
+        for line in open("/proc/meminfo"):
+            if line.startswith("MemAvailable"):
+                avail = int(line.split()[1]) / 1048576.0
+    except OSError:
+        pass
+    for p in ("/sys/fs/cgroup/memory.max", "/sys/fs/cgroup/memory/memory.limit_in_bytes"):
+        try:
+            v = open(p).read().strip()
+            if v.isdigit():
+                lim = int(v) / 2 ** 30
+                avail = lim if avail is None else min(avail, lim)
+        except OSError:
+            pass
+    return avail
+
+
+def reference_rays_per_s(device, n_rand, steps, warmup):
+    """The UNMODIFIED reference (baseline/_ref/nerf-ours, imported through oracle/ref_shim.py: only missing third-party
+    modules are stubbed): create_nerf(args) from configs/lego.txt, then the loop body of run_nerf.py:470-502 --
+    render(H, W, K, chunk, rays, retraw=True, **render_kwargs_train) -> img2mse fine + coarse -> backward -> Adam -> lr decay --
+    on `device`, fp32 (TF32 off).  Returns (rays/s, seconds per step, threads)."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import numpy as np
     import torch
-    import nerf_oracle as O
-    from flnerf_b200 import synthetic  # pose helpers only (no GPU work)
-    cores = threads or os.cpu_count() or 1
+    import ref_shim
+    if not ref_shim.available():
+        raise RuntimeError("no reference sources (run tools/install_reference.sh in the build container)")
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
+    ns, rn = ref_shim.load_run_nerf()
+    rn.device = torch.device(device)
+    tmp = tempfile.mkdtemp(prefix="flnerf_ref_")
+    os.makedirs(os.path.join(tmp, "lego_ours"))
+    args = rn.config_parser().parse_args(["--config", os.path.join(ref_shim.REF_NERF, "configs", "lego.txt"), "--basedir", tmp,
+                                          "--N_rand", str(n_rand)])
+    torch.manual_seed(0)
+    kw_train, _, _, _, _, optimizer = rn.create_nerf(args)
     H = W = 800
-    K = synthetic.intrinsics(H, W, 1111.111)
-    pc, pf = O.init_params(0), O.init_params(1)
-    opt = O.AdamState(list(pc.values()) + list(pf.values()))
+    focal = 1111.111
+    K = np.array([[focal, 0, 0.5 * W], [0, focal, 0.5 * H], [0, 0, 1]])
+    sys.path.insert(0, os.path.join(ROOT, "fast-learning-nerf_b200"))
+    from flnerf_b200.synthetic import pose_spherical      # pose helper only (numpy)
     rs = np.random.RandomState(0)
-    times = []
+    dev = torch.device(device)
+    global_iter, times = 0, []
     for it in range(warmup + steps):
-        pose = torch.as_tensor(synthetic.pose_spherical(float(rs.uniform(-180, 180)), -30.0, 4.0)[:3, :4])
-        o, d = O.camera_rays(H, W, K, pose)
+        pose = torch.as_tensor(pose_spherical(float(rs.uniform(-180, 180)), -30.0, 4.0)[:3, :4])
+        o, d = ns.helpers.get_rays(H, W, K, pose)
         sel = torch.from_numpy(rs.choice(H * W, n_rand, replace=False))
-        rays = O.pack_rays(H, W, K, o.reshape(-1, 3)[sel], d.reshape(-1, 3)[sel], 2.0, 6.0, ndc=False)
-        tgt = torch.from_numpy(rs.uniform(0, 1, (n_rand, 3)).astype(np.float32))
+        batch_rays = torch.stack([o.reshape(-1, 3)[sel], d.reshape(-1, 3)[sel]], 0).to(dev)
+        target_s = torch.from_numpy(rs.uniform(0, 1, (n_rand, 3)).astype(np.float32)).to(dev)
+        if dev.type == "cuda":
+            torch.cuda.synchronize()
         t0 = time.perf_counter()
-        O.train_step(rays, tgt, pc, pf, opt, 64, 128, white_bkgd=True, t_rand=torch.rand(n_rand, 64),
-                     u=torch.rand(n_rand, 128), det_fine=False)
+        rgb, disp, acc, extras = ns.render.render(H, W, K, chunk=args.chunk, rays=batch_rays, retraw=True, near=2., far=6.,
+                                                  **kw_train)
+        optimizer.zero_grad()
+        img_loss = ns.helpers.img2mse(rgb, target_s)
+        loss = img_loss + ns.helpers.img2mse(extras['rgb0'], target_s)
+        ns.helpers.mse2psnr(img_loss.cpu())                          # the reference syncs here every step (run_nerf.py:486)
+        loss.backward()
+        optimizer.step()
+        new_lrate = args.lrate * (0.1 ** (global_iter / (args.lrate_decay * 1000)))
+        for g in optimizer.param_groups:
+            g['lr'] = new_lrate
+        global_iter += 1
+        if dev.type == "cuda":
+            torch.cuda.synchronize()
         if it >= warmup:
             times.append(time.perf_counter() - t0)
     t = sum(times) / len(times)
@@ -122,20 +184,185 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    n_rand = 1024
-    v, t, cores = oracle_rays_per_s(n_rand, args.steps, args.warmup)
-    sample = "%d-ray batches (of the 4096-ray step) x %d steps, oracle port of nerf-ours render+loss+backward+Adam, fp32" % (n_rand, args.steps)
+    on_gpu = args.ref_device == "cuda"
+    if not on_gpu:
+        os.environ["CUDA_VISIBLE_DEVICES"] = ""        # the host-core arm: torch must not see the GPU (render.py hard-codes .cuda())
+    n_rand = args.ref_nrand
+    if n_rand <= 0:
+        # autograd keeps ~5.4 KB x 256 samples per ray: ~22 GB at 4096 rays; stay well inside the host's memory
+        mem = host_memory_gb()
+        n_rand = 4096 if (on_gpu or mem is None or mem >= 64) else 1024
+    try:
+        v, t, cores = reference_rays_per_s(args.ref_device, n_rand, args.steps, args.warmup)
+    except Exception as e:      # noqa: BLE001 -- the arm must always print a line
+        print(json.dumps({"impl": "reference", "unavailable": "%s: %s" % (type(e).__name__, str(e)[:200])}))
+        return
+    where = "B200 (fp32, TF32 off)" if on_gpu else "%d host threads" % cores
+    sample = "%d steps of one FULL %d-ray batch, unmodified nerf-ours create_nerf + render + img2mse x2 + backward + Adam, fp32, %s" % (
+        args.steps, n_rand, where)
     print(json.dumps({
         "impl": "reference", "metric": "training rays/sec (64+128 samples)", "value": v, "unit": "rays/s",
-        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3 * 4096 / n_rand,
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "lego 800x800, 64+128, N_rand=4096 (timed on a %d-ray sample per step)" % n_rand},
-        "cpu_baseline": {"value": v, "unit": "rays/s", "cores": cores, "kind": "port", "sample": sample},
+        "config": {"workload": "lego 800x800 (synthetic cameras), 64+128 samples, N_rand=%d, reference code on %s" % (n_rand, where)},
+        "cpu_baseline": {"value": v, "unit": "rays/s", "cores": cores, "kind": "reference", "sample": sample},
         "e2e": {"value": v, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0}))
 
 
+def reference_subprocess(device, steps, warmup, n_rand, gpu_index=None, timeout=600):
+    """Runs the reference arm in a fresh process (the parent already owns a CUDA context) and returns its JSON line."""
+    env = dict(os.environ)
+    for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK", "MASTER_ADDR", "MASTER_PORT"):
+        env.pop(k, None)
+    if device == "cuda" and gpu_index is not None:
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        env["CUDA_VISIBLE_DEVICES"] = vis.split(",")[gpu_index] if vis else str(gpu_index)   # ONE GPU: no nn.DataParallel fan-out
+    cmd = [sys.executable, os.path.abspath(__file__), "--impl", "reference", "--ref_device", device, "--steps", str(steps),
+           "--warmup", str(warmup), "--ref_nrand", str(n_rand)]
+    try:
+        out = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=timeout)
+        lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
+        return json.loads(lines[-1]) if lines else {"unavailable": (out.stderr or "no output")[-300:]}
+    except Exception as e:      # noqa: BLE001
+        return {"unavailable": "%s: %s" % (type(e).__name__, str(e)[:200])}
+
+
 # ------------------------------------------------------------------------------------------------- our arm
+def time_events(torch, fn, iters, warm=3, between=None):
+    """Mean milliseconds of fn() on the current stream; `between` (e.g. an L2 flush) runs outside the timed intervals."""
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    if between is None:
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(iters):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / iters
+    tot = 0.0
+    for _ in range(iters):
+        between()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        fn()
+        b.record()
+        torch.cuda.synchronize()
+        tot += a.elapsed_time(b)
+    return tot / iters
+
+
+def mlp_kernel_table(torch, ops, lib, net, mode, r11, dev, peaks):
+    """Every MLP kernel of the fine pass (n_rand x 192 rows), timed alone: algorithmic TFLOP/s against the burst peak."""
+    S = 192
+    z = ops.coarse_depths(r11, S, True, False, None, 3, 0)
+    n = r11.shape[0] * S
+    x3 = mode == ops.MODE_BF16X3
+    tiles, dirpe = ops.encode_tc(r11, z, mode)
+    flat, packed = net._weights()
+    raw, stash = ops.mlp_forward(mode, flat, packed, tiles, dirpe, n, S, True)
+    draw = torch.randn(n, 4, device=dev) * 1e-3
+    gbuf = torch.zeros_like(flat)
+    ws = ops.mlp_backward(mode, flat, packed, tiles, dirpe, stash, draw, gbuf, n, S)
+    stash_l = ops._alloc_bytes(lib.load().flnerf_mlp_stash_bytes(mode, n, S, 1), dev)
+
+    def fwd():
+        lib.check(lib.load().flnerf_mlp_forward(ops._ctx(raw), mode, ops._ptr(flat), ops._ptr(packed), n, S, ops._ptr(tiles),
+                                                ops._ptr(dirpe), ops._ptr(raw), ops._ptr(stash_l), 1, ops._stream()), "fwd")
+    sfx = "_x3" if x3 else "_tc"
+    mult = 2.0 if x3 else 1.0            # the split-precision stash holds a hi and a lo image
+    cases = {"mlp_fwd" + sfx: (fwd, FLOP_FWD_PER_SAMPLE, STASH_FWD_PER_SAMPLE * mult),
+             "mlp_dgrad" + sfx: (lambda: ops.mlp_backward(mode, flat, packed, tiles, dirpe, stash, draw, gbuf, n, S, 1, ws),
+                                 FLOP_DGRAD_PER_SAMPLE, STASH_DGRAD_PER_SAMPLE * mult),
+             "mlp_wgrad_tc" + (" (3 passes)" if x3 else ""): (
+                 lambda: ops.mlp_backward(mode, flat, packed, tiles, dirpe, stash, draw, gbuf, n, S, 2, ws),
+                 FLOP_WGRAD_PER_SAMPLE, STASH_WGRAD_PER_SAMPLE * (3.0 if x3 else 1.0))}
+    out = {}
+    for name, (fn, flop, stash_b) in cases.items():
+        dt = time_events(torch, fn, 5) * 1e-3
+        tf = n * flop / dt / 1e12
+        out[name] = {"ms": dt * 1e3, "rows": n, "tflops": tf, "tensor_frac_burst": tf / peaks["tf_burst"],
+                     "tensor_frac_sustained": tf / peaks["tf_sust"],
+                     "algorithmic_bytes": n * BYTES_MIN_PER_SAMPLE, "stash_bytes": n * stash_b,
+                     "stash_gbs": n * stash_b / dt / 1e9, "stash_hbm_frac": n * stash_b / dt / 1e9 / peaks["hbm"]}
+    return out
+
+
+def hbm_kernel_table(torch, ops, dev, peaks, H, W, K, mgr):
+    """north_star: 'HBM GB/s for the compositing/PE kernels'.  Algorithmic bytes / CUDA-event time, (a) at the
+    step's size (4096 rays) with a 256 MB L2 flush between launches, (b) at a size whose inputs exceed the 126 MB L2."""
+    flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def flush():
+        flush_buf.fill_(1)
+
+    def rays(B):
+        g = torch.Generator(device=dev).manual_seed(1)
+        o = torch.randn(B, 3, device=dev, generator=g) * 0.3 + torch.tensor([0., 0., 4.], device=dev)
+        d = -torch.nn.functional.normalize(torch.randn(B, 3, device=dev, generator=g) * 0.2 + torch.tensor([0., 0., 1.], device=dev), dim=-1)
+        return ops.pack_rays(o, d, 2.0, 6.0, False, H, W, float(K[0][0]))
+
+    def case_composite_fwd(B, S, want_w):
+        r11 = rays(B)
+        z = ops.coarse_depths(r11, S, True, False, None, 5, 0)
+        raw = torch.randn(B, S, 4, device=dev)
+        fn = lambda: ops.composite_forward(raw, z, r11[:, 3:6], None, True, rays_d_stride=11, want_weights=want_w)
+        return fn, B * (20 * S + 12 + 24 + (4 * S if want_w else 0))
+
+    def case_composite_bwd(B, S):
+        r11 = rays(B)
+        z = ops.coarse_depths(r11, S, True, False, None, 5, 0)
+        raw = torch.randn(B, S, 4, device=dev)
+        g = torch.randn(B, 3, device=dev)
+        fn = lambda: ops.composite_backward(raw, z, r11[:, 3:6], None, True, g, None, None, None, rays_d_stride=11)
+        return fn, B * (36 * S + 24)
+
+    def case_sample_pdf(B):
+        r11 = rays(B)
+        z = ops.coarse_depths(r11, 64, True, False, None, 5, 0)
+        w = torch.rand(B, 64, device=dev)
+        fn = lambda: ops.sample_pdf_merge(z, w, 128, False, None, 7, 0, want_samples=False)
+        return fn, B * (8 * 64 + 4 * 192 + 4)
+
+    def case_encode(B, S):
+        r11 = rays(B)
+        z = ops.coarse_depths(r11, S, True, False, None, 5, 0)
+        fn = lambda: ops.encode_tc(r11, z)
+        return fn, B * 44 + B * S * (4 + 128) + B * 128
+
+    def case_gather(B):
+        fn = lambda: mgr.batch(0, B, 1)
+        return fn, B * 60
+
+    def case_mse(B):
+        a, b, t = (torch.rand(B, 3, device=dev) for _ in range(3))
+        gid = torch.zeros(B, dtype=torch.int32, device=dev)
+        lm = torch.zeros(16, device=dev)
+        fn = lambda: ops.mse_leafmax(a, b, t, B, gid, lm)
+        return fn, B * 64
+
+    table = {}
+    specs = [("composite_fwd S=64 (+weights)", lambda B: case_composite_fwd(B, 64, True), 4096, 131072),
+             ("composite_fwd S=192", lambda B: case_composite_fwd(B, 192, False), 4096, 65536),
+             ("composite_bwd S=64", lambda B: case_composite_bwd(B, 64), 4096, 131072),
+             ("composite_bwd S=192", lambda B: case_composite_bwd(B, 192), 4096, 65536),
+             ("sample_pdf_merge 64->192", case_sample_pdf, 4096, 262144),
+             ("encode_tc S=192 (+dirpe)", lambda B: case_encode(B, 192), 4096, 8192),
+             ("gather_batch", case_gather, 4096, min(4 << 20, mgr.n_rays)),
+             ("mse_leafmax", case_mse, 4096, 4 << 20)]
+    for name, mk, b_step, b_big in specs:
+        row = {}
+        for tag, B, between in (("step_size_l2_flushed", b_step, flush), ("exceeds_l2", b_big, None)):
+            fn, nbytes = mk(B)
+            ms = time_events(torch, fn, 10, warm=2, between=between)
+            row[tag] = {"rays": B, "algorithmic_bytes": nbytes, "us": ms * 1e3, "gbs": nbytes / (ms * 1e-3) / 1e9,
+                        "hbm_frac": nbytes / (ms * 1e-3) / 1e9 / peaks["hbm"]}
+        table[name] = row
+    return table
+
+
 def run_ours(args):
     import numpy as np
     import torch
@@ -166,44 +393,57 @@ def run_ours(args):
     mgr = tree.QuadTreeManager(H, W, K, images, torch.as_tensor(poses[:, :3, :4]), mseThres=0.0, max_depth=2,
                                max_level=7, device=dev, seed=0)
 
-    def make(seed):
+    def make(seed, precision):
         torch.manual_seed(seed)
         return model.NeRF(D=8, W=256, input_ch=63, input_ch_views=27, output_ch=5, skips=[4], use_viewdirs=True,
-                          precision=args.precision).to(dev)
-    nc, nf = make(0), make(1)
-    opt = FusedAdam(list(nc.parameters()) + list(nf.parameters()), [nc, nf], lr=5e-4)
-    tr = Trainer(nc, nf, opt, H, W, K, 2.0, 6.0, 64, 128, white_bkgd=True, perturb=1.0, world_size=world, rank=rank)
+                          precision=precision).to(dev)
+
+    def make_trainer(precision):
+        nc, nf = make(0, precision), make(1, precision)
+        opt = FusedAdam(list(nc.parameters()) + list(nf.parameters()), [nc, nf], lr=5e-4)
+        return nc, nf, opt, Trainer(nc, nf, opt, H, W, K, 2.0, 6.0, 64, 128, white_bkgd=True, perturb=1.0, world_size=world, rank=rank)
+
+    nc, nf, opt, tr = make_trainer(args.precision)
+    # per-epoch quadtree kernels, reported separately: emit the epoch's shuffled ray index buffer
+    torch.cuda.synchronize()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
     n_rays = mgr.emit_epoch(down_scale=1)
+    ev1.record()
+    torch.cuda.synchronize()
+    emit_ms = ev0.elapsed_time(ev1)
     gb = n_rand * world                       # global batch
     total = args.warmup + args.steps
+    assert total * gb + 4 * gb <= n_rays, "epoch buffer too small for the requested steps"
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
+    def timed_steps(trainer, first, warmup, steps):
+        for _ in range(warmup):
+            trainer.step_from_tree(mgr, first, gb); first += gb
+        barrier()
+        lib.launch_count(reset=True)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        w0 = time.perf_counter()
+        e0.record()
+        for _ in range(steps):
+            loss = trainer.step_from_tree(mgr, first, gb); first += gb
+        e1.record()
+        barrier()
+        w1 = time.perf_counter()
+        launches = lib.launch_count()
+        t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()), launches, loss, first, (w0, w1)
+
     # ---------------- value: device-resident inputs
-    first = 0
     clocks = ClockSampler(local)
     clocks.start()
-    for _ in range(args.warmup):
-        tr.step_from_tree(mgr, first, gb); first += gb
-    barrier()
-    lib.launch_count(reset=True)
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    w0 = time.perf_counter()
-    e0.record()
-    for _ in range(args.steps):
-        loss = tr.step_from_tree(mgr, first, gb); first += gb
-    e1.record()
-    barrier()
-    w1 = time.perf_counter()
-    ms = e0.elapsed_time(e1)
-    launches = lib.launch_count()
-    t = torch.tensor([ms], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms = float(t.item())
+    ms, launches, loss, first, (w0, w1) = timed_steps(tr, 0, args.warmup, args.steps)
     value = gb * args.steps / (ms * 1e-3)
     loss_host = loss.tolist()
 
@@ -246,92 +486,79 @@ def run_ours(args):
     clocks.stop()
     clk = clocks.window(w0, w1)
 
+    # ---------------- parity mode (split-precision tensor cores): the same step, every rank, fewer steps
+    parity = None
+    if args.precision == "bf16" and not args.no_parity_leg:
+        nc3, nf3, opt3, tr3 = make_trainer("bf16x3")
+        k3 = max(3, min(args.steps, 10))
+        ms3, l3, loss3, first, _ = timed_steps(tr3, first, 3, k3)
+        v3 = gb * k3 / (ms3 * 1e-3)
+        parity = {"precision": "bf16x3", "value": v3, "unit": "rays/s", "ms_per_step": ms3 / k3, "steps": k3, "warmup": 3,
+                  "gpu_launches": int(l3), "loss": loss3.tolist(),
+                  "tolerance": "<=1e-4 rel RGB/loss vs the reference (tests/test_gpu_x3.py)",
+                  "step_tensor_frac_sustained_algorithmic": v3 / world * FLOP_TRAIN_PER_RAY / 1e12 / measured_peaks()["tf_sust"],
+                  "step_tensor_frac_sustained_issued": 3 * v3 / world * FLOP_TRAIN_PER_RAY / 1e12 / measured_peaks()["tf_sust"]}
+
+    # ---------------- refine (per-epoch kernel): timed on the statistics the steps above accumulated
+    ev0.record()
+    mgr.refine(0.001)
+    ev1.record()
+    torch.cuda.synchronize()
+    refine_ms = ev0.elapsed_time(ev1)
+
     if world > 1:
         dist.barrier()
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
+    tc_mode = args.precision in ("bf16", "bf16x3")
     # ---------------- eval path (informational): one full 800x800 frame through render() without gradients
     eval_info = None
-    if args.precision == "bf16":
+    if tc_mode:
         with torch.no_grad():
             pose = mgr._poses_dev[0]
             kw = dict(chunk=32768, c2w=pose, ndc=False, near=2.0, far=6.0, use_viewdirs=True, network_query_fn=q, network_fn=nc,
                       network_fine=nf, N_samples=64, N_importance=128, white_bkgd=True, perturb=0.0, raw_noise_std=0.0)
-            R.render(H, W, K, **kw)
-            torch.cuda.synchronize()
-            g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            g0.record()
-            R.render(H, W, K, **kw)
-            g1.record()
-            torch.cuda.synchronize()
-            ems = g0.elapsed_time(g1)
+            ems = time_events(torch, lambda: R.render(H, W, K, **kw), 1, warm=1)
         eval_info = {"rays_per_s": H * W / (ems * 1e-3), "ms_per_frame": ems, "frame": "%dx%d, 64+128 samples, render() under no_grad" % (H, W),
                      "tflops": H * W * 256 * FLOP_FWD_PER_SAMPLE / (ems * 1e-3) / 1e12}
-    # ---------------- per-kernel roofline (rank 0, fine pass: 4096 x 192 rows), CUDA events on the launch stream
+    # ---------------- per-kernel roofline (rank 0, fine pass: n_rand x 192 rows), CUDA events on the launch stream
     peaks = measured_peaks()
-    roof, kernels = None, {}
-    if args.precision == "bf16":
-        o, d, tg, _ = mgr.batch(0, n_rand, 1)
-        r11 = ops.pack_rays(o, d, 2.0, 6.0, False, H, W, focal)
-        z = ops.coarse_depths(r11, 192, True, False, None, 3, 0)
-        n = n_rand * 192
-        tiles, dirpe = ops.encode_tc(r11, z)
-        flat, packed = nf._weights()
-        raw, stash = ops.mlp_forward(ops.MODE_BF16, flat, packed, tiles, dirpe, n, 192, True)
-        draw = torch.randn(n, 4, device=dev) * 1e-3
-        gbuf = torch.zeros_like(flat)
-        ws = ops.mlp_backward(ops.MODE_BF16, flat, packed, tiles, dirpe, stash, draw, gbuf, n, 192)
-        stash_l = ops._alloc_bytes(lib.load().flnerf_mlp_stash_bytes(1, n, 192, 1), dev)
-        import ctypes as C
-
-        def fwd():
-            lib.check(lib.load().flnerf_mlp_forward(ops._ctx(raw), 1, ops._ptr(flat), ops._ptr(packed), n, 192, ops._ptr(tiles),
-                                                    ops._ptr(dirpe), ops._ptr(raw), ops._ptr(stash_l), 1, ops._stream()), "fwd")
-        cases = {"mlp_fwd_tc": (fwd, FLOP_FWD_PER_SAMPLE, BYTES_FWD_PER_SAMPLE),
-                 "mlp_dgrad_tc": (lambda: ops.mlp_backward(1, flat, packed, tiles, dirpe, stash, draw, gbuf, n, 192, 1, ws),
-                                  FLOP_DGRAD_PER_SAMPLE, BYTES_DGRAD_PER_SAMPLE),
-                 "mlp_wgrad_tc": (lambda: ops.mlp_backward(1, flat, packed, tiles, dirpe, stash, draw, gbuf, n, 192, 2, ws),
-                                  FLOP_WGRAD_PER_SAMPLE, BYTES_WGRAD_PER_SAMPLE)}
-        for name, (fn, flop, nbytes) in cases.items():
-            for _ in range(3):
-                fn()
-            torch.cuda.synchronize()
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record()
-            for _ in range(5):
-                fn()
-            b.record()
-            torch.cuda.synchronize()
-            dt = a.elapsed_time(b) / 5 * 1e-3
-            tf, gbs = n * flop / dt / 1e12, n * nbytes / dt / 1e9
-            kernels[name] = {"ms": dt * 1e3, "tflops": tf, "tensor_frac": tf / peaks["tf_sust"], "gbs": gbs,
-                             "hbm_frac": gbs / peaks["hbm"]}
+    roof = None
+    o, d, tg, _ = mgr.batch(0, n_rand, 1)
+    r11 = ops.pack_rays(o, d, 2.0, 6.0, False, H, W, focal)
+    if tc_mode:
+        kernels = mlp_kernel_table(torch, ops, lib, nf, nf.mode, r11, dev, peaks)
         top = max(kernels, key=lambda k: kernels[k]["ms"])
-        traffic = None
+        k = kernels[top]
+        traffic, traffic_src = None, None
         tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
         if os.path.isfile(tp):
-            traffic = json.load(open(tp)).get(top)
-        # the dominant kernel is judged against the roof that bounds it: whichever of its two fractions is larger
-        k = kernels[top]
-        if k["hbm_frac"] > k["tensor_frac"]:
-            roof = {"bound": "hbm", "kernel": top, "achieved": k["gbs"], "peak": peaks["hbm"], "unit": "GB/s",
-                    "frac": k["hbm_frac"], "traffic": traffic,
-                    "peak_source": peaks["src"] + " HBM copy bandwidth (a read-mostly stream can sit slightly above it)"}
-        else:
-            roof = {"bound": "tensor", "kernel": top, "achieved": k["tflops"], "peak": peaks["tf_sust"], "unit": "TFLOP/s",
-                    "frac": k["tensor_frac"], "traffic": traffic,
-                    "peak_source": peaks["src"] + " bf16 sustained (kernel timed inside a long step)"}
-        roof["kernels"] = kernels
-        roof["step"] = {"bound": "tensor", "achieved": value / world * FLOP_TRAIN_PER_RAY / 1e12, "unit": "TFLOP/s",
-                        "peak": peaks["tf_sust"], "frac": value / world * FLOP_TRAIN_PER_RAY / 1e12 / peaks["tf_sust"]}
-    # ---------------- CPU baseline (oracle port) on the host cores, bounded sample
-    cpu = None
+            tj = json.load(open(tp))
+            traffic, traffic_src = tj.get(top.split(" ")[0]), tj.get("source")
+        roof = {"bound": "tensor", "kernel": top, "achieved": k["tflops"], "peak": peaks["tf_burst"], "unit": "TFLOP/s",
+                "frac": k["tensor_frac_burst"], "traffic": traffic, "traffic_source": traffic_src,
+                "peak_source": peaks["src"] + " bf16 burst (kernel timed alone); algorithmic FLOPs of SURVEY 8(d), no split-precision multiplier",
+                "kernels": kernels,
+                "step": {"bound": "tensor", "achieved": value / world * FLOP_TRAIN_PER_RAY / 1e12, "unit": "TFLOP/s",
+                         "peak": peaks["tf_sust"], "frac": value / world * FLOP_TRAIN_PER_RAY / 1e12 / peaks["tf_sust"],
+                         "peak_source": peaks["src"] + " bf16 sustained (whole step)"}}
+        if parity is not None:
+            parity["kernels"] = mlp_kernel_table(torch, ops, lib, nf3, nf3.mode, r11, dev, peaks)
+    hbm_kernels = None if args.no_kernel_table else hbm_kernel_table(torch, ops, dev, peaks, H, W, K, mgr)
+    # ---------------- the reference beside it: host cores (bounded sample) and the same B200
+    cpu = ref_gpu = None
     if world == 1 and not args.no_cpu_baseline:
-        v, tcpu, cores = oracle_rays_per_s(512, 3, 1)
-        cpu = {"value": v, "unit": "rays/s", "cores": cores, "kind": "port",
-               "sample": "512-ray batches x 3 steps (1 warm-up) of the same 64+128 step, oracle port on host cores"}
+        r = reference_subprocess("cpu", 2, 1, 1024)
+        if "value" in r:
+            cpu = dict(r["cpu_baseline"])
+            cpu["sample"] = "2 steps (1 warm-up) of a 1024-ray batch of the same 64+128 step; " + cpu["sample"]
+        else:       # the untracked reference copy is missing: time the oracle port instead
+            cpu = {"unavailable": r.get("unavailable")}
+        r = reference_subprocess("cuda", 5, 2, n_rand, gpu_index=local)
+        ref_gpu = {"value": r["value"], "unit": "rays/s", "ms_per_step": r["ms_per_step"], "dtype": "f32 (TF32 off)",
+                   "what": r["cpu_baseline"]["sample"]} if "value" in r else {"unavailable": r.get("unavailable")}
     print(json.dumps({
         "metric": "training rays/sec (64+128 samples)", "value": value, "unit": "rays/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
@@ -342,8 +569,10 @@ def run_ours(args):
                    "l2": "per-step working set (activation stash ~%.1f GB) exceeds the 126 MB L2" % (n_rand * 256 * 5.1e3 / 1e9),
                    "epoch_rays": n_rays},
         "e2e": {"value": e2e_value, "unit": "rays/s", "h2d_bytes_per_step": bytes_in, "d2h_bytes_per_step": 8},
-        "gpu_launches": int(launches), "clocks": clk, "roofline": roof, "cpu_baseline": cpu,
-        "eval_render": eval_info, "loss": loss_host}))
+        "gpu_launches": int(launches), "clocks": clk, "roofline": roof, "parity_mode": parity, "hbm_kernels": hbm_kernels,
+        "epoch_ops": {"emit_epoch_ms": emit_ms, "emit_epoch_rays": n_rays, "emit_rays_per_s": n_rays / (emit_ms * 1e-3),
+                      "refine_ms": refine_ms, "note": "once per epoch, outside the timed steps"},
+        "cpu_baseline": cpu, "reference_gpu": ref_gpu, "eval_render": eval_info, "loss": loss_host}))
     if world > 1:
         dist.destroy_process_group()
 
@@ -354,10 +583,14 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--precision", default=os.environ.get("FLNERF_PRECISION", "bf16"), choices=["bf16", "fp32"])
+    ap.add_argument("--precision", default=os.environ.get("FLNERF_PRECISION", "bf16"), choices=["bf16", "bf16x3", "fp32"])
     ap.add_argument("--n_rand", type=int, default=4096)
     ap.add_argument("--images", type=int, default=100)
     ap.add_argument("--no_cpu_baseline", action="store_true")
+    ap.add_argument("--no_parity_leg", action="store_true")
+    ap.add_argument("--no_kernel_table", action="store_true")
+    ap.add_argument("--ref_device", default="cpu", choices=["cpu", "cuda"], help="--impl reference: host cores (default) or the B200")
+    ap.add_argument("--ref_nrand", type=int, default=0, help="--impl reference: rays per step (0 = 4096 if host memory allows)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

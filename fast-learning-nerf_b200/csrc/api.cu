@@ -26,12 +26,12 @@ int mlp_simt_backward_g(int in_pts, int in_views, const float *P, int64_t n, con
 int mlp_simt_layout_selfcheck();
 // mlp_tc.cu
 size_t mlp_tc_packed_bytes();
-size_t mlp_tc_stash_bytes(int64_t n, int S, int training);
-size_t mlp_tc_bwd_workspace_bytes(int64_t n);
+size_t mlp_tc_stash_bytes(int64_t n, int S, int training, bool x3);
+size_t mlp_tc_bwd_workspace_bytes(int64_t n, bool x3);
 int mlp_tc_pack_weights(flnerf_ctx *ctx, const float *params, void *packed, cudaStream_t st);
-int mlp_tc_forward(flnerf_ctx *ctx, const float *params, const void *packed, int64_t n, int S, const void *pe_tiles,
+int mlp_tc_forward(flnerf_ctx *ctx, bool x3, const float *params, const void *packed, int64_t n, int S, const void *pe_tiles,
                    const float *dirpe, float *raw, void *stash, int training, cudaStream_t st);
-int mlp_tc_backward(flnerf_ctx *ctx, const float *params, const void *packed, int64_t n, int S, const void *pe_tiles,
+int mlp_tc_backward(flnerf_ctx *ctx, bool x3, const float *params, const void *packed, int64_t n, int S, const void *pe_tiles,
                     const float *dirpe, const void *stash, const float *draw, float *grads, void *ws, int stages,
                     cudaStream_t st);
 
@@ -77,12 +77,12 @@ size_t flnerf_mlp_packed_bytes(void) { return mlp_tc_packed_bytes(); }
 
 size_t flnerf_mlp_stash_bytes(int mode, int64_t n, int S, int training) {
   if (mode == FLNERF_MODE_FP32) return mlp_simt_stash_bytes(n);
-  return mlp_tc_stash_bytes(n, S, training);
+  return mlp_tc_stash_bytes(n, S, training, mode == FLNERF_MODE_BF16X3);
 }
 
 size_t flnerf_mlp_bwd_workspace_bytes(int mode, int64_t n) {
   if (mode == FLNERF_MODE_FP32) return mlp_simt_bwd_workspace_bytes(n);
-  return mlp_tc_bwd_workspace_bytes(n);
+  return mlp_tc_bwd_workspace_bytes(n, mode == FLNERF_MODE_BF16X3);
 }
 
 int flnerf_mlp_pack_weights(flnerf_ctx *ctx, const float *params, void *packed, void *stream) {
@@ -96,11 +96,12 @@ int flnerf_mlp_forward(flnerf_ctx *ctx, int mode, const float *params, const voi
   FL_REQUIRE(ctx && params && x && raw_out && stash && n > 0 && S > 0, "flnerf_mlp_forward: bad arguments");
   FL_REQUIRE(((uintptr_t)raw_out & 15) == 0, "flnerf_mlp_forward: raw_out must be 16-byte aligned");
   if (mode == FLNERF_MODE_FP32) return mlp_simt_forward(params, n, (const float *)x, raw_out, (float *)stash, (cudaStream_t)stream);
-  FL_REQUIRE(mode == FLNERF_MODE_BF16, "flnerf_mlp_forward: unknown mode %d", mode);
-  FL_REQUIRE(packed && dirpe, "flnerf_mlp_forward: bf16 mode needs packed weights and dirpe");
+  FL_REQUIRE(mode == FLNERF_MODE_BF16 || mode == FLNERF_MODE_BF16X3, "flnerf_mlp_forward: unknown mode %d", mode);
+  FL_REQUIRE(packed && dirpe, "flnerf_mlp_forward: the tensor-core modes need packed weights and dirpe");
   FL_REQUIRE((((uintptr_t)packed | (uintptr_t)x | (uintptr_t)stash) & 1023) == 0,
              "flnerf_mlp_forward: packed / pe_tiles / stash must be 1024-byte aligned");
-  return mlp_tc_forward(ctx, params, packed, n, S, x, dirpe, raw_out, stash, training, (cudaStream_t)stream);
+  return mlp_tc_forward(ctx, mode == FLNERF_MODE_BF16X3, params, packed, n, S, x, dirpe, raw_out, stash, training,
+                        (cudaStream_t)stream);
 }
 
 int flnerf_mlp_backward_stages(flnerf_ctx *ctx, int mode, const float *params, const void *packed, int64_t n, int S,
@@ -124,12 +125,12 @@ int flnerf_mlp_backward_stages(flnerf_ctx *ctx, int mode, const float *params, c
   if (mode == FLNERF_MODE_FP32)
     return mlp_simt_backward(params, n, (const float *)x, (const float *)stash, draw, grads, (float *)workspace,
                              (cudaStream_t)stream);
-  FL_REQUIRE(mode == FLNERF_MODE_BF16, "flnerf_mlp_backward: unknown mode %d", mode);
-  FL_REQUIRE(packed && dirpe, "flnerf_mlp_backward: bf16 mode needs packed weights and dirpe");
+  FL_REQUIRE(mode == FLNERF_MODE_BF16 || mode == FLNERF_MODE_BF16X3, "flnerf_mlp_backward: unknown mode %d", mode);
+  FL_REQUIRE(packed && dirpe, "flnerf_mlp_backward: the tensor-core modes need packed weights and dirpe");
   FL_REQUIRE((((uintptr_t)packed | (uintptr_t)x | (uintptr_t)stash | (uintptr_t)workspace) & 1023) == 0,
              "flnerf_mlp_backward: packed / pe_tiles / stash / workspace must be 1024-byte aligned");
-  return mlp_tc_backward(ctx, params, packed, n, S, x, dirpe, stash, draw, grads, workspace, stages,
-                         (cudaStream_t)stream);
+  return mlp_tc_backward(ctx, mode == FLNERF_MODE_BF16X3, params, packed, n, S, x, dirpe, stash, draw, grads, workspace,
+                         stages, (cudaStream_t)stream);
 }
 
 int64_t flnerf_mlp_param_count_g(int in_pts, int in_views) {

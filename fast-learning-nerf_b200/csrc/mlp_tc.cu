@@ -88,9 +88,12 @@ struct ChunkSrc {
 };
 __constant__ ChunkSrc c_chunks[FWD_CHUNKS + DG_CHUNKS];
 
-// one thread = one 16-byte chunk (8 bf16) of the packed image
+// one thread = one 16-byte chunk (8 bf16) of the packed image; blockIdx.z = part: 0 = hi = bf16(w), 1 = lo =
+// bf16(w - hi) (the split-precision mode multiplies by hi + lo; the bf16 mode reads part 0 only)
 __global__ void pack_weights_kernel(const float *__restrict__ P, uint8_t *__restrict__ packed) {
   int ci = blockIdx.y;
+  const bool lo = blockIdx.z != 0;
+  packed += (size_t)blockIdx.z * PACKED_BYTES;
   ChunkSrc s = c_chunks[ci];
   int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= s.nrows * 8) return;
@@ -102,6 +105,7 @@ __global__ void pack_weights_kernel(const float *__restrict__ P, uint8_t *__rest
     float a = (c0 < s.kvalid) ? P[s.base + r * s.row_mul + c0 * s.col_mul] : 0.f;
     float b = (c0 + 1 < s.kvalid) ? P[s.base + r * s.row_mul + (c0 + 1) * s.col_mul] : 0.f;
     w[e] = pack_bf16(a, b);
+    if (lo) w[e] = pack_bf16(a - bf16_lo(w[e]), b - bf16_hi(w[e]));
   }
   *reinterpret_cast<uint4 *>(packed + s.byte_off + sw128_offset(r, q * 8)) = make_uint4(w[0], w[1], w[2], w[3]);
 }
@@ -801,6 +805,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) mlp_dgr
   if (warp == 0) tmem_dealloc2(tmem_base, 512);
 }
 
+#include "mlp_tc_x3.cuh"
+
 // =================================================================================================
 // backward, weight gradients:  dW[out][in] += sum_rows dY[row][out] * X[row][in]
 // Both operands are the stashed [rows x features] SWIZZLE_128B images read as MN-major UMMA operands
@@ -834,6 +840,14 @@ struct WgradParams {
   int64_t n;
   int S;
   int n_tiles;  // 128-row tiles
+  // operand addressing: a tile's slots are slot_stride apart, tiles tile_stride apart; a_part / b_part select the hi (0)
+  // or lo (65536) image of the dY / activation slot, pe_part the hi (0) or lo PE tile set (split-precision mode; the
+  // bf16 mode has slot_stride 65536 and all parts 0)
+  size_t tile_stride, slot_stride, a_part, b_part, pe_part;
+  // which CUDA-core reductions this pass carries (the split-precision mode runs three passes over the same rows):
+  // bit 0: sums over dY (biases, view-direction columns), bit 1: sums over activations (w_alpha, W_rgb),
+  // bit 2: sums over d_raw alone (b_alpha, b_rgb)
+  int helper_flags;
 };
 
 constexpr int WG_STAGES = 3;
@@ -888,14 +902,14 @@ __global__ void __launch_bounds__(kWgThreads, 1) mlp_wgrad_tc(WgradParams p) {
         const uint32_t draw_bytes = (un.alpha && nv > 0) ? (uint32_t)(nv < 64 ? nv : 64) * 16u : 0u;
         mbar_arrive_expect_tx(full, a_bytes + b_bytes + (un.alpha == 2 ? 16384u : 0u) + draw_bytes);
         const size_t tile = (size_t)(h >> 1), half_off = (size_t)(h & 1) * 8192;
-        const uint8_t *a_src = p.dy + tile * TILE_ACT_BYTES + (size_t)un.a_slot * 65536 + half_off;
+        const uint8_t *a_src = p.dy + tile * p.tile_stride + (size_t)un.a_slot * p.slot_stride + p.a_part + half_off;
         uint32_t sa = smem_u32(smem + stage * WG_STAGE_BYTES), sb = sa + WG_A_BYTES;
         for (int s = 0; s < un.a_slabs; ++s) bulk_g2s(sa + s * 8192, a_src + (size_t)s * SLAB_BYTES, 8192u, full);
-        const uint8_t *b_src = un.b_kind == 0 ? p.stash_act + tile * TILE_ACT_BYTES + (size_t)un.b_slot * 65536 + half_off
-                                              : p.pe_tiles + tile * PE_BYTES + half_off;
+        const uint8_t *b_src = un.b_kind == 0 ? p.stash_act + tile * p.tile_stride + (size_t)un.b_slot * p.slot_stride + p.b_part + half_off
+                                              : p.pe_tiles + p.pe_part + tile * PE_BYTES + half_off;
         for (int s = 0; s < un.b_slabs; ++s) bulk_g2s(sb + s * 8192, b_src + (size_t)s * SLAB_BYTES, 8192u, full);
         if (un.alpha == 2) {  // h9 (stash slot 9, 2 slabs) rides in the unused upper half of the A region
-          const uint8_t *h9 = p.stash_act + tile * TILE_ACT_BYTES + (size_t)9 * 65536 + half_off;
+          const uint8_t *h9 = p.stash_act + tile * p.tile_stride + (size_t)9 * p.slot_stride + p.b_part + half_off;
           for (int s = 0; s < 2; ++s) bulk_g2s(sa + 16384 + s * 8192, h9 + (size_t)s * SLAB_BYTES, 8192u, full);
         }
         if (draw_bytes) bulk_g2s(smem_u32(smem + WG_OFF_DRAW + stage * 1024), p.draw + row0 * 4, draw_bytes, full);
@@ -950,6 +964,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) mlp_wgrad_tc(WgradParams p) {
     }
     const bool pair_valid = 2 * (int)hh < un.a_slabs * 64;
     int rem = (int)(((int64_t)h_begin * 64) % p.S);  // position of the next row inside its ray (heads unit)
+    const int hf = p.helper_flags;
     uint32_t stage = 0, phase = 0;
     const long long t_start = clock64();
     for (int h = h_begin; h < h_end; ++h) {
@@ -960,7 +975,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) mlp_wgrad_tc(WgradParams p) {
       const int64_t row0 = (int64_t)h * 64;
       const int nv = (int)((p.n - row0) < 64 ? (p.n - row0 < 0 ? 0 : p.n - row0) : 64);
       if (un.alpha == 0) {
-        if (un.bias_off >= 0 && pair_valid) {  // rows [32*upper, 32*upper + 32)
+        if (un.bias_off >= 0 && pair_valid && (hf & 1)) {  // rows [32*upper, 32*upper + 32)
 #pragma unroll
           for (uint32_t g = 0; g < 4; ++g)
 #pragma unroll
@@ -972,6 +987,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) mlp_wgrad_tc(WgradParams p) {
         }
       } else if (un.alpha == 1) {
         if (!upper) {
+          if (hf & 1)
 #pragma unroll
           for (uint32_t g = 0; g < 8; ++g)
 #pragma unroll
@@ -980,7 +996,8 @@ __global__ void __launch_bounds__(kWgThreads, 1) mlp_wgrad_tc(WgradParams p) {
               s0 += bf16_lo(w);
               s1 += bf16_hi(w);
             }
-        } else {
+        } else if (hf & 6) {
+          const float xs = (hf & 2) ? 1.f : 0.f, dsel = (hf & 4) ? 1.f : 0.f;
 #pragma unroll
           for (uint32_t g = 0; g < 8; ++g)
 #pragma unroll
@@ -988,13 +1005,14 @@ __global__ void __launch_bounds__(kWgThreads, 1) mlp_wgrad_tc(WgradParams p) {
               const int rr = (int)(g * 8 + j);
               const float ds = rr < nv ? sd[rr].w : 0.f;
               const uint32_t w = *reinterpret_cast<const uint32_t *>(sb + g * 1024u + offp[j]);
-              t0 = fmaf(ds, bf16_lo(w), t0);
-              t1 = fmaf(ds, bf16_hi(w), t1);
-              if (hh == 0) db3 += ds;
+              t0 = fmaf(ds * xs, bf16_lo(w), t0);
+              t1 = fmaf(ds * xs, bf16_hi(w), t1);
+              if (hh == 0) db3 += ds * dsel;
             }
         }
       } else {
         if (!upper) {
+         if (hf & 1) {
           // the ray segment sum is carried across the consecutive half tiles of this CTA: it is folded with the ray's
           // 27 PE values only when the ray ends (every S rows) or at the CTA's last row
           const bool last_stage = (h == h_end - 1);
@@ -1029,18 +1047,20 @@ __global__ void __launch_bounds__(kWgThreads, 1) mlp_wgrad_tc(WgradParams p) {
               }
             }
           }
-        } else {
+         }
+        } else if (hf & 6) {
+          const float xs = (hf & 2) ? 1.f : 0.f, dsel = (hf & 4) ? 1.f : 0.f;
 #pragma unroll
           for (uint32_t g = 0; g < 8; ++g)
 #pragma unroll
             for (uint32_t j = 0; j < 8; ++j) {
               const int rr = (int)(g * 8 + j);
               const float4 d = rr < nv ? sd[rr] : make_float4(0.f, 0.f, 0.f, 0.f);
-              const float hv = bf16_at(sa + 16384 + g * 1024u + offs[j]);
+              const float hv = bf16_at(sa + 16384 + g * 1024u + offs[j]) * xs;
               t0 = fmaf(d.x, hv, t0);
               t1 = fmaf(d.y, hv, t1);
               t2 = fmaf(d.z, hv, t2);
-              if (hh == 0) { db0 += d.x; db1 += d.y; db2 += d.z; }
+              if (hh == 0) { db0 += d.x * dsel; db1 += d.y * dsel; db2 += d.z * dsel; }
             }
         }
       }
@@ -1326,6 +1346,8 @@ static int setup_tables(int sm_count) {
   if (cudaFuncSetAttribute(mlp_dgrad_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, LayD::SMEM) != cudaSuccess) return 1;
   if (cudaFuncSetAttribute(mlp_dgrad_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, LayD::SMEM) != cudaSuccess) return 1;
   if (cudaFuncSetAttribute(mlp_wgrad_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_WG) != cudaSuccess) return 1;
+  if (cudaFuncSetAttribute(mlp_fwd_x3, cudaFuncAttributeMaxDynamicSharedMemorySize, LayF::SMEM) != cudaSuccess) return 1;
+  if (cudaFuncSetAttribute(mlp_dgrad_x3, cudaFuncAttributeMaxDynamicSharedMemorySize, LayD::SMEM) != cudaSuccess) return 1;
   g_tables_ready = true;
   return 0;
 }
@@ -1333,26 +1355,28 @@ static int setup_tables(int sm_count) {
 }  // namespace tc
 
 // ---- entry points used by api.cu -------------------------------------------------------------------
-size_t mlp_tc_packed_bytes() { return tc::PACKED_BYTES; }
+// packed image of one net: [part 0 = hi: forward chunks | dgrad chunks][part 1 = lo: same layout]
+size_t mlp_tc_packed_bytes() { return 2 * tc::PACKED_BYTES; }
 
 static size_t tc_vb_bytes(int64_t n, int S) {
   int64_t B = (n + S - 1) / S;
   return (size_t)((B * 128 * 4 + 1023) / 1024) * 1024;
 }
-size_t mlp_tc_stash_bytes(int64_t n, int S, int training) {
+static size_t tc_tile_act_bytes(bool x3) { return x3 ? tc::TILE_ACT_BYTES_X3 : tc::TILE_ACT_BYTES; }
+size_t mlp_tc_stash_bytes(int64_t n, int S, int training, bool x3) {
   size_t tiles = (size_t)(flnerf_padded_rows(n) / 128);
-  return tc_vb_bytes(n, S) + (training ? tiles * (tc::TILE_ACT_BYTES + tc::TILE_MASK_BYTES) : 0);
+  return tc_vb_bytes(n, S) + (training ? tiles * (tc_tile_act_bytes(x3) + tc::TILE_MASK_BYTES) : 0);
 }
-size_t mlp_tc_bwd_workspace_bytes(int64_t n) { return (size_t)(flnerf_padded_rows(n) / 128) * tc::TILE_ACT_BYTES; }
+size_t mlp_tc_bwd_workspace_bytes(int64_t n, bool x3) { return (size_t)(flnerf_padded_rows(n) / 128) * tc_tile_act_bytes(x3); }
 
 int mlp_tc_pack_weights(flnerf_ctx *ctx, const float *params, void *packed, cudaStream_t st) {
   FL_REQUIRE(tc::setup_tables(ctx->sm_count) == 0, "mlp_tc: table setup failed: %s", cudaGetErrorString(cudaGetLastError()));
-  dim3 grid(8, tc::FWD_CHUNKS + tc::DG_CHUNKS);
+  dim3 grid(8, tc::FWD_CHUNKS + tc::DG_CHUNKS, 2);
   FL_LAUNCH(tc::pack_weights_kernel, grid, 256, 0, st, params, (uint8_t *)packed);
   return 0;
 }
 
-int mlp_tc_forward(flnerf_ctx *ctx, const float *params, const void *packed, int64_t n, int S, const void *pe_tiles,
+int mlp_tc_forward(flnerf_ctx *ctx, bool x3, const float *params, const void *packed, int64_t n, int S, const void *pe_tiles,
                    const float *dirpe, float *raw, void *stash, int training, cudaStream_t st) {
   FL_REQUIRE(tc::setup_tables(ctx->sm_count) == 0, "mlp_tc: table setup failed: %s", cudaGetErrorString(cudaGetLastError()));
   FL_REQUIRE(n % S == 0, "mlp_tc_forward: n=%lld is not a multiple of S=%d", (long long)n, S);
@@ -1366,9 +1390,14 @@ int mlp_tc_forward(flnerf_ctx *ctx, const float *params, const void *packed, int
   p.n_pairs = (int)(n_pad / 256);
   if (training) {
     p.stash_act = (uint8_t *)stash + tc_vb_bytes(n, S);
-    p.stash_mask = (uint32_t *)(p.stash_act + (size_t)(n_pad / 128) * tc::TILE_ACT_BYTES);
+    p.stash_mask = (uint32_t *)(p.stash_act + (size_t)(n_pad / 128) * tc_tile_act_bytes(x3));
   }
   FL_CHECK_CUDA(cudaMemsetAsync(raw, 0, (size_t)n * 4 * sizeof(float), st));  // column-half warps accumulate into it
+  if (x3) {
+    const int grid = tc::pair_grid(p.n_pairs * 2, ctx->sm_count);
+    FL_LAUNCH(tc::mlp_fwd_x3, grid, tc::kThreads, tc::LayF::SMEM, st, p);
+    return 0;
+  }
   { const char *e = getenv("FLNERF_FWD_DBG"); p.dbg = e ? atoi(e) : 0; }
   p.prof = tc::prof_buffer();
   const int grid = tc::pair_grid(p.n_pairs, ctx->sm_count);
@@ -1381,17 +1410,20 @@ int mlp_tc_forward(flnerf_ctx *ctx, const float *params, const void *packed, int
   return 0;
 }
 
-int mlp_tc_backward(flnerf_ctx *ctx, const float *params, const void *packed, int64_t n, int S, const void *pe_tiles,
+int mlp_tc_backward(flnerf_ctx *ctx, bool x3, const float *params, const void *packed, int64_t n, int S, const void *pe_tiles,
                     const float *dirpe, const void *stash, const float *draw, float *grads, void *ws, int stages,
                     cudaStream_t st) {
   FL_REQUIRE(tc::setup_tables(ctx->sm_count) == 0, "mlp_tc: table setup failed: %s", cudaGetErrorString(cudaGetLastError()));
   int64_t n_pad = flnerf_padded_rows(n);
   const uint8_t *stash_act = (const uint8_t *)stash + tc_vb_bytes(n, S);
-  const uint32_t *stash_mask = (const uint32_t *)(stash_act + (size_t)(n_pad / 128) * tc::TILE_ACT_BYTES);
+  const uint32_t *stash_mask = (const uint32_t *)(stash_act + (size_t)(n_pad / 128) * tc_tile_act_bytes(x3));
   tc::DgradParams d{};
   d.P = params; d.packed_dg = (const uint8_t *)packed + tc::FWD_BYTES; d.draw = draw; d.stash_mask = stash_mask;
   d.dy = (uint8_t *)ws; d.n = n; d.n_pairs = (int)(n_pad / 256);
-  if (stages & 1) {
+  if ((stages & 1) && x3) {
+    const int grid = tc::pair_grid(d.n_pairs * 2, ctx->sm_count);
+    FL_LAUNCH(tc::mlp_dgrad_x3, grid, tc::kThreads, tc::LayD::SMEM, st, d);
+  } else if (stages & 1) {
     const int grid = tc::pair_grid(d.n_pairs, ctx->sm_count);
     d.prof = tc::prof_buffer();
     if (d.prof) {
@@ -1404,11 +1436,24 @@ int mlp_tc_backward(flnerf_ctx *ctx, const float *params, const void *packed, in
   tc::WgradParams w{};
   w.dy = (const uint8_t *)ws; w.stash_act = stash_act; w.pe_tiles = (const uint8_t *)pe_tiles; w.draw = draw;
   w.G = grads; w.n = n; w.n_tiles = (int)(n_pad / 128); w.dirpe = dirpe; w.S = S;
+  w.tile_stride = tc_tile_act_bytes(x3); w.slot_stride = x3 ? tc::SLOT_BYTES_X3 : 65536;
+  w.helper_flags = 7;
   static long long *dbg = nullptr;
   const bool want_dbg = getenv("FLNERF_WG_DEBUG") != nullptr;
   if (want_dbg && !dbg) cudaMalloc(&dbg, sizeof(long long) * 4 * 1024);
   w.dbg = want_dbg ? dbg : nullptr;
-  if (stages & 2) FL_LAUNCH(tc::mlp_wgrad_tc, tc::g_wgrad_grid, tc::kWgThreads, tc::SMEM_WG, st, w);
+  if ((stages & 2) && x3) {
+    // dW = (dYhi + dYlo)^T (Xhi + Xlo) ~= dYhi^T Xhi + dYhi^T Xlo + dYlo^T Xhi: three passes of the same kernel over the
+    // hi / lo images, each with the CUDA-core reductions that belong to its operands
+    const size_t pe_lo = (size_t)w.n_tiles * tc::PE_BYTES;
+    FL_LAUNCH(tc::mlp_wgrad_tc, tc::g_wgrad_grid, tc::kWgThreads, tc::SMEM_WG, st, w);
+    w.b_part = 65536; w.pe_part = pe_lo; w.helper_flags = 2;
+    FL_LAUNCH(tc::mlp_wgrad_tc, tc::g_wgrad_grid, tc::kWgThreads, tc::SMEM_WG, st, w);
+    w.a_part = 65536; w.b_part = 0; w.pe_part = 0; w.helper_flags = 1;
+    FL_LAUNCH(tc::mlp_wgrad_tc, tc::g_wgrad_grid, tc::kWgThreads, tc::SMEM_WG, st, w);
+  } else if (stages & 2) {
+    FL_LAUNCH(tc::mlp_wgrad_tc, tc::g_wgrad_grid, tc::kWgThreads, tc::SMEM_WG, st, w);
+  }
   if (want_dbg && (stages & 2)) {
     static int printed = 0;
     if (printed++ == 3) {  // a warmed-up launch
@@ -1420,7 +1465,8 @@ int mlp_tc_backward(flnerf_ctx *ctx, const float *params, const void *packed, in
     }
   }
   const int tpb = 8;
-  if (stages & 8) FL_LAUNCH(tc::wgrad_small_kernel, (unsigned)((w.n_tiles + tpb - 1) / tpb), 512, 0, st, stash_act, w.dy, draw, dirpe,
-            grads, n, S, w.n_tiles, tpb);
+  if ((stages & 8) && !x3)
+    FL_LAUNCH(tc::wgrad_small_kernel, (unsigned)((w.n_tiles + tpb - 1) / tpb), 512, 0, st, stash_act, w.dy, draw, dirpe,
+              grads, n, S, w.n_tiles, tpb);
   return 0;
 }

@@ -149,14 +149,16 @@ __global__ void encode_f32_kernel(int64_t B, int S, const float *__restrict__ ra
 // one thread = one row (63 channels + zero pad) of a [128 x 64] bf16 SWIZZLE_128B tile.  The tile holds bf16 (8
 // mantissa bits), so only the octaves k = 0 and k = 5 take an exact sincosf; the four octaves after each come from the
 // double-angle recurrence (error <= 2^4 ulp(fp32) ~ 2e-6, 2000x below the bf16 rounding step).  The fp32 parity path
-// (encode_f32_kernel / posenc_kernel) evaluates every channel exactly.
+// (encode_f32_kernel / posenc_kernel) evaluates every channel exactly, and so does kX3 (FLNERF_MODE_BF16X3), which
+// also writes the residual tile lo = bf16(v - hi) at tiles + lo_off.
+template <bool kX3>
 __global__ void __launch_bounds__(128) encode_tc_kernel(int64_t n, int64_t n_pad, int S, const float *__restrict__ rays11,
-                                                        const float *__restrict__ z, uint8_t *__restrict__ tiles) {
+                                                        const float *__restrict__ z, uint8_t *__restrict__ tiles, size_t lo_off) {
   const int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (row >= n_pad) return;
-  uint32_t pk[32];
+  uint32_t pk[32], pl[32];
 #pragma unroll
-  for (int i = 0; i < 32; ++i) pk[i] = 0u;
+  for (int i = 0; i < 32; ++i) { pk[i] = 0u; pl[i] = 0u; }
   if (row < n) {
     float v[64];
     float p[3], sn[3], cs[3];
@@ -167,7 +169,7 @@ __global__ void __launch_bounds__(128) encode_tc_kernel(int64_t n, int64_t n_pad
     for (int k = 0; k < 10; ++k) {
 #pragma unroll
       for (int a = 0; a < 3; ++a) {
-        if (k == 0 || k == 5) {
+        if (kX3 || k == 0 || k == 5) {
           sincosf(p[a] * (float)(1u << k), &sn[a], &cs[a]);  // exact power-of-two scale (helpers:32,38)
         } else {
           const float s2 = 2.f * sn[a] * cs[a], c2 = fmaf(-2.f * sn[a], sn[a], 1.f);
@@ -182,23 +184,30 @@ __global__ void __launch_bounds__(128) encode_tc_kernel(int64_t n, int64_t n_pad
     for (int i = 0; i < 32; ++i) {
       __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
       pk[i] = *reinterpret_cast<uint32_t *>(&h);
+      if (kX3) {
+        __nv_bfloat162 l = __floats2bfloat162_rn(v[2 * i] - __low2float(h), v[2 * i + 1] - __high2float(h));
+        pl[i] = *reinterpret_cast<uint32_t *>(&l);
+      }
     }
   }
   const uint32_t r = (uint32_t)(row & 127);
   uint8_t *dst = tiles + (row >> 7) * 16384 + (r >> 3) * 1024u + (r & 7u) * 128u;
 #pragma unroll
-  for (uint32_t q = 0; q < 8; ++q)
+  for (uint32_t q = 0; q < 8; ++q) {
     *reinterpret_cast<uint4 *>(dst + ((q ^ (r & 7u)) << 4)) = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+    if (kX3)
+      *reinterpret_cast<uint4 *>(dst + lo_off + ((q ^ (r & 7u)) << 4)) = make_uint4(pl[4 * q], pl[4 * q + 1], pl[4 * q + 2], pl[4 * q + 3]);
+  }
 }
 
 // generic NeRF.forward(x[n,90]) entry for the tensor-core MLP: already-embedded fp32 rows -> bf16 tile image
 __global__ void pack_x90_kernel(int64_t n, int64_t n_pad, const float *__restrict__ x90, uint8_t *__restrict__ tiles,
-                                float *__restrict__ dirpe) {
+                                float *__restrict__ dirpe, size_t lo_off) {
   int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= n_pad * 8) return;
   int64_t row = idx >> 3;
   int q = (int)(idx & 7);
-  uint32_t packed[4] = {0u, 0u, 0u, 0u};
+  uint32_t packed[4] = {0u, 0u, 0u, 0u}, packed_lo[4] = {0u, 0u, 0u, 0u};
   if (row < n) {
     const float *src = x90 + row * 90;
 #pragma unroll
@@ -208,6 +217,8 @@ __global__ void pack_x90_kernel(int64_t n, int64_t n_pad, const float *__restric
       float b = (c0 + 1 < 63) ? src[c0 + 1] : 0.0f;
       __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
       packed[e] = *reinterpret_cast<uint32_t *>(&h);
+      __nv_bfloat162 l = __floats2bfloat162_rn(a - __low2float(h), b - __high2float(h));
+      packed_lo[e] = *reinterpret_cast<uint32_t *>(&l);
     }
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
@@ -219,6 +230,9 @@ __global__ void pack_x90_kernel(int64_t n, int64_t n_pad, const float *__restric
   uint32_t r = (uint32_t)(row & 127);
   *reinterpret_cast<uint4 *>(tiles + tile * 16384 + sw128_offset(r, (uint32_t)q * 8)) =
       make_uint4(packed[0], packed[1], packed[2], packed[3]);
+  if (lo_off)  // FLNERF_MODE_BF16X3: the residual tile set
+    *reinterpret_cast<uint4 *>(tiles + lo_off + tile * 16384 + sw128_offset(r, (uint32_t)q * 8)) =
+        make_uint4(packed_lo[0], packed_lo[1], packed_lo[2], packed_lo[3]);
 }
 
 __global__ void dirpe_kernel(int64_t B, const float *__restrict__ rays11, float *__restrict__ dirpe) {
@@ -315,8 +329,19 @@ int flnerf_encode_tc(flnerf_ctx *ctx, int64_t B, int S, const float *rays11, con
   FL_REQUIRE(ctx && rays11 && z && pe_tiles && dirpe && S > 0 && B >= 0, "flnerf_encode_tc: bad arguments");
   if (B == 0) return 0;
   int64_t n = B * S, n_pad = flnerf_padded_rows(n);
-  FL_LAUNCH(encode_tc_kernel, (unsigned)ceil_div64(n_pad, 128), 128, 0, stream, n, n_pad, S, rays11, z,
-            (uint8_t *)pe_tiles);
+  FL_LAUNCH(encode_tc_kernel<false>, (unsigned)ceil_div64(n_pad, 128), 128, 0, stream, n, n_pad, S, rays11, z,
+            (uint8_t *)pe_tiles, (size_t)0);
+  FL_LAUNCH(dirpe_kernel, (unsigned)ceil_div64(B * 32, 256), 256, 0, stream, B, rays11, dirpe);
+  return 0;
+}
+
+int flnerf_encode_tc_x3(flnerf_ctx *ctx, int64_t B, int S, const float *rays11, const float *z, void *pe_tiles,
+                        float *dirpe, void *stream) {
+  FL_REQUIRE(ctx && rays11 && z && pe_tiles && dirpe && S > 0 && B >= 0, "flnerf_encode_tc_x3: bad arguments");
+  if (B == 0) return 0;
+  int64_t n = B * S, n_pad = flnerf_padded_rows(n);
+  FL_LAUNCH(encode_tc_kernel<true>, (unsigned)ceil_div64(n_pad, 128), 128, 0, stream, n, n_pad, S, rays11, z,
+            (uint8_t *)pe_tiles, (size_t)(n_pad / 128) * 16384);
   FL_LAUNCH(dirpe_kernel, (unsigned)ceil_div64(B * 32, 256), 256, 0, stream, B, rays11, dirpe);
   return 0;
 }
@@ -326,7 +351,16 @@ int flnerf_pack_x90(flnerf_ctx *ctx, int64_t n, const float *x90, void *pe_tiles
   if (n == 0) return 0;
   int64_t n_pad = flnerf_padded_rows(n);
   FL_LAUNCH(pack_x90_kernel, (unsigned)ceil_div64(n_pad * 8, 256), 256, 0, stream, n, n_pad, x90, (uint8_t *)pe_tiles,
-            dirpe);
+            dirpe, (size_t)0);
+  return 0;
+}
+
+int flnerf_pack_x90_x3(flnerf_ctx *ctx, int64_t n, const float *x90, void *pe_tiles, float *dirpe, void *stream) {
+  FL_REQUIRE(ctx && x90 && pe_tiles && dirpe && n >= 0, "flnerf_pack_x90_x3: bad arguments");
+  if (n == 0) return 0;
+  int64_t n_pad = flnerf_padded_rows(n);
+  FL_LAUNCH(pack_x90_kernel, (unsigned)ceil_div64(n_pad * 8, 256), 256, 0, stream, n, n_pad, x90, (uint8_t *)pe_tiles,
+            dirpe, (size_t)(n_pad / 128) * 16384);
   return 0;
 }
 

@@ -108,6 +108,38 @@ class Trainer:
         self.world, self.rank = int(world_size), int(rank)
         self.bucket = share_grad_bucket([net_coarse, net_fine])
         self.last = {}
+        self.sync_replicas()
+
+    def sync_replicas(self):
+        """nn.DataParallel held ONE copy of the weights (run_nerf.py:82,90).  Replicas built from unseeded RNGs or resumed
+        from different files would never converge to each other (only gradients are exchanged), so rank 0's parameters,
+        Adam moments and step counters are broadcast once -- at construction and after any checkpoint load."""
+        if self.world <= 1 or not (torch.distributed.is_available() and torch.distributed.is_initialized()):
+            return
+        dist = torch.distributed
+        for net in (self.nc, self.nf):
+            flat = net.flat_parameters()
+            dist.broadcast(flat, 0)
+            net.weights_version += 1
+            m, v = self.opt._m[id(net)], self.opt._v[id(net)]
+            dist.broadcast(m, 0)
+            dist.broadcast(v, 0)
+            st = torch.tensor([float(self.opt._step[id(net)])], dtype=torch.float64, device=flat.device)
+            dist.broadcast(st, 0)
+            self.opt._step[id(net)] = int(st.item())
+        lr = torch.tensor([float(self.opt.param_groups[0]["lr"])], dtype=torch.float64, device=self.bucket.device)
+        dist.broadcast(lr, 0)
+        for g in self.opt.param_groups:
+            g["lr"] = float(lr.item())
+
+    def global_loss(self, loss):
+        """``step`` returns this rank's SHARE of the two MSEs (its rows, divided by the global ray count); their sum over
+        ranks is the reference's img_loss / img_loss0.  One 8-byte all-reduce -- call it at log time only."""
+        if self.world <= 1:
+            return loss
+        out = loss.clone()
+        torch.distributed.all_reduce(out)
+        return out
 
     # -- one MLP evaluation over [B,S] samples without autograd
     def _forward_net(self, net, rays11, z):
@@ -116,7 +148,7 @@ class Trainer:
         if net.mode == ops.MODE_FP32:
             x, dirpe = ops.encode_f32(rays11, z), None
         else:
-            x, dirpe = ops.encode_tc(rays11, z)
+            x, dirpe = ops.encode_tc(rays11, z, net.mode)
         raw, stash = ops.mlp_forward(net.mode, flat, packed, x, dirpe, B * S, S, True)
         return raw, (x, dirpe, stash)
 
@@ -127,36 +159,52 @@ class Trainer:
 
     @torch.no_grad()
     def step(self, rays_o, rays_d, target, leaf_gid=None, leaf_max=None, global_batch: Optional[int] = None):
-        """Returns loss[2] = (fine mse, coarse mse) as a DEVICE tensor (no sync)."""
+        """Returns loss[2] = (fine mse, coarse mse) as a DEVICE tensor (no sync); under data parallelism it is this
+        rank's share (see ``global_loss``).  A rank whose share of a ragged last batch is EMPTY still joins the
+        collectives and the optimiser step with a zero gradient."""
         B = rays_o.shape[0]
         Nc, Nf = self.Nc, self.Nf
-        rays11 = ops.pack_rays(rays_o, rays_d, self.near, self.far, self.ndc, self.H, self.W, float(self.K[0][0]))
-        off = self.calls
-        self.calls += B * (Nc + Nf)
-        z_c = ops.coarse_depths(rays11, Nc, self.perturb > 0, self.lindisp, None, self.seed, off)
-        noise_c = noise_f = None
-        if self.noise_std > 0:
-            noise_c = torch.randn(B, Nc, device=rays11.device) * self.noise_std
-            noise_f = torch.randn(B, Nc + Nf, device=rays11.device) * self.noise_std
-        raw_c, sv_c = self._forward_net(self.nc, rays11, z_c)
-        rgb0, _, _, w_c, _ = ops.composite_forward(raw_c, z_c, rays11[:, 3:6], noise_c, self.white, rays_d_stride=11)
-        z_f, _, _ = ops.sample_pdf_merge(z_c, w_c, Nf, self.perturb == 0, None, self.seed + 1, off, want_samples=False)
-        raw_f, sv_f = self._forward_net(self.nf, rays11, z_f)
-        rgb, disp, acc, _, _ = ops.composite_forward(raw_f, z_f, rays11[:, 3:6], noise_f, self.white, rays_d_stride=11,
-                                                     want_weights=False)
-        denom = int(global_batch) if global_batch is not None else B * self.world
-        loss, d_rgb, d_rgb0 = ops.mse_leafmax(rgb, rgb0, target, denom, leaf_gid, leaf_max)
-        self.opt.zero_grad()
-        draw_f = ops.composite_backward(raw_f, z_f, rays11[:, 3:6], noise_f, self.white, d_rgb, None, None, None,
-                                        rays_d_stride=11)
-        self._backward_net(self.nf, sv_f, draw_f, B * (Nc + Nf), Nc + Nf)
-        draw_c = ops.composite_backward(raw_c, z_c, rays11[:, 3:6], noise_c, self.white, d_rgb0, None, None, None,
-                                        rays_d_stride=11)
-        self._backward_net(self.nc, sv_c, draw_c, B * Nc, Nc)
+        half = self.bucket.numel() // 2
+        work = None
+        if B == 0:
+            self.opt.zero_grad()
+            loss = torch.zeros(2, dtype=torch.float32, device=self.bucket.device)
+        else:
+            rays11 = ops.pack_rays(rays_o, rays_d, self.near, self.far, self.ndc, self.H, self.W, float(self.K[0][0]))
+            off = self.calls
+            self.calls += B * (Nc + Nf)
+            z_c = ops.coarse_depths(rays11, Nc, self.perturb > 0, self.lindisp, None, self.seed, off)
+            noise_c = noise_f = None
+            if self.noise_std > 0:
+                noise_c = torch.randn(B, Nc, device=rays11.device) * self.noise_std
+                noise_f = torch.randn(B, Nc + Nf, device=rays11.device) * self.noise_std
+            raw_c, sv_c = self._forward_net(self.nc, rays11, z_c)
+            rgb0, _, _, w_c, _ = ops.composite_forward(raw_c, z_c, rays11[:, 3:6], noise_c, self.white, rays_d_stride=11)
+            z_f, _, _ = ops.sample_pdf_merge(z_c, w_c, Nf, self.perturb == 0, None, self.seed + 1, off, want_samples=False)
+            raw_f, sv_f = self._forward_net(self.nf, rays11, z_f)
+            rgb, disp, acc, _, _ = ops.composite_forward(raw_f, z_f, rays11[:, 3:6], noise_f, self.white, rays_d_stride=11,
+                                                         want_weights=False)
+            denom = int(global_batch) if global_batch is not None else B * self.world
+            loss, d_rgb, d_rgb0 = ops.mse_leafmax(rgb, rgb0, target, denom, leaf_gid, leaf_max)
+            self.opt.zero_grad()
+            draw_f = ops.composite_backward(raw_f, z_f, rays11[:, 3:6], noise_f, self.white, d_rgb, None, None, None,
+                                            rays_d_stride=11)
+            self._backward_net(self.nf, sv_f, draw_f, B * (Nc + Nf), Nc + Nf)
+            if self.world > 1:
+                # the fine net's half of the bucket is complete: its all-reduce (NCCL's own stream) overlaps the coarse
+                # net's backward pass (SURVEY 8e)
+                work = torch.distributed.all_reduce(self.bucket[half:], async_op=True)
+            draw_c = ops.composite_backward(raw_c, z_c, rays11[:, 3:6], noise_c, self.white, d_rgb0, None, None, None,
+                                            rays_d_stride=11)
+            self._backward_net(self.nc, sv_c, draw_c, B * Nc, Nc)
+            self.last = {"rgb": rgb, "rgb0": rgb0, "disp": disp, "acc": acc}
         if self.world > 1:
-            torch.distributed.all_reduce(self.bucket)       # the ONE collective of the step (SURVEY 8e)
+            if work is None:
+                torch.distributed.all_reduce(self.bucket[half:])
+            torch.distributed.all_reduce(self.bucket[:half])
+            if work is not None:
+                work.wait()
         self.opt.step()
-        self.last = {"rgb": rgb, "rgb0": rgb0, "disp": disp, "acc": acc}
         return loss
 
     @torch.no_grad()

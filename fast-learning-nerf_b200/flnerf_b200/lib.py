@@ -12,6 +12,7 @@ LIB_PATH = os.path.join(_HERE, "libflnerf.so")
 
 MODE_FP32 = 0
 MODE_BF16 = 1
+MODE_BF16X3 = 2
 MLP_PARAMS = 595844
 
 _vp, _i, _i64, _u64, _f, _d, _sz = C.c_void_p, C.c_int, C.c_int64, C.c_uint64, C.c_float, C.c_double, C.c_size_t
@@ -30,6 +31,8 @@ SIGNATURES = {
     "flnerf_encode_f32": (_i, [_vp, _i64, _i, _vp, _vp, _vp, _vp]),
     "flnerf_encode_tc": (_i, [_vp, _i64, _i, _vp, _vp, _vp, _vp, _vp]),
     "flnerf_pack_x90": (_i, [_vp, _i64, _vp, _vp, _vp, _vp]),
+    "flnerf_encode_tc_x3": (_i, [_vp, _i64, _i, _vp, _vp, _vp, _vp, _vp]),
+    "flnerf_pack_x90_x3": (_i, [_vp, _i64, _vp, _vp, _vp, _vp]),
     "flnerf_padded_rows": (_i64, [_i64]),
     "flnerf_mlp_stash_bytes": (_sz, [_i, _i64, _i, _i]),
     "flnerf_mlp_bwd_workspace_bytes": (_sz, [_i, _i64]),

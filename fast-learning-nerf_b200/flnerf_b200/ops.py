@@ -11,7 +11,7 @@ import torch
 
 from . import lib as L
 
-MODE_FP32, MODE_BF16 = L.MODE_FP32, L.MODE_BF16
+MODE_FP32, MODE_BF16, MODE_BF16X3 = L.MODE_FP32, L.MODE_BF16, L.MODE_BF16X3
 
 
 def _ptr(t: Optional[torch.Tensor]):
@@ -104,20 +104,24 @@ def padded_rows(n: int) -> int:
     return (n + 255) // 256 * 256
 
 
-def encode_tc(rays11, z):
+def encode_tc(rays11, z, mode=MODE_BF16):
+    """Sample points + PE as tensor-core tiles; MODE_BF16X3 writes the hi and the lo tile set back to back."""
     B, S = z.shape
-    tiles = _alloc_bytes(padded_rows(B * S) // 128 * 16384, z.device)
+    x3 = mode == MODE_BF16X3
+    tiles = _alloc_bytes(padded_rows(B * S) // 128 * 16384 * (2 if x3 else 1), z.device)
     dirpe = torch.empty(B, 32, dtype=torch.float32, device=z.device)
-    L.check(L.load().flnerf_encode_tc(_ctx(z), B, S, _ptr(rays11), _ptr(z), _ptr(tiles), _ptr(dirpe), _stream()),
-            "flnerf_encode_tc")
+    fn = L.load().flnerf_encode_tc_x3 if x3 else L.load().flnerf_encode_tc
+    L.check(fn(_ctx(z), B, S, _ptr(rays11), _ptr(z), _ptr(tiles), _ptr(dirpe), _stream()), "flnerf_encode_tc")
     return tiles, dirpe
 
 
-def pack_x90(x90):
+def pack_x90(x90, mode=MODE_BF16):
     n = x90.shape[0]
-    tiles = _alloc_bytes(padded_rows(n) // 128 * 16384, x90.device)
+    x3 = mode == MODE_BF16X3
+    tiles = _alloc_bytes(padded_rows(n) // 128 * 16384 * (2 if x3 else 1), x90.device)
     dirpe = torch.empty(n, 32, dtype=torch.float32, device=x90.device)
-    L.check(L.load().flnerf_pack_x90(_ctx(x90), n, _ptr(x90), _ptr(tiles), _ptr(dirpe), _stream()), "flnerf_pack_x90")
+    fn = L.load().flnerf_pack_x90_x3 if x3 else L.load().flnerf_pack_x90
+    L.check(fn(_ctx(x90), n, _ptr(x90), _ptr(tiles), _ptr(dirpe), _stream()), "flnerf_pack_x90")
     return tiles, dirpe
 
 

@@ -2,7 +2,8 @@
 names/shapes (state_dict compatible, model.py:20-34) and ``forward(x[n, 63+27]) -> [n, 4]``.
 
 The arithmetic is NOT torch: forward and backward run in libflnerf.so (csrc/mlp_simt.cu for the fp32
-parity mode, csrc/mlp_tc.cu -- tcgen05 -- for the bf16 throughput mode).  All 24 parameter tensors are
+parity mode, csrc/mlp_tc.cu -- tcgen05 -- for the bf16 throughput mode and the split-precision bf16x3
+tensor-core parity mode).  All 24 parameter tensors are
 views into one flat fp32 buffer in ``parameters()`` order, their ``.grad`` are views into one flat
 gradient bucket (what the fused Adam and the single NCCL all-reduce operate on).
 """
@@ -16,7 +17,7 @@ from flnerf_b200 import ops
 from flnerf_b200.lib import FlnerfError, MLP_PARAMS
 
 DEFAULT_PRECISION = os.environ.get("FLNERF_PRECISION", "bf16")
-_MODES = {"fp32": ops.MODE_FP32, "bf16": ops.MODE_BF16}
+_MODES = {"fp32": ops.MODE_FP32, "bf16": ops.MODE_BF16, "bf16x3": ops.MODE_BF16X3}
 
 
 class _NerfFn(torch.autograd.Function):
@@ -120,7 +121,7 @@ class NeRF(nn.Module):
 
     def _weights(self):
         self._ensure_flat()
-        if self.mode == ops.MODE_BF16:
+        if self.mode != ops.MODE_FP32:
             key = (self._flat._version, self.weights_version, sum(p._version for p in self.parameters()))
             if self._packed is None or key != self._packed_key:
                 self._packed = ops.mlp_pack_weights(self._flat, self._packed)
@@ -139,7 +140,7 @@ class NeRF(nn.Module):
         if self.mode == ops.MODE_FP32:
             raw = _NerfFn.apply(proxy, self, x2, None, n, 1)
         else:
-            tiles, dirpe = ops.pack_x90(x2)
+            tiles, dirpe = ops.pack_x90(x2, self.mode)
             raw = _NerfFn.apply(proxy, self, tiles, dirpe, n, 1)
         return raw.reshape(*lead, 4)
 
@@ -153,7 +154,7 @@ class NeRF(nn.Module):
             x = ops.encode_f32(rays11, z)
             raw = _NerfFn.apply(proxy, self, x, None, B * S, S)
         else:
-            tiles, dirpe = ops.encode_tc(rays11, z)
+            tiles, dirpe = ops.encode_tc(rays11, z, self.mode)
             raw = _NerfFn.apply(proxy, self, tiles, dirpe, B * S, S)
         return raw.reshape(B, S, 4)
 

@@ -244,7 +244,9 @@ def train(argv=None):
                       world_size=world, rank=rank)
 
     def log(tag, it, loss):
-        l = loss.tolist()           # the only host sync, every 50/400 iterations like the reference's prints
+        l = trainer.global_loss(loss).tolist()   # the only host sync (+ an 8-byte all-reduce), every 50/400 iterations
+        if rank != 0:
+            return
         print('{}//iter {}: coarse/loss {:.4f}, coarse/psnr {:.4f}, fine/loss {:.4f}, fine/psnr {:.4f}'.format(
             time.strftime("%Y-%m-%d %H:%M:%S", time.localtime()), it, l[0], -10 * np.log10(max(l[0], 1e-12)), l[1],
             -10 * np.log10(max(l[1], 1e-12))))
@@ -260,6 +262,10 @@ def train(argv=None):
         randNum = int(N_rand * 500 / treeManager.n_images)
         sel = coords[np.random.choice(coords.shape[0], size=[min(randNum, coords.shape[0])], replace=False)]
         pix = (sel[:, 0] * W + sel[:, 1]).to(torch.int32)
+        if world > 1:       # every rank must hold the SAME index buffer (rank r consumes rows first + r, first + r + world, ...)
+            pix = pix.to(device)
+            torch.distributed.broadcast(pix, 0)
+            pix = pix.cpu()
         n_img = treeManager.n_images
         ray_pix = pix.repeat(n_img).to(device)
         ray_gid = (torch.arange(n_img, dtype=torch.int32).repeat_interleave(pix.shape[0]) * treeManager.cap).to(device)
@@ -270,7 +276,7 @@ def train(argv=None):
             local = (rows_ - rank + world - 1) // world
             o, d, tgt, _ = treeManager.batch(first + rank, local, world)
             loss = trainer.step(o, d, tgt, None, None, global_batch=rows_)      # lr is not decayed here (quirk 5)
-            if it % 50 == 0 and rank == 0:
+            if it % 50 == 0:
                 log('crop', it, loss)
             it += 1
         torch.cuda.synchronize()
@@ -295,7 +301,7 @@ def train(argv=None):
             for g in optimizer.param_groups:
                 g['lr'] = new_lrate
             global_iter += 1
-            if it % 400 == 0 and rank == 0:
+            if it % 400 == 0:
                 log('train', it, loss)
             it += 1
         print('{}//total: {} iters.'.format(time.strftime("%Y-%m-%d %H:%M:%S", time.localtime()), it))

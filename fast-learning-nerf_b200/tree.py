@@ -106,7 +106,10 @@ class QuadTreeManager:
         self._images_dev = torch.as_tensor(images, dtype=torch.float32).to(self.device).contiguous()
         self._poses_dev = torch.as_tensor(poses, dtype=torch.float32)[:, :3, :4].to(self.device).contiguous()
         self.max_level = int(max_level) if max_level is not None else int(max_depth) + 6
-        self.cap = 4 ** (self.max_level - 1)
+        # leaf capacity per image.  A leaf is split only if rays fell into it (leaf_max > thres), i.e. if it held at least
+        # one pixel (int(area * rays_per_pixel) >= 1, tree.py:581), so a tree never has more than 4*H*W leaves however deep
+        # the schedule goes (the reference's defaults n_epoch=12, init_level=3, subdivide_every=1 give max_level 13).
+        self.cap = min(4 ** (self.max_level - 1), 4 * self.h * self.w)
         n = self.n_images
         self._boxes = [torch.zeros(n, self.cap, 4, dtype=torch.float64, device=self.device) for _ in range(2)]
         self._count = [torch.zeros(n, dtype=torch.int32, device=self.device) for _ in range(2)]

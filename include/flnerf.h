@@ -29,6 +29,8 @@ typedef struct flnerf_ctx flnerf_ctx;
 /* MLP arithmetic modes (model.py:38-63 is fp32; see DESIGN.md "precision modes") */
 #define FLNERF_MODE_FP32 0 /* CUDA-core fp32 GEMMs: the parity path (<=1e-4 rel of the reference)      */
 #define FLNERF_MODE_BF16 1 /* tcgen05 bf16 x bf16 -> fp32 TMEM accumulators: the throughput path        */
+#define FLNERF_MODE_BF16X3 2 /* tcgen05, every operand split into bf16 hi + lo, products hi*hi + lo*hi + hi*lo into the
+                              * same fp32 accumulator: the tensor-core parity path (<=1e-4 rel of the reference)  */
 
 #define FLNERF_MLP_PARAMS 595844 /* parameters of one NeRF(D=8,W=256,skips=[4],use_viewdirs) (model.py:20-34) */
 #define FLNERF_TILE_ROWS 128
@@ -65,6 +67,11 @@ int flnerf_encode_tc(flnerf_ctx *, int64_t B, int S, const float *rays11, const 
                      float *dirpe, void *stream);
 /* already-embedded rows x90[n,90] (NeRF.forward API) -> pe_tiles + dirpe[n,32] (one "ray" per row, S = 1) */
 int flnerf_pack_x90(flnerf_ctx *, int64_t n, const float *x90, void *pe_tiles, float *dirpe, void *stream);
+/* the same two for FLNERF_MODE_BF16X3: pe_tiles holds TWO tile sets back to back, hi = bf16(PE) then lo = bf16(PE - hi)
+ * (2 x 16 KB per 128 rows), and every octave takes an exact sincosf */
+int flnerf_encode_tc_x3(flnerf_ctx *, int64_t B, int S, const float *rays11, const float *z, void *pe_tiles,
+                        float *dirpe, void *stream);
+int flnerf_pack_x90_x3(flnerf_ctx *, int64_t n, const float *x90, void *pe_tiles, float *dirpe, void *stream);
 int64_t flnerf_padded_rows(int64_t n);                  /* n rounded up to FLNERF_PAIR_ROWS */
 
 /* ---- a6: NeRF MLP (model.py:38-63).  params/grads: flat fp32[FLNERF_MLP_PARAMS] in parameters() order:
@@ -73,10 +80,11 @@ int64_t flnerf_padded_rows(int64_t n);                  /* n rounded up to FLNER
  * buffer for inference (FP32 mode always keeps the per-layer activations). */
 size_t flnerf_mlp_stash_bytes(int mode, int64_t n, int S, int training);
 size_t flnerf_mlp_bwd_workspace_bytes(int mode, int64_t n);
-size_t flnerf_mlp_packed_bytes(void);                   /* bf16 tensor-core weight image of one net */
-/* fp32 master weights -> pre-swizzled bf16 chunks (forward and transposed for dgrad) + fp32 small tensors */
+size_t flnerf_mlp_packed_bytes(void);                   /* tensor-core weight image of one net (hi part, then lo part) */
+/* fp32 master weights -> pre-swizzled bf16 chunks (forward and transposed for dgrad), hi = bf16(w) and lo = bf16(w - hi) */
 int flnerf_mlp_pack_weights(flnerf_ctx *, const float *params, void *packed, void *stream);
-/* mode FP32: x = x90 fp32 [n,90];  mode BF16: x = pe_tiles, dirpe[B,32], S = samples per ray (row -> ray = row/S).
+/* mode FP32: x = x90 fp32 [n,90];  modes BF16 / BF16X3: x = pe_tiles (of flnerf_encode_tc / flnerf_encode_tc_x3),
+ * dirpe[B,32], S = samples per ray (row -> ray = row/S).
  * raw_out [n,4] = (r,g,b,sigma).  stash: flnerf_mlp_stash_bytes(mode, n, S, training) bytes, 1 KB aligned. */
 int flnerf_mlp_forward(flnerf_ctx *, int mode, const float *params, const void *packed, int64_t n, int S,
                        const void *x, const float *dirpe, float *raw_out, void *stash, int training, void *stream);

@@ -1,9 +1,10 @@
-"""TEST INFRASTRUCTURE -- loads the UNMODIFIED reference modules from /root/reference.
+"""TEST INFRASTRUCTURE -- loads the UNMODIFIED reference modules from /root/reference, or from the untracked copy
+``baseline/_ref/`` that ``tools/install_reference.sh`` makes of it (git-ignored, travels to the GPU box with the snapshot).
 
-Only usable inside the build container (the GPU box has no /root/reference).  It is
-used by ``oracle/make_golden.py`` to generate the committed fixtures under
-``tests/golden/`` and by ``tests/test_oracle_vs_reference.py`` (skipped when the
-reference tree is absent) to pin the oracle restatement against the real code.
+It is used by ``oracle/make_golden.py`` to generate the committed fixtures under
+``tests/golden/``, by ``tests/test_oracle_vs_reference.py`` (skipped when no reference tree is
+present) to pin the oracle restatement against the real code, and by ``bench.py --impl reference`` /
+``tools/psnr_check.py`` to TIME and TRAIN the reference's own code beside ours.
 
 The reference hot path (nerf-ours/{run_nerf_helpers,render,model,tree}.py) imports a
 few modules that are not installed here (imageio, matplotlib, colour, threadpool,
@@ -15,7 +16,18 @@ import os
 import sys
 import types
 
-REF_ROOT = os.environ.get("FLNERF_REFERENCE_ROOT", "/root/reference")
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _find_root():
+    for cand in (os.environ.get("FLNERF_REFERENCE_ROOT"), "/root/reference",
+                 os.path.join(os.path.dirname(_HERE), "baseline", "_ref")):
+        if cand and os.path.isfile(os.path.join(cand, "nerf-ours", "render.py")):
+            return cand
+    return "/root/reference"
+
+
+REF_ROOT = _find_root()
 REF_NERF = os.path.join(REF_ROOT, "nerf-ours")
 
 
@@ -85,6 +97,80 @@ def load():
                 sys.modules[k] = v
             setattr(ns, "_" + k, cur)
     return ns
+
+
+def _configargparse_stub():
+    """``configargparse`` is not installed: an argparse subclass covering what argument_parser.py:4-123 uses of it --
+    ``add_argument(..., is_config_file=True)`` and ``key = value`` config files (command-line flags win)."""
+    import argparse
+
+    class ArgumentParser(argparse.ArgumentParser):
+        def __init__(self, *a, **k):
+            super().__init__(*a, **k)
+            self._cfg_dests = []
+
+        def add_argument(self, *names, **kw):
+            is_cfg = kw.pop("is_config_file", False)
+            act = super().add_argument(*names, **kw)
+            if is_cfg:
+                self._cfg_dests.append(act.dest)
+            return act
+
+        def parse_args(self, args=None, namespace=None):
+            args = list(sys.argv[1:] if args is None else args)
+            pre, _ = super().parse_known_args(args)
+            extra = []
+            for dest in self._cfg_dests:
+                path = getattr(pre, dest, None)
+                if not path:
+                    continue
+                for line in open(path):
+                    line = line.split("#", 1)[0].strip()
+                    if "=" not in line:
+                        continue
+                    k, v = [t.strip() for t in line.split("=", 1)]
+                    act = next((a for a in self._actions if a.dest == k), None)
+                    if act is None:
+                        continue
+                    if act.nargs == 0:                      # store_true style flag
+                        if v.lower() in ("true", "1", "yes"):
+                            extra.append("--" + k)
+                    else:
+                        extra += ["--" + k, v]
+            return super().parse_args(extra + args, namespace)
+
+    m = types.ModuleType("configargparse")
+    m.ArgumentParser = ArgumentParser
+    return m
+
+
+def load_run_nerf():
+    """The reference's driver module nerf-ours/run_nerf.py, imported UNMODIFIED (its create_nerf / run_network / render are
+    the stock code path ``bench.py --impl reference`` and tools/psnr_check.py time and train).  Returns (ns, run_nerf)."""
+    ns = load()
+    if "configargparse" not in sys.modules:
+        sys.modules["configargparse"] = _configargparse_stub()
+    names = ["run_nerf_helpers", "model", "render", "tree", "image_process", "tree_utils", "argument_parser", "run_nerf",
+             "load_llff", "load_deepvoxels", "load_blender", "load_LINEMOD"]
+    saved_path = list(sys.path)
+    saved_mods = {k: sys.modules.get(k) for k in names}
+    for k in names:
+        sys.modules.pop(k, None)
+    # the same module objects load() imported, so that run_nerf's star-imports see them
+    for k in ("run_nerf_helpers", "model", "render", "tree", "image_process"):
+        m = getattr(ns, "_" + k, None)
+        if m is not None:
+            sys.modules[k] = m
+    sys.path.insert(0, REF_NERF)
+    try:
+        rn = importlib.import_module("run_nerf")
+    finally:
+        sys.path[:] = saved_path
+        for k, v in saved_mods.items():
+            sys.modules.pop(k, None)
+            if v is not None:
+                sys.modules[k] = v
+    return ns, rn
 
 
 def ref_run_network(ns, inputs, viewdirs, fn, embed_fn, embeddirs_fn, netchunk=1024 * 64):

@@ -15,6 +15,22 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA (B200) device; run with -m gpu")
 
 
+def pytest_collection_modifyitems(config, items):
+    """Without a CUDA device (or without the built library) the gpu tests are SKIPPED, not failed: a plain `pytest tests`
+    on a CPU box is green; `-m gpu` on a GPU box still fails loudly if libflnerf.so is missing (the product raises)."""
+    try:
+        import torch
+        has_gpu = torch.cuda.is_available()
+    except Exception:
+        has_gpu = False
+    if has_gpu:
+        return
+    skip = pytest.mark.skip(reason="needs a CUDA (B200) device")
+    for item in items:
+        if "gpu" in item.keywords:
+            item.add_marker(skip)
+
+
 @pytest.fixture(scope="session")
 def golden():
     import numpy as np

@@ -33,7 +33,8 @@ def test_library_exports_every_declared_symbol():
     lib = L.load()
     assert lib.flnerf_version() >= 100
     assert lib.flnerf_padded_rows(1) == 256 and lib.flnerf_padded_rows(512) == 512
-    assert lib.flnerf_mlp_packed_bytes() == (34 * 32768 + 4 * 16384) + 34 * 32768
+    # hi part + lo part (bf16x3), each = 38 forward chunks + 34 transposed dgrad chunks
+    assert lib.flnerf_mlp_packed_bytes() == 2 * ((34 * 32768 + 4 * 16384) + 34 * 32768)
 
 
 def test_no_cpu_fallback_without_gpu():
