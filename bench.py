@@ -364,6 +364,8 @@ def hbm_kernel_table(torch, ops, dev, peaks, H, W, K, mgr):
 
 
 def run_ours(args):
+    if args.warmup < 2 and not args.no_graph:
+        args.warmup = 2          # the first batch runs eagerly, the second is captured: both belong to the warm-up
     import numpy as np
     import torch
     import torch.distributed as dist
@@ -401,7 +403,8 @@ def run_ours(args):
     def make_trainer(precision):
         nc, nf = make(0, precision), make(1, precision)
         opt = FusedAdam(list(nc.parameters()) + list(nf.parameters()), [nc, nf], lr=5e-4)
-        return nc, nf, opt, Trainer(nc, nf, opt, H, W, K, 2.0, 6.0, 64, 128, white_bkgd=True, perturb=1.0, world_size=world, rank=rank)
+        return nc, nf, opt, Trainer(nc, nf, opt, H, W, K, 2.0, 6.0, 64, 128, white_bkgd=True, perturb=1.0, world_size=world, rank=rank,
+                                    graph=not args.no_graph)
 
     nc, nf, opt, tr = make_trainer(args.precision)
     # per-epoch quadtree kernels, reported separately: emit the epoch's shuffled ray index buffer
@@ -446,6 +449,7 @@ def run_ours(args):
     ms, launches, loss, first, (w0, w1) = timed_steps(tr, 0, args.warmup, args.steps)
     value = gb * args.steps / (ms * 1e-3)
     loss_host = loss.tolist()
+    tr.use_graph = False                      # the kernel tables and the API loop below launch eagerly
 
     # ---------------- e2e: reference-facing API with host buffers
     q = run_nerf.NetworkQuery(Hh.get_embedder(10)[0], Hh.get_embedder(4)[0], 65536)
@@ -492,6 +496,7 @@ def run_ours(args):
         nc3, nf3, opt3, tr3 = make_trainer("bf16x3")
         k3 = max(3, min(args.steps, 10))
         ms3, l3, loss3, first, _ = timed_steps(tr3, first, 3, k3)
+        loss3 = loss3.clone()
         v3 = gb * k3 / (ms3 * 1e-3)
         parity = {"precision": "bf16x3", "value": v3, "unit": "rays/s", "ms_per_step": ms3 / k3, "steps": k3, "warmup": 3,
                   "gpu_launches": int(l3), "loss": loss3.tolist(),
@@ -569,7 +574,8 @@ def run_ours(args):
                    "l2": "per-step working set (activation stash ~%.1f GB) exceeds the 126 MB L2" % (n_rand * 256 * 5.1e3 / 1e9),
                    "epoch_rays": n_rays},
         "e2e": {"value": e2e_value, "unit": "rays/s", "h2d_bytes_per_step": bytes_in, "d2h_bytes_per_step": 8},
-        "gpu_launches": int(launches), "clocks": clk, "roofline": roof, "parity_mode": parity, "hbm_kernels": hbm_kernels,
+        "gpu_launches": int(launches), "launch_mode": "kernel by kernel" if args.no_graph else
+        "one CUDA graph per step (%d kernels) + 1 step-record kernel" % tr._graph_launches, "clocks": clk, "roofline": roof, "parity_mode": parity, "hbm_kernels": hbm_kernels,
         "epoch_ops": {"emit_epoch_ms": emit_ms, "emit_epoch_rays": n_rays, "emit_rays_per_s": n_rays / (emit_ms * 1e-3),
                       "refine_ms": refine_ms, "note": "once per epoch, outside the timed steps"},
         "cpu_baseline": cpu, "reference_gpu": ref_gpu, "eval_render": eval_info, "loss": loss_host}))
@@ -589,6 +595,7 @@ def main():
     ap.add_argument("--no_cpu_baseline", action="store_true")
     ap.add_argument("--no_parity_leg", action="store_true")
     ap.add_argument("--no_kernel_table", action="store_true")
+    ap.add_argument("--no_graph", action="store_true", help="launch the step kernel by kernel instead of replaying one CUDA graph")
     ap.add_argument("--ref_device", default="cpu", choices=["cpu", "cuda"], help="--impl reference: host cores (default) or the B200")
     ap.add_argument("--ref_nrand", type=int, default=0, help="--impl reference: rays per step (0 = 4096 if host memory allows)")
     args = ap.parse_args()

@@ -63,7 +63,9 @@ _FLAGS = [
     ("i_testset", int, 50000, "frequency of testset saving"),
     ("i_video", int, 50000, "frequency of render_poses video saving"),
     # flnerf additions (not in the reference)
-    ("precision", str, None, "MLP arithmetic: bf16 (tcgen05) or fp32 (parity path); default $FLNERF_PRECISION or bf16"),
+    ("precision", str, None, "MLP arithmetic: bf16 (tcgen05 throughput mode), bf16x3 (split-precision tcgen05, meets the "
+                             "reference's 1e-4 tolerance) or fp32 (CUDA-core parity path); default $FLNERF_PRECISION or bf16"),
+    ("no_graph", "flag", False, "launch every training step kernel by kernel instead of replaying one CUDA graph"),
 ]
 
 

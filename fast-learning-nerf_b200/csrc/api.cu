@@ -73,6 +73,8 @@ int64_t flnerf_launch_count(int reset) {
   return v;
 }
 
+void flnerf_launch_count_add(int64_t n) { g_flnerf_launches += n; }
+
 size_t flnerf_mlp_packed_bytes(void) { return mlp_tc_packed_bytes(); }
 
 size_t flnerf_mlp_stash_bytes(int mode, int64_t n, int S, int training) {

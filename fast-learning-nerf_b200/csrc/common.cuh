@@ -12,6 +12,9 @@ struct flnerf_ctx {
   int device;
   int sm_count;
   int max_smem_optin;
+  // device-side per-step scalars (flnerf_set_step_record): when set, the batch start, the Philox offsets and the Adam
+  // step size come from device memory, so that a whole training step can be replayed as ONE CUDA graph
+  const flnerf_step_record *step_rec = nullptr;
 };
 
 void flnerf_set_error(const char *fmt, ...);

@@ -207,8 +207,10 @@ template <bool kBins, int kPP>
 __global__ void __launch_bounds__(kRaysPerBlock * 32)
 sample_pdf_merge_kernel(int64_t B, int Nc, int Nf, int P2, const float *__restrict__ z, const float *__restrict__ wts,
                         const float *__restrict__ u_in, int det, uint64_t seed, uint64_t offset,
-                        float *__restrict__ z_merged, float *__restrict__ z_samples, float *__restrict__ z_std) {
+                        float *__restrict__ z_merged, float *__restrict__ z_samples, float *__restrict__ z_std,
+                        const flnerf_step_record *__restrict__ rec) {
   extern __shared__ float sm[];
+  if (rec) offset += rec->rng_offset;
   int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   int64_t ray = (int64_t)blockIdx.x * kRaysPerBlock + wib;
   if (ray >= B) return;
@@ -349,7 +351,7 @@ int flnerf_sample_pdf_merge(flnerf_ctx *ctx, int64_t B, int Nc, int Nf, const fl
   size_t smem = (size_t)kRaysPerBlock * (Nc - 1 + P2) * sizeof(float);
   FL_REQUIRE(smem <= 48 * 1024, "flnerf_sample_pdf_merge: Nc+Nf=%d too large", Nc + Nf);
   FL_LAUNCH(k_merge, (unsigned)ceil_div64(B, kRaysPerBlock), kRaysPerBlock * 32, smem, stream, B,
-            Nc, Nf, P2, z, weights, u, det, seed, offset, z_merged, z_samples, z_std);
+            Nc, Nf, P2, z, weights, u, det, seed, offset, z_merged, z_samples, z_std, ctx->step_rec);
   return 0;
 }
 
@@ -361,7 +363,7 @@ int flnerf_sample_pdf(flnerf_ctx *ctx, int64_t B, int n_bins, int Nf, const floa
   size_t smem = (size_t)kRaysPerBlock * (Nc - 1 + Nc) * sizeof(float);
   FL_REQUIRE(smem <= 48 * 1024, "flnerf_sample_pdf: too many bins (%d)", n_bins);
   FL_LAUNCH(k_bins, (unsigned)ceil_div64(B, kRaysPerBlock), kRaysPerBlock * 32, smem, stream, B,
-            Nc, Nf, Nc, bins, weights, u, det, seed, offset, nullptr, z_samples, nullptr);
+            Nc, Nf, Nc, bins, weights, u, det, seed, offset, nullptr, z_samples, nullptr, (const flnerf_step_record *)nullptr);
   return 0;
 }
 
@@ -377,7 +379,7 @@ int flnerf_pp_sample_pdf_merge(flnerf_ctx *ctx, int64_t B, int Nc, int Nf, const
   size_t smem = (size_t)kRaysPerBlock * (Nc - 1 + P2) * sizeof(float);
   FL_REQUIRE(smem <= 48 * 1024, "flnerf_pp_sample_pdf_merge: Nc+Nf=%d too large", Nc + Nf);
   FL_LAUNCH(k_merge_pp, (unsigned)ceil_div64(B, kRaysPerBlock), kRaysPerBlock * 32, smem, stream, B,
-            Nc, Nf, P2, z, weights, u, det, seed, offset, z_merged, z_samples, nullptr);
+            Nc, Nf, P2, z, weights, u, det, seed, offset, z_merged, z_samples, nullptr, (const flnerf_step_record *)nullptr);
   return 0;
 }
 

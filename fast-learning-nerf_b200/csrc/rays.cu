@@ -79,9 +79,10 @@ __device__ __forceinline__ float base_depth(float near_, float far_, float t, in
 
 __global__ void coarse_depths_kernel(int64_t B, int Nc, const float *__restrict__ rays11, const float *__restrict__ tv,
                                      const float *__restrict__ t_rand, int perturb, int lindisp, uint64_t seed,
-                                     uint64_t offset, float *__restrict__ z) {
+                                     uint64_t offset, const flnerf_step_record *__restrict__ rec, float *__restrict__ z) {
   int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= B * Nc) return;
+  if (rec) offset += rec->rng_offset;
   int64_t ray = idx / Nc;
   int j = (int)(idx % Nc);
   float near_ = rays11[ray * 11 + 6], far_ = rays11[ray * 11 + 7];
@@ -248,10 +249,10 @@ __global__ void gather_batch_kernel(int64_t B, int64_t first, int64_t stride, co
                                     const int32_t *__restrict__ ray_gid, int cap, int H, int W, Cam cam,
                                     const float *__restrict__ poses, const float *__restrict__ images,
                                     float *__restrict__ ro, float *__restrict__ rd, float *__restrict__ target,
-                                    int32_t *__restrict__ leaf_gid) {
+                                    int32_t *__restrict__ leaf_gid, const flnerf_step_record *__restrict__ rec) {
   int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= B) return;
-  int64_t j = first + k * stride;
+  int64_t j = first + (rec ? rec->first : 0) + k * stride;
   int pix = ray_pix[j], gid = ray_gid[j];
   int img = gid / cap;
   int row = pix / W, col = pix % W;
@@ -303,7 +304,7 @@ int flnerf_coarse_depths(flnerf_ctx *ctx, int64_t B, int Nc, const float *rays11
   FL_REQUIRE(ctx && rays11 && t_vals && z && Nc > 0 && B >= 0, "flnerf_coarse_depths: bad arguments");
   if (B == 0) return 0;
   FL_LAUNCH(coarse_depths_kernel, (unsigned)ceil_div64(B * Nc, 256), 256, 0, stream, B, Nc, rays11, t_vals, t_rand,
-            perturb, lindisp, seed, offset, z);
+            perturb, lindisp, seed, offset, ctx->step_rec, z);
   return 0;
 }
 
@@ -372,7 +373,7 @@ int flnerf_gather_batch(flnerf_ctx *ctx, int64_t B, int64_t first, int64_t strid
              "flnerf_gather_batch: bad arguments");
   if (B == 0) return 0;
   FL_LAUNCH(gather_batch_kernel, (unsigned)ceil_div64(B, 256), 256, 0, stream, B, first, stride, ray_pix, ray_gid, cap,
-            H, W, make_cam(h_K), poses, images, rays_o, rays_d, target, leaf_gid);
+            H, W, make_cam(h_K), poses, images, rays_o, rays_d, target, leaf_gid, ctx->step_rec);
   return 0;
 }
 

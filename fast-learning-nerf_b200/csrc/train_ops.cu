@@ -63,9 +63,10 @@ mse_leafmax_kernel(int64_t B, const float *__restrict__ rgb, const float *__rest
 // torch.optim.Adam single-tensor update order (exp_avg.lerp, exp_avg_sq.mul.addcmul, sqrt/bc2_sqrt + eps, addcdiv)
 __global__ void adam_kernel(int64_t n, float *__restrict__ p, float *__restrict__ m, float *__restrict__ v,
                             const float *__restrict__ g, float omb1, float b2, float omb2, float eps, float step_size,
-                            float bc2_sqrt) {
+                            float bc2_sqrt, const flnerf_step_record *__restrict__ rec) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
+  if (rec) { step_size = rec->adam_step_size; bc2_sqrt = rec->adam_bc2_sqrt; }
   float gi = g[i];
   float mi = m[i] + (gi - m[i]) * omb1;
   float vi = v[i] * b2 + omb2 * gi * gi;
@@ -448,7 +449,27 @@ int flnerf_adam_step(flnerf_ctx *ctx, int64_t n, float *param, float *m, float *
   if (n == 0) return 0;
   double bc1 = 1.0 - pow(b1, (double)t), bc2 = 1.0 - pow(b2, (double)t);
   FL_LAUNCH(adam_kernel, (unsigned)ceil_div64(n, 256), 256, 0, stream, n, param, m, v, grad, (float)(1.0 - b1),
-            (float)b2, (float)(1.0 - b2), (float)eps, (float)(lr / bc1), (float)sqrt(bc2));
+            (float)b2, (float)(1.0 - b2), (float)eps, (float)(lr / bc1), (float)sqrt(bc2), ctx->step_rec);
+  return 0;
+}
+
+__global__ void step_record_kernel(flnerf_step_record *rec, flnerf_step_record v) { *rec = v; }
+
+int flnerf_set_step_record(flnerf_ctx *ctx, const flnerf_step_record *rec) {
+  FL_REQUIRE(ctx, "flnerf_set_step_record: bad arguments");
+  ctx->step_rec = rec;
+  return 0;
+}
+
+int flnerf_step_record_write(flnerf_ctx *ctx, flnerf_step_record *rec, int64_t first, uint64_t rng_offset, double lr,
+                             double b1, double b2, int64_t t, void *stream) {
+  FL_REQUIRE(ctx && rec && t >= 1, "flnerf_step_record_write: bad arguments");
+  flnerf_step_record v;
+  v.first = first;
+  v.rng_offset = rng_offset;
+  v.adam_step_size = (float)(lr / (1.0 - pow(b1, (double)t)));     // the same host-side doubles as flnerf_adam_step
+  v.adam_bc2_sqrt = (float)sqrt(1.0 - pow(b2, (double)t));
+  FL_LAUNCH(step_record_kernel, 1, 1, 0, stream, rec, v);
   return 0;
 }
 

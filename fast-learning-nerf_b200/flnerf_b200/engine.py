@@ -4,6 +4,7 @@ autograd graph, no per-iteration D2H copy and no host synchronisation.  ``FusedA
 torch.optim.Adam's state_dict format (checkpoints stay interchangeable with the reference).
 """
 import math
+import os
 from typing import List, Optional
 
 import torch
@@ -88,6 +89,12 @@ class FusedAdam(torch.optim.Adam):
                           b1, b2, g["eps"], self._step[id(net)])
             net.weights_version += 1
 
+    def replayed(self):
+        """Host bookkeeping for one optimiser step that ran on the device without this object (CUDA-graph replay)."""
+        for net in self._nets:
+            self._step[id(net)] += 1
+            net.weights_version += 1
+
 
 class Trainer:
     """The fused training step.  Rays come either from the caller (``step``) or from the GPU-resident quadtree
@@ -95,7 +102,7 @@ class Trainer:
 
     def __init__(self, net_coarse, net_fine, optimizer: FusedAdam, H, W, K, near, far, N_samples=64, N_importance=128,
                  white_bkgd=True, perturb=1.0, lindisp=False, ndc=False, raw_noise_std=0.0, seed=0, world_size=1,
-                 rank=0):
+                 rank=0, graph=None):
         if N_importance <= 0 or net_fine is None:
             raise FlnerfError("Trainer implements the coarse+fine loop (N_importance > 0), like run_nerf.train()")
         self.nc, self.nf, self.opt = net_coarse, net_fine, optimizer
@@ -108,6 +115,11 @@ class Trainer:
         self.world, self.rank = int(world_size), int(rank)
         self.bucket = share_grad_bucket([net_coarse, net_fine])
         self.last = {}
+        # one CUDA graph per full batch of step_from_tree: opt-in, because a replayed step returns
+        # the SAME loss / output tensors every time (the graph's static outputs)
+        self.use_graph = bool(int(os.environ.get("FLNERF_GRAPH", "0"))) if graph is None else bool(graph)
+        self._graph = self._graph_key = self._graph_out = self._rec = None
+        self._graph_seen, self._graph_launches = {}, 0
         self.sync_replicas()
 
     def sync_replicas(self):
@@ -212,9 +224,70 @@ class Trainer:
         """One batch of ``n_rand`` rows of the quadtree index buffer starting at ``first``; under data parallelism
         rank r consumes rows first + r, first + r + world, ... (every rank holds the same index buffer)."""
         rows = min(n_rand, mgr.n_rays - first)
+        if self.use_graph and rows == n_rand and rows % self.world == 0:
+            return self._graph_step(mgr, first, n_rand)
         local = (rows - self.rank + self.world - 1) // self.world
         o, d, tgt, gid = mgr.batch(first + self.rank, local, self.world)
         return self.step(o, d, tgt, gid, mgr.leaf_max, global_batch=rows)
+
+    # -- the same step as ONE CUDA graph: the ~30 launches of a step carry no per-step host value once the batch start,
+    #    the Philox offsets and the Adam scalars come from the device-side step record (include/flnerf.h)
+    def _record_step(self, mgr, first, n_rand):
+        g = self.opt.param_groups[0]
+        t = self.opt._step[id(self.nc)] + 1
+        ops.step_record_write(self._rec, first, self.calls, float(g["lr"]), g["betas"][0], g["betas"][1], t)
+
+    def _step_on_record(self, mgr, n_rand):
+        """step_from_tree with every per-step scalar taken from the attached record (host values are zero / biases)."""
+        local = n_rand // self.world
+        calls = self.calls
+        self.calls = 0                      # Philox offset = rec.rng_offset + 0
+        ops.set_step_record(self._rec)
+        try:
+            o, d, tgt, gid = mgr.batch(self.rank, local, self.world)        # rows rec.first + rank + k * world
+            loss = self.step(o, d, tgt, gid, mgr.leaf_max, global_batch=n_rand)
+        finally:
+            ops.set_step_record(None, self.bucket.device)
+            self.calls = calls
+        return loss
+
+    def _graph_step(self, mgr, first, n_rand):
+        from . import lib
+        key = (id(mgr), mgr.ray_pix.data_ptr(), mgr.ray_gid.data_ptr(), mgr.leaf_max.data_ptr(), n_rand,
+               float(self.opt.param_groups[0]["betas"][0]), self.nc.mode, self.nf.mode)
+        if self._rec is None:
+            self._rec = torch.zeros(ops.STEP_RECORD_BYTES, dtype=torch.uint8, device=self.bucket.device)
+        local = n_rand // self.world
+        if self._graph_key != key:
+            seen = self._graph_seen.get(key, 0)
+            self._graph_seen[key] = seen + 1
+            if seen == 0:
+                # first batch of this shape: run it eagerly (lazy initialisation of the library, allocator warm-up)
+                o, d, tgt, gid = mgr.batch(first + self.rank, local, self.world)
+                return self.step(o, d, tgt, gid, mgr.leaf_max, global_batch=n_rand)
+            # second batch: capture.  Capturing executes nothing, so the host counters are restored afterwards and the
+            # step then runs as the first replay.
+            steps = {id(n): self.opt._step[id(n)] for n in (self.nc, self.nf)}
+            versions = (self.nc.weights_version, self.nf.weights_version)
+            self._record_step(mgr, first, n_rand)
+            torch.cuda.synchronize()
+            c0 = lib.launch_count()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                out = self._step_on_record(mgr, n_rand)
+            self._graph_launches = lib.launch_count() - c0
+            lib.load().flnerf_launch_count_add(-self._graph_launches)         # captured, not launched
+            for n in (self.nc, self.nf):
+                self.opt._step[id(n)] = steps[id(n)]
+            self.nc.weights_version, self.nf.weights_version = versions
+            self._graph, self._graph_key, self._graph_out = graph, key, (out, dict(self.last))
+        self._record_step(mgr, first, n_rand)
+        self._graph.replay()
+        lib.load().flnerf_launch_count_add(self._graph_launches)
+        self.calls += local * (self.Nc + self.Nf)
+        self.opt.replayed()
+        loss, self.last = self._graph_out
+        return loss
 
 
 def lr_at(lrate, lrate_decay, global_iter):

@@ -66,6 +66,9 @@ SIGNATURES = {
     "flnerf_pp_composite_backward": (_i, [_vp, _i64, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "flnerf_pp_sample_pdf_merge": (_i, [_vp, _i64, _i, _i, _vp, _vp, _vp, _i, _u64, _u64, _vp, _vp, _vp]),
     "flnerf_launch_count": (_i64, [_i]),
+    "flnerf_launch_count_add": (None, [_i64]),
+    "flnerf_set_step_record": (_i, [_vp, _vp]),
+    "flnerf_step_record_write": (_i, [_vp, _vp, _i64, _u64, _d, _d, _d, _i64, _vp]),
 }
 
 _lib = None

@@ -244,6 +244,21 @@ def adam_step(param, m, v, grad, lr: float, b1: float, b2: float, eps: float, t:
                                       eps, int(t), _stream()), "flnerf_adam_step")
 
 
+# ------------------------------------------------------------------------------------------ step record (CUDA graphs)
+STEP_RECORD_BYTES = 24
+
+
+def set_step_record(rec: Optional[torch.Tensor], device=None):
+    """Attach (or with None detach) the device-side per-step scalars (include/flnerf.h: flnerf_step_record)."""
+    idx = rec.device.index if rec is not None else (device.index if device is not None else torch.cuda.current_device())
+    L.check(L.load().flnerf_set_step_record(C.c_void_p(L.context(idx)), _ptr(rec)), "flnerf_set_step_record")
+
+
+def step_record_write(rec: torch.Tensor, first: int, rng_offset: int, lr: float, b1: float, b2: float, t: int):
+    L.check(L.load().flnerf_step_record_write(_ctx(rec), _ptr(rec), int(first), int(rng_offset), float(lr), float(b1),
+                                              float(b2), int(t), _stream()), "flnerf_step_record_write")
+
+
 # ------------------------------------------------------------------------------------------ quadtree
 def qt_init(n_images, cap, H, W, max_depth, boxes, count, min_area):
     L.check(L.load().flnerf_qt_init(_ctx(boxes), n_images, cap, H, W, max_depth, _ptr(boxes), _ptr(count),

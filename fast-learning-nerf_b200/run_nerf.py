@@ -241,7 +241,7 @@ def train(argv=None):
     nc, nf = _unwrap(render_kwargs_train['network_fn']), _unwrap(render_kwargs_train['network_fine'])
     trainer = Trainer(nc, nf, optimizer, H, W, K, near, far, args.N_samples, args.N_importance, args.white_bkgd,
                       args.perturb, args.lindisp, render_kwargs_train.get('ndc', True), args.raw_noise_std,
-                      world_size=world, rank=rank)
+                      world_size=world, rank=rank, graph=not getattr(args, "no_graph", False))
 
     def log(tag, it, loss):
         l = trainer.global_loss(loss).tolist()   # the only host sync (+ an 8-byte all-reduce), every 50/400 iterations

@@ -215,8 +215,11 @@ class QuadTreeManager:
             boxes, count, min_area = self.boxes, self.counts, self._min_area
         ops.qt_count(n, self.cap, boxes, count, min_area, rpp, self._ray_offset)
         self.n_rays = int(self._ray_offset[-1].item())        # one 8-byte D2H per epoch
-        self.ray_pix = torch.empty(self.n_rays, dtype=torch.int32, device=self.device)
-        self.ray_gid = torch.empty(self.n_rays, dtype=torch.int32, device=self.device)
+        # the index buffer keeps its ADDRESS from epoch to epoch (it only ever grows): a training step captured as a CUDA
+        # graph has the two pointers baked in
+        if getattr(self, "_ray_store", None) is None or self._ray_store.shape[1] < self.n_rays:
+            self._ray_store = torch.empty(2, max(self.n_rays, self.epoch_size), dtype=torch.int32, device=self.device)
+        self.ray_pix, self.ray_gid = self._ray_store[0, :self.n_rays], self._ray_store[1, :self.n_rays]
         self._epoch += 1
         s = self.seed * 1000003 + self._epoch if seed is None else int(seed)
         if prob:

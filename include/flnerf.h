@@ -220,8 +220,25 @@ int flnerf_pp_sample_pdf_merge(flnerf_ctx *, int64_t B, int Nc, int Nf, const fl
                                const float *u, int det, uint64_t seed, uint64_t offset, float *z_merged,
                                float *z_samples, void *stream);
 
-/* ---- diagnostics: number of kernels this library launched since the counter was last reset */
+/* ---- one CUDA graph per training step (run_nerf.py:470-516 is a fixed kernel sequence; only four scalars change from
+ * one iteration to the next).  While a device-side step record is attached to the context, flnerf_gather_batch ADDS
+ * rec->first to its `first`, flnerf_coarse_depths / flnerf_sample_pdf_merge ADD rec->rng_offset to their `offset`, and
+ * flnerf_adam_step takes its step size and bias correction from the record instead of (lr, t): the captured launches carry
+ * no per-step host value, and the host updates the record with ONE tiny kernel before each replay. */
+typedef struct flnerf_step_record {
+  int64_t first;        /* row of the epoch's ray index buffer where this step's batch starts */
+  uint64_t rng_offset;  /* Philox counter offset of this step's uniforms */
+  float adam_step_size; /* lr / (1 - b1^t) */
+  float adam_bc2_sqrt;  /* sqrt(1 - b2^t) */
+} flnerf_step_record;
+int flnerf_set_step_record(flnerf_ctx *, const flnerf_step_record *rec /* device pointer, or NULL to detach */);
+int flnerf_step_record_write(flnerf_ctx *, flnerf_step_record *rec, int64_t first, uint64_t rng_offset, double lr, double b1,
+                             double b2, int64_t t, void *stream);
+
+/* ---- diagnostics: number of kernels this library launched since the counter was last reset; _add accounts for
+ * launches replayed from a captured graph (the capture itself counts once) */
 int64_t flnerf_launch_count(int reset);
+void flnerf_launch_count_add(int64_t n);
 
 #ifdef __cplusplus
 }
