@@ -25,13 +25,14 @@ int mlp_simt_backward_g(int in_pts, int in_views, const float *P, int64_t n, con
                         const float *draw, float *G, float *ws, cudaStream_t st);
 int mlp_simt_layout_selfcheck();
 // mlp_tc.cu
-size_t mlp_tc_packed_bytes();
+size_t mlp_tc_packed_bytes(int kind);
+int64_t mlp_tc_param_count(int kind);
 size_t mlp_tc_stash_bytes(int64_t n, int S, int training, bool x3);
 size_t mlp_tc_bwd_workspace_bytes(int64_t n, bool x3);
-int mlp_tc_pack_weights(flnerf_ctx *ctx, const float *params, void *packed, cudaStream_t st);
-int mlp_tc_forward(flnerf_ctx *ctx, bool x3, const float *params, const void *packed, int64_t n, int S, const void *pe_tiles,
+int mlp_tc_pack_weights(flnerf_ctx *ctx, int kind, const float *params, void *packed, cudaStream_t st);
+int mlp_tc_forward(flnerf_ctx *ctx, bool x3, int kind, const float *params, const void *packed, int64_t n, int S, const void *pe_tiles,
                    const float *dirpe, float *raw, void *stash, int training, cudaStream_t st);
-int mlp_tc_backward(flnerf_ctx *ctx, bool x3, const float *params, const void *packed, int64_t n, int S, const void *pe_tiles,
+int mlp_tc_backward(flnerf_ctx *ctx, bool x3, int kind, const float *params, const void *packed, int64_t n, int S, const void *pe_tiles,
                     const float *dirpe, const void *stash, const float *draw, float *grads, void *ws, int stages,
                     cudaStream_t st);
 
@@ -75,7 +76,10 @@ int64_t flnerf_launch_count(int reset) {
 
 void flnerf_launch_count_add(int64_t n) { g_flnerf_launches += n; }
 
-size_t flnerf_mlp_packed_bytes(void) { return mlp_tc_packed_bytes(); }
+size_t flnerf_mlp_packed_bytes(void) { return mlp_tc_packed_bytes(0); }
+
+static int net_kind(int in_pts) { return in_pts == 63 ? 0 : (in_pts == 84 ? 1 : -1); }
+size_t flnerf_mlp_packed_bytes_g(int in_pts) { return net_kind(in_pts) < 0 ? 0 : mlp_tc_packed_bytes(net_kind(in_pts)); }
 
 size_t flnerf_mlp_stash_bytes(int mode, int64_t n, int S, int training) {
   if (mode == FLNERF_MODE_FP32) return mlp_simt_stash_bytes(n);
@@ -90,7 +94,13 @@ size_t flnerf_mlp_bwd_workspace_bytes(int mode, int64_t n) {
 int flnerf_mlp_pack_weights(flnerf_ctx *ctx, const float *params, void *packed, void *stream) {
   FL_REQUIRE(ctx && params && packed, "flnerf_mlp_pack_weights: bad arguments");
   FL_CHECK_CUDA(cudaSetDevice(ctx->device));
-  return mlp_tc_pack_weights(ctx, params, packed, (cudaStream_t)stream);
+  return mlp_tc_pack_weights(ctx, 0, params, packed, (cudaStream_t)stream);
+}
+
+int flnerf_mlp_pack_weights_g(flnerf_ctx *ctx, int in_pts, const float *params, void *packed, void *stream) {
+  FL_REQUIRE(ctx && params && packed && net_kind(in_pts) >= 0, "flnerf_mlp_pack_weights_g: bad arguments (in_pts must be 63 or 84)");
+  FL_CHECK_CUDA(cudaSetDevice(ctx->device));
+  return mlp_tc_pack_weights(ctx, net_kind(in_pts), params, packed, (cudaStream_t)stream);
 }
 
 int flnerf_mlp_forward(flnerf_ctx *ctx, int mode, const float *params, const void *packed, int64_t n, int S,
@@ -102,8 +112,33 @@ int flnerf_mlp_forward(flnerf_ctx *ctx, int mode, const float *params, const voi
   FL_REQUIRE(packed && dirpe, "flnerf_mlp_forward: the tensor-core modes need packed weights and dirpe");
   FL_REQUIRE((((uintptr_t)packed | (uintptr_t)x | (uintptr_t)stash) & 1023) == 0,
              "flnerf_mlp_forward: packed / pe_tiles / stash must be 1024-byte aligned");
-  return mlp_tc_forward(ctx, mode == FLNERF_MODE_BF16X3, params, packed, n, S, x, dirpe, raw_out, stash, training,
+  return mlp_tc_forward(ctx, mode == FLNERF_MODE_BF16X3, 0, params, packed, n, S, x, dirpe, raw_out, stash, training,
                         (cudaStream_t)stream);
+}
+
+int flnerf_mlp_forward_g(flnerf_ctx *ctx, int mode, int in_pts, const float *params, const void *packed, int64_t n, int S,
+                         const void *x, const float *dirpe, float *raw_out, void *stash, int training, void *stream) {
+  FL_REQUIRE(ctx && params && x && raw_out && stash && packed && dirpe && n > 0 && S > 0 && net_kind(in_pts) >= 0,
+             "flnerf_mlp_forward_g: bad arguments (in_pts must be 63 or 84)");
+  FL_REQUIRE(mode == FLNERF_MODE_BF16 || mode == FLNERF_MODE_BF16X3, "flnerf_mlp_forward_g: tensor-core modes only (mode %d)", mode);
+  FL_REQUIRE(((uintptr_t)raw_out & 15) == 0 && (((uintptr_t)packed | (uintptr_t)x | (uintptr_t)stash) & 1023) == 0,
+             "flnerf_mlp_forward_g: raw_out must be 16-byte, packed / pe_tiles / stash 1024-byte aligned");
+  return mlp_tc_forward(ctx, mode == FLNERF_MODE_BF16X3, net_kind(in_pts), params, packed, n, S, x, dirpe, raw_out, stash,
+                        training, (cudaStream_t)stream);
+}
+
+int flnerf_mlp_backward_g(flnerf_ctx *ctx, int mode, int in_pts, const float *params, const void *packed, int64_t n, int S,
+                          const void *x, const float *dirpe, const void *stash, const float *draw, float *grads, void *workspace,
+                          size_t workspace_bytes, void *stream) {
+  FL_REQUIRE(ctx && params && x && stash && draw && grads && workspace && packed && dirpe && n > 0 && S > 0 &&
+                 net_kind(in_pts) >= 0,
+             "flnerf_mlp_backward_g: bad arguments (in_pts must be 63 or 84)");
+  FL_REQUIRE(mode == FLNERF_MODE_BF16 || mode == FLNERF_MODE_BF16X3, "flnerf_mlp_backward_g: tensor-core modes only (mode %d)", mode);
+  FL_REQUIRE(workspace_bytes >= flnerf_mlp_bwd_workspace_bytes(mode, n), "flnerf_mlp_backward_g: workspace too small");
+  FL_REQUIRE(((uintptr_t)draw & 15) == 0 && (((uintptr_t)packed | (uintptr_t)x | (uintptr_t)stash | (uintptr_t)workspace) & 1023) == 0,
+             "flnerf_mlp_backward_g: draw must be 16-byte, packed / pe_tiles / stash / workspace 1024-byte aligned");
+  return mlp_tc_backward(ctx, mode == FLNERF_MODE_BF16X3, net_kind(in_pts), params, packed, n, S, x, dirpe, stash, draw, grads,
+                         workspace, 7, (cudaStream_t)stream);
 }
 
 int flnerf_mlp_backward_stages(flnerf_ctx *ctx, int mode, const float *params, const void *packed, int64_t n, int S,
@@ -131,7 +166,7 @@ int flnerf_mlp_backward_stages(flnerf_ctx *ctx, int mode, const float *params, c
   FL_REQUIRE(packed && dirpe, "flnerf_mlp_backward: the tensor-core modes need packed weights and dirpe");
   FL_REQUIRE((((uintptr_t)packed | (uintptr_t)x | (uintptr_t)stash | (uintptr_t)workspace) & 1023) == 0,
              "flnerf_mlp_backward: packed / pe_tiles / stash / workspace must be 1024-byte aligned");
-  return mlp_tc_backward(ctx, mode == FLNERF_MODE_BF16X3, params, packed, n, S, x, dirpe, stash, draw, grads, workspace,
+  return mlp_tc_backward(ctx, mode == FLNERF_MODE_BF16X3, 0, params, packed, n, S, x, dirpe, stash, draw, grads, workspace,
                          stages, (cudaStream_t)stream);
 }
 

@@ -74,6 +74,47 @@ constexpr size_t FWD_BYTES = (size_t)34 * 32768 + 4 * 16384;
 constexpr size_t DG_BYTES = (size_t)34 * 32768;
 constexpr size_t PACKED_BYTES = FWD_BYTES + DG_BYTES;
 
+// Where a network's tensors live inside its flat fp32 parameter buffer (parameters() order) and how many 64-wide slabs its
+// positional input takes.  kind 0: 63 position channels (1 slab) -- nerf-ours model.NeRF and the nerf++ foreground MLPNet;
+// kind 1: 84 channels (2 slabs, PE of (x, y, z, 1/r)) -- the nerf++ background MLPNet (nerf++-ours/nerf_network.py:70-142).
+// Everything behind the first layer and the skip concatenation has the same shape in both.
+constexpr int kNetKinds = 2;
+constexpr int MAX_FWD_CHUNKS = 40;     // kind 1: 36 full + 4 half chunks
+struct NetDesc {
+  int kind, in_pts, pe_slabs;
+  int fwd_full;                        // full (32 KB) forward chunks = 32 + 2 * pe_slabs; 4 half chunks (views layer) follow
+  int k5;                              // row length of pts_linears.5 = 256 + in_pts
+  int w_pts[8], b_pts[8];
+  int w_views, b_views, w_feat, b_feat, w_alpha, b_alpha, w_rgb, b_rgb, total;
+  size_t fwd_bytes, packed_bytes;      // one part (hi or lo) of the packed image
+};
+static NetDesc make_desc(int kind) {
+  NetDesc d{};
+  d.kind = kind;
+  d.in_pts = kind == 0 ? 63 : 84;
+  d.pe_slabs = (d.in_pts + 63) / 64;
+  d.fwd_full = 32 + 2 * d.pe_slabs;
+  d.k5 = 256 + d.in_pts;
+  int off = 0;
+  for (int l = 0; l < 8; ++l) {
+    const int K = l == 0 ? d.in_pts : (l == 5 ? d.k5 : 256);
+    d.w_pts[l] = off; off += 256 * K;
+    d.b_pts[l] = off; off += 256;
+  }
+  d.w_views = off; off += 128 * 283;
+  d.b_views = off; off += 128;
+  d.w_feat = off; off += 256 * 256;
+  d.b_feat = off; off += 256;
+  d.w_alpha = off; off += 256;
+  d.b_alpha = off; off += 1;
+  d.w_rgb = off; off += 3 * 128;
+  d.b_rgb = off; off += 3;
+  d.total = off;
+  d.fwd_bytes = (size_t)d.fwd_full * 32768 + 4 * 16384;
+  d.packed_bytes = d.fwd_bytes + DG_BYTES;
+  return d;
+}
+
 // stash (bf16 mode): [viewbias B*128 fp32 (1 KB aligned)] [acts: tiles x 10 x 64 KB] [masks: tiles x 9 x 4 x 128 x 8 B]
 constexpr size_t TILE_ACT_BYTES = 10 * 65536;
 constexpr size_t TILE_MASK_BYTES = 9 * 128 * 32;
@@ -86,15 +127,16 @@ struct ChunkSrc {
   int nrows;    // 256 or 128
   int byte_off; // byte offset of the chunk in the packed image
 };
-__constant__ ChunkSrc c_chunks[FWD_CHUNKS + DG_CHUNKS];
+__constant__ ChunkSrc c_chunks[kNetKinds][MAX_FWD_CHUNKS + DG_CHUNKS];
+__constant__ NetDesc c_desc[kNetKinds];   // the kernels take the network KIND as a parameter and read its layout from here
 
 // one thread = one 16-byte chunk (8 bf16) of the packed image; blockIdx.z = part: 0 = hi = bf16(w), 1 = lo =
 // bf16(w - hi) (the split-precision mode multiplies by hi + lo; the bf16 mode reads part 0 only)
-__global__ void pack_weights_kernel(const float *__restrict__ P, uint8_t *__restrict__ packed) {
+__global__ void pack_weights_kernel(const float *__restrict__ P, uint8_t *__restrict__ packed, int kind, size_t part_bytes) {
   int ci = blockIdx.y;
   const bool lo = blockIdx.z != 0;
-  packed += (size_t)blockIdx.z * PACKED_BYTES;
-  ChunkSrc s = c_chunks[ci];
+  packed += (size_t)blockIdx.z * part_bytes;
+  ChunkSrc s = c_chunks[kind][ci];
   int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= s.nrows * 8) return;
   int r = idx >> 3, q = idx & 7;
@@ -113,7 +155,7 @@ __global__ void pack_weights_kernel(const float *__restrict__ P, uint8_t *__rest
 // viewbias[ray][c] = b_v[c] + sum_j W_v[c][256+j] * PE4(viewdir)[j]  -- the 27 view-direction inputs of
 // views_linears.0 are constant along a ray, so their contribution is a per-ray bias (fp32, exact)
 __global__ void __launch_bounds__(128) viewbias_kernel(int64_t B, const float *__restrict__ P, const float *__restrict__ dirpe,
-                                                       float *__restrict__ vb) {
+                                                       float *__restrict__ vb, int W_VIEWS, int B_VIEWS) {
   // thread = output channel c: its 27 view-direction weights stay in registers for kRays rays (the strided weight reads
   // are paid once per block); the ray's PE values are warp-uniform loads, the stores are coalesced
   constexpr int kRays = 16;
@@ -143,7 +185,8 @@ __device__ __forceinline__ void issue_chunk(uint32_t tmem_d, uint32_t a_smem, ui
 // barrier / TMEM / constant-vector set-up shared by the two kernels; returns the TMEM base
 template <class L>
 __device__ __forceinline__ uint32_t pair_setup(uint8_t *smem, uint32_t bar, uint32_t cr, int warp, uint32_t lane,
-                                               const float *P) {
+                                               const float *P, int kind) {
+  const NetDesc &nd = c_desc[kind];
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + L::OFF_BAR + 128);
   if ((smem_u32(smem) & 1023u) != 0) __trap();
   // biases of the 9 tensor layers that have one (pts 0..7, feature) and the small heads: resident for the whole
@@ -152,12 +195,12 @@ __device__ __forceinline__ uint32_t pair_setup(uint8_t *smem, uint32_t bar, uint
     float *bias = reinterpret_cast<float *>(smem + L::OFF_VEC);
     for (int i = threadIdx.x; i < (int)BIAS_FLOATS; i += blockDim.x) {
       const int l = i >> 8, c = i & 255;
-      bias[i] = P[(l < 8 ? b_pts(l) : B_FEAT) + c];
+      bias[i] = P[(l < 8 ? nd.b_pts[l] : nd.b_feat) + c];
     }
   }
   float *head = reinterpret_cast<float *>(smem + L::OFF_HEAD);
   for (int i = threadIdx.x; i < (int)HEAD_FLOATS; i += blockDim.x)
-    head[i] = i < 387 ? P[W_RGB + i] : (i == 387 ? P[B_ALPHA] : P[W_ALPHA + (i - 388)]);
+    head[i] = i < 387 ? P[nd.w_rgb + i] : (i == 387 ? P[nd.b_alpha] : P[nd.w_alpha + (i - 388)]);
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < L::NST; ++i) {
       mbar_init(L::w_full(bar, i), cr == 0 ? 2 : 1);  // leader: own producer + the follower's relay
@@ -382,6 +425,7 @@ struct FwdParams {
   int n_pairs;
   int dbg;   // profiling switches (bit 0: skip mask generation, bit 1: skip the activation bulk stores)
   long long *prof;  // per-CTA cycle accounting of the roles (PROF_SLOTS per CTA) when FLNERF_TC_PROF is set, else null
+  int kind;         // network kind (index into c_desc)
 };
 constexpr int PROF_SLOTS = 24;
 
@@ -401,7 +445,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) mlp_fwd
   const uint32_t lane = lane_id();
   const uint32_t bar = smem_u32(smem + LayF::OFF_BAR);
   const uint32_t cr = cluster_ctarank();
-  const uint32_t tmem_base = pair_setup<LayF>(smem, bar, cr, warp, lane, p.P);
+  const uint32_t tmem_base = pair_setup<LayF>(smem, bar, cr, warp, lane, p.P, p.kind);
   const uint32_t s_act = smem_u32(smem + OFF_ACT), s_w = smem_u32(smem + OFF_W);
   const int iters = (p.n_pairs + (int)gridDim.x - 1) / (int)gridDim.x;
   const bool prof_on = kProf && p.prof != nullptr;  // the accounting is compiled out of the production instantiation
@@ -642,6 +686,7 @@ struct DgradParams {
   int64_t n;
   int n_pairs;
   long long *prof;
+  int kind;
 };
 
 template <bool kProf>
@@ -651,7 +696,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) mlp_dgr
   const uint32_t lane = lane_id();
   const uint32_t bar = smem_u32(smem + LayD::OFF_BAR);
   const uint32_t cr = cluster_ctarank();
-  const uint32_t tmem_base = pair_setup<LayD>(smem, bar, cr, warp, lane, p.P);
+  const uint32_t tmem_base = pair_setup<LayD>(smem, bar, cr, warp, lane, p.P, p.kind);
   const uint32_t s_act = smem_u32(smem + OFF_ACT), s_w = smem_u32(smem + OFF_W);
   const int iters = (p.n_pairs + (int)gridDim.x - 1) / (int)gridDim.x;
   const bool prof_on = kProf && p.prof != nullptr;  // the accounting is compiled out of the production instantiation
@@ -827,7 +872,7 @@ struct WUnit {
   int splits;   // number of row ranges this unit is cut into
 };
 constexpr int kUnits = 11;
-__constant__ WUnit c_units[kUnits];
+__constant__ WUnit c_units[kNetKinds][kUnits];
 
 struct WgradParams {
   const uint8_t *dy;
@@ -848,6 +893,7 @@ struct WgradParams {
   // bit 0: sums over dY (biases, view-direction columns), bit 1: sums over activations (w_alpha, W_rgb),
   // bit 2: sums over d_raw alone (b_alpha, b_rgb)
   int helper_flags;
+  int kind;
 };
 
 constexpr int WG_STAGES = 3;
@@ -885,8 +931,11 @@ __global__ void __launch_bounds__(kWgThreads, 1) mlp_wgrad_tc(WgradParams p) {
 
   // which (unit, row range) does this CTA own?
   int u = 0, part = blockIdx.x;
-  while (u < kUnits - 1 && part >= c_units[u].splits) { part -= c_units[u].splits; ++u; }
-  const WUnit un = c_units[u];
+  while (u < kUnits - 1 && part >= c_units[p.kind][u].splits) { part -= c_units[p.kind][u].splits; ++u; }
+  const WUnit un = c_units[p.kind][u];
+  const int W_ALPHA = c_desc[p.kind].w_alpha, B_ALPHA = c_desc[p.kind].b_alpha, W_RGB = c_desc[p.kind].w_rgb,
+            B_RGB = c_desc[p.kind].b_rgb, W_VIEWS = c_desc[p.kind].w_views;
+  const int in_pts = c_desc[p.kind].in_pts, pe_slabs = c_desc[p.kind].pe_slabs;
   const int nhalf = p.n_tiles * 2;  // 64-row half tiles
   const int h_begin = (int)((int64_t)nhalf * part / un.splits), h_end = (int)((int64_t)nhalf * (part + 1) / un.splits);
   const uint32_t a_bytes = un.a_slabs * 8192u, b_bytes = un.b_slabs * 8192u;
@@ -906,7 +955,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) mlp_wgrad_tc(WgradParams p) {
         uint32_t sa = smem_u32(smem + stage * WG_STAGE_BYTES), sb = sa + WG_A_BYTES;
         for (int s = 0; s < un.a_slabs; ++s) bulk_g2s(sa + s * 8192, a_src + (size_t)s * SLAB_BYTES, 8192u, full);
         const uint8_t *b_src = un.b_kind == 0 ? p.stash_act + tile * p.tile_stride + (size_t)un.b_slot * p.slot_stride + p.b_part + half_off
-                                              : p.pe_tiles + p.pe_part + tile * PE_BYTES + half_off;
+                                              : p.pe_tiles + p.pe_part + tile * (size_t)(pe_slabs * PE_BYTES) + half_off;
         for (int s = 0; s < un.b_slabs; ++s) bulk_g2s(sb + s * 8192, b_src + (size_t)s * SLAB_BYTES, 8192u, full);
         if (un.alpha == 2) {  // h9 (stash slot 9, 2 slabs) rides in the unused upper half of the A region
           const uint8_t *h9 = p.stash_act + tile * p.tile_stride + (size_t)9 * p.slot_stride + p.b_part + half_off;
@@ -1123,8 +1172,8 @@ __global__ void __launch_bounds__(kWgThreads, 1) mlp_wgrad_tc(WgradParams p) {
           for (int i = 0; i < 32; ++i) tr[lane * 33 + i] = __uint_as_float(v[i]);
           __syncwarp();
           const int col = cb * 32 + lane;
-          // PE units have 63 valid inputs: column 63 is the zero pad and must not be written
-          const bool ok = !(un.b_kind == 1 && col >= 63);
+          // PE units have in_pts (63 / 84) valid inputs: the zero-pad columns behind them must not be written
+          const bool ok = !(un.b_kind == 1 && col >= in_pts);
 #pragma unroll 4
           for (int rr = 0; rr < 32; ++rr)
             if (ok) atomicAdd(p.G + un.w_off + (size_t)(out0 + rr) * un.ldw + col, tr[rr * 33 + lane]);
@@ -1275,78 +1324,94 @@ static void prof_report(const char *name, int grid, int n_pairs, cudaStream_t st
   fprintf(stderr, "\n");
 }
 
+static NetDesc g_desc[kNetKinds];
+
 static int setup_tables(int sm_count) {
   if (g_tables_ready) return 0;
-  ChunkSrc ch[FWD_CHUNKS + DG_CHUNKS];
-  int ci = 0, off = 0;
-  auto add = [&](int base, int row_mul, int col_mul, int kvalid, int nrows) {
-    ch[ci].base = base; ch[ci].row_mul = row_mul; ch[ci].col_mul = col_mul; ch[ci].kvalid = kvalid;
-    ch[ci].nrows = nrows; ch[ci].byte_off = off;
-    off += nrows * 128;
-    ++ci;
-  };
-  // forward: B operand rows = output feature, columns = 64 consecutive input features
-  add(W_PTS[0], 63, 1, 63, 256);
-  for (int l = 1; l < 8; ++l) {
-    if (l == 5) {
-      add(W_PTS[5], 319, 1, 63, 256);
-      for (int c = 0; c < 4; ++c) add(W_PTS[5] + 63 + c * 64, 319, 1, 64, 256);
-    } else {
-      for (int c = 0; c < 4; ++c) add(W_PTS[l] + c * 64, 256, 1, 64, 256);
+  static ChunkSrc ch[kNetKinds][MAX_FWD_CHUNKS + DG_CHUNKS];
+  static WUnit units[kNetKinds][kUnits];
+  for (int kind = 0; kind < kNetKinds; ++kind) {
+    const NetDesc d = make_desc(kind);
+    g_desc[kind] = d;
+    if (kind == 0 && (d.total != TOTAL || d.w_views != W_VIEWS || d.w_rgb != W_RGB || d.b_pts[5] != B_PTS[5] ||
+                      d.fwd_bytes != FWD_BYTES)) return 1;     // the generic layout reproduces mlp_layout.h
+    int ci = 0, off = 0;
+    auto add = [&](int base, int row_mul, int col_mul, int kvalid, int nrows) {
+      ChunkSrc &c = ch[kind][ci];
+      c.base = base; c.row_mul = row_mul; c.col_mul = col_mul; c.kvalid = kvalid; c.nrows = nrows; c.byte_off = off;
+      off += nrows * 128;
+      ++ci;
+    };
+    const int P = d.pe_slabs;
+    // forward: B operand rows = output feature, columns = 64 consecutive input features.  Chunk order: layer 0 = its P
+    // positional slabs; layers 1..4; layer 5 = its P positional slabs (columns [0, in_pts) of the 256+in_pts wide row), then
+    // its four activation slabs; layers 6, 7; feature_linear; views_linears.0 (128 rows: half-size chunks)
+    for (int sl = 0; sl < P; ++sl) add(d.w_pts[0] + sl * 64, d.in_pts, 1, d.in_pts - sl * 64 < 64 ? d.in_pts - sl * 64 : 64, 256);
+    for (int l = 1; l < 8; ++l) {
+      if (l == 5) {
+        for (int sl = 0; sl < P; ++sl) add(d.w_pts[5] + sl * 64, d.k5, 1, d.in_pts - sl * 64 < 64 ? d.in_pts - sl * 64 : 64, 256);
+        for (int c = 0; c < 4; ++c) add(d.w_pts[5] + d.in_pts + c * 64, d.k5, 1, 64, 256);
+      } else {
+        for (int c = 0; c < 4; ++c) add(d.w_pts[l] + c * 64, 256, 1, 64, 256);
+      }
     }
-  }
-  for (int c = 0; c < 4; ++c) add(W_FEAT + c * 64, 256, 1, 64, 256);
-  for (int c = 0; c < 4; ++c) add(W_VIEWS + c * 64, 283, 1, 64, 128);
-  if (ci != FWD_CHUNKS || (size_t)off != FWD_BYTES) return 1;
-  // dgrad: B operand rows = input feature j, columns = 64 consecutive output features: W[out][in_off + j]
-  for (int c = 0; c < 2; ++c) add(W_VIEWS + c * 64 * 283, 1, 283, 64, 256);
-  for (int c = 0; c < 4; ++c) add(W_FEAT + c * 64 * 256, 1, 256, 64, 256);
-  for (int l = 7; l >= 1; --l) {
-    int ld = K_PTS[l], in_off = (l == 5) ? 63 : 0;
-    for (int c = 0; c < 4; ++c) add(W_PTS[l] + in_off + c * 64 * ld, 1, ld, 64, 256);
-  }
-  if (ci != FWD_CHUNKS + DG_CHUNKS || (size_t)off != PACKED_BYTES) return 1;
-  if (cudaMemcpyToSymbol(c_chunks, ch, sizeof(ch)) != cudaSuccess) return 1;
+    for (int c = 0; c < 4; ++c) add(d.w_feat + c * 64, 256, 1, 64, 256);
+    for (int c = 0; c < 4; ++c) add(d.w_views + c * 64, 283, 1, 64, 128);
+    if (ci != d.fwd_full + 4 || (size_t)off != d.fwd_bytes) return 1;
+    // dgrad: B operand rows = input feature j, columns = 64 consecutive output features: W[out][in_off + j]
+    for (int c = 0; c < 2; ++c) add(d.w_views + c * 64 * 283, 1, 283, 64, 256);
+    for (int c = 0; c < 4; ++c) add(d.w_feat + c * 64 * 256, 1, 256, 64, 256);
+    for (int l = 7; l >= 1; --l) {
+      const int ld = l == 5 ? d.k5 : 256, in_off = (l == 5) ? d.in_pts : 0;
+      for (int c = 0; c < 4; ++c) add(d.w_pts[l] + in_off + c * 64 * ld, 1, ld, 64, 256);
+    }
+    if (ci != d.fwd_full + 4 + DG_CHUNKS || (size_t)off != d.packed_bytes) return 1;
 
-  WUnit un[kUnits] = {
-      // a_slot a_slabs b_kind b_slot b_slabs w_off             ldw  bias_off   alpha splits
-      {0, 4, 1, 0, 1, W_PTS[0], 63, B_PTS[0], 0, 0},
-      {1, 4, 0, 0, 4, W_PTS[1], 256, B_PTS[1], 0, 0},
-      {2, 4, 0, 1, 4, W_PTS[2], 256, B_PTS[2], 0, 0},
-      {3, 4, 0, 2, 4, W_PTS[3], 256, B_PTS[3], 0, 0},
-      {4, 4, 0, 3, 4, W_PTS[4], 256, B_PTS[4], 0, 0},
-      {5, 4, 0, 4, 4, W_PTS[5] + 63, 319, B_PTS[5], 0, 0},
-      {5, 4, 1, 0, 1, W_PTS[5], 319, -1, 0, 0},
-      {6, 4, 0, 5, 4, W_PTS[6], 256, B_PTS[6], 0, 0},
-      {7, 4, 0, 6, 4, W_PTS[7], 256, B_PTS[7], 0, 0},
-      {8, 4, 0, 7, 4, W_FEAT, 256, B_FEAT, 1, 0},
-      {9, 2, 0, 8, 4, W_VIEWS, 283, B_VIEWS, 2, 0},
-  };
-  // split the row range of every unit in proportion to the bytes it streams, one work item per SM
-  double cost[kUnits], total = 0;
-  for (int i = 0; i < kUnits; ++i) {
-    // relative time per half tile, measured per unit with FLNERF_WG_DEBUG (bytes streamed + CUDA-core helper work)
-    cost[i] = un[i].b_slabs == 1 ? 0.85 : (un[i].alpha ? 1.2 : 1.0);
-    total += cost[i];
+    const WUnit un[kUnits] = {
+        // a_slot a_slabs b_kind b_slot b_slabs w_off             ldw  bias_off   alpha splits
+        {0, 4, 1, 0, P, d.w_pts[0], d.in_pts, d.b_pts[0], 0, 0},
+        {1, 4, 0, 0, 4, d.w_pts[1], 256, d.b_pts[1], 0, 0},
+        {2, 4, 0, 1, 4, d.w_pts[2], 256, d.b_pts[2], 0, 0},
+        {3, 4, 0, 2, 4, d.w_pts[3], 256, d.b_pts[3], 0, 0},
+        {4, 4, 0, 3, 4, d.w_pts[4], 256, d.b_pts[4], 0, 0},
+        {5, 4, 0, 4, 4, d.w_pts[5] + d.in_pts, d.k5, d.b_pts[5], 0, 0},
+        {5, 4, 1, 0, P, d.w_pts[5], d.k5, -1, 0, 0},
+        {6, 4, 0, 5, 4, d.w_pts[6], 256, d.b_pts[6], 0, 0},
+        {7, 4, 0, 6, 4, d.w_pts[7], 256, d.b_pts[7], 0, 0},
+        {8, 4, 0, 7, 4, d.w_feat, 256, d.b_feat, 1, 0},
+        {9, 2, 0, 8, 4, d.w_views, 283, d.b_views, 2, 0},
+    };
+    // split the row range of every unit in proportion to the bytes it streams, one work item per SM
+    double cost[kUnits], total = 0;
+    for (int i = 0; i < kUnits; ++i) {
+      // relative time per half tile, measured per unit with FLNERF_WG_DEBUG (bytes streamed + CUDA-core helper work)
+      cost[i] = un[i].b_kind == 1 ? (un[i].b_slabs == 1 ? 0.85 : 0.9) : (un[i].alpha ? 1.2 : 1.0);
+      total += cost[i];
+      units[kind][i] = un[i];
+    }
+    int used = 0;
+    for (int i = 0; i < kUnits; ++i) {
+      int sp = (int)(sm_count * cost[i] / total);
+      if (sp < 1) sp = 1;
+      units[kind][i].splits = sp;
+      used += sp;
+    }
+    for (int i = 0; used < sm_count; i = (i + 1) % kUnits) {
+      if (un[i].a_slabs == 4 && un[i].b_kind == 0 && un[i].b_slabs == 4) { ++units[kind][i].splits; ++used; }
+    }
+    g_wgrad_grid = used;       // = sm_count for both kinds
   }
-  int used = 0;
-  for (int i = 0; i < kUnits; ++i) {
-    int s = (int)(sm_count * cost[i] / total);
-    if (s < 1) s = 1;
-    un[i].splits = s;
-    used += s;
-  }
-  for (int i = 0; used < sm_count; i = (i + 1) % kUnits) {
-    if (un[i].a_slabs == 4 && un[i].b_slabs == 4) { ++un[i].splits; ++used; }
-  }
-  g_wgrad_grid = used;
-  if (cudaMemcpyToSymbol(c_units, un, sizeof(un)) != cudaSuccess) return 1;
+  if (cudaMemcpyToSymbol(c_chunks, ch, sizeof(ch)) != cudaSuccess) return 1;
+  if (cudaMemcpyToSymbol(c_units, units, sizeof(units)) != cudaSuccess) return 1;
+  if (cudaMemcpyToSymbol(c_desc, g_desc, sizeof(g_desc)) != cudaSuccess) return 1;
   if (cudaFuncSetAttribute(mlp_fwd_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, LayF::SMEM) != cudaSuccess) return 1;
   if (cudaFuncSetAttribute(mlp_fwd_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, LayF::SMEM) != cudaSuccess) return 1;
   if (cudaFuncSetAttribute(mlp_dgrad_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, LayD::SMEM) != cudaSuccess) return 1;
   if (cudaFuncSetAttribute(mlp_dgrad_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, LayD::SMEM) != cudaSuccess) return 1;
   if (cudaFuncSetAttribute(mlp_wgrad_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_WG) != cudaSuccess) return 1;
-  if (cudaFuncSetAttribute(mlp_fwd_x3, cudaFuncAttributeMaxDynamicSharedMemorySize, LayF::SMEM) != cudaSuccess) return 1;
+  if (cudaFuncSetAttribute(mlp_fwd_gen<3, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, LayF::SMEM) != cudaSuccess) return 1;
+  if (cudaFuncSetAttribute(mlp_fwd_gen<3, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, LayF::SMEM) != cudaSuccess) return 1;
+  if (cudaFuncSetAttribute(mlp_fwd_gen<1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, LayF::SMEM) != cudaSuccess) return 1;
   if (cudaFuncSetAttribute(mlp_dgrad_x3, cudaFuncAttributeMaxDynamicSharedMemorySize, LayD::SMEM) != cudaSuccess) return 1;
   g_tables_ready = true;
   return 0;
@@ -1355,8 +1420,11 @@ static int setup_tables(int sm_count) {
 }  // namespace tc
 
 // ---- entry points used by api.cu -------------------------------------------------------------------
+// kind: 0 = 63 position channels (nerf-ours NeRF / nerf++ foreground), 1 = 84 (nerf++ background)
 // packed image of one net: [part 0 = hi: forward chunks | dgrad chunks][part 1 = lo: same layout]
-size_t mlp_tc_packed_bytes() { return 2 * tc::PACKED_BYTES; }
+size_t mlp_tc_packed_bytes(int kind) { return 2 * tc::make_desc(kind).packed_bytes; }
+int64_t mlp_tc_param_count(int kind) { return tc::make_desc(kind).total; }
+size_t mlp_tc_pe_tile_bytes(int kind, bool x3) { return (size_t)tc::make_desc(kind).pe_slabs * tc::PE_BYTES * (x3 ? 2 : 1); }
 
 static size_t tc_vb_bytes(int64_t n, int S) {
   int64_t B = (n + S - 1) / S;
@@ -1369,23 +1437,25 @@ size_t mlp_tc_stash_bytes(int64_t n, int S, int training, bool x3) {
 }
 size_t mlp_tc_bwd_workspace_bytes(int64_t n, bool x3) { return (size_t)(flnerf_padded_rows(n) / 128) * tc_tile_act_bytes(x3); }
 
-int mlp_tc_pack_weights(flnerf_ctx *ctx, const float *params, void *packed, cudaStream_t st) {
+int mlp_tc_pack_weights(flnerf_ctx *ctx, int kind, const float *params, void *packed, cudaStream_t st) {
   FL_REQUIRE(tc::setup_tables(ctx->sm_count) == 0, "mlp_tc: table setup failed: %s", cudaGetErrorString(cudaGetLastError()));
-  dim3 grid(8, tc::FWD_CHUNKS + tc::DG_CHUNKS, 2);
-  FL_LAUNCH(tc::pack_weights_kernel, grid, 256, 0, st, params, (uint8_t *)packed);
+  const tc::NetDesc &nd = tc::g_desc[kind];
+  dim3 grid(8, nd.fwd_full + 4 + tc::DG_CHUNKS, 2);
+  FL_LAUNCH(tc::pack_weights_kernel, grid, 256, 0, st, params, (uint8_t *)packed, kind, nd.packed_bytes);
   return 0;
 }
 
-int mlp_tc_forward(flnerf_ctx *ctx, bool x3, const float *params, const void *packed, int64_t n, int S, const void *pe_tiles,
-                   const float *dirpe, float *raw, void *stash, int training, cudaStream_t st) {
+int mlp_tc_forward(flnerf_ctx *ctx, bool x3, int kind, const float *params, const void *packed, int64_t n, int S,
+                   const void *pe_tiles, const float *dirpe, float *raw, void *stash, int training, cudaStream_t st) {
   FL_REQUIRE(tc::setup_tables(ctx->sm_count) == 0, "mlp_tc: table setup failed: %s", cudaGetErrorString(cudaGetLastError()));
   FL_REQUIRE(n % S == 0, "mlp_tc_forward: n=%lld is not a multiple of S=%d", (long long)n, S);
+  const tc::NetDesc &nd = tc::g_desc[kind];
   int64_t B = n / S;
   float *vb = (float *)stash;
-  FL_LAUNCH(tc::viewbias_kernel, (unsigned)ceil_div64(B, 16), 128, 0, st, B, params, dirpe, vb);
+  FL_LAUNCH(tc::viewbias_kernel, (unsigned)ceil_div64(B, 16), 128, 0, st, B, params, dirpe, vb, nd.w_views, nd.b_views);
   tc::FwdParams p{};
   p.P = params; p.packed = (const uint8_t *)packed; p.pe_tiles = (const uint8_t *)pe_tiles; p.viewbias = vb;
-  p.raw = raw; p.n = n; p.S = S;
+  p.raw = raw; p.n = n; p.S = S; p.kind = kind;
   int64_t n_pad = flnerf_padded_rows(n);
   p.n_pairs = (int)(n_pad / 256);
   if (training) {
@@ -1393,9 +1463,12 @@ int mlp_tc_forward(flnerf_ctx *ctx, bool x3, const float *params, const void *pa
     p.stash_mask = (uint32_t *)(p.stash_act + (size_t)(n_pad / 128) * tc_tile_act_bytes(x3));
   }
   FL_CHECK_CUDA(cudaMemsetAsync(raw, 0, (size_t)n * 4 * sizeof(float), st));  // column-half warps accumulate into it
-  if (x3) {
+  if (x3 || kind != 0) {
+    // one 128-row tile per CTA, ring items consumed in order: any number of positional slabs, one or three MMA passes
     const int grid = tc::pair_grid(p.n_pairs * 2, ctx->sm_count);
-    FL_LAUNCH(tc::mlp_fwd_x3, grid, tc::kThreads, tc::LayF::SMEM, st, p);
+    if (x3 && kind == 0) FL_LAUNCH((tc::mlp_fwd_gen<3, 1>), grid, tc::kThreads, tc::LayF::SMEM, st, p);
+    else if (x3) FL_LAUNCH((tc::mlp_fwd_gen<3, 2>), grid, tc::kThreads, tc::LayF::SMEM, st, p);
+    else FL_LAUNCH((tc::mlp_fwd_gen<1, 2>), grid, tc::kThreads, tc::LayF::SMEM, st, p);
     return 0;
   }
   { const char *e = getenv("FLNERF_FWD_DBG"); p.dbg = e ? atoi(e) : 0; }
@@ -1410,16 +1483,17 @@ int mlp_tc_forward(flnerf_ctx *ctx, bool x3, const float *params, const void *pa
   return 0;
 }
 
-int mlp_tc_backward(flnerf_ctx *ctx, bool x3, const float *params, const void *packed, int64_t n, int S, const void *pe_tiles,
-                    const float *dirpe, const void *stash, const float *draw, float *grads, void *ws, int stages,
-                    cudaStream_t st) {
+int mlp_tc_backward(flnerf_ctx *ctx, bool x3, int kind, const float *params, const void *packed, int64_t n, int S,
+                    const void *pe_tiles, const float *dirpe, const void *stash, const float *draw, float *grads, void *ws,
+                    int stages, cudaStream_t st) {
   FL_REQUIRE(tc::setup_tables(ctx->sm_count) == 0, "mlp_tc: table setup failed: %s", cudaGetErrorString(cudaGetLastError()));
+  const tc::NetDesc &nd = tc::g_desc[kind];
   int64_t n_pad = flnerf_padded_rows(n);
   const uint8_t *stash_act = (const uint8_t *)stash + tc_vb_bytes(n, S);
   const uint32_t *stash_mask = (const uint32_t *)(stash_act + (size_t)(n_pad / 128) * tc_tile_act_bytes(x3));
   tc::DgradParams d{};
-  d.P = params; d.packed_dg = (const uint8_t *)packed + tc::FWD_BYTES; d.draw = draw; d.stash_mask = stash_mask;
-  d.dy = (uint8_t *)ws; d.n = n; d.n_pairs = (int)(n_pad / 256);
+  d.P = params; d.packed_dg = (const uint8_t *)packed + nd.fwd_bytes; d.draw = draw; d.stash_mask = stash_mask;
+  d.dy = (uint8_t *)ws; d.n = n; d.n_pairs = (int)(n_pad / 256); d.kind = kind;
   if ((stages & 1) && x3) {
     const int grid = tc::pair_grid(d.n_pairs * 2, ctx->sm_count);
     FL_LAUNCH(tc::mlp_dgrad_x3, grid, tc::kThreads, tc::LayD::SMEM, st, d);
@@ -1435,7 +1509,7 @@ int mlp_tc_backward(flnerf_ctx *ctx, bool x3, const float *params, const void *p
   }
   tc::WgradParams w{};
   w.dy = (const uint8_t *)ws; w.stash_act = stash_act; w.pe_tiles = (const uint8_t *)pe_tiles; w.draw = draw;
-  w.G = grads; w.n = n; w.n_tiles = (int)(n_pad / 128); w.dirpe = dirpe; w.S = S;
+  w.G = grads; w.n = n; w.n_tiles = (int)(n_pad / 128); w.dirpe = dirpe; w.S = S; w.kind = kind;
   w.tile_stride = tc_tile_act_bytes(x3); w.slot_stride = x3 ? tc::SLOT_BYTES_X3 : 65536;
   w.helper_flags = 7;
   static long long *dbg = nullptr;
@@ -1445,12 +1519,18 @@ int mlp_tc_backward(flnerf_ctx *ctx, bool x3, const float *params, const void *p
   if ((stages & 2) && x3) {
     // dW = (dYhi + dYlo)^T (Xhi + Xlo) ~= dYhi^T Xhi + dYhi^T Xlo + dYlo^T Xhi: three passes of the same kernel over the
     // hi / lo images, each with the CUDA-core reductions that belong to its operands
-    const size_t pe_lo = (size_t)w.n_tiles * tc::PE_BYTES;
+    const size_t pe_lo = (size_t)w.n_tiles * nd.pe_slabs * tc::PE_BYTES;
+    static int passes = -1;     // experiment knob: how many of the three terms the weight gradient carries (default all)
+    if (passes < 0) { const char *e = getenv("FLNERF_X3_WGRAD_PASSES"); passes = e ? atoi(e) : 3; }
     FL_LAUNCH(tc::mlp_wgrad_tc, tc::g_wgrad_grid, tc::kWgThreads, tc::SMEM_WG, st, w);
-    w.b_part = 65536; w.pe_part = pe_lo; w.helper_flags = 2;
-    FL_LAUNCH(tc::mlp_wgrad_tc, tc::g_wgrad_grid, tc::kWgThreads, tc::SMEM_WG, st, w);
-    w.a_part = 65536; w.b_part = 0; w.pe_part = 0; w.helper_flags = 1;
-    FL_LAUNCH(tc::mlp_wgrad_tc, tc::g_wgrad_grid, tc::kWgThreads, tc::SMEM_WG, st, w);
+    if (passes >= 2) {
+      w.b_part = 65536; w.pe_part = pe_lo; w.helper_flags = 2;
+      FL_LAUNCH(tc::mlp_wgrad_tc, tc::g_wgrad_grid, tc::kWgThreads, tc::SMEM_WG, st, w);
+    }
+    if (passes >= 3) {
+      w.a_part = 65536; w.b_part = 0; w.pe_part = 0; w.helper_flags = 1;
+      FL_LAUNCH(tc::mlp_wgrad_tc, tc::g_wgrad_grid, tc::kWgThreads, tc::SMEM_WG, st, w);
+    }
   } else if (stages & 2) {
     FL_LAUNCH(tc::mlp_wgrad_tc, tc::g_wgrad_grid, tc::kWgThreads, tc::SMEM_WG, st, w);
   }
@@ -1465,7 +1545,7 @@ int mlp_tc_backward(flnerf_ctx *ctx, bool x3, const float *params, const void *p
     }
   }
   const int tpb = 8;
-  if ((stages & 8) && !x3)
+  if ((stages & 8) && !x3 && kind == 0)
     FL_LAUNCH(tc::wgrad_small_kernel, (unsigned)((w.n_tiles + tpb - 1) / tpb), 512, 0, st, stash_act, w.dy, draw, dirpe,
               grads, n, S, w.n_tiles, tpb);
   return 0;

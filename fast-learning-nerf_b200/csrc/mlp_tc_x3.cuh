@@ -16,12 +16,6 @@
 // The heads (alpha, rgb), biases, the per-ray view-direction bias and the ReLU masks are fp32 / exact as in the bf16 mode,
 // but are fed the un-rounded fp32 activations.
 
-// ring items of ONE tile, in consumption order:
-//   L0     : PEhi PElo W0hi W0lo
-//   L1..L4 : 4 x (Whi Wlo)
-//   L5     : 4 x (Whi Wlo) for the activation slabs, then Wpe_hi Wpe_lo PEhi PElo
-//   L6..L9 : 4 x (Whi Wlo)
-constexpr int X3_FWD_ITEMS = 4 + 4 * 8 + 12 + 4 * 8;
 constexpr int X3_DG_ITEMS = 2 * DG_CHUNKS;
 constexpr size_t TILE_ACT_BYTES_X3 = 2 * TILE_ACT_BYTES;  // per slot: [hi 64 KB][lo 64 KB]
 constexpr size_t SLOT_BYTES_X3 = 2 * 65536;
@@ -153,29 +147,32 @@ __device__ __forceinline__ void warp_store_slab_x3(uint8_t *dst_slot, const uint
 }
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 
-// the three MMA groups of one 64-wide K chunk whose B items are ring stages (b_hi, b_lo): the hi item is released
-// after the two groups that read it
-template <class L>
-__device__ __forceinline__ void issue_chunk_x3(uint32_t d, uint32_t a_hi, uint32_t a_lo, uint32_t b_hi, uint32_t b_lo,
-                                               uint32_t idesc, bool first) {
-  issue_chunk(d, a_hi, b_hi, idesc, first);
-  issue_chunk(d, a_lo, b_hi, idesc, false);
-  issue_chunk(d, a_hi, b_lo, idesc, false);
-}
-
 // =================================================================================================
-// forward, split precision
+// forward, one tile per CTA.  kPasses = 3: split precision (hi and lo images, three MMA groups per chunk); kPasses = 1: plain
+// bf16 (hi image only) -- used for networks whose positional input does not fit the ping-pong kernel's ring program
+// (kPeSlabs = 2: the 84-channel nerf++ background network, nerf++-ours/nerf_network.py:70-142).
+// Ring items of one tile, in consumption order (each "x" below is one item when kPasses = 1, a (hi, lo) pair when 3):
+//   L0     : for every positional slab s: PE_s, W0_s
+//   L1..L4 : 4 x W
+//   L5     : 4 x W (activation slabs), then for every positional slab s: Wpe_s, PE_s
+//   L6..L9 : 4 x W
 // =================================================================================================
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) mlp_fwd_x3(FwdParams p) {
+template <int kPasses, int kPeSlabs>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) mlp_fwd_gen(FwdParams p) {
+  constexpr bool kX3 = kPasses == 3;
+  constexpr int kPer = kX3 ? 2 : 1;                                    // ring items per operand
+  constexpr int kItems = kPer * (2 * kPeSlabs + 16 + 4 + 2 * kPeSlabs + 16);
   extern __shared__ __align__(1024) uint8_t smem[];
   const int warp = threadIdx.x >> 5;
   const uint32_t lane = lane_id();
   const uint32_t bar = smem_u32(smem + LayF::OFF_BAR);
   const uint32_t cr = cluster_ctarank();
-  const uint32_t tmem_base = pair_setup<LayF>(smem, bar, cr, warp, lane, p.P);
+  const uint32_t tmem_base = pair_setup<LayF>(smem, bar, cr, warp, lane, p.P, p.kind);
   const uint32_t s_act = smem_u32(smem + OFF_ACT), s_w = smem_u32(smem + OFF_W);
   const int n_tiles = p.n_pairs * 2;
   const int iters = (n_tiles + (int)gridDim.x - 1) / (int)gridDim.x;
+  const int F = c_desc[p.kind].fwd_full;
+  const size_t part_bytes = c_desc[p.kind].packed_bytes;
 
   if (warp == 0) {
     // ---------------------------------------------------------------- producer (both CTAs): local halves
@@ -187,26 +184,29 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) mlp_fwd
         bulk_g2s(s_w + ring.stage * WSTAGE, src, bytes, LayF::w_full(bar, ring.stage));
         ring.next();
       };
-      auto push_w2 = [&](int cc) {  // this CTA's half (N/2 rows) of forward chunk cc: hi part, then lo part
-        const uint32_t half = cc < 34 ? 16384u : 8192u;
-        const size_t off = cc < 34 ? (size_t)cc * 32768 : (size_t)34 * 32768 + (size_t)(cc - 34) * 16384;
+      auto push_w = [&](int cc) {  // this CTA's half (N/2 rows) of forward chunk cc: hi part (, then lo part)
+        const uint32_t half = cc < F ? 16384u : 8192u;
+        const size_t off = cc < F ? (size_t)cc * 32768 : (size_t)F * 32768 + (size_t)(cc - F) * 16384;
         push(p.packed + off + (size_t)cr * half, half);
-        push(p.packed + PACKED_BYTES + off + (size_t)cr * half, half);
+        if (kX3) push(p.packed + part_bytes + off + (size_t)cr * half, half);
       };
+      const size_t pe_lo = (size_t)n_tiles * kPeSlabs * PE_BYTES;
       for (int it = 0; it < iters; ++it) {
         const int tile = min(n_tiles - 1, (int)blockIdx.x + it * (int)gridDim.x);
-        const uint8_t *pe_hi = p.pe_tiles + (size_t)tile * PE_BYTES;
-        const uint8_t *pe_lo = pe_hi + (size_t)n_tiles * PE_BYTES;
-        push(pe_hi, PE_BYTES); push(pe_lo, PE_BYTES); push_w2(0);
-        int ci = 1;
+        const uint8_t *pe = p.pe_tiles + (size_t)tile * kPeSlabs * PE_BYTES;
+        auto push_pe = [&](int sl) {
+          push(pe + (size_t)sl * PE_BYTES, PE_BYTES);
+          if (kX3) push(pe + pe_lo + (size_t)sl * PE_BYTES, PE_BYTES);
+        };
+        for (int sl = 0; sl < kPeSlabs; ++sl) { push_pe(sl); push_w(sl); }
+        int ci = kPeSlabs;
         for (int L = 1; L < 10; ++L) {
           if (L == 5) {
-            for (int c = 1; c < 5; ++c) push_w2(ci + c);
-            push_w2(ci);
-            push(pe_hi, PE_BYTES); push(pe_lo, PE_BYTES);
-            ci += 5;
+            for (int c = 0; c < 4; ++c) push_w(ci + kPeSlabs + c);
+            for (int sl = 0; sl < kPeSlabs; ++sl) { push_w(ci + sl); push_pe(sl); }
+            ci += kPeSlabs + 4;
           } else {
-            for (int c = 0; c < 4; ++c) push_w2(ci + c);
+            for (int c = 0; c < 4; ++c) push_w(ci + c);
             ci += 4;
           }
         }
@@ -217,7 +217,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) mlp_fwd
       // -------------------------------------------------------------- relay (follower): local full -> leader's full
       LayF::Ring ring;
       const uint32_t remote_full = mapa_cluster(LayF::w_full(bar, 0), 0);
-      const int total = iters * X3_FWD_ITEMS;
+      const int total = iters * kItems;
       for (int q = 0; q < total; ++q) {
         mbar_wait(LayF::w_full(bar, ring.stage), ring.phase);
         mbar_arrive_cluster(remote_full + 8u * ring.stage);
@@ -231,13 +231,17 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) mlp_fwd
       auto release = [&](uint32_t i) { umma2_commit_multicast(LayF::w_empty(bar, LayF::item_stage(i)), (uint16_t)3); };
       auto st = [&](uint32_t i) { return s_w + LayF::item_stage(i) * WSTAGE; };
       const uint32_t a_hi = s_act, a_lo = s_act + ACT_BYTES;
-      // the PE group (layers 0 and 5): items (A hi, A lo, W hi, W lo) at ring positions (ah, al, wh, wl)
-      auto pe_group = [&](uint32_t ah, uint32_t al, uint32_t wh, uint32_t wl, bool first) {
-        for (uint32_t i = 0; i < 4; ++i) wait_full(q + i);
+      // one positional slab: its PE item(s) and its weight item(s) sit at ring positions pe0.. and w0.. (kPer items each)
+      auto pe_group = [&](uint32_t pe0, uint32_t w0, bool first) {
+        for (uint32_t i = 0; i < 2u * kPer; ++i) wait_full(q + i);
         tc_fence_after();
-        issue_chunk_x3<LayF>(tmem_base, st(ah), st(al), st(wh), st(wl), idesc256, first);
-        for (uint32_t i = 0; i < 4; ++i) release(q + i);
-        q += 4;
+        issue_chunk(tmem_base, st(pe0), st(w0), idesc256, first);
+        if (kX3) {
+          issue_chunk(tmem_base, st(pe0 + 1), st(w0), idesc256, false);
+          issue_chunk(tmem_base, st(pe0), st(w0 + 1), idesc256, false);
+        }
+        for (uint32_t i = 0; i < 2u * kPer; ++i) release(q + i);
+        q += 2 * kPer;
       };
       for (int it = 0; it < iters; ++it) {
         for (int L = 0; L < 10; ++L) {
@@ -247,22 +251,27 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) mlp_fwd
           }
           tc_fence_after();
           if (L == 0) {
-            pe_group(q, q + 1, q + 2, q + 3, true);
+            for (int sl = 0; sl < kPeSlabs; ++sl) pe_group(q, q + kPer, sl == 0);
           } else {
             const uint32_t idesc = L == 9 ? idesc128 : idesc256;
             for (uint32_t c = 0; c < 4; ++c) {
               wait_full(q);
               tc_fence_after();
               issue_chunk(tmem_base, a_hi + c * SLAB_BYTES, st(q), idesc, c == 0);
-              issue_chunk(tmem_base, a_lo + c * SLAB_BYTES, st(q), idesc, false);
-              release(q);
-              wait_full(q + 1);
-              tc_fence_after();
-              issue_chunk(tmem_base, a_hi + c * SLAB_BYTES, st(q + 1), idesc, false);
-              release(q + 1);
-              q += 2;
+              if (kX3) {
+                issue_chunk(tmem_base, a_lo + c * SLAB_BYTES, st(q), idesc, false);
+                release(q);
+                wait_full(q + 1);
+                tc_fence_after();
+                issue_chunk(tmem_base, a_hi + c * SLAB_BYTES, st(q + 1), idesc, false);
+                release(q + 1);
+              } else {
+                release(q);
+              }
+              q += kPer;
             }
-            if (L == 5) pe_group(q + 2, q + 3, q, q + 1, false);
+            if (L == 5)
+              for (int sl = 0; sl < kPeSlabs; ++sl) pe_group(q + kPer, q, false);
           }
           umma2_commit_multicast(LayF::acc_full(bar, 0), (uint16_t)3);
         }
@@ -280,6 +289,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) mlp_fwd
     float *s_alpha = reinterpret_cast<float *>(smem + LayF::OFF_ALPHA);
     uint8_t *act_hi = smem + OFF_ACT;
     const uint32_t tmem_rc = tmem_base + ((quarter * 32) << 16) + cq * 64;
+    const size_t tile_bytes = kX3 ? TILE_ACT_BYTES_X3 : TILE_ACT_BYTES, slot_bytes = kX3 ? SLOT_BYTES_X3 : 65536;
     uint32_t n_layer = 0;
     bool store_pending = false;
     for (int it = 0; it < iters; ++it) {
@@ -300,23 +310,40 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) mlp_fwd
         float alpha = 0.f;
         uint2 mk = make_uint2(0u, 0u);
         const bool want_mask = stash_mask != nullptr;
-        if (L < 7) {
-          if (want_mask) mk = fwd_epilogue_x3<0, true>(tmem_rc, cq, s_bias + L * 256, act_hi, r, s_wa, alpha);
-          else fwd_epilogue_x3<0, false>(tmem_rc, cq, s_bias + L * 256, act_hi, r, s_wa, alpha);
-        } else if (L == 7) {
-          if (want_mask) mk = fwd_epilogue_x3<1, true>(tmem_rc, cq, s_bias + 7 * 256, act_hi, r, s_wa, alpha);
-          else fwd_epilogue_x3<1, false>(tmem_rc, cq, s_bias + 7 * 256, act_hi, r, s_wa, alpha);
-          // alpha_linear: the four column quarters of a row are summed in a fixed order (bit-reproducible)
-          s_alpha[cq * 128 + r] = alpha;
-          named_bar_sync(1 + quarter, 128);
-          if (cq == 0 && live && row < p.n) {
-            const float *pa = s_alpha + r;
-            p.raw[row * 4 + 3] = ((pa[0] + pa[128]) + (pa[256] + pa[384])) + s_head[387];
+        if (L <= 7) {
+          const float *sb = s_bias + L * 256;
+          if (kX3) {
+            if (L < 7) {
+              if (want_mask) mk = fwd_epilogue_x3<0, true>(tmem_rc, cq, sb, act_hi, r, s_wa, alpha);
+              else fwd_epilogue_x3<0, false>(tmem_rc, cq, sb, act_hi, r, s_wa, alpha);
+            } else {
+              if (want_mask) mk = fwd_epilogue_x3<1, true>(tmem_rc, cq, sb, act_hi, r, s_wa, alpha);
+              else fwd_epilogue_x3<1, false>(tmem_rc, cq, sb, act_hi, r, s_wa, alpha);
+            }
+          } else {
+            if (L < 7) {
+              if (want_mask) mk = fwd_epilogue_q<0, true>(tmem_rc, cq, sb, act_hi, r, s_wa, alpha);
+              else fwd_epilogue_q<0, false>(tmem_rc, cq, sb, act_hi, r, s_wa, alpha);
+            } else {
+              if (want_mask) mk = fwd_epilogue_q<1, true>(tmem_rc, cq, sb, act_hi, r, s_wa, alpha);
+              else fwd_epilogue_q<1, false>(tmem_rc, cq, sb, act_hi, r, s_wa, alpha);
+            }
+          }
+          if (L == 7) {
+            // alpha_linear: the four column quarters of a row are summed in a fixed order (bit-reproducible)
+            s_alpha[cq * 128 + r] = alpha;
+            named_bar_sync(1 + quarter, 128);
+            if (cq == 0 && live && row < p.n) {
+              const float *pa = s_alpha + r;
+              p.raw[row * 4 + 3] = ((pa[0] + pa[128]) + (pa[256] + pa[384])) + s_head[387];
+            }
           }
         } else if (L == 8) {
-          fwd_epilogue_x3<2, false>(tmem_rc, cq, s_bias + 8 * 256, act_hi, r, s_wa, alpha);
+          if (kX3) fwd_epilogue_x3<2, false>(tmem_rc, cq, s_bias + 8 * 256, act_hi, r, s_wa, alpha);
+          else fwd_epilogue_q<2, false>(tmem_rc, cq, s_bias + 8 * 256, act_hi, r, s_wa, alpha);
         } else if (has_cols) {
-          mk = fwd_views_rgb_x3(p, tmem_rc - cq * 64, cq, act_hi, r, row, live, s_head);
+          if (kX3) mk = fwd_views_rgb_x3(p, tmem_rc - cq * 64, cq, act_hi, r, row, live, s_head);
+          else mk = fwd_views_rgb(p, tmem_rc - cq * 64, cq, act_hi, r, row, live, s_head);
         }
         tc_fence_before();
         fence_async_smem();
@@ -324,7 +351,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) mlp_fwd
         if (lane == 0) {
           mbar_arrive_cluster(mapa_cluster(LayF::act_ready(bar, 0), 0));  // the leader's barrier
           if (stash_act && has_cols) {
-            warp_store_slab_x3(stash_act + (size_t)tile * TILE_ACT_BYTES_X3 + (size_t)L * SLOT_BYTES_X3, act_hi, quarter, cq);
+            uint8_t *dst = stash_act + (size_t)tile * tile_bytes + (size_t)L * slot_bytes;
+            if (kX3) warp_store_slab_x3(dst, act_hi, quarter, cq);
+            else warp_store_slabs(dst, act_hi, quarter, cq, 1);
             store_pending = true;
           }
         }
@@ -405,7 +434,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) mlp_dgr
   const uint32_t lane = lane_id();
   const uint32_t bar = smem_u32(smem + LayD::OFF_BAR);
   const uint32_t cr = cluster_ctarank();
-  const uint32_t tmem_base = pair_setup<LayD>(smem, bar, cr, warp, lane, p.P);
+  const uint32_t tmem_base = pair_setup<LayD>(smem, bar, cr, warp, lane, p.P, p.kind);
   const uint32_t s_act = smem_u32(smem + OFF_ACT), s_w = smem_u32(smem + OFF_W);
   const int n_tiles = p.n_pairs * 2;
   const int iters = (n_tiles + (int)gridDim.x - 1) / (int)gridDim.x;
@@ -418,7 +447,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) mlp_dgr
           for (int part = 0; part < 2; ++part) {
             mbar_wait(LayD::w_empty(bar, ring.stage), ring.phase ^ 1);
             mbar_arrive_expect_tx(LayD::w_full(bar, ring.stage), 16384u);
-            bulk_g2s(s_w + ring.stage * WSTAGE, p.packed_dg + (size_t)part * PACKED_BYTES + (size_t)ci * 32768 + (size_t)cr * 16384,
+            bulk_g2s(s_w + ring.stage * WSTAGE, p.packed_dg + (size_t)part * c_desc[p.kind].packed_bytes + (size_t)ci * 32768 + (size_t)cr * 16384,
                      16384u, LayD::w_full(bar, ring.stage));
             ring.next();
           }

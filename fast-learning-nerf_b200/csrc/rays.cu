@@ -42,16 +42,13 @@ __global__ void raygen_kernel(int H, int W, Cam cam, Pose pose, float *__restric
   }
 }
 
-__global__ void pack_rays_kernel(int64_t B, const float *__restrict__ ro, const float *__restrict__ rd, float near_,
-                                 float far_, int ndc, float sx, float sy, float *__restrict__ out) {
-  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= B) return;
-  float o0 = ro[i * 3], o1 = ro[i * 3 + 1], o2 = ro[i * 3 + 2];
-  float d0 = rd[i * 3], d1 = rd[i * 3 + 1], d2 = rd[i * 3 + 2];
-  // viewdirs from the un-warped direction (render.py:59-66)
+// viewdir normalisation (from the un-warped direction, render.py:59-66), optional NDC warp (run_nerf_helpers.py:91-108 with
+// near = 1) and the [o, d, near, far, viewdir] row of render.py:74-80
+__device__ __forceinline__ void pack_ray(float o0, float o1, float o2, float d0, float d1, float d2, float near_, float far_, int ndc,
+                                         float sx, float sy, float q[11]) {
   float nrm = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(d0, d0), __fmul_rn(d1, d1)), __fmul_rn(d2, d2)));
   float v0 = __fdiv_rn(d0, nrm), v1 = __fdiv_rn(d1, nrm), v2 = __fdiv_rn(d2, nrm);
-  if (ndc) {  // run_nerf_helpers.py:91-108 with near = 1
+  if (ndc) {
     const float nr = 1.0f;
     float t = -__fdiv_rn(__fadd_rn(nr, o2), d2);
     o0 = __fadd_rn(o0, __fmul_rn(t, d0));
@@ -65,9 +62,18 @@ __global__ void pack_rays_kernel(int64_t B, const float *__restrict__ ro, const 
     float b2 = __fdiv_rn(-2.0f * nr, o2);
     o0 = a0; o1 = a1; o2 = a2; d0 = b0; d1 = b1; d2 = b2;
   }
-  float *q = out + i * 11;
   q[0] = o0; q[1] = o1; q[2] = o2; q[3] = d0; q[4] = d1; q[5] = d2;
   q[6] = near_; q[7] = far_; q[8] = v0; q[9] = v1; q[10] = v2;
+}
+
+__global__ void pack_rays_kernel(int64_t B, const float *__restrict__ ro, const float *__restrict__ rd, float near_,
+                                 float far_, int ndc, float sx, float sy, float *__restrict__ out) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B) return;
+  float q[11];
+  pack_ray(ro[i * 3], ro[i * 3 + 1], ro[i * 3 + 2], rd[i * 3], rd[i * 3 + 1], rd[i * 3 + 2], near_, far_, ndc, sx, sy, q);
+#pragma unroll
+  for (int a = 0; a < 11; ++a) out[i * 11 + a] = q[a];
 }
 
 __device__ __forceinline__ float base_depth(float near_, float far_, float t, int lindisp) {
@@ -152,9 +158,25 @@ __global__ void encode_f32_kernel(int64_t B, int S, const float *__restrict__ ra
 // double-angle recurrence (error <= 2^4 ulp(fp32) ~ 2e-6, 2000x below the bf16 rounding step).  The fp32 parity path
 // (encode_f32_kernel / posenc_kernel) evaluates every channel exactly, and so does kX3 (FLNERF_MODE_BF16X3), which
 // also writes the residual tile lo = bf16(v - hi) at tiles + lo_off.
-template <bool kX3>
+// kFrame (the eval path, render.py:94-146 -> render(c2w=...)): the rays are not read but GENERATED -- row -> ray = row / S ->
+// pixel pixel0 + ray of the frame -> get_rays + (ndc) + packing, depths = the un-jittered coarse depths of render.py:244-249 --
+// so one launch goes from the camera pose to the MLP's input tiles; the first sample's thread also writes rays11[ray],
+// dirpe[ray] (for the fine pass and the compositing kernels) and every thread its z.
+struct FrameArgs {
+  Cam cam;
+  Pose pose;
+  int W;
+  int ndc, lindisp;
+  float near_, far_, sx, sy;
+  int64_t pixel0;
+  const float *tv;      // linspace(0, 1, S)
+  float *rays11, *z, *dirpe;
+};
+
+template <bool kX3, bool kFrame>
 __global__ void __launch_bounds__(128) encode_tc_kernel(int64_t n, int64_t n_pad, int S, const float *__restrict__ rays11,
-                                                        const float *__restrict__ z, uint8_t *__restrict__ tiles, size_t lo_off) {
+                                                        const float *__restrict__ z, uint8_t *__restrict__ tiles, size_t lo_off,
+                                                        FrameArgs fa) {
   const int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (row >= n_pad) return;
   uint32_t pk[32], pl[32];
@@ -163,7 +185,25 @@ __global__ void __launch_bounds__(128) encode_tc_kernel(int64_t n, int64_t n_pad
   if (row < n) {
     float v[64];
     float p[3], sn[3], cs[3];
-    sample_point(rays11 + (row / S) * 11, z[row], p);
+    if (kFrame) {
+      const int64_t ray = row / S;
+      const int j = (int)(row - ray * S);
+      const int64_t pix = fa.pixel0 + ray;
+      float o[3], d[3], q[11];
+      pixel_ray(fa.cam, fa.pose.m, (int)(pix / fa.W), (int)(pix % fa.W), o, d);
+      pack_ray(o[0], o[1], o[2], d[0], d[1], d[2], fa.near_, fa.far_, fa.ndc, fa.sx, fa.sy, q);
+      const float zj = base_depth(fa.near_, fa.far_, fa.tv[j], fa.lindisp);
+      fa.z[row] = zj;
+      if (j == 0) {
+#pragma unroll
+        for (int a = 0; a < 11; ++a) fa.rays11[ray * 11 + a] = q[a];
+        const float vd[3] = {q[8], q[9], q[10]};
+        for (int ch = 0; ch < 32; ++ch) fa.dirpe[ray * 32 + ch] = ch < 27 ? pe_channel(vd, ch) : 0.0f;
+      }
+      sample_point(q, zj, p);
+    } else {
+      sample_point(rays11 + (row / S) * 11, z[row], p);
+    }
     v[0] = p[0]; v[1] = p[1]; v[2] = p[2];
     v[63] = 0.f;
 #pragma unroll
@@ -236,6 +276,43 @@ __global__ void pack_x90_kernel(int64_t n, int64_t n_pad, const float *__restric
         make_uint4(packed_lo[0], packed_lo[1], packed_lo[2], packed_lo[3]);
 }
 
+// already-embedded rows x[n, in_pts + in_views] (in_views = 27) -> tensor-core tiles with ceil(in_pts / 64) slabs of [128 x 64]
+// per 128-row tile (slab-major inside a tile; zero pad behind in_pts), hi set and -- lo_off != 0 -- lo set; the view part of
+// the FIRST row of every S-row ray -> dirpe[ray, 32].  One thread = one 16-byte chunk.
+__global__ void pack_xrows_kernel(int64_t n, int64_t n_pad, int in_pts, int n_slabs, int ld, int S, const float *__restrict__ x,
+                                  uint8_t *__restrict__ tiles, float *__restrict__ dirpe, size_t lo_off) {
+  int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int per_row = n_slabs * 8;
+  if (idx >= n_pad * per_row) return;
+  const int64_t row = idx / per_row;
+  const int qq = (int)(idx % per_row), sl = qq >> 3, q = qq & 7;
+  uint32_t hi[4] = {0u, 0u, 0u, 0u}, lo[4] = {0u, 0u, 0u, 0u};
+  if (row < n) {
+    const float *src = x + row * ld;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int c0 = sl * 64 + q * 8 + 2 * e;
+      const float a = c0 < in_pts ? src[c0] : 0.0f, b = c0 + 1 < in_pts ? src[c0 + 1] : 0.0f;
+      __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+      hi[e] = *reinterpret_cast<uint32_t *>(&h);
+      __nv_bfloat162 l = __floats2bfloat162_rn(a - __low2float(h), b - __high2float(h));
+      lo[e] = *reinterpret_cast<uint32_t *>(&l);
+    }
+    if (sl == 0 && row % S == 0) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int j = q * 4 + e;
+        dirpe[(row / S) * 32 + j] = j < 27 ? src[in_pts + j] : 0.0f;
+      }
+    }
+  }
+  const int64_t tile = row >> 7;
+  const uint32_t r = (uint32_t)(row & 127);
+  const size_t off = ((size_t)tile * n_slabs + sl) * 16384 + sw128_offset(r, (uint32_t)q * 8);
+  *reinterpret_cast<uint4 *>(tiles + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+  if (lo_off) *reinterpret_cast<uint4 *>(tiles + lo_off + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+}
+
 __global__ void dirpe_kernel(int64_t B, const float *__restrict__ rays11, float *__restrict__ dirpe) {
   int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= B * 32) return;
@@ -245,9 +322,12 @@ __global__ void dirpe_kernel(int64_t B, const float *__restrict__ rays11, float 
   dirpe[idx] = ch < 27 ? pe_channel(v, ch) : 0.0f;
 }
 
+// images: fp32 [n,H,W,3], or -- lut != nullptr -- uint8 [n,H,W,3] decoded through lut[256] (the loaders' float32(u / 255.)
+// values, load_blender.py:37: a quarter of the bytes, the same floats)
 __global__ void gather_batch_kernel(int64_t B, int64_t first, int64_t stride, const int32_t *__restrict__ ray_pix,
                                     const int32_t *__restrict__ ray_gid, int cap, int H, int W, Cam cam,
-                                    const float *__restrict__ poses, const float *__restrict__ images,
+                                    const float *__restrict__ poses, const void *__restrict__ images_any,
+                                    const float *__restrict__ lut,
                                     float *__restrict__ ro, float *__restrict__ rd, float *__restrict__ target,
                                     int32_t *__restrict__ leaf_gid, const flnerf_step_record *__restrict__ rec) {
   int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -258,12 +338,13 @@ __global__ void gather_batch_kernel(int64_t B, int64_t first, int64_t stride, co
   int row = pix / W, col = pix % W;
   float o[3], d[3];
   pixel_ray(cam, poses + (int64_t)img * 12, row, col, o, d);
-  const float *src = images + (((int64_t)img * H + row) * W + col) * 3;
+  const int64_t pidx = (((int64_t)img * H + row) * W + col) * 3;
 #pragma unroll
   for (int a = 0; a < 3; ++a) {
     ro[k * 3 + a] = o[a];
     rd[k * 3 + a] = d[a];
-    target[k * 3 + a] = src[a];
+    target[k * 3 + a] = lut ? lut[reinterpret_cast<const uint8_t *>(images_any)[pidx + a]]
+                            : reinterpret_cast<const float *>(images_any)[pidx + a];
   }
   if (leaf_gid) leaf_gid[k] = gid;
 }
@@ -330,8 +411,8 @@ int flnerf_encode_tc(flnerf_ctx *ctx, int64_t B, int S, const float *rays11, con
   FL_REQUIRE(ctx && rays11 && z && pe_tiles && dirpe && S > 0 && B >= 0, "flnerf_encode_tc: bad arguments");
   if (B == 0) return 0;
   int64_t n = B * S, n_pad = flnerf_padded_rows(n);
-  FL_LAUNCH(encode_tc_kernel<false>, (unsigned)ceil_div64(n_pad, 128), 128, 0, stream, n, n_pad, S, rays11, z,
-            (uint8_t *)pe_tiles, (size_t)0);
+  FL_LAUNCH((encode_tc_kernel<false, false>), (unsigned)ceil_div64(n_pad, 128), 128, 0, stream, n, n_pad, S, rays11, z,
+            (uint8_t *)pe_tiles, (size_t)0, FrameArgs{});
   FL_LAUNCH(dirpe_kernel, (unsigned)ceil_div64(B * 32, 256), 256, 0, stream, B, rays11, dirpe);
   return 0;
 }
@@ -341,9 +422,32 @@ int flnerf_encode_tc_x3(flnerf_ctx *ctx, int64_t B, int S, const float *rays11, 
   FL_REQUIRE(ctx && rays11 && z && pe_tiles && dirpe && S > 0 && B >= 0, "flnerf_encode_tc_x3: bad arguments");
   if (B == 0) return 0;
   int64_t n = B * S, n_pad = flnerf_padded_rows(n);
-  FL_LAUNCH(encode_tc_kernel<true>, (unsigned)ceil_div64(n_pad, 128), 128, 0, stream, n, n_pad, S, rays11, z,
-            (uint8_t *)pe_tiles, (size_t)(n_pad / 128) * 16384);
+  FL_LAUNCH((encode_tc_kernel<true, false>), (unsigned)ceil_div64(n_pad, 128), 128, 0, stream, n, n_pad, S, rays11, z,
+            (uint8_t *)pe_tiles, (size_t)(n_pad / 128) * 16384, FrameArgs{});
   FL_LAUNCH(dirpe_kernel, (unsigned)ceil_div64(B * 32, 256), 256, 0, stream, B, rays11, dirpe);
+  return 0;
+}
+
+int flnerf_encode_frame_tc(flnerf_ctx *ctx, int x3, int H, int W, const double *h_K, const float *h_c2w, float near_, float far_,
+                           int ndc, int lindisp, int64_t pixel0, int64_t B, int S, const float *t_vals, float *rays11, float *z,
+                           void *pe_tiles, float *dirpe, void *stream) {
+  FL_REQUIRE(ctx && h_K && h_c2w && t_vals && rays11 && z && pe_tiles && dirpe && S > 0 && B >= 0 && H > 0 && W > 0 &&
+                 pixel0 >= 0 && pixel0 + B <= (int64_t)H * W,
+             "flnerf_encode_frame_tc: bad arguments");
+  if (B == 0) return 0;
+  FrameArgs fa;
+  fa.cam = make_cam(h_K);
+  for (int i = 0; i < 12; ++i) fa.pose.m[i] = h_c2w[i];
+  fa.W = W; fa.ndc = ndc; fa.lindisp = lindisp; fa.near_ = near_; fa.far_ = far_;
+  fa.sx = (float)(-1.0 / (W / (2.0 * h_K[0]))); fa.sy = (float)(-1.0 / (H / (2.0 * h_K[0])));   // focal = K[0][0] (render.py:71)
+  fa.pixel0 = pixel0; fa.tv = t_vals; fa.rays11 = rays11; fa.z = z; fa.dirpe = dirpe;
+  int64_t n = B * S, n_pad = flnerf_padded_rows(n);
+  if (x3)
+    FL_LAUNCH((encode_tc_kernel<true, true>), (unsigned)ceil_div64(n_pad, 128), 128, 0, stream, n, n_pad, S, nullptr, nullptr,
+              (uint8_t *)pe_tiles, (size_t)(n_pad / 128) * 16384, fa);
+  else
+    FL_LAUNCH((encode_tc_kernel<false, true>), (unsigned)ceil_div64(n_pad, 128), 128, 0, stream, n, n_pad, S, nullptr, nullptr,
+              (uint8_t *)pe_tiles, (size_t)0, fa);
   return 0;
 }
 
@@ -365,6 +469,18 @@ int flnerf_pack_x90_x3(flnerf_ctx *ctx, int64_t n, const float *x90, void *pe_ti
   return 0;
 }
 
+int flnerf_pack_xrows(flnerf_ctx *ctx, int x3, int in_pts, int in_views, int64_t n, int S, const float *x, void *pe_tiles,
+                      float *dirpe, void *stream) {
+  FL_REQUIRE(ctx && x && pe_tiles && dirpe && n >= 0 && S > 0 && in_pts > 0 && in_pts <= 128 && in_views == 27,
+             "flnerf_pack_xrows: bad arguments (in_views must be 27, in_pts <= 128)");
+  if (n == 0) return 0;
+  const int n_slabs = (in_pts + 63) / 64;
+  int64_t n_pad = flnerf_padded_rows(n);
+  FL_LAUNCH(pack_xrows_kernel, (unsigned)ceil_div64(n_pad * n_slabs * 8, 256), 256, 0, stream, n, n_pad, in_pts, n_slabs,
+            in_pts + in_views, S, x, (uint8_t *)pe_tiles, dirpe, x3 ? (size_t)(n_pad / 128) * n_slabs * 16384 : (size_t)0);
+  return 0;
+}
+
 int flnerf_gather_batch(flnerf_ctx *ctx, int64_t B, int64_t first, int64_t stride, const int32_t *ray_pix,
                         const int32_t *ray_gid, int cap, int H, int W, const double *h_K, const float *poses,
                         const float *images, float *rays_o, float *rays_d, float *target, int32_t *leaf_gid,
@@ -373,7 +489,19 @@ int flnerf_gather_batch(flnerf_ctx *ctx, int64_t B, int64_t first, int64_t strid
              "flnerf_gather_batch: bad arguments");
   if (B == 0) return 0;
   FL_LAUNCH(gather_batch_kernel, (unsigned)ceil_div64(B, 256), 256, 0, stream, B, first, stride, ray_pix, ray_gid, cap,
-            H, W, make_cam(h_K), poses, images, rays_o, rays_d, target, leaf_gid, ctx->step_rec);
+            H, W, make_cam(h_K), poses, (const void *)images, (const float *)nullptr, rays_o, rays_d, target, leaf_gid, ctx->step_rec);
+  return 0;
+}
+
+int flnerf_gather_batch_u8(flnerf_ctx *ctx, int64_t B, int64_t first, int64_t stride, const int32_t *ray_pix,
+                           const int32_t *ray_gid, int cap, int H, int W, const double *h_K, const float *poses,
+                           const uint8_t *images, const float *lut256, float *rays_o, float *rays_d, float *target,
+                           int32_t *leaf_gid, void *stream) {
+  FL_REQUIRE(ctx && ray_pix && ray_gid && h_K && poses && images && lut256 && rays_o && rays_d && target && cap > 0,
+             "flnerf_gather_batch_u8: bad arguments");
+  if (B == 0) return 0;
+  FL_LAUNCH(gather_batch_kernel, (unsigned)ceil_div64(B, 256), 256, 0, stream, B, first, stride, ray_pix, ray_gid, cap,
+            H, W, make_cam(h_K), poses, (const void *)images, lut256, rays_o, rays_d, target, leaf_gid, ctx->step_rec);
   return 0;
 }
 

@@ -60,6 +60,31 @@ mse_leafmax_kernel(int64_t B, const float *__restrict__ rgb, const float *__rest
   }
 }
 
+// The refinement statistic of the nerf++ / plenoxels copies of the quadtree (nerf++-ours/tree.py:613-622: a leaf splits when
+// the MEAN of |gt - pred| over its rays and channels exceeds the threshold; nerf-ours uses the max, tree.py:642).  Sums are
+// accumulated in double (the order of the atomics cannot matter), counts in int32.
+__global__ void leaf_sum_kernel(int64_t B, const float *__restrict__ pred, const float *__restrict__ target,
+                                const int32_t *__restrict__ leaf_gid, double *__restrict__ leaf_sum,
+                                int32_t *__restrict__ leaf_cnt) {
+  int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= B) return;
+  const int g = leaf_gid[r];
+  if (g < 0) return;
+  float s = 0.f;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) s += fabsf(target[r * 3 + c] - pred[r * 3 + c]);
+  atomicAdd(leaf_sum + g, (double)s);
+  atomicAdd(leaf_cnt + g, 1);
+}
+// leaf_stat[g] = mean, or -1 for a leaf without rays (the reference's NaN mean never splits either)
+__global__ void leaf_mean_kernel(int64_t n, const double *__restrict__ leaf_sum, const int32_t *__restrict__ leaf_cnt,
+                                 float *__restrict__ leaf_stat) {
+  int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= n) return;
+  const int c = leaf_cnt[g];
+  leaf_stat[g] = c > 0 ? (float)(leaf_sum[g] / (3.0 * c)) : -1.0f;
+}
+
 // torch.optim.Adam single-tensor update order (exp_avg.lerp, exp_avg_sq.mul.addcmul, sqrt/bc2_sqrt + eps, addcdiv)
 __global__ void adam_kernel(int64_t n, float *__restrict__ p, float *__restrict__ m, float *__restrict__ v,
                             const float *__restrict__ g, float omb1, float b2, float omb2, float eps, float step_size,
@@ -440,6 +465,22 @@ int flnerf_mse_leafmax(flnerf_ctx *ctx, int64_t B, const float *rgb, const float
   float inv = (float)(1.0 / (3.0 * (double)denom));
   FL_LAUNCH(mse_leafmax_kernel, 1, 1024, 0, stream, B, rgb, rgb0, target, inv, leaf_gid, loss_out, d_rgb, d_rgb0,
             leaf_max);
+  return 0;
+}
+
+int flnerf_leaf_sum(flnerf_ctx *ctx, int64_t B, const float *pred, const float *target, const int32_t *leaf_gid,
+                    double *leaf_sum, int32_t *leaf_cnt, void *stream) {
+  FL_REQUIRE(ctx && pred && target && leaf_gid && leaf_sum && leaf_cnt && B >= 0, "flnerf_leaf_sum: bad arguments");
+  if (B == 0) return 0;
+  FL_LAUNCH(leaf_sum_kernel, (unsigned)ceil_div64(B, 256), 256, 0, stream, B, pred, target, leaf_gid, leaf_sum, leaf_cnt);
+  return 0;
+}
+
+int flnerf_leaf_mean(flnerf_ctx *ctx, int64_t n_slots, const double *leaf_sum, const int32_t *leaf_cnt, float *leaf_stat,
+                     void *stream) {
+  FL_REQUIRE(ctx && leaf_sum && leaf_cnt && leaf_stat && n_slots >= 0, "flnerf_leaf_mean: bad arguments");
+  if (n_slots == 0) return 0;
+  FL_LAUNCH(leaf_mean_kernel, (unsigned)ceil_div64(n_slots, 256), 256, 0, stream, n_slots, leaf_sum, leaf_cnt, leaf_stat);
   return 0;
 }
 

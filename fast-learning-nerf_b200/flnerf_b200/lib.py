@@ -33,6 +33,8 @@ SIGNATURES = {
     "flnerf_pack_x90": (_i, [_vp, _i64, _vp, _vp, _vp, _vp]),
     "flnerf_encode_tc_x3": (_i, [_vp, _i64, _i, _vp, _vp, _vp, _vp, _vp]),
     "flnerf_pack_x90_x3": (_i, [_vp, _i64, _vp, _vp, _vp, _vp]),
+    "flnerf_encode_frame_tc": (_i, [_vp, _i, _i, _i, _vp, _vp, _f, _f, _i, _i, _i64, _i64, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "flnerf_ssim_psnr": (_i, [_vp, _i, _i, _vp, _vp, _d, _vp, _vp]),
     "flnerf_padded_rows": (_i64, [_i64]),
     "flnerf_mlp_stash_bytes": (_sz, [_i, _i64, _i, _i]),
     "flnerf_mlp_bwd_workspace_bytes": (_sz, [_i, _i64]),
@@ -46,6 +48,8 @@ SIGNATURES = {
     "flnerf_sample_pdf_merge": (_i, [_vp, _i64, _i, _i, _vp, _vp, _vp, _i, _u64, _u64, _vp, _vp, _vp, _vp]),
     "flnerf_sample_pdf": (_i, [_vp, _i64, _i, _i, _vp, _vp, _vp, _i, _u64, _u64, _vp, _vp]),
     "flnerf_mse_leafmax": (_i, [_vp, _i64, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "flnerf_leaf_sum": (_i, [_vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "flnerf_leaf_mean": (_i, [_vp, _i64, _vp, _vp, _vp, _vp]),
     "flnerf_adam_step": (_i, [_vp, _i64, _vp, _vp, _vp, _vp, _d, _d, _d, _d, _i64, _vp]),
     "flnerf_qt_init": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "flnerf_qt_refine": (_i, [_vp, _i, _i, _vp, _vp, _vp, _vp, _f, _vp, _vp, _vp]),
@@ -57,6 +61,12 @@ SIGNATURES = {
     "flnerf_qt_emit_prob": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp, _i64, _u64, _d, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp,
                                  _vp]),
     "flnerf_gather_batch": (_i, [_vp, _i64, _i64, _i64, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "flnerf_gather_batch_u8": (_i, [_vp, _i64, _i64, _i64, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "flnerf_mlp_packed_bytes_g": (_sz, [_i]),
+    "flnerf_mlp_pack_weights_g": (_i, [_vp, _i, _vp, _vp, _vp]),
+    "flnerf_mlp_forward_g": (_i, [_vp, _i, _i, _vp, _vp, _i64, _i, _vp, _vp, _vp, _vp, _i, _vp]),
+    "flnerf_mlp_backward_g": (_i, [_vp, _i, _i, _vp, _vp, _i64, _i, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "flnerf_pack_xrows": (_i, [_vp, _i, _i, _i, _i64, _i, _vp, _vp, _vp, _vp]),
     "flnerf_mlp_param_count_g": (_i64, [_i, _i]),
     "flnerf_mlp_fp32_forward_g": (_i, [_vp, _i, _i, _vp, _i64, _vp, _vp, _vp, _vp]),
     "flnerf_mlp_fp32_backward_g": (_i, [_vp, _i, _i, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),

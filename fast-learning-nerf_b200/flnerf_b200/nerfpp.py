@@ -1,8 +1,8 @@
-"""First complete CUDA path of the nerf++ row, FP32 parity mode: NerfNet.forward (nerf++-ours/
-ddp_model.py:74-143) and its backward as a sequence of libflnerf.so kernels -- foreground network on the nerf-ours
-encode + MLP kernels, background network through ``flnerf_pp_bg_encode`` + the generic-width fp32 MLP, both composited by
-``flnerf_pp_composite_forward/backward``.  The tensor-core (bf16) path for the 84-channel background network, the cascade
-training loop and the reference-facing module API are still to come."""
+"""The nerf++ row: NerfNet.forward (nerf++-ours/ddp_model.py:74-143) and its backward as a sequence of
+libflnerf.so kernels -- foreground network on the nerf-ours encode + MLP kernels, background network (84 position channels:
+two 64-wide input slabs) through ``flnerf_pp_bg_encode`` and the generic-width MLP entry points, both composited by
+``flnerf_pp_composite_forward/backward`` -- in any of the three MLP modes: fp32 (CUDA cores), bf16 and bf16x3 (tcgen05; the
+split-precision mode meets the fp32 tolerances).  ``cascade_train_step`` is one iteration of ddp_train_nerf.train_step."""
 from typing import Dict
 
 import torch
@@ -34,26 +34,46 @@ def mlpnet_from_flat(flat: torch.Tensor, like: Dict[str, torch.Tensor]) -> Dict[
     return out
 
 
-class NerfNetFP32:
-    """NerfNet.forward + backward without autograd (fp32 parity path)."""
+_MODES = {"fp32": ops.MODE_FP32, "bf16": ops.MODE_BF16, "bf16x3": ops.MODE_BF16X3}
 
-    def __init__(self, flat_fg: torch.Tensor, flat_bg: torch.Tensor, in_pts_bg: int = 84, in_views: int = 27):
+
+class NerfNet:
+    """NerfNet.forward + backward without autograd over two flat parameter buffers (foreground 63, background 84 position
+    channels).  precision: "fp32" (CUDA-core parity path), "bf16" or "bf16x3" (tensor cores)."""
+
+    def __init__(self, flat_fg: torch.Tensor, flat_bg: torch.Tensor, in_pts_bg: int = 84, in_views: int = 27,
+                 precision: str = "fp32"):
         self.fg, self.bg, self.in_bg, self.in_views = flat_fg, flat_bg, int(in_pts_bg), int(in_views)
         self.grad_fg, self.grad_bg = torch.zeros_like(flat_fg), torch.zeros_like(flat_bg)
+        self.mode = _MODES[precision]
+        self._packed_fg = self._packed_bg = None
         self._saved = None
 
+    def _pack(self):
+        """fp32 master weights -> tensor-core images (once per optimiser step; the buffers keep their addresses)."""
+        self._packed_fg = ops.mlp_pack_weights(self.fg, self._packed_fg)
+        self._packed_bg = ops.mlp_pack_weights_g(self.in_bg, self.bg, self._packed_bg)
+
     @torch.no_grad()
-    def forward(self, ray_o, ray_d, fg_z_max, fg_z_vals, bg_z_vals):
+    def forward(self, ray_o, ray_d, fg_z_max, fg_z_vals, bg_z_vals, training=True):
         B, Sf = fg_z_vals.shape
         Sb = bg_z_vals.shape[1]
         rays11 = ops.pack_rays(ray_o, ray_d, 0.0, 1.0, False, 1, 1, 1.0)       # o, d, -, -, viewdir = d/|d|
-        x_fg = ops.encode_f32(rays11, fg_z_vals)
-        raw_fg, st_fg = ops.mlp_forward(ops.MODE_FP32, self.fg, None, x_fg, None, B * Sf, Sf, True)
         x_bg, bg_flip, _ = ops.pp_bg_encode(ray_o, ray_d, bg_z_vals)
-        raw_bg, st_bg = ops.mlp_fp32_forward_g(self.in_bg, self.in_views, self.bg, x_bg.view(B * Sb, -1), B * Sb)
+        if self.mode == ops.MODE_FP32:
+            x_fg, dp_fg, dp_bg = ops.encode_f32(rays11, fg_z_vals), None, None
+            raw_fg, st_fg = ops.mlp_forward(ops.MODE_FP32, self.fg, None, x_fg, None, B * Sf, Sf, True)
+            x_bg = x_bg.view(B * Sb, -1)
+            raw_bg, st_bg = ops.mlp_fp32_forward_g(self.in_bg, self.in_views, self.bg, x_bg, B * Sb)
+        else:
+            self._pack()
+            x_fg, dp_fg = ops.encode_tc(rays11, fg_z_vals, self.mode)
+            raw_fg, st_fg = ops.mlp_forward(self.mode, self.fg, self._packed_fg, x_fg, dp_fg, B * Sf, Sf, training)
+            x_bg, dp_bg = ops.pack_xrows(self.mode, self.in_bg, x_bg.view(B * Sb, -1), Sb)
+            raw_bg, st_bg = ops.mlp_forward_g(self.mode, self.in_bg, self.bg, self._packed_bg, x_bg, dp_bg, B * Sb, Sb, training)
         rgb, fw, bw, aux = ops.pp_composite_forward(raw_fg.view(B, Sf, 4), fg_z_vals, fg_z_max, raw_bg.view(B, Sb, 4), bg_flip,
                                                     ray_d)
-        self._saved = (B, Sf, Sb, x_fg, st_fg, raw_fg, x_bg, st_bg, raw_bg, fg_z_vals, fg_z_max, bg_flip, ray_d)
+        self._saved = (B, Sf, Sb, x_fg, dp_fg, st_fg, raw_fg, x_bg, dp_bg, st_bg, raw_bg, fg_z_vals, fg_z_max, bg_flip, ray_d)
         return {"rgb": rgb, "fg_weights": fw, "bg_weights": bw, "fg_rgb": aux[:, 0:3], "fg_depth": aux[:, 3],
                 "bg_rgb": aux[:, 4:7], "bg_depth": aux[:, 7], "bg_lambda": aux[:, 8]}
 
@@ -61,14 +81,25 @@ class NerfNetFP32:
     def backward(self, g_rgb):
         """Accumulates d(loss)/d(params) into grad_fg / grad_bg for a loss whose gradient w.r.t. ret['rgb'] is g_rgb."""
         if self._saved is None:
-            raise FlnerfError("NerfNetFP32.backward() without a forward()")
-        B, Sf, Sb, x_fg, st_fg, raw_fg, x_bg, st_bg, raw_bg, fg_z, fg_far, bg_flip, ray_d = self._saved
+            raise FlnerfError("NerfNet.backward() without a forward()")
+        B, Sf, Sb, x_fg, dp_fg, st_fg, raw_fg, x_bg, dp_bg, st_bg, raw_bg, fg_z, fg_far, bg_flip, ray_d = self._saved
         d_fg, d_bg = ops.pp_composite_backward(raw_fg.view(B, Sf, 4), fg_z, fg_far, raw_bg.view(B, Sb, 4), bg_flip, ray_d, g_rgb)
-        ops.mlp_backward(ops.MODE_FP32, self.fg, None, x_fg, None, st_fg, d_fg.view(B * Sf, 4), self.grad_fg, B * Sf, Sf)
-        ops.mlp_fp32_backward_g(self.in_bg, self.in_views, self.bg, x_bg.view(B * Sb, -1), st_bg, d_bg.view(B * Sb, 4),
-                                self.grad_bg, B * Sb)
+        if self.mode == ops.MODE_FP32:
+            ops.mlp_backward(ops.MODE_FP32, self.fg, None, x_fg, None, st_fg, d_fg.view(B * Sf, 4), self.grad_fg, B * Sf, Sf)
+            ops.mlp_fp32_backward_g(self.in_bg, self.in_views, self.bg, x_bg, st_bg, d_bg.view(B * Sb, 4), self.grad_bg, B * Sb)
+        else:
+            ops.mlp_backward(self.mode, self.fg, self._packed_fg, x_fg, dp_fg, st_fg, d_fg.view(B * Sf, 4), self.grad_fg, B * Sf, Sf)
+            ops.mlp_backward_g(self.mode, self.in_bg, self.bg, self._packed_bg, x_bg, dp_bg, st_bg, d_bg.view(B * Sb, 4),
+                               self.grad_bg, B * Sb, Sb)
         self._saved = None
         return self.grad_fg, self.grad_bg
+
+
+class NerfNetFP32(NerfNet):
+    """The fp32 parity path under its round-1 name."""
+
+    def __init__(self, flat_fg, flat_bg, in_pts_bg: int = 84, in_views: int = 27):
+        super().__init__(flat_fg, flat_bg, in_pts_bg, in_views, "fp32")
 
 
 class FlatAdam:

@@ -115,6 +115,37 @@ def encode_tc(rays11, z, mode=MODE_BF16):
     return tiles, dirpe
 
 
+def encode_frame_tc(mode, H, W, K, c2w, near, far, ndc, lindisp, pixel0: int, B: int, n_samples: int):
+    """The eval path's fused front end (render.py:52-80, 244-249, run_nerf.py:50-64): pixels [pixel0, pixel0+B) of the frame
+    -> (rays11[B,11], z[B,S], pe_tiles, dirpe[B,32]) in ONE launch (no [H,W,3] ray images, no separate packing / depth /
+    direction-PE kernels)."""
+    dev = c2w.device
+    x3 = mode == MODE_BF16X3
+    rays11 = torch.empty(B, 11, dtype=torch.float32, device=dev)
+    z = torch.empty(B, n_samples, dtype=torch.float32, device=dev)
+    tiles = _alloc_bytes(padded_rows(B * n_samples) // 128 * 16384 * (2 if x3 else 1), dev)
+    dirpe = torch.empty(B, 32, dtype=torch.float32, device=dev)
+    Kh = (C.c_double * 9)(*[float(K[i][j]) for i in range(3) for j in range(3)])
+    Ph = (C.c_float * 12)(*c2w[:3, :4].detach().float().cpu().reshape(-1).tolist())
+    L.check(L.load().flnerf_encode_frame_tc(_ctx(rays11), int(x3), int(H), int(W), Kh, Ph, float(near), float(far), int(bool(ndc)),
+                                            int(bool(lindisp)), int(pixel0), int(B), int(n_samples),
+                                            _ptr(_t_vals(n_samples, dev)), _ptr(rays11), _ptr(z), _ptr(tiles), _ptr(dirpe),
+                                            _stream()), "flnerf_encode_frame_tc")
+    return rays11, z, tiles, dirpe
+
+
+def ssim_psnr(img0, img1, max_val: float = 1.0):
+    """(mean SSIM, PSNR) of two [H,W,3] images as a 2-element float64 DEVICE tensor (compute_ssim of run_nerf_helpers.py:158-228
+    and render.py:120) -- one kernel, no host sync."""
+    a, b = _f32c(img0), _f32c(img1)
+    H, W, _ = a.shape
+    sums = torch.empty(2, dtype=torch.float64, device=a.device)
+    L.check(L.load().flnerf_ssim_psnr(_ctx(a), int(H), int(W), _ptr(a), _ptr(b), float(max_val), _ptr(sums), _stream()),
+            "flnerf_ssim_psnr")
+    n = 3.0 * H * W
+    return torch.stack([sums[0] / n, -10.0 * torch.log10(sums[1] / n)])
+
+
 def pack_x90(x90, mode=MODE_BF16):
     n = x90.shape[0]
     x3 = mode == MODE_BF16X3
@@ -239,6 +270,18 @@ def mse_leafmax(rgb, rgb0, target, denom: int, leaf_gid=None, leaf_max=None, wan
     return loss, d_rgb, d_rgb0
 
 
+def leaf_sum(pred, target, leaf_gid, leaf_sum_t, leaf_cnt_t):
+    """Accumulates the nerf++ refinement statistic (nerf++-ours/tree.py:613-622) of one batch into the per-leaf tables."""
+    B = pred.shape[0]
+    L.check(L.load().flnerf_leaf_sum(_ctx(pred), B, _ptr(_f32c(pred)), _ptr(_f32c(target)), _ptr(leaf_gid), _ptr(leaf_sum_t),
+                                     _ptr(leaf_cnt_t), _stream()), "flnerf_leaf_sum")
+
+
+def leaf_mean(leaf_sum_t, leaf_cnt_t, leaf_stat):
+    L.check(L.load().flnerf_leaf_mean(_ctx(leaf_stat), leaf_stat.numel(), _ptr(leaf_sum_t), _ptr(leaf_cnt_t), _ptr(leaf_stat),
+                                      _stream()), "flnerf_leaf_mean")
+
+
 def adam_step(param, m, v, grad, lr: float, b1: float, b2: float, eps: float, t: int):
     L.check(L.load().flnerf_adam_step(_ctx(param), param.numel(), _ptr(param), _ptr(m), _ptr(v), _ptr(grad), lr, b1, b2,
                                       eps, int(t), _stream()), "flnerf_adam_step")
@@ -314,13 +357,19 @@ def qt_emit_prob(n_images, cap, H, W, boxes, count, ray_offset, n_rays, seed, ra
                                          _ptr(ray_pix), _ptr(ray_gid), _stream()), "flnerf_qt_emit_prob")
 
 
-def gather_batch(B, first, stride, ray_pix, ray_gid, cap, H, W, K, poses, images, want_gid=True):
+def gather_batch(B, first, stride, ray_pix, ray_gid, cap, H, W, K, poses, images, want_gid=True, lut=None):
+    """images: fp32 [n,H,W,3], or uint8 [n,H,W,3] with lut[256] = float32(u / 255.) (the loaders' division, done per batch)."""
     dev = images.device
     o = torch.empty(B, 3, dtype=torch.float32, device=dev)
     d = torch.empty(B, 3, dtype=torch.float32, device=dev)
     t = torch.empty(B, 3, dtype=torch.float32, device=dev)
     gid = torch.empty(B, dtype=torch.int32, device=dev) if want_gid else None
     Kh = (C.c_double * 9)(*[float(K[i][j]) for i in range(3) for j in range(3)])
+    if images.dtype == torch.uint8:
+        L.check(L.load().flnerf_gather_batch_u8(_ctx(images), int(B), int(first), int(stride), _ptr(ray_pix), _ptr(ray_gid),
+                                                int(cap), int(H), int(W), Kh, _ptr(poses), _ptr(images), _ptr(lut), _ptr(o),
+                                                _ptr(d), _ptr(t), _ptr(gid), _stream()), "flnerf_gather_batch_u8")
+        return o, d, t, gid
     L.check(L.load().flnerf_gather_batch(_ctx(images), int(B), int(first), int(stride), _ptr(ray_pix), _ptr(ray_gid),
                                          int(cap), int(H), int(W), Kh, _ptr(poses), _ptr(images), _ptr(o), _ptr(d),
                                          _ptr(t), _ptr(gid), _stream()), "flnerf_gather_batch")
@@ -389,6 +438,46 @@ def pp_sample_pdf_merge(z, weights, Nf, det, u=None, seed=0, offset=0):
                                                 int(bool(det)), int(seed), int(offset), _ptr(zm), _ptr(zs), _stream()),
             "flnerf_pp_sample_pdf_merge")
     return zm, zs
+
+
+def pack_xrows(mode, in_pts, x, S):
+    """Already-embedded fp32 rows x[n, in_pts + 27] (S rows per ray) -> (pe_tiles, dirpe[n/S, 32]) for the tensor-core MLP of a
+    network with in_pts position channels (ceil(in_pts/64) slabs per 128-row tile; MODE_BF16X3: hi set then lo set)."""
+    n = x.shape[0]
+    x3 = mode == MODE_BF16X3
+    slabs = (in_pts + 63) // 64
+    tiles = _alloc_bytes(padded_rows(n) // 128 * 16384 * slabs * (2 if x3 else 1), x.device)
+    dirpe = torch.empty(n // S, 32, dtype=torch.float32, device=x.device)
+    L.check(L.load().flnerf_pack_xrows(_ctx(x), int(x3), int(in_pts), 27, int(n), int(S), _ptr(_f32c(x)), _ptr(tiles), _ptr(dirpe),
+                                       _stream()), "flnerf_pack_xrows")
+    return tiles, dirpe
+
+
+def mlp_pack_weights_g(in_pts, flat_params, packed=None):
+    if packed is None:
+        packed = _alloc_bytes(L.load().flnerf_mlp_packed_bytes_g(int(in_pts)), flat_params.device)
+    L.check(L.load().flnerf_mlp_pack_weights_g(_ctx(flat_params), int(in_pts), _ptr(flat_params), _ptr(packed), _stream()),
+            "flnerf_mlp_pack_weights_g")
+    return packed
+
+
+def mlp_forward_g(mode, in_pts, flat_params, packed, tiles, dirpe, n: int, S: int, training: bool):
+    """The tensor-core MLP of a network with in_pts (63 / 84) position channels -> (raw[n,4], stash)."""
+    dev = flat_params.device
+    raw = torch.empty(n, 4, dtype=torch.float32, device=dev)
+    stash = _alloc_bytes(L.load().flnerf_mlp_stash_bytes(mode, n, S, int(training)), dev)
+    L.check(L.load().flnerf_mlp_forward_g(_ctx(raw), mode, int(in_pts), _ptr(flat_params), _ptr(packed), n, S, _ptr(tiles),
+                                          _ptr(dirpe), _ptr(raw), _ptr(stash), int(training), _stream()), "flnerf_mlp_forward_g")
+    return raw, stash
+
+
+def mlp_backward_g(mode, in_pts, flat_params, packed, tiles, dirpe, stash, draw, flat_grad, n: int, S: int):
+    ws_bytes = L.load().flnerf_mlp_bwd_workspace_bytes(mode, n)
+    ws = _alloc_bytes(ws_bytes, flat_params.device)
+    draw = _f32c(draw.reshape(n, 4))
+    L.check(L.load().flnerf_mlp_backward_g(_ctx(draw), mode, int(in_pts), _ptr(flat_params), _ptr(packed), n, S, _ptr(tiles),
+                                           _ptr(dirpe), _ptr(stash), _ptr(draw), _ptr(flat_grad), _ptr(ws), ws_bytes, _stream()),
+            "flnerf_mlp_backward_g")
 
 
 def mlp_fp32_forward_g(in_pts, in_views, flat_params, x, n):

@@ -158,6 +158,13 @@ class NeRF(nn.Module):
             raw = _NerfFn.apply(proxy, self, tiles, dirpe, B * S, S)
         return raw.reshape(B, S, 4)
 
+    def query_tiles(self, tiles, dirpe, B, S):
+        """The MLP on input tiles some other kernel already produced (the eval path's fused frame encoder)."""
+        self._ensure_flat()
+        proxy = self._proxy if (torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())) \
+            else self._proxy.detach()
+        return _NerfFn.apply(proxy, self, tiles, dirpe, B * S, S).reshape(B, S, 4)
+
     def load_weights_from_keras(self, weights):
         """model.py:65-92: weights = [W0,b0,...] in Keras order (kernels stored [in,out])."""
         assert self.use_viewdirs, "Not implemented if use_viewdirs=False"

@@ -38,6 +38,8 @@ def batchify_rays(rays_flat, chunk=1024 * 32, **kwargs):
 def render(H, W, K, chunk=1024 * 32, rays=None, c2w=None, ndc=True, near=0., far=1., use_viewdirs=False,
            c2w_staticcam=None, **kwargs):
     """render.py:26-91.  Returns [rgb_map, disp_map, acc_map, extras]."""
+    if c2w is not None and c2w_staticcam is None and use_viewdirs and _frame_path_ok(near, far, kwargs):
+        return _render_frame(H, W, K, chunk, c2w, ndc, float(near), float(far), kwargs)
     if c2w is not None:
         rays_o, rays_d = get_rays(H, W, K, c2w)
     else:
@@ -59,6 +61,39 @@ def render(H, W, K, chunk=1024 * 32, rays=None, c2w=None, ndc=True, near=0., far
     all_ret = batchify_rays(rays11, chunk, **kwargs)
     for k in all_ret:
         all_ret[k] = all_ret[k].reshape(list(sh[:-1]) + list(all_ret[k].shape[1:]))
+    head = ['rgb_map', 'disp_map', 'acc_map']
+    return [all_ret[k] for k in head] + [{k: v for k, v in all_ret.items() if k not in head}]
+
+
+def _frame_path_ok(near, far, kw):
+    """Full-frame rendering from a pose with un-jittered depths through a tensor-core network: the fused front end applies."""
+    if torch.is_tensor(near) or torch.is_tensor(far) or kw.get("perturb", 0.) > 0. or kw.get("pytest", False):
+        return False
+    if getattr(kw.get("network_query_fn"), "fused_rays", None) is None:
+        return False
+    net = kw.get("network_fn")
+    net = net.module if hasattr(net, "module") else net
+    return getattr(net, "mode", ops.MODE_FP32) != ops.MODE_FP32
+
+
+def _render_frame(H, W, K, chunk, c2w, ndc, near, far, kw):
+    """render(c2w=...) (render.py:52-91) with the coarse pass's inputs produced by ONE kernel per chunk of pixels
+    (ops.encode_frame_tc) instead of get_rays over the whole frame + packing + depths + PE."""
+    net = kw["network_fn"]
+    net = net.module if hasattr(net, "module") else net
+    kw = dict(kw)
+    N_samples, lindisp = kw["N_samples"], kw.get("lindisp", False)
+    parts = {}
+    for p0 in range(0, H * W, chunk):
+        B = min(chunk, H * W - p0)
+        rays11, z, tiles, dirpe = ops.encode_frame_tc(net.mode, H, W, K, torch.as_tensor(c2w), near, far, ndc, lindisp, p0, B,
+                                                      N_samples)
+        out = render_rays(rays11, _coarse=(z, tiles, dirpe), **kw)
+        for k, v in out.items():
+            parts.setdefault(k, []).append(v)
+    all_ret = {k: (v[0] if len(v) == 1 else torch.cat(v, 0)) for k, v in parts.items()}
+    for k in all_ret:
+        all_ret[k] = all_ret[k].reshape([H, W] + list(all_ret[k].shape[1:]))
     head = ['rgb_map', 'disp_map', 'acc_map']
     return [all_ret[k] for k in head] + [{k: v for k, v in all_ret.items() if k not in head}]
 
@@ -87,20 +122,26 @@ def _query(network_query_fn, rays11, z, net):
 
 
 def render_rays(ray_batch, network_fn, network_query_fn, N_samples, retraw=False, lindisp=False, perturb=0.,
-                N_importance=0, network_fine=None, white_bkgd=False, raw_noise_std=0., verbose=False, pytest=False):
+                N_importance=0, network_fine=None, white_bkgd=False, raw_noise_std=0., verbose=False, pytest=False,
+                _coarse=None):
     """Volumetric rendering of a ray batch (render.py:195-305); same keys in the returned dict."""
     if ray_batch.shape[-1] < 11:
         raise FlnerfError("flnerf render_rays needs [o,d,near,far,viewdir] rays (use_viewdirs=True)")
     rays11 = ray_batch.float().contiguous()
     B = rays11.shape[0]
-    t_rand = None
-    if perturb > 0. and pytest:
-        np.random.seed(0)
-        t_rand = torch.tensor(np.random.rand(B, N_samples), dtype=torch.float32, device=rays11.device)
-    z_vals = ops.coarse_depths(rays11, N_samples, perturb > 0., lindisp, t_rand, _SEED["base"],
-                               _next_offset(B * N_samples) if (perturb > 0. and t_rand is None) else 0)
     rays_d = rays11[:, 3:6]
-    raw = _query(network_query_fn, rays11, z_vals, network_fn)
+    if _coarse is not None:     # eval path: depths + the coarse network's input tiles came with the rays (ops.encode_frame_tc)
+        z_vals, tiles, dirpe = _coarse
+        net = network_fn.module if hasattr(network_fn, "module") else network_fn
+        raw = net.query_tiles(tiles, dirpe, B, N_samples)
+    else:
+        t_rand = None
+        if perturb > 0. and pytest:
+            np.random.seed(0)
+            t_rand = torch.tensor(np.random.rand(B, N_samples), dtype=torch.float32, device=rays11.device)
+        z_vals = ops.coarse_depths(rays11, N_samples, perturb > 0., lindisp, t_rand, _SEED["base"],
+                                   _next_offset(B * N_samples) if (perturb > 0. and t_rand is None) else 0)
+        raw = _query(network_query_fn, rays11, z_vals, network_fn)
     rgb_map, disp_map, acc_map, weights, depth_map = raw2outputs(raw, z_vals, rays_d, raw_noise_std, white_bkgd, pytest)
     if N_importance > 0:
         rgb0, disp0, acc0 = rgb_map, disp_map, acc_map
@@ -145,9 +186,8 @@ def render_path(render_poses, hwf, K, chunk, render_kwargs, gt_imgs=None, savedi
         if i == 0:
             print(rgb.shape, disp.shape)
         if gt_imgs is not None and render_factor == 0:
-            gt = torch.as_tensor(gt_imgs[i]).float().to(rgb.device)
-            psnr = float(-10. * torch.log10(torch.mean((rgb - gt) ** 2)))
-            ssim = compute_ssim(gt, rgb).item()
+            gt = torch.as_tensor(gt_imgs[i]).float().to(rgb.device)[..., :3]
+            ssim, psnr = ops.ssim_psnr(gt, rgb).tolist()         # one kernel on the device (csrc/eval.cu)
             lp = float('nan')
             if lpips_vgg is not None:
                 lp = lpips_vgg(gt.permute(2, 0, 1).contiguous(), rgb.permute(2, 0, 1).contiguous(), normalize=True).item()
@@ -169,6 +209,6 @@ def _imwrite(path, img8):
     try:
         import imageio
         imageio.imwrite(path, img8)
-    except ImportError:
+    except (ImportError, AttributeError):      # absent, or a stub module without imwrite
         import cv2
-        cv2.imwrite(path, img8[..., ::-1])
+        cv2.imwrite(path, np.ascontiguousarray(img8[..., ::-1]))

@@ -105,6 +105,10 @@ def sample_pdf(bins, weights, N_samples, det=False, pytest=False):
 
 # --- SSIM (run_nerf_helpers.py:158-234): evaluation metric, separable Gaussian window as in tf.image.ssim
 def compute_ssim(img0, img1, max_val=1.0, filter_size=11, filter_sigma=1.5, k1=0.01, k2=0.03, return_map=False):
+    if (img0.is_cuda and img0.dim() == 3 and img0.shape[-1] == 3 and not return_map
+            and (filter_size, filter_sigma, k1, k2) == (11, 1.5, 0.01, 0.03)):
+        return ops.ssim_psnr(img0, img1, max_val)[0:1].float()       # csrc/eval.cu: one kernel, no conv library
+    # general arguments / CPU tensors / the per-pixel map: the reference's formula on torch ops
     w_, h_, c_ = img0.shape[-3:]
     a = img0.reshape(-1, w_, h_, c_).permute(0, 3, 1, 2)
     b = img1.reshape(-1, w_, h_, c_).permute(0, 3, 1, 2)

@@ -95,7 +95,8 @@ class QuadTree:
 class QuadTreeManager:
     """GPU-resident replacement of tree.py:159-566 (constructor and the two methods run_nerf.py calls)."""
 
-    def __init__(self, H, W, K, images, poses, mseThres=0.1, max_depth=5, max_level=None, device=None, seed=0):
+    def __init__(self, H, W, K, images, poses, mseThres=0.1, max_depth=5, max_level=None, device=None, seed=0,
+                 use_mean=False):
         self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
         self.n_images, self.h, self.w = int(poses.shape[0]), int(H), int(W)
         self.K = np.asarray(K, dtype=np.float64)
@@ -104,6 +105,14 @@ class QuadTreeManager:
         self.processor = None           # the reference's ImageProcessor; here the sharpness maps live on the GPU and are
         self._sharp = None              # computed on first use (only prob=True reads them: tree.py:583-595)
         self._images_dev = torch.as_tensor(images, dtype=torch.float32).to(self.device).contiguous()
+        # uint8 image store: images that are exactly the loaders' float32(u / 255.) (load_blender.py:37 on opaque pixels, every
+        # LLFF image) are kept as the bytes they were read from -- a quarter of the memory, decoded per batch through a
+        # 256-entry table of the same floats.  Anything else (alpha-blended backgrounds, synthetic images) stays fp32.
+        self._lut = torch.from_numpy((np.arange(256) / 255.).astype(np.float32)).to(self.device)
+        q = torch.round(self._images_dev * 255.0).clamp_(0, 255).to(torch.uint8)
+        if self._images_dev.numel() > 0 and torch.equal(self._lut[q.long()], self._images_dev):
+            self._images_dev = q
+        del q
         self._poses_dev = torch.as_tensor(poses, dtype=torch.float32)[:, :3, :4].to(self.device).contiguous()
         self.max_level = int(max_level) if max_level is not None else int(max_depth) + 6
         # leaf capacity per image.  A leaf is split only if rays fell into it (leaf_max > thres), i.e. if it held at least
@@ -125,6 +134,11 @@ class QuadTreeManager:
             ops.qt_init(n, self.cap, self.h, self.w, int(max_depth), self._boxes[0], self._count[0], self._min_area)
         self.cur_level = max_depth
         self.leaf_max = torch.full((n * self.cap,), -1.0, dtype=torch.float32, device=self.device)
+        # use_mean: the nerf++ / plenoxels copies of the tree refine on the MEAN |gt - pred| of a leaf's rays
+        # (nerf++-ours/tree.py:622) instead of the max (tree.py:642): two more tables, folded into leaf_max before refine()
+        self.use_mean = bool(use_mean)
+        self.leaf_sum = torch.zeros(n * self.cap, dtype=torch.float64, device=self.device) if use_mean else None
+        self.leaf_cnt = torch.zeros(n * self.cap, dtype=torch.int32, device=self.device) if use_mean else None
         self._ray_offset = torch.zeros(n * self.cap + 1, dtype=torch.int64, device=self.device)
         self.ray_pix = self.ray_gid = None
         self.n_rays = 0
@@ -132,6 +146,11 @@ class QuadTreeManager:
         self.seed = int(seed)
 
     # ------------------------------------------------------------------ GPU state
+    def _images_f32(self, img_id=None):
+        """The training images as fp32 (decoding the uint8 store)."""
+        x = self._images_dev if img_id is None else self._images_dev[img_id]
+        return self._lut[x.long()] if x.dtype == torch.uint8 else x
+
     @property
     def boxes(self):
         return self._boxes[self._cur]
@@ -198,7 +217,7 @@ class QuadTreeManager:
     def sharp_imgs(self):
         """ImageProcessor.sharp_imgs (image_process.py:24-39) as one [n,H,W] GPU tensor."""
         if self._sharp is None:
-            self._sharp = ops.sharp_map(self._images_dev)
+            self._sharp = ops.sharp_map(self._images_f32())
         return self._sharp
 
     def emit_epoch(self, down_scale=1, last_epoch=False, seed=None, prob=False, randSamp_proc=0.95, u=None, shuffle=True):
@@ -234,22 +253,73 @@ class QuadTreeManager:
     def batch(self, first, B, stride=1):
         """rays_o, rays_d, target_rgb, leaf_gid for rows first, first+stride, ... of the index buffer."""
         return ops.gather_batch(B, first, stride, self.ray_pix, self.ray_gid, self.cap, self.h, self.w, self.K,
-                                self._poses_dev, self._images_dev)
+                                self._poses_dev, self._images_dev, lut=self._lut)
 
     def gen_rays_v3_multiThread(self, down_scale=16, prob=True, randSamp_proc=0.95, debug=False, last_epoch=False):
         """tree.py:377-428 -> (origins[N,3], dirs[N,3], rgb[N,3]) (GPU tensors, already shuffled)."""
         n = self.emit_epoch(down_scale, last_epoch, prob=bool(prob), randSamp_proc=randSamp_proc)
         o, d, rgb, _ = ops.gather_batch(n, 0, 1, self.ray_pix, self.ray_gid, self.cap, self.h, self.w, self.K,
-                                        self._poses_dev, self._images_dev, want_gid=False)
+                                        self._poses_dev, self._images_dev, want_gid=False, lut=self._lut)
         return o, d, rgb
+
+    def gen_rays_v3_1(self, down_scale=16, debug=False, last_epoch=False):
+        """tree.py:309-375, the single-thread integer-pixel version: same semantics as gen_rays_v3_multiThread(prob=False)."""
+        return self.gen_rays_v3_multiThread(down_scale=down_scale, prob=False, debug=debug, last_epoch=last_epoch)
+
+    def gen_rays_v4(self, sampler_ret, down_scale=1, debug=False):
+        """tree.py:430-491 indexes rays pre-generated by tree_utils.RaySampler.pre_gen_rays_v3 -- an offline table the driver
+        never builds (run_nerf.py:357-366 is commented out).  On-the-fly emission (emit_epoch) replaces it."""
+        raise FlnerfError("gen_rays_v4 needs tree_utils.RaySampler's offline ray table (dead code in the reference driver); "
+                          "use gen_rays_v3_multiThread / emit_epoch")
+
+    # ------------------------------------------------------------------ debug pictures (tree.py:148-229)
+    def _draw(self, img_id, points=None):
+        import cv2
+        img = self._images_f32(img_id).detach().cpu().numpy().copy() * 255.0
+        boxes, _ = self.leaf_lists()[img_id]
+        for x0, y0, x1, y1 in boxes:
+            img = cv2.rectangle(img, (int(y0), int(x0)), (int(y1), int(x1)), (0, 0, 0), 1)
+        if points is not None:
+            for x, y in np.asarray(points.detach().cpu() if torch.is_tensor(points) else points):
+                img = cv2.circle(img, (int(y), int(x)), 0, (255, 0, 0), -1)
+        return img
+
+    def _write(self, name, img):
+        import os
+        import cv2
+        os.makedirs('debug', exist_ok=True)
+        cv2.imwrite(os.path.join('debug', name + '.jpg'), img[:, :, [2, 1, 0]])
+        return img
+
+    def visualize_subdivide(self, tree_id=-1, filename_prefix='tree_subdivide'):
+        for i in (range(self.n_images) if tree_id == -1 else [tree_id]):
+            self._write('tree_subdivide_' + str(i), self._draw(i))
+
+    def visualize_split(self, img_id):
+        return self._write('tree_split_{}'.format(img_id), self._draw(img_id))
+
+    def visualize_split_and_sample_points(self, img_id, selected_pixel):
+        return self._write('tree_sample_points_{}'.format(img_id), self._draw(img_id, selected_pixel))
 
     # ------------------------------------------------------------------ refinement
     def reset_leaf_stats(self):
         self.leaf_max.fill_(-1.0)
+        if self.use_mean:
+            self.leaf_sum.zero_()
+            self.leaf_cnt.zero_()
+
+    def accumulate(self, pred, target, leaf_gid):
+        """Adds one batch to the refinement statistic (use_mean trees; the max variant is fused into the loss kernel)."""
+        if self.use_mean:
+            ops.leaf_sum(pred, target, leaf_gid, self.leaf_sum, self.leaf_cnt)
+        else:
+            ops.mse_leafmax(pred, None, target, max(pred.shape[0], 1), leaf_gid, self.leaf_max, want_grads=False)
 
     def refine(self, thres):
         """adjust_tree on the accumulated per-leaf table (tree.py:629-652), then clears the table."""
         nxt = 1 - self._cur
+        if self.use_mean:
+            ops.leaf_mean(self.leaf_sum, self.leaf_cnt, self.leaf_max)
         ops.qt_refine(self.n_images, self.cap, self._boxes[self._cur], self._count[self._cur], self._min_area,
                       self.leaf_max, thres, self._boxes[nxt], self._count[nxt])
         self._cur = nxt
@@ -257,12 +327,31 @@ class QuadTreeManager:
         self.cur_level += 1
         self.reset_leaf_stats()
 
+    def adjust_tree(self, rgb_gt, rgb_pred, thres=0.01, debug=False):
+        """tree.py:493-531, the single-thread variant: it splits on the MEAN leaf loss (:515), unlike the multi-thread one the
+        driver calls (max, :642)."""
+        gt = torch.as_tensor(rgb_gt, dtype=torch.float32).to(self.device)
+        pr = torch.as_tensor(rgb_pred, dtype=torch.float32).to(self.device)
+        n = gt.shape[0]
+        keep = self.use_mean, self.leaf_sum, self.leaf_cnt
+        self.use_mean = True
+        if self.leaf_sum is None:
+            self.leaf_sum = torch.zeros(self.n_images * self.cap, dtype=torch.float64, device=self.device)
+            self.leaf_cnt = torch.zeros(self.n_images * self.cap, dtype=torch.int32, device=self.device)
+        try:
+            self.reset_leaf_stats()
+            self.accumulate(pr, gt, self.ray_gid[:n].contiguous())
+            self.refine(thres)
+        finally:
+            self.use_mean = keep[0]
+        print('After sudivide, there are {} child nodes'.format(int(self.counts.sum().item())))
+
     def adjust_tree_multiThread(self, rgb_gt, rgb_pred, thres=0.001, debug=False):
         """tree.py:533-557: rgb_gt / rgb_pred are the epoch's [N,3] targets and predictions in emission order."""
         gt = torch.as_tensor(rgb_gt, dtype=torch.float32).to(self.device)
         pr = torch.as_tensor(rgb_pred, dtype=torch.float32).to(self.device)
         n = gt.shape[0]
         self.reset_leaf_stats()
-        ops.mse_leafmax(pr, None, gt, max(n, 1), self.ray_gid[:n].contiguous(), self.leaf_max, want_grads=False)
+        self.accumulate(pr, gt, self.ray_gid[:n].contiguous())
         self.refine(thres)
         print('After sudivide, there are {} child nodes'.format(int(self.counts.sum().item())))

@@ -65,6 +65,13 @@ int flnerf_encode_f32(flnerf_ctx *, int64_t B, int S, const float *rays11, const
  * the SWIZZLE_128B K-major shared-memory image (16 KB each, column 63 = 0); dirpe[B,32] fp32 (27 used). */
 int flnerf_encode_tc(flnerf_ctx *, int64_t B, int S, const float *rays11, const float *z, void *pe_tiles,
                      float *dirpe, void *stream);
+/* the eval path (render.py:94-146 -> render(c2w=...)): ONE launch from the camera pose to the coarse network's input -- for the
+ * B pixels [pixel0, pixel0 + B) of an H x W frame: get_rays + (ndc) + ray packing -> rays11[B,11]; un-jittered coarse depths
+ * z[B,S] (render.py:244-249; t_vals = linspace(0,1,S)); sample points + PE tiles (x3 != 0: hi and lo tile sets, as
+ * flnerf_encode_tc_x3) and dirpe[B,32].  Replaces flnerf_raygen + flnerf_pack_rays + flnerf_coarse_depths + flnerf_encode_tc. */
+int flnerf_encode_frame_tc(flnerf_ctx *, int x3, int H, int W, const double *h_K, const float *h_c2w, float near_, float far_,
+                           int ndc, int lindisp, int64_t pixel0, int64_t B, int S, const float *t_vals, float *rays11, float *z,
+                           void *pe_tiles, float *dirpe, void *stream);
 /* already-embedded rows x90[n,90] (NeRF.forward API) -> pe_tiles + dirpe[n,32] (one "ray" per row, S = 1) */
 int flnerf_pack_x90(flnerf_ctx *, int64_t n, const float *x90, void *pe_tiles, float *dirpe, void *stream);
 /* the same two for FLNERF_MODE_BF16X3: pe_tiles holds TWO tile sets back to back, hi = bf16(PE) then lo = bf16(PE - hi)
@@ -92,6 +99,23 @@ int flnerf_mlp_forward(flnerf_ctx *, int mode, const float *params, const void *
 int flnerf_mlp_backward(flnerf_ctx *, int mode, const float *params, const void *packed, int64_t n, int S,
                         const void *x, const float *dirpe, const void *stash, const float *draw, float *grads,
                         void *workspace, size_t workspace_bytes, void *stream);
+
+/* ---- the same tensor-core MLP for a network with in_pts position channels: 63 (model.NeRF, the nerf++ foreground MLPNet) or
+ * 84 (the nerf++ background MLPNet, PE of (x,y,z,1/r): nerf++-ours/nerf_network.py:70-142 -- two 64-wide input slabs; layer 5
+ * is 340 wide).  params / grads: flat fp32[flnerf_mlp_param_count_g(in_pts, 27)] in the order above; packed image of
+ * flnerf_mlp_packed_bytes_g(in_pts) bytes; x = pe_tiles with ceil(in_pts/64) slabs per 128-row tile as written by
+ * flnerf_pack_xrows (mode BF16X3: hi set then lo set); stash / workspace sizes are those of flnerf_mlp_stash_bytes(mode, ..). */
+size_t flnerf_mlp_packed_bytes_g(int in_pts);
+int flnerf_mlp_pack_weights_g(flnerf_ctx *, int in_pts, const float *params, void *packed, void *stream);
+int flnerf_mlp_forward_g(flnerf_ctx *, int mode, int in_pts, const float *params, const void *packed, int64_t n, int S,
+                         const void *x, const float *dirpe, float *raw_out, void *stash, int training, void *stream);
+int flnerf_mlp_backward_g(flnerf_ctx *, int mode, int in_pts, const float *params, const void *packed, int64_t n, int S,
+                          const void *x, const float *dirpe, const void *stash, const float *draw, float *grads, void *workspace,
+                          size_t workspace_bytes, void *stream);
+/* already-embedded fp32 rows x[n, in_pts + 27] -> pe_tiles (ceil(in_pts/64) slabs per tile; x3 != 0: + the lo set) and, from the
+ * first row of every S-row ray, dirpe[n/S, 32] */
+int flnerf_pack_xrows(flnerf_ctx *, int x3, int in_pts, int in_views, int64_t n, int S, const float *x, void *pe_tiles,
+                      float *dirpe, void *stream);
 
 /* ---- the same MLP with a caller-chosen number of position / view channels, FP32 (CUDA-core) path only: in_pts = 63,
  * in_views = 27 is the nerf-ours network; in_pts = 84 is the nerf++ background network (nerf++-ours/nerf_network.py:70-142,
@@ -139,6 +163,15 @@ int flnerf_sample_pdf(flnerf_ctx *, int64_t B, int n_bins, int Nf, const float *
 int flnerf_mse_leafmax(flnerf_ctx *, int64_t B, const float *rgb, const float *rgb0, const float *target,
                        int64_t denom, const int32_t *leaf_gid, float *loss_out, float *d_rgb, float *d_rgb0,
                        float *leaf_max, void *stream);
+
+/* ---- the MEAN refinement statistic of the nerf++ / plenoxels copies of the quadtree (nerf++-ours/tree.py:613-622): per leaf
+ * leaf_sum[gid] += sum_c |target - pred| (double), leaf_cnt[gid] += 1 for every ray with leaf_gid >= 0; flnerf_leaf_mean turns
+ * the two tables into leaf_stat[gid] = sum / (3 cnt) (-1 for a leaf without rays), which flnerf_qt_refine takes in place of the
+ * per-leaf max. */
+int flnerf_leaf_sum(flnerf_ctx *, int64_t B, const float *pred, const float *target, const int32_t *leaf_gid,
+                    double *leaf_sum, int32_t *leaf_cnt, void *stream);
+int flnerf_leaf_mean(flnerf_ctx *, int64_t n_slots, const double *leaf_sum, const int32_t *leaf_cnt, float *leaf_stat,
+                     void *stream);
 
 /* ---- torch.optim.Adam step (run_nerf.py:99,494) over flat buffers, t = 1-based step number; the bias
  * corrections are computed on the host in double like torch does. */
@@ -192,6 +225,13 @@ int flnerf_gather_batch(flnerf_ctx *, int64_t B, int64_t first, int64_t stride, 
                         const float *images, float *rays_o, float *rays_d, float *target, int32_t *leaf_gid,
                         void *stream);
 
+/* the same with the training images held as uint8 [n,H,W,3] (what the loaders read from disk: load_blender.py:37 divides by
+ * 255 on the host) and decoded through lut256[u] = float32(u / 255.): 192 MB instead of 768 MB at lego size, the same targets */
+int flnerf_gather_batch_u8(flnerf_ctx *, int64_t B, int64_t first, int64_t stride, const int32_t *ray_pix,
+                           const int32_t *ray_gid, int cap, int H, int W, const double *h_K, const float *poses,
+                           const uint8_t *images, const float *lut256, float *rays_o, float *rays_d, float *target,
+                           int32_t *leaf_gid, void *stream);
+
 /* ---- next row: nerf++-ours dual-MLP path -- parity-tested building blocks, no complete path yet.
  * Level-0 sample placement (ddp_train_nerf.py:54-81,352-366): fg_far[B] = unit-sphere exit depth, fg_z[B,N] linear in
  * [1e-4, fg_far], bg_z[B,N] = linspace(0,1) inverse depths; perturb != 0 jitters both inside their mid-point intervals with
@@ -219,6 +259,12 @@ int flnerf_pp_composite_backward(flnerf_ctx *, int64_t B, int Sf, int Sb, const 
 int flnerf_pp_sample_pdf_merge(flnerf_ctx *, int64_t B, int Nc, int Nf, const float *z, const float *weights,
                                const float *u, int det, uint64_t seed, uint64_t offset, float *z_merged,
                                float *z_samples, void *stream);
+
+/* ---- eval metrics (render.py:120-126): sums[0] = sum of the per-pixel, per-channel SSIM map of compute_ssim
+ * (run_nerf_helpers.py:158-228: 11-tap Gaussian, sigma 1.5, zero padding, k1 0.01, k2 0.03), sums[1] = sum (img0 - img1)^2;
+ * images [H,W,3] fp32; mean = sum / (3 H W), PSNR = -10 log10(sums[1] / (3 H W)). */
+int flnerf_ssim_psnr(flnerf_ctx *, int H, int W, const float *img0, const float *img1, double max_val, double *sums,
+                     void *stream);
 
 /* ---- one CUDA graph per training step (run_nerf.py:470-516 is a fixed kernel sequence; only four scalars change from
  * one iteration to the next).  While a device-side step record is attached to the context, flnerf_gather_batch ADDS

@@ -163,3 +163,57 @@ def test_baseline_config1_coarse_only_step(precision):
     before = nc.flat_parameters().clone()
     opt.step()
     assert float((nc.flat_parameters() - before).abs().max()) > 0
+
+
+def _replica_worker(rank, world, port, out):
+    """Every rank builds its networks through run_nerf.create_nerf from its OWN unseeded RNG (as `torchrun run_nerf.py` does);
+    the Trainer must leave all replicas with rank 0's weights and optimiser state, and a rank whose share of a ragged batch is
+    EMPTY must still join the collectives."""
+    sys.path.insert(0, PKG)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.cuda.set_device(0)
+    import tempfile
+    import run_nerf
+    from flnerf_b200.engine import Trainer
+    torch.manual_seed(1000 + rank)                      # different initial weights on every rank
+    args = run_nerf.config_parser().parse_args(["--basedir", tempfile.mkdtemp(), "--expname", "r", "--use_viewdirs", "--N_importance", "16",
+                                                "--N_samples", "16", "--precision", "fp32", "--no_reload"])
+    kw, _, _, _, _, opt = run_nerf.create_nerf(args)
+    nc, nf = kw["network_fn"].module, kw["network_fine"].module
+    before = torch.cat([nc.flat_parameters(), nf.flat_parameters()]).clone()
+    K = np.array([[100.0, 0, 50], [0, 100.0, 50], [0, 0, 1]])
+    tr = Trainer(nc, nf, opt, 100, 100, K, 2.0, 6.0, 16, 16, white_bkgd=True, perturb=0.0, world_size=world, rank=rank)
+    after = torch.cat([nc.flat_parameters(), nf.flat_parameters()])
+    gathered = [torch.empty_like(after) for _ in range(world)]
+    dist.all_gather(gathered, after)
+    same = all(torch.equal(gathered[0], g) for g in gathered)
+    changed = not torch.equal(before, after)
+    # ragged tail: 1 row over 2 ranks -> rank 1 has nothing, yet the step must complete on both
+    o, d, tgt = rays(1)
+    sel = torch.arange(rank, 1, world).cuda()
+    loss = tr.step(o[sel].contiguous(), d[sel].contiguous(), tgt[sel].contiguous(), global_batch=1)
+    total = tr.global_loss(loss)
+    w = torch.cat([nc.flat_parameters(), nf.flat_parameters()])
+    dist.all_gather(gathered, w)
+    out.put((rank, same, changed, all(torch.equal(gathered[0], g) for g in gathered), total.cpu().numpy(), float(loss.sum())))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_replicas_start_identical_and_empty_shares_do_not_hang():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31600 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_replica_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=300) for _ in range(2))
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    (r0, same0, ch0, eq0, tot0, l0), (r1, same1, ch1, eq1, tot1, l1) = res
+    assert same0 and same1 and eq0 and eq1          # identical after construction and after the step
+    assert not ch0 and ch1                          # rank 0's weights are the ones kept
+    np.testing.assert_allclose(tot0, tot1)          # the global loss is the same on every rank ...
+    assert l1 == 0.0 and abs(l0 - float(tot0.sum())) < 1e-7     # ... and equals the only non-empty share

@@ -347,3 +347,64 @@ def test_variance_driven_initial_trees_on_device(golden, ops):
     assert n == 2 * int(exp.sum())
     cnt = np.bincount(mgr.ray_gid.cpu().numpy(), minlength=2 * mgr.cap).reshape(2, mgr.cap)[:, :len(want)]
     assert np.array_equal(cnt, np.stack([exp, exp]))
+
+
+def test_uint8_image_store_gathers_the_same_targets(ops):
+    """Images that are exactly the loaders' float32(u / 255.) (load_blender.py:37) are kept as uint8 on the GPU and decoded per
+    batch: a quarter of the bytes, bit-identical targets; anything else stays fp32."""
+    import tree
+    rs = np.random.RandomState(0)
+    H, W, n = 24, 40, 3
+    u8 = rs.randint(0, 256, (n, H, W, 3)).astype(np.uint8)
+    imgs = (u8 / 255.).astype(np.float32)                           # what imageio + "/ 255." hands the driver
+    poses = torch.eye(4)[None, :3, :4].repeat(n, 1, 1)
+    K = np.array([[50.0, 0, W / 2], [0, 50.0, H / 2], [0, 0, 1]])
+    m8 = tree.QuadTreeManager(H, W, K, torch.from_numpy(imgs), poses, mseThres=0.0, max_depth=2, max_level=4, seed=3)
+    assert m8._images_dev.dtype == torch.uint8 and torch.equal(m8._images_dev.cpu(), torch.from_numpy(u8))
+    blended = imgs * 0.7 + 0.3 * 0.123                             # alpha-blended: not on the u/255 grid
+    m32 = tree.QuadTreeManager(H, W, K, torch.from_numpy(blended), poses, mseThres=0.0, max_depth=2, max_level=4, seed=3)
+    assert m32._images_dev.dtype == torch.float32
+    N = m8.emit_epoch()
+    o, d, t, gid = m8.batch(0, N, 1)
+    pix, g = m8.ray_pix.cpu().numpy(), m8.ray_gid.cpu().numpy()
+    want = imgs[g // m8.cap, pix // W, pix % W]
+    assert np.array_equal(t.cpu().numpy(), want)                    # bit-identical to indexing the float images
+    assert torch.equal(m8.sharp_imgs, ops.sharp_map(torch.from_numpy(imgs).cuda()))
+
+
+def _decode_tiles(tiles, n):
+    raw = tiles.cpu().numpy().view(np.uint16).reshape(-1, 128, 64)
+    r, t = np.arange(n) % 128, np.arange(n) // 128
+    got = np.zeros((n, 64), np.float32)
+    for c in range(64):
+        pos = (((c >> 3) ^ (r & 7)) << 3) + (c & 7)
+        got[:, c] = (raw[t, r, pos].astype(np.uint32) << 16).view(np.float32)
+    return got
+
+
+def test_encode_tc_double_angle_recurrence_is_bounded_at_large_arguments(ops):
+    """PE arguments reach |x * 512| ~ 2000 for lego (|x| <= 4).  The bf16 tile kernel evaluates sincosf exactly at
+    octaves 0 and 5 and doubles the angle in between; its result, rounded to bf16, must be the correctly rounded value or its
+    bf16 NEIGHBOUR (the recurrence error is ~2e-6, the bf16 step 4e-3: only values sitting on a rounding boundary can move), at
+    most 1 % of the entries.  The split-precision kernel evaluates every octave exactly: hi + lo reproduces fp32 PE to 2^-17."""
+    from flnerf_b200 import ops as OPS
+    g = torch.Generator().manual_seed(5)
+    B, S = 64, 32
+    o = (torch.rand(B, 3, generator=g) * 2 - 1) * 3.9                    # points out to |x| ~ 3.9 -> 512 x ~ 2000
+    rays = torch.cat([o, torch.zeros(B, 3), torch.zeros(B, 1), torch.ones(B, 1), torch.nn.functional.normalize(torch.randn(B, 3, generator=g), dim=-1)], -1)
+    z = torch.zeros(B, S)
+    ref = O.posenc(o[:, None, :].expand(B, S, 3).reshape(-1, 3), 10)                                   # fp32, exact sin/cos
+    assert float(ref[:, :3].abs().max() * 512) > 1900
+    n = B * S
+    tiles, _ = ops.encode_tc(rays.cuda(), z.cuda())
+    got = _decode_tiles(tiles, n)[:, :63]
+    want = ref.to(torch.bfloat16).float().numpy()
+    ulp = np.maximum(np.abs(want), 2.0 ** -126) * 2.0 ** -7                # one bf16 step at the value's magnitude (upper bound)
+    diff = np.abs(got - want)
+    assert np.all(diff <= ulp + 1e-30), float((diff / ulp).max())
+    assert float((diff > 0).mean()) < 0.01, float((diff > 0).mean())
+    t3, _ = ops.encode_tc(rays.cuda(), z.cuda(), OPS.MODE_BF16X3)
+    nt = t3.numel() // 2
+    hi, lo = _decode_tiles(t3[:nt], n)[:, :63], _decode_tiles(t3[nt:], n)[:, :63]
+    assert np.array_equal(hi, want)                                        # every octave exact -> hi IS the correctly rounded bf16
+    np.testing.assert_allclose(hi + lo, ref.numpy(), atol=2.0 ** -17, rtol=2.0 ** -16)

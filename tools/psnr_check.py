@@ -1,7 +1,26 @@
-"""PSNR at equal iterations: the bf16 tensor-core path vs the fp32 parity path (== the reference arithmetic, see
-tests/test_gpu_mlp.py) on the synthetic blob scene; same seed => same init, same ray batches, same jitter.
-Reports PSNR on training views (fit) and held-out views.  Prints one JSON line."""
-import json, os, sys
+"""PSNR at equal iterations (BASELINE.json north_star: "rendered PSNR within 0.1 dB of reference at equal iterations").
+
+Arms, all trained on the same synthetic blob scene (flnerf_b200/synthetic.py) for the same number of iterations with the
+same batch size, and paired per seed (same initial weights, same ray batches):
+  bf16      the single-pass tcgen05 throughput mode                       (engine.Trainer, one CUDA graph per step)
+  bf16x3    the split-precision tcgen05 mode = the reference's fp32 arithmetic to ~1e-6 (tests/test_gpu_x3.py)
+  x3p       bf16x3 again with every initial weight perturbed by 1e-6 relative: |x3p - bf16x3| is the NOISE FLOOR of
+            the comparison (training is chaotic: a 1e-6 perturbation moves the final PSNR by tenths of a dB)
+  reference the UNMODIFIED reference code (baseline/_ref/nerf-ours: create_nerf + render + img2mse + Adam + lr decay,
+            fp32, TF32 off) fed the very same ray batches and initial weights (PC_REF_SEEDS of the seeds; it is ~30x slower)
+Held-out and training views are rendered with the SAME renderer for every arm (ours, bf16x3, perturb=0), the reference
+arm's trained weights being loaded through the shared state_dict format.  Prints one JSON document: per-seed PSNRs, paired
+deltas, their mean, standard deviation and 95 % confidence interval (Student t).
+
+  PC_RES=200 PC_VIEWS=40 PC_ITERS=5000 PC_NRAND=1024 PC_SEEDS=0,1,2,3,4,5,6,7 PC_REF_SEEDS=2 python tools/psnr_check.py
+"""
+import json
+import math
+import os
+import sys
+import tempfile
+import time
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "fast-learning-nerf_b200"))
 import numpy as np
@@ -10,16 +29,40 @@ import model, tree, render as R, run_nerf, run_nerf_helpers as H
 from flnerf_b200 import synthetic
 from flnerf_b200.engine import FusedAdam, Trainer
 
-RES, VIEWS = int(os.environ.get("PC_RES", 100)), int(os.environ.get("PC_VIEWS", 40))
-ITERS, NRAND = int(os.environ.get("PC_ITERS", 2000)), int(os.environ.get("PC_NRAND", 1024))
-SEEDS = [int(s) for s in os.environ.get("PC_SEEDS", "0,1,2").split(",")]
+RES, VIEWS = int(os.environ.get("PC_RES", 200)), int(os.environ.get("PC_VIEWS", 40))
+ITERS, NRAND = int(os.environ.get("PC_ITERS", 5000)), int(os.environ.get("PC_NRAND", 1024))
+SEEDS = [int(s) for s in os.environ.get("PC_SEEDS", "0,1,2,3,4,5,6,7").split(",")]
+REF_SEEDS = SEEDS[:int(os.environ.get("PC_REF_SEEDS", "0"))]
+ARMS = os.environ.get("PC_ARMS", "bf16x3,bf16,x3p").split(",")
+LRATE = 5e-4
+# the reference decays the learning rate by 10x over lrate_decay*1000 = 500 000 iterations of a 200 000+ iteration run
+# (run_nerf.py:498-502); the schedule is compressed to this run's length (10x over PC_DECAY_ITERS, default = PC_ITERS) for
+# every arm alike -- at a constant 5e-4 the PSNR of a single iterate jitters by +-1 dB and hides the effect measured here
+DECAY_ITERS = int(os.environ.get("PC_DECAY_ITERS", ITERS))
+PERTURB = float(os.environ.get("PC_PERTURB", 1.0))
+N_EVAL = int(os.environ.get("PC_EVALS", 4))        # PSNR = mean over the last N_EVAL checkpoints (every 5 % of the run)
+EVAL_AT = sorted({ITERS - k * max(1, ITERS // 20) for k in range(N_EVAL)})
+N_TEST = int(os.environ.get("PC_TEST_VIEWS", 8))
 dev = torch.device("cuda")
 K = synthetic.intrinsics(RES, RES, 0.5 * RES / np.tan(0.5 * 0.6911112070083618))
 poses = synthetic.lego_like_poses(VIEWS)
-test_poses = synthetic.lego_like_poses(4, phi=-25.0)
+test_poses = synthetic.lego_like_poses(N_TEST, phi=-25.0)
 imgs = synthetic.render_scene(RES, RES, K, poses, n_samples=128)
 test_imgs = synthetic.render_scene(RES, RES, K, test_poses, n_samples=128)
 q = run_nerf.NetworkQuery(H.get_embedder(10)[0], H.get_embedder(4)[0], 65536)
+
+
+def make_nets(seed, precision, perturb=False):
+    torch.manual_seed(seed)
+    nets = [model.NeRF(8, 256, 63, 27, 5, [4], True, precision=precision).to(dev) for _ in range(2)]
+    if perturb:
+        with torch.no_grad():
+            g = torch.Generator(device=dev).manual_seed(1234 + seed)
+            for net in nets:
+                for prm in net.parameters():
+                    prm.mul_(1 + 1e-6 * torch.randn(prm.shape, device=dev, generator=g))
+                net.weights_version += 1
+    return nets
 
 
 def psnr_on(nc, nf, ps, gts):
@@ -33,44 +76,134 @@ def psnr_on(nc, nf, ps, gts):
     return float(np.mean(out))
 
 
-res = {}
+_EVAL_NETS = []
+
+
+def evaluate(state_c, state_f):
+    """PSNR of a (coarse, fine) pair, rendered by the bf16x3 renderer whatever arm trained it."""
+    if not _EVAL_NETS:
+        _EVAL_NETS.extend(make_nets(0, "bf16x3"))
+    nc, nf = _EVAL_NETS
+    nc.load_state_dict(state_c); nf.load_state_dict(state_f)
+    nc.weights_version += 1; nf.weights_version += 1
+    return {"train": psnr_on(nc, nf, poses[::max(1, VIEWS // 4)], imgs[::max(1, VIEWS // 4)]), "test": psnr_on(nc, nf, test_poses, test_imgs)}
+
+
+def mean_eval(evals):
+    return {k: float(np.mean([e[k] for e in evals])) for k in ("train", "test")}
+
+
+def lr_of(it):
+    return LRATE * (0.1 ** (it / float(DECAY_ITERS)))
+
+
+def batches(seed):
+    """The seed's ray batches: the quadtree manager's emission (uniform tree, refinement every epoch), shared by all arms."""
+    mgr = tree.QuadTreeManager(RES, RES, K, imgs, torch.as_tensor(poses[:, :3, :4]), mseThres=0.0, max_depth=2, max_level=5, seed=seed)
+    return mgr
+
+
+def train_ours(seed, arm):
+    nc, nf = make_nets(seed, "bf16" if arm == "bf16" else "bf16x3", perturb=(arm == "x3p"))
+    opt = FusedAdam(list(nc.parameters()) + list(nf.parameters()), [nc, nf], lr=LRATE)
+    tr = Trainer(nc, nf, opt, RES, RES, K, 2.0, 6.0, 64, 128, white_bkgd=True, perturb=PERTURB, seed=seed, graph=True)
+    mgr = batches(seed)
+    it, evals = 0, []
+    while it < ITERS:
+        n = mgr.emit_epoch()
+        for first in range(0, n - NRAND, NRAND):
+            tr.step_from_tree(mgr, first, NRAND)
+            for g in opt.param_groups:
+                g["lr"] = lr_of(it)                   # applied from the next step on, like run_nerf.py:498-502
+            it += 1
+            if it in EVAL_AT:
+                evals.append(evaluate(nc.state_dict(), nf.state_dict()))
+            if it >= ITERS:
+                break
+        # no refinement: every arm must see the same batches (the refined tree depends on the arm's own predictions)
+    return mean_eval(evals)
+
+
+def train_reference(seed):
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import ref_shim
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    ns, rn = ref_shim.load_run_nerf()
+    rn.device = dev
+    tmp = tempfile.mkdtemp(prefix="flnerf_psnr_")
+    os.makedirs(os.path.join(tmp, "lego_ours"))
+    args = rn.config_parser().parse_args(["--config", os.path.join(ref_shim.REF_NERF, "configs", "lego.txt"), "--basedir", tmp,
+                                          "--N_rand", str(NRAND)])
+    kw_train, _, _, _, _, optimizer = rn.create_nerf(args)
+    kw_train["perturb"] = PERTURB
+    ours_c, ours_f = make_nets(seed, "bf16x3")              # the seed's initial weights, moved into the reference modules
+    kw_train["network_fn"].module.load_state_dict(ours_c.state_dict())
+    kw_train["network_fine"].module.load_state_dict(ours_f.state_dict())
+    mgr = batches(seed)
+    it, evals = 0, []
+    while it < ITERS:
+        n = mgr.emit_epoch()
+        for first in range(0, n - NRAND, NRAND):
+            o, d, tgt, _ = mgr.batch(first, NRAND, 1)
+            rgb, disp, acc, extras = ns.render.render(RES, RES, K, chunk=args.chunk, rays=torch.stack([o, d], 0), retraw=True,
+                                                      near=2., far=6., **kw_train)
+            optimizer.zero_grad()
+            loss = ns.helpers.img2mse(rgb, tgt) + ns.helpers.img2mse(extras["rgb0"], tgt)
+            loss.backward()
+            optimizer.step()
+            for g in optimizer.param_groups:
+                g["lr"] = lr_of(it)
+            it += 1
+            if it in EVAL_AT:
+                evals.append(evaluate(kw_train["network_fn"].module.state_dict(), kw_train["network_fine"].module.state_dict()))
+            if it >= ITERS:
+                break
+    return mean_eval(evals)
+
+
+def stats(d):
+    d = np.asarray(d, dtype=np.float64)
+    n = len(d)
+    if n < 2:
+        return {"n": n, "mean": float(d.mean()) if n else None}
+    tq = {2: 12.706, 3: 4.303, 4: 3.182, 5: 2.776, 6: 2.571, 7: 2.447, 8: 2.365, 9: 2.306, 10: 2.262, 12: 2.201, 16: 2.131,
+          20: 2.093, 24: 2.069, 32: 2.040}
+    t = tq.get(n) or tq[min(tq, key=lambda k: abs(k - n))]
+    sd = float(d.std(ddof=1))
+    half = t * sd / math.sqrt(n)
+    return {"n": n, "mean": float(d.mean()), "sd": sd, "ci95": [float(d.mean() - half), float(d.mean() + half)],
+            "mean_abs": float(np.abs(d).mean())}
+
+
+res = {"config": dict(res=RES, views=VIEWS, test_views=N_TEST, iters=ITERS, n_rand=NRAND, seeds=SEEDS, ref_seeds=REF_SEEDS,
+                      lrate=LRATE, lr_decay_10x_over_iters=DECAY_ITERS, perturb=PERTURB, psnr_mean_over_checkpoints=EVAL_AT),
+       "psnr": {}, "seconds": {}}
+import contextlib
 for seed in SEEDS:
-    # "fp32p" = the fp32 run again with every initial weight perturbed by 1e-6 relative: its distance from "fp32" is the
-    # noise floor of the comparison (training trajectories are chaotic), the yardstick for the bf16 - fp32 difference
-    for prec in ("fp32", "bf16") + (("fp32p",) if os.environ.get("PC_NOISE_FLOOR", "1") == "1" else ()):
-        torch.manual_seed(seed)
-        nc = model.NeRF(8, 256, 63, 27, 5, [4], True, precision=prec[:4]).to(dev)
-        nf = model.NeRF(8, 256, 63, 27, 5, [4], True, precision=prec[:4]).to(dev)
-        if prec == "fp32p":
-            with torch.no_grad():
-                g = torch.Generator(device=dev).manual_seed(1234 + seed)
-                for net in (nc, nf):
-                    for prm in net.parameters():
-                        prm.mul_(1 + 1e-6 * torch.randn(prm.shape, device=dev, generator=g))
-                    if hasattr(net, "weights_version"):
-                        net.weights_version += 1
-        opt = FusedAdam(list(nc.parameters()) + list(nf.parameters()), [nc, nf], lr=5e-4)
-        tr = Trainer(nc, nf, opt, RES, RES, K, 2.0, 6.0, 64, 128, white_bkgd=True, perturb=1.0, seed=seed)
-        mgr = tree.QuadTreeManager(RES, RES, K, imgs, torch.as_tensor(poses[:, :3, :4]), mseThres=0.0, max_depth=2, max_level=5, seed=seed)
-        it = 0
-        while it < ITERS:
-            n = mgr.emit_epoch()
-            for first in range(0, n - NRAND, NRAND):
-                tr.step_from_tree(mgr, first, NRAND)
-                it += 1
-                if it >= ITERS:
-                    break
-            mgr.refine(0.001)
-        res["%s.seed%d" % (prec, seed)] = {"train": psnr_on(nc, nf, poses[::10], imgs[::10]), "test": psnr_on(nc, nf, test_poses, test_imgs)}
-        print("partial", prec, seed, res["%s.seed%d" % (prec, seed)], file=sys.stderr, flush=True)
-for k in ("train", "test"):
-    d = [res["bf16.seed%d" % s][k] - res["fp32.seed%d" % s][k] for s in SEEDS]
-    res["delta_%s_db" % k] = d
-    res["mean_delta_%s_db" % k] = float(np.mean(d))
-    if "fp32p.seed%d" % SEEDS[0] in res:
-        f = [res["fp32p.seed%d" % s][k] - res["fp32.seed%d" % s][k] for s in SEEDS]
-        res["noise_floor_%s_db" % k] = f
-        res["mean_abs_noise_floor_%s_db" % k] = float(np.mean(np.abs(f)))
-        res["mean_abs_delta_%s_db" % k] = float(np.mean(np.abs(d)))
-res["config"] = dict(res=RES, views=VIEWS, iters=ITERS, n_rand=NRAND)
+    for arm in ARMS + (["reference"] if seed in REF_SEEDS else []):
+        t0 = time.time()
+        with contextlib.redirect_stdout(sys.stderr):          # the reference prints ("Found ckpts", ...) go to stderr
+            ps = train_reference(seed) if arm == "reference" else train_ours(seed, arm)
+        torch.cuda.synchronize()
+        res["seconds"].setdefault(arm, []).append(time.time() - t0)
+        res["psnr"]["%s.seed%d" % (arm, seed)] = ps
+        print("partial", arm, seed, res["psnr"]["%s.seed%d" % (arm, seed)], "%.1fs" % (time.time() - t0), file=sys.stderr, flush=True)
+
+
+def delta(a, b, seeds, k):
+    return [res["psnr"]["%s.seed%d" % (a, s)][k] - res["psnr"]["%s.seed%d" % (b, s)][k] for s in seeds]
+
+
+res["delta_db"] = {}
+for k in ("test", "train"):
+    out = {}
+    if "bf16" in ARMS and "bf16x3" in ARMS:
+        out["bf16_minus_bf16x3"] = stats(delta("bf16", "bf16x3", SEEDS, k))
+    if "x3p" in ARMS and "bf16x3" in ARMS:
+        out["noise_floor_x3p_minus_bf16x3"] = stats(delta("x3p", "bf16x3", SEEDS, k))
+    if REF_SEEDS:
+        for arm in ARMS:
+            out["%s_minus_reference" % arm] = stats(delta(arm, "reference", REF_SEEDS, k))
+    res["delta_db"][k] = out
 print(json.dumps(res))
