@@ -272,13 +272,14 @@ def mlp_kernel_table(torch, ops, lib, net, mode, r11, dev, peaks):
         lib.check(lib.load().flnerf_mlp_forward(ops._ctx(raw), mode, ops._ptr(flat), ops._ptr(packed), n, S, ops._ptr(tiles),
                                                 ops._ptr(dirpe), ops._ptr(raw), ops._ptr(stash_l), 1, ops._stream()), "fwd")
     sfx = "_x3" if x3 else "_tc"
-    mult = 2.0 if x3 else 1.0            # the split-precision stash holds a hi and a lo image
+    passes = int(os.environ.get("FLNERF_X3_WGRAD_PASSES", "1")) if x3 else 1     # weight-gradient terms of the split mode
+    mult = 2.0 if passes > 1 else 1.0    # with more than one term the stash holds a hi and a lo image
     cases = {"mlp_fwd" + sfx: (fwd, FLOP_FWD_PER_SAMPLE, STASH_FWD_PER_SAMPLE * mult),
              "mlp_dgrad" + sfx: (lambda: ops.mlp_backward(mode, flat, packed, tiles, dirpe, stash, draw, gbuf, n, S, 1, ws),
                                  FLOP_DGRAD_PER_SAMPLE, STASH_DGRAD_PER_SAMPLE * mult),
-             "mlp_wgrad_tc" + (" (3 passes)" if x3 else ""): (
+             "mlp_wgrad_tc" + (" (%d passes)" % passes if passes > 1 else ""): (
                  lambda: ops.mlp_backward(mode, flat, packed, tiles, dirpe, stash, draw, gbuf, n, S, 2, ws),
-                 FLOP_WGRAD_PER_SAMPLE, STASH_WGRAD_PER_SAMPLE * (3.0 if x3 else 1.0))}
+                 FLOP_WGRAD_PER_SAMPLE, STASH_WGRAD_PER_SAMPLE * passes)}
     out = {}
     for name, (fn, flop, stash_b) in cases.items():
         dt = time_events(torch, fn, 5) * 1e-3

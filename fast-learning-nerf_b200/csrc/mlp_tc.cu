@@ -426,6 +426,7 @@ struct FwdParams {
   int dbg;   // profiling switches (bit 0: skip mask generation, bit 1: skip the activation bulk stores)
   long long *prof;  // per-CTA cycle accounting of the roles (PROF_SLOTS per CTA) when FLNERF_TC_PROF is set, else null
   int kind;         // network kind (index into c_desc)
+  int stash_lo;     // split-precision kernels: 1 = the stash keeps the lo images too ([hi 64 KB][lo 64 KB] per slot), 0 = hi only
 };
 constexpr int PROF_SLOTS = 24;
 
@@ -687,6 +688,7 @@ struct DgradParams {
   int n_pairs;
   long long *prof;
   int kind;
+  int stash_lo;      // as FwdParams::stash_lo, for the gradient slots
 };
 
 template <bool kProf>
@@ -1430,7 +1432,21 @@ static size_t tc_vb_bytes(int64_t n, int S) {
   int64_t B = (n + S - 1) / S;
   return (size_t)((B * 128 * 4 + 1023) / 1024) * 1024;
 }
-static size_t tc_tile_act_bytes(bool x3) { return x3 ? tc::TILE_ACT_BYTES_X3 : tc::TILE_ACT_BYTES; }
+// How many of the three terms dYhi^T Xhi + dYhi^T Xlo + dYlo^T Xhi the split-precision weight gradient carries.  Measured at
+// 2048 rays x (64+128) against the oracle (tools/x3_wgrad_passes.py, profiles/r02g_wgrad_passes.log): gradient rel-L2 3.3e-5 /
+// 3.2e-5 / 3.0e-5 for 1 / 2 / 3 terms -- a sum over 10^5..10^6 rows averages the bf16 rounding of its operands away -- so the
+// default is ONE term, and then the stash keeps only the hi images (half the bytes).  $FLNERF_X3_WGRAD_PASSES=3 restores all.
+static int x3_wgrad_passes() {
+  static int passes = -1;
+  if (passes < 0) {
+    const char *e = getenv("FLNERF_X3_WGRAD_PASSES");
+    passes = e ? atoi(e) : 1;
+    if (passes < 1 || passes > 3) passes = 1;
+  }
+  return passes;
+}
+static bool x3_stash_lo(bool x3) { return x3 && x3_wgrad_passes() > 1; }
+static size_t tc_tile_act_bytes(bool x3) { return x3_stash_lo(x3) ? tc::TILE_ACT_BYTES_X3 : tc::TILE_ACT_BYTES; }
 size_t mlp_tc_stash_bytes(int64_t n, int S, int training, bool x3) {
   size_t tiles = (size_t)(flnerf_padded_rows(n) / 128);
   return tc_vb_bytes(n, S) + (training ? tiles * (tc_tile_act_bytes(x3) + tc::TILE_MASK_BYTES) : 0);
@@ -1455,7 +1471,7 @@ int mlp_tc_forward(flnerf_ctx *ctx, bool x3, int kind, const float *params, cons
   FL_LAUNCH(tc::viewbias_kernel, (unsigned)ceil_div64(B, 16), 128, 0, st, B, params, dirpe, vb, nd.w_views, nd.b_views);
   tc::FwdParams p{};
   p.P = params; p.packed = (const uint8_t *)packed; p.pe_tiles = (const uint8_t *)pe_tiles; p.viewbias = vb;
-  p.raw = raw; p.n = n; p.S = S; p.kind = kind;
+  p.raw = raw; p.n = n; p.S = S; p.kind = kind; p.stash_lo = x3_stash_lo(x3) ? 1 : 0;
   int64_t n_pad = flnerf_padded_rows(n);
   p.n_pairs = (int)(n_pad / 256);
   if (training) {
@@ -1493,7 +1509,7 @@ int mlp_tc_backward(flnerf_ctx *ctx, bool x3, int kind, const float *params, con
   const uint32_t *stash_mask = (const uint32_t *)(stash_act + (size_t)(n_pad / 128) * tc_tile_act_bytes(x3));
   tc::DgradParams d{};
   d.P = params; d.packed_dg = (const uint8_t *)packed + nd.fwd_bytes; d.draw = draw; d.stash_mask = stash_mask;
-  d.dy = (uint8_t *)ws; d.n = n; d.n_pairs = (int)(n_pad / 256); d.kind = kind;
+  d.dy = (uint8_t *)ws; d.n = n; d.n_pairs = (int)(n_pad / 256); d.kind = kind; d.stash_lo = x3_stash_lo(x3) ? 1 : 0;
   if ((stages & 1) && x3) {
     const int grid = tc::pair_grid(d.n_pairs * 2, ctx->sm_count);
     FL_LAUNCH(tc::mlp_dgrad_x3, grid, tc::kThreads, tc::LayD::SMEM, st, d);
@@ -1510,18 +1526,17 @@ int mlp_tc_backward(flnerf_ctx *ctx, bool x3, int kind, const float *params, con
   tc::WgradParams w{};
   w.dy = (const uint8_t *)ws; w.stash_act = stash_act; w.pe_tiles = (const uint8_t *)pe_tiles; w.draw = draw;
   w.G = grads; w.n = n; w.n_tiles = (int)(n_pad / 128); w.dirpe = dirpe; w.S = S; w.kind = kind;
-  w.tile_stride = tc_tile_act_bytes(x3); w.slot_stride = x3 ? tc::SLOT_BYTES_X3 : 65536;
+  w.tile_stride = tc_tile_act_bytes(x3); w.slot_stride = x3_stash_lo(x3) ? tc::SLOT_BYTES_X3 : 65536;
   w.helper_flags = 7;
   static long long *dbg = nullptr;
   const bool want_dbg = getenv("FLNERF_WG_DEBUG") != nullptr;
   if (want_dbg && !dbg) cudaMalloc(&dbg, sizeof(long long) * 4 * 1024);
   w.dbg = want_dbg ? dbg : nullptr;
   if ((stages & 2) && x3) {
-    // dW = (dYhi + dYlo)^T (Xhi + Xlo) ~= dYhi^T Xhi + dYhi^T Xlo + dYlo^T Xhi: three passes of the same kernel over the
-    // hi / lo images, each with the CUDA-core reductions that belong to its operands
+    // dW = (dYhi + dYlo)^T (Xhi + Xlo) ~= dYhi^T Xhi [+ dYhi^T Xlo [+ dYlo^T Xhi]]: up to three passes of the same kernel over
+    // the hi / lo images, each with the CUDA-core reductions that belong to its operands (see x3_wgrad_passes)
     const size_t pe_lo = (size_t)w.n_tiles * nd.pe_slabs * tc::PE_BYTES;
-    static int passes = -1;     // experiment knob: how many of the three terms the weight gradient carries (default all)
-    if (passes < 0) { const char *e = getenv("FLNERF_X3_WGRAD_PASSES"); passes = e ? atoi(e) : 3; }
+    const int passes = x3_wgrad_passes();
     FL_LAUNCH(tc::mlp_wgrad_tc, tc::g_wgrad_grid, tc::kWgThreads, tc::SMEM_WG, st, w);
     if (passes >= 2) {
       w.b_part = 65536; w.pe_part = pe_lo; w.helper_flags = 2;

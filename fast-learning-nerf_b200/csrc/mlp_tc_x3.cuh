@@ -289,7 +289,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) mlp_fwd
     float *s_alpha = reinterpret_cast<float *>(smem + LayF::OFF_ALPHA);
     uint8_t *act_hi = smem + OFF_ACT;
     const uint32_t tmem_rc = tmem_base + ((quarter * 32) << 16) + cq * 64;
-    const size_t tile_bytes = kX3 ? TILE_ACT_BYTES_X3 : TILE_ACT_BYTES, slot_bytes = kX3 ? SLOT_BYTES_X3 : 65536;
+    const bool stash_lo = kX3 && p.stash_lo;
+    const size_t tile_bytes = stash_lo ? TILE_ACT_BYTES_X3 : TILE_ACT_BYTES, slot_bytes = stash_lo ? SLOT_BYTES_X3 : 65536;
     uint32_t n_layer = 0;
     bool store_pending = false;
     for (int it = 0; it < iters; ++it) {
@@ -352,7 +353,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) mlp_fwd
           mbar_arrive_cluster(mapa_cluster(LayF::act_ready(bar, 0), 0));  // the leader's barrier
           if (stash_act && has_cols) {
             uint8_t *dst = stash_act + (size_t)tile * tile_bytes + (size_t)L * slot_bytes;
-            if (kX3) warp_store_slab_x3(dst, act_hi, quarter, cq);
+            if (stash_lo) warp_store_slab_x3(dst, act_hi, quarter, cq);
             else warp_store_slabs(dst, act_hi, quarter, cq, 1);
             store_pending = true;
           }
@@ -539,7 +540,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) mlp_dgr
           if (D < 8) mbar_arrive_cluster(mapa_cluster(LayD::act_ready(bar, 0), 0));  // the last stage feeds no further MMA
           if (live && has_cols) {
             const int slot = (D < 0) ? 9 : 8 - D;  // D=0 -> dF (8), D=1 -> dH7 (7) ... D=8 -> dH0 (0)
-            warp_store_slab_x3(p.dy + (size_t)tile * TILE_ACT_BYTES_X3 + (size_t)slot * SLOT_BYTES_X3, act_hi, quarter, cq);
+            if (p.stash_lo) warp_store_slab_x3(p.dy + (size_t)tile * TILE_ACT_BYTES_X3 + (size_t)slot * SLOT_BYTES_X3, act_hi, quarter, cq);
+            else warp_store_slabs(p.dy + (size_t)tile * TILE_ACT_BYTES + (size_t)slot * 65536, act_hi, quarter, cq, 1);
             store_pending = true;
           }
         }

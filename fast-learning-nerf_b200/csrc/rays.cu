@@ -349,6 +349,52 @@ __global__ void gather_batch_kernel(int64_t B, int64_t first, int64_t stride, co
   if (leaf_gid) leaf_gid[k] = gid;
 }
 
+// gen_rays_v3's gather (tree.py:270-285): colour, direction and origin images of image `img` sampled with
+// F.grid_sample(bilinear, zeros padding, align_corners=False) at the grid ((x / (H/2)) - 1, (y / (W/2)) - 1).  grid_sample reads
+// a grid's FIRST component as the WIDTH coordinate, so the reference's (row, col) pairs land TRANSPOSED: ix = (gx + 1) W / 2 - 0.5
+// with gx made from the ROW x, iy from the column y (a quirk of the reference, reproduced: rays and colours stay consistent).
+// The direction / origin images are get_rays of the image's pose, regenerated per corner.
+__global__ void gather_sub_kernel(int64_t B, const float *__restrict__ ray_xy, const int32_t *__restrict__ ray_gid, int cap, int H,
+                                  int W, Cam cam, const float *__restrict__ poses, const void *__restrict__ images_any,
+                                  const float *__restrict__ lut, float *__restrict__ ro, float *__restrict__ rd,
+                                  float *__restrict__ target) {
+  int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= B) return;
+  const int img = ray_gid[k] / cap;
+  const float gx = __fsub_rn(__fdiv_rn(ray_xy[k * 2], (float)H / 2.0f), 1.0f);
+  const float gy = __fsub_rn(__fdiv_rn(ray_xy[k * 2 + 1], (float)W / 2.0f), 1.0f);
+  const float ix = __fsub_rn(__fmul_rn(__fadd_rn(gx, 1.0f), (float)W / 2.0f), 0.5f);
+  const float iy = __fsub_rn(__fmul_rn(__fadd_rn(gy, 1.0f), (float)H / 2.0f), 0.5f);
+  const float fx = floorf(ix), fy = floorf(iy);
+  const int x0 = (int)fx, y0 = (int)fy;
+  const float wx1 = __fsub_rn(ix, fx), wx0 = __fsub_rn(__fadd_rn(fx, 1.0f), ix);
+  const float wy1 = __fsub_rn(iy, fy), wy0 = __fsub_rn(__fadd_rn(fy, 1.0f), iy);
+  const float w4[4] = {__fmul_rn(wx0, wy0), __fmul_rn(wx1, wy0), __fmul_rn(wx0, wy1), __fmul_rn(wx1, wy1)};   // nw, ne, sw, se
+  float c[3] = {0.f, 0.f, 0.f}, o[3] = {0.f, 0.f, 0.f}, d[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int col = x0 + (q & 1), row = y0 + (q >> 1);
+    if (col < 0 || col >= W || row < 0 || row >= H) continue;          // zeros padding
+    float po[3], pd[3];
+    pixel_ray(cam, poses + (int64_t)img * 12, row, col, po, pd);
+    const int64_t pidx = (((int64_t)img * H + row) * W + col) * 3;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      const float v = lut ? lut[reinterpret_cast<const uint8_t *>(images_any)[pidx + a]]
+                          : reinterpret_cast<const float *>(images_any)[pidx + a];
+      c[a] = __fadd_rn(c[a], __fmul_rn(v, w4[q]));
+      o[a] = __fadd_rn(o[a], __fmul_rn(po[a], w4[q]));
+      d[a] = __fadd_rn(d[a], __fmul_rn(pd[a], w4[q]));
+    }
+  }
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    ro[k * 3 + a] = o[a];
+    rd[k * 3 + a] = d[a];
+    target[k * 3 + a] = c[a];
+  }
+}
+
 Cam make_cam(const double *K) {
   Cam c;
   c.fx = (float)K[0]; c.cx = (float)K[2]; c.fy = (float)K[4]; c.cy = (float)K[5];
@@ -490,6 +536,17 @@ int flnerf_gather_batch(flnerf_ctx *ctx, int64_t B, int64_t first, int64_t strid
   if (B == 0) return 0;
   FL_LAUNCH(gather_batch_kernel, (unsigned)ceil_div64(B, 256), 256, 0, stream, B, first, stride, ray_pix, ray_gid, cap,
             H, W, make_cam(h_K), poses, (const void *)images, (const float *)nullptr, rays_o, rays_d, target, leaf_gid, ctx->step_rec);
+  return 0;
+}
+
+int flnerf_gather_sub(flnerf_ctx *ctx, int64_t B, const float *ray_xy, const int32_t *ray_gid, int cap, int H, int W,
+                      const double *h_K, const float *poses, const void *images, const float *lut256_or_null, float *rays_o,
+                      float *rays_d, float *target, void *stream) {
+  FL_REQUIRE(ctx && ray_xy && ray_gid && h_K && poses && images && rays_o && rays_d && target && cap > 0,
+             "flnerf_gather_sub: bad arguments");
+  if (B == 0) return 0;
+  FL_LAUNCH(gather_sub_kernel, (unsigned)ceil_div64(B, 256), 256, 0, stream, B, ray_xy, ray_gid, cap, H, W, make_cam(h_K), poses,
+            images, lut256_or_null, rays_o, rays_d, target);
   return 0;
 }
 

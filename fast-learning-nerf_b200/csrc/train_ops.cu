@@ -280,6 +280,29 @@ __global__ void qt_emit_kernel(int n_images, int cap, int W, const double *__res
   ray_gid[pos] = (int32_t)lo;
 }
 
+// gen_rays_v3 (tree.py:231-307): SUB-PIXEL positions on a 1/1000 grid -- x = randint[int(1000 x0), int(1000 (x1 - 0.01))) / 1000,
+// y likewise (:265-268) -- written as float pairs at the shuffled position
+__global__ void qt_emit_sub_kernel(int n_images, int cap, const double *__restrict__ boxes, const int64_t *__restrict__ ray_offset,
+                                   int64_t N, int half, uint64_t seed, float *__restrict__ ray_xy, int32_t *__restrict__ ray_gid) {
+  int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= N) return;
+  int64_t lo = 0, hi = (int64_t)n_images * cap;
+  while (hi - lo > 1) {
+    int64_t mid = (lo + hi) >> 1;
+    if (ray_offset[mid] <= j) lo = mid; else hi = mid;
+  }
+  const double *b = boxes + lo * 4;
+  const int x_lo = (int)(b[0] * 1000), x_hi = (int)((b[2] - 0.01) * 1000);
+  const int y_lo = (int)(b[1] * 1000), y_hi = (int)((b[3] - 0.01) * 1000);
+  uint32_t r[4];
+  philox4x32(seed, (uint64_t)j, 0x9E18ull, r);
+  const int kx = x_lo + (int)(r[0] % (uint32_t)max(1, x_hi - x_lo));
+  const int ky = y_lo + (int)(r[1] % (uint32_t)max(1, y_hi - y_lo));
+  int64_t pos = (int64_t)feistel_perm((uint64_t)j, (uint64_t)N, half, seed ^ 0xA5A5A5A55A5A5A5Aull);
+  ray_xy[pos * 2] = __fdiv_rn((float)kx, 1000.0f);
+  ray_xy[pos * 2 + 1] = __fdiv_rn((float)ky, 1000.0f);
+  ray_gid[pos] = (int32_t)lo;
+}
 
 // ---------------------------------------------------------------------------------------------
 // probability-guided pixel sampling (prob=True): image_process.py:26-96 + tree.py:583-595
@@ -554,6 +577,17 @@ int flnerf_qt_emit(flnerf_ctx *ctx, int n_images, int cap, int W, const double *
   int half = (bits + 1) / 2;
   FL_LAUNCH(qt_emit_kernel, (unsigned)ceil_div64(n_rays, 256), 256, 0, stream, n_images, cap, W, boxes, ray_offset,
             n_rays, half, seed, ray_pix, ray_gid);
+  return 0;
+}
+
+int flnerf_qt_emit_sub(flnerf_ctx *ctx, int n_images, int cap, const double *boxes, const int64_t *ray_offset, int64_t n_rays,
+                       uint64_t seed, float *ray_xy, int32_t *ray_gid, void *stream) {
+  FL_REQUIRE(ctx && boxes && ray_offset && ray_xy && ray_gid && n_rays >= 0, "flnerf_qt_emit_sub: bad arguments");
+  if (n_rays == 0) return 0;
+  int bits = 2;
+  while ((1ull << bits) < (uint64_t)n_rays) ++bits;
+  FL_LAUNCH(qt_emit_sub_kernel, (unsigned)ceil_div64(n_rays, 256), 256, 0, stream, n_images, cap, boxes, ray_offset, n_rays,
+            (bits + 1) / 2, seed, ray_xy, ray_gid);
   return 0;
 }
 

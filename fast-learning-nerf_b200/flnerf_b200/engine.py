@@ -118,6 +118,11 @@ class Trainer:
         # one CUDA graph per full batch of step_from_tree: opt-in, because a replayed step returns
         # the SAME loss / output tensors every time (the graph's static outputs)
         self.use_graph = bool(int(os.environ.get("FLNERF_GRAPH", "0"))) if graph is None else bool(graph)
+        # Single process only: a CUDA graph that captured NCCL kernels keeps the communicator alive -- on 2 x B200 the step
+        # itself replayed correctly (1.78 M vs 1.76 M rays/s) but destroy_process_group() never returned at exit
+        # (profiles/r02g_*), so under data parallelism the step is launched kernel by kernel (costs ~1 %).
+        if self.world > 1:
+            self.use_graph = False
         self._graph = self._graph_key = self._graph_out = self._rec = None
         self._graph_seen, self._graph_launches = {}, 0
         self.sync_replicas()

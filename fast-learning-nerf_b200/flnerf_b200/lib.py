@@ -62,6 +62,8 @@ SIGNATURES = {
                                  _vp]),
     "flnerf_gather_batch": (_i, [_vp, _i64, _i64, _i64, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "flnerf_gather_batch_u8": (_i, [_vp, _i64, _i64, _i64, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "flnerf_qt_emit_sub": (_i, [_vp, _i, _i, _vp, _vp, _i64, _u64, _vp, _vp, _vp]),
+    "flnerf_gather_sub": (_i, [_vp, _i64, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "flnerf_mlp_packed_bytes_g": (_sz, [_i]),
     "flnerf_mlp_pack_weights_g": (_i, [_vp, _i, _vp, _vp, _vp]),
     "flnerf_mlp_forward_g": (_i, [_vp, _i, _i, _vp, _vp, _i64, _i, _vp, _vp, _vp, _vp, _i, _vp]),

@@ -376,6 +376,26 @@ def gather_batch(B, first, stride, ray_pix, ray_gid, cap, H, W, K, poses, images
     return o, d, t, gid
 
 
+def qt_emit_sub(n_images, cap, boxes, ray_offset, n_rays, seed, ray_xy, ray_gid):
+    """gen_rays_v3's sub-pixel emission (tree.py:231-268): ray_xy[N,2] on a 1/1000-pixel grid, shuffled like qt_emit."""
+    L.check(L.load().flnerf_qt_emit_sub(_ctx(boxes), n_images, cap, _ptr(boxes), _ptr(ray_offset), int(n_rays), int(seed),
+                                        _ptr(ray_xy), _ptr(ray_gid), _stream()), "flnerf_qt_emit_sub")
+
+
+def gather_sub(ray_xy, ray_gid, cap, H, W, K, poses, images, lut=None):
+    """gen_rays_v3's gather (tree.py:270-285): F.grid_sample(bilinear, zeros, align_corners=False) of the colour / direction /
+    origin images at sub-pixel positions, with the reference's transposed grid -> (origins, dirs, rgb) [N,3]."""
+    B, dev = ray_xy.shape[0], images.device
+    o = torch.empty(B, 3, dtype=torch.float32, device=dev)
+    d = torch.empty(B, 3, dtype=torch.float32, device=dev)
+    t = torch.empty(B, 3, dtype=torch.float32, device=dev)
+    Kh = (C.c_double * 9)(*[float(K[i][j]) for i in range(3) for j in range(3)])
+    L.check(L.load().flnerf_gather_sub(_ctx(images), int(B), _ptr(_f32c(ray_xy)), _ptr(ray_gid), int(cap), int(H), int(W), Kh,
+                                       _ptr(poses), _ptr(images), _ptr(lut if images.dtype == torch.uint8 else None), _ptr(o),
+                                       _ptr(d), _ptr(t), _stream()), "flnerf_gather_sub")
+    return o, d, t
+
+
 # ------------------------------------------------------------------------------------------ nerf++ building blocks
 # (SURVEY 8f rank 1, the next row: parity-tested kernels, no complete path yet -- see DESIGN.md section 8)
 def pp_depths0(rays_o, rays_d, N, perturb, t_fg=None, t_bg=None, seed=0, offset=0):

@@ -262,6 +262,31 @@ class QuadTreeManager:
                                         self._poses_dev, self._images_dev, want_gid=False, lut=self._lut)
         return o, d, rgb
 
+    def gen_rays_v3(self, down_scale=16, debug=False, last_epoch=False):
+        """tree.py:231-307: the sub-pixel variant -- positions on a 1/1000-pixel grid inside every leaf, colours / directions /
+        origins interpolated bilinearly (F.grid_sample semantics, including the reference's transposed grid).  Returns
+        (origins[N,3], dirs[N,3], rgb[N,3]); result_leaf_id follows.  The positions stay in ``ray_xy`` (emission is shuffled)."""
+        rpp = self.epoch_size / self.n_images / down_scale / self.h / self.w
+        n = self.n_images
+        if last_epoch:
+            boxes = torch.zeros(n, self.cap, 4, dtype=torch.float64, device=self.device)
+            count = torch.zeros(n, dtype=torch.int32, device=self.device)
+            min_area = torch.zeros(n, dtype=torch.float64, device=self.device)
+            ops.qt_init(n, self.cap, self.h, self.w, 1, boxes, count, min_area)
+        else:
+            boxes, count, min_area = self.boxes, self.counts, self._min_area
+        ops.qt_count(n, self.cap, boxes, count, min_area, rpp, self._ray_offset)
+        self.n_rays = int(self._ray_offset[-1].item())
+        self.ray_xy = torch.empty(self.n_rays, 2, dtype=torch.float32, device=self.device)
+        self.ray_gid = torch.empty(self.n_rays, dtype=torch.int32, device=self.device)
+        self.ray_pix = None
+        self._epoch += 1
+        ops.qt_emit_sub(n, self.cap, boxes, self._ray_offset, self.n_rays, self.seed * 1000003 + self._epoch, self.ray_xy, self.ray_gid)
+        if debug:
+            for i in range(n):
+                self.visualize_split_and_sample_points(i, self.ray_xy[(self.ray_gid // self.cap) == i])
+        return ops.gather_sub(self.ray_xy, self.ray_gid, self.cap, self.h, self.w, self.K, self._poses_dev, self._images_dev, self._lut)
+
     def gen_rays_v3_1(self, down_scale=16, debug=False, last_epoch=False):
         """tree.py:309-375, the single-thread integer-pixel version: same semantics as gen_rays_v3_multiThread(prob=False)."""
         return self.gen_rays_v3_multiThread(down_scale=down_scale, prob=False, debug=debug, last_epoch=last_epoch)

@@ -232,6 +232,16 @@ int flnerf_gather_batch_u8(flnerf_ctx *, int64_t B, int64_t first, int64_t strid
                            const uint8_t *images, const float *lut256, float *rays_o, float *rays_d, float *target,
                            int32_t *leaf_gid, void *stream);
 
+/* ---- gen_rays_v3 (tree.py:231-307), the sub-pixel variant of the emitter: positions on a 1/1000 grid inside every leaf,
+ * ray_xy[N,2] fp32 = (x = row coordinate, y = column coordinate) at the shuffled position; then colour / direction / origin by
+ * F.grid_sample(bilinear, zeros, align_corners=False) semantics INCLUDING the reference's transposed grid (it passes (row, col)
+ * where grid_sample expects (width, height)).  images: fp32 [n,H,W,3], or uint8 with lut256. */
+int flnerf_qt_emit_sub(flnerf_ctx *, int n_images, int cap, const double *boxes, const int64_t *ray_offset, int64_t n_rays,
+                       uint64_t seed, float *ray_xy, int32_t *ray_gid, void *stream);
+int flnerf_gather_sub(flnerf_ctx *, int64_t B, const float *ray_xy, const int32_t *ray_gid, int cap, int H, int W,
+                      const double *h_K, const float *poses, const void *images, const float *lut256_or_null, float *rays_o,
+                      float *rays_d, float *target, void *stream);
+
 /* ---- next row: nerf++-ours dual-MLP path -- parity-tested building blocks, no complete path yet.
  * Level-0 sample placement (ddp_train_nerf.py:54-81,352-366): fg_far[B] = unit-sphere exit depth, fg_z[B,N] linear in
  * [1e-4, fg_far], bg_z[B,N] = linspace(0,1) inverse depths; perturb != 0 jitters both inside their mid-point intervals with

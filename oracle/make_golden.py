@@ -118,6 +118,48 @@ def variance_tree_golden(ref):
     np.savez_compressed(os.path.join(OUT, "variance_tree.npz"), **g)
 
 
+def subpixel_golden(ref):
+    """gen_rays_v3 (tree.py:231-307): the reference's own sub-pixel emission replayed with a seeded torch RNG.  The oracle
+    re-draws the same positions (same randint calls in the same order, then the same randperm) and must reproduce origins /
+    directions / colours bit for bit; the fixture keeps positions (emission order), leaf ids and the three outputs."""
+    T = ref.tree
+    rs = np.random.RandomState(7)
+    H, W, n = 20, 28, 2                                 # H != W: the transposed grid_sample grid shows
+    K = lego_K(H, W, 30.0)
+    imgs = torch.from_numpy(rs.uniform(0, 1, (n, H, W, 3)).astype(np.float32))
+    poses = torch.stack([torch.from_numpy(pose_spherical(a, -30.0, 4.0)[:3, :4]) for a in (10.0, 100.0)]).float()
+    mgr = T.QuadTreeManager(H, W, K, imgs, poses, mseThres=0.0, max_depth=3)
+    torch.manual_seed(123)
+    o_ref, d_ref, c_ref = mgr.gen_rays_v3(down_scale=1)
+    lid_ref = mgr.result_leaf_id.clone()
+    # replay
+    torch.manual_seed(123)
+    rpp = mgr.epoch_size / mgr.n_images / 1 / H / W
+    xy, lid, outs = [], [], []
+    for i in range(n):
+        xy_i = []
+        for leaf_id, ch in enumerate(mgr.childrens[i]):
+            b = (ch.x0, ch.y0, ch.x1, ch.y1)
+            num = O.leaf_ray_count(b, mgr.quadTrees[i].minArea, rpp)
+            x_lo, x_hi, y_lo, y_hi = O.subpixel_range(b)
+            sx = torch.randint(x_lo, x_hi, (num,)) / 1000
+            sy = torch.randint(y_lo, y_hi, (num,)) / 1000
+            xy_i.append(torch.stack([sx, sy], 1))
+            lid.append(torch.Tensor([[i, leaf_id]]).repeat([num, 1]))
+        xy_i = torch.cat(xy_i, 0)
+        xy.append(xy_i)
+        outs.append(O.subpixel_gather(imgs[i], mgr.dirs[i], mgr.origins[i], xy_i))
+    perm = torch.randperm(sum(x.shape[0] for x in xy))
+    o = torch.cat([t[0] for t in outs], 0)
+    d = torch.cat([t[1] for t in outs], 0)
+    c = torch.cat([t[2] for t in outs], 0)
+    lid = torch.cat(lid, 0)
+    assert torch.equal(o[perm], o_ref) and torch.equal(d[perm], d_ref) and torch.equal(c[perm], c_ref) and torch.equal(lid[perm], lid_ref)
+    np.savez_compressed(os.path.join(OUT, "subpixel.npz"), **t2n(dict(
+        H=H, W=W, K=K, images=imgs, poses=poses, xy=torch.cat(xy, 0), leaf_id=lid, origins=o, dirs=d, rgb=c,
+        counts=np.array([x.shape[0] for x in xy]))))
+
+
 def nerfpp_golden():
     """nerf++-ours fixtures produced by the reference's own nerf_network / ddp_model / ddp_train_nerf
     functions; the oracle (oracle/nerfpp_oracle.py) is asserted against them on the way."""
@@ -166,6 +208,10 @@ def main():
     if os.environ.get("GOLDEN_ONLY") == "vartree":
         variance_tree_golden(ref)
         print("wrote variance_tree.npz")
+        return
+    if os.environ.get("GOLDEN_ONLY") == "subpixel":
+        subpixel_golden(ref)
+        print("wrote subpixel.npz")
         return
     if os.environ.get("GOLDEN_ONLY") == "prob":
         prob_sampling_golden(ref)
@@ -385,6 +431,7 @@ def main():
     np.savez_compressed(os.path.join(OUT, "quadtree.npz"), **q)
     prob_sampling_golden(ref)
     variance_tree_golden(ref)
+    subpixel_golden(ref)
     nerfpp_golden()
     print("golden fixtures written to", OUT)
     for f in sorted(os.listdir(OUT)):

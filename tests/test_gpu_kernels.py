@@ -408,3 +408,32 @@ def test_encode_tc_double_angle_recurrence_is_bounded_at_large_arguments(ops):
     hi, lo = _decode_tiles(t3[:nt], n)[:, :63], _decode_tiles(t3[nt:], n)[:, :63]
     assert np.array_equal(hi, want)                                        # every octave exact -> hi IS the correctly rounded bf16
     np.testing.assert_allclose(hi + lo, ref.numpy(), atol=2.0 ** -17, rtol=2.0 ** -16)
+
+
+def test_gen_rays_v3_subpixel_variant(golden, ops):
+    """tree.py:231-307: (1) the gather kernel on the fixture's positions against the UNMODIFIED reference's F.grid_sample outputs
+    (transposed grid and zero padding included); (2) the emitter: per-leaf counts as gen_rays_v3_1, every position on the
+    1/1000 grid inside the reference's integer ranges."""
+    import tree
+    g = golden("subpixel")
+    H, W = int(g["H"]), int(g["W"])
+    imgs, poses = torch.from_numpy(g["images"]), torch.from_numpy(g["poses"])
+    mgr = tree.QuadTreeManager(H, W, g["K"], imgs, poses, mseThres=0.0, max_depth=3, max_level=5, seed=2)
+    gid = torch.from_numpy((g["leaf_id"][:, 0] * mgr.cap + g["leaf_id"][:, 1]).astype(np.int32)).cuda()
+    o, d, c = ops.gather_sub(torch.from_numpy(g["xy"]).cuda(), gid, mgr.cap, H, W, g["K"], mgr._poses_dev, mgr._images_dev, mgr._lut)
+    np.testing.assert_allclose(c.cpu().numpy(), g["rgb"], atol=2e-6)
+    np.testing.assert_allclose(o.cpu().numpy(), g["origins"], atol=2e-6)
+    np.testing.assert_allclose(d.cpu().numpy(), g["dirs"], atol=2e-6)
+    oo, dd, cc = mgr.gen_rays_v3(down_scale=1)
+    assert oo.shape == dd.shape == cc.shape == (mgr.n_rays, 3) and mgr.n_rays == len(g["xy"])
+    xy, gg = mgr.ray_xy.cpu().numpy().astype(np.float64), mgr.ray_gid.cpu().numpy().astype(np.int64)
+    lists = mgr.leaf_lists()
+    for i in range(2):
+        cnt = np.bincount(gg[gg // mgr.cap == i] % mgr.cap, minlength=len(lists[i][0]))
+        assert cnt.tolist() == [O.leaf_ray_count(tuple(b), lists[i][1], 1.0) for b in lists[i][0]]
+    k = np.rint(xy * 1000)
+    assert np.abs(xy * 1000 - k).max() < 1e-3                                # on the 1/1000 grid
+    bx = np.concatenate([np.pad(l[0], ((0, mgr.cap - len(l[0])), (0, 0))) for l in lists], 0)[gg]
+    rng = np.array([O.subpixel_range(tuple(b)) for b in bx])
+    assert np.all(k[:, 0] >= rng[:, 0]) and np.all(k[:, 0] < rng[:, 1]) and np.all(k[:, 1] >= rng[:, 2]) and np.all(k[:, 1] < rng[:, 3])
+    assert mgr.result_leaf_id.shape == (mgr.n_rays, 2)

@@ -164,3 +164,23 @@ def test_prob_sampling(golden):
         assert k == len(pix)
     p = O.to_prob_v2(g["sharp1"][3:11, 2:12])
     assert abs(p.sum() - 1) < 1e-12 and p.min() > 0
+
+
+def test_subpixel_gather_golden(golden):
+    """gen_rays_v3 (tree.py:231-307): the fixture holds the UNMODIFIED reference's outputs for seeded positions (make_golden.py
+    replays its RNG); the oracle's grid_sample restatement reproduces them bit for bit, per image."""
+    import warnings
+    g = golden("subpixel")
+    H, W = int(g["H"]), int(g["W"])
+    imgs, poses = torch.from_numpy(g["images"]), torch.from_numpy(g["poses"])
+    off = 0
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        for i, n in enumerate(g["counts"]):
+            o, d = O.camera_rays(H, W, g["K"], poses[i])
+            oo, dd, cc = O.subpixel_gather(imgs[i], d, o, torch.from_numpy(g["xy"][off:off + n]))
+            assert np.array_equal(oo.numpy(), g["origins"][off:off + n]) and np.array_equal(dd.numpy(), g["dirs"][off:off + n])
+            assert np.array_equal(cc.numpy(), g["rgb"][off:off + n])
+            assert np.all(g["leaf_id"][off:off + n, 0] == i)
+            off += n
+    assert O.subpixel_range((0.0, 5.0, 10.0, 12.5)) == (0, 9990, 5000, 12490)
