@@ -154,23 +154,36 @@ __global__ void pack_weights_kernel(const float *__restrict__ P, uint8_t *__rest
 
 // viewbias[ray][c] = b_v[c] + sum_j W_v[c][256+j] * PE4(viewdir)[j]  -- the 27 view-direction inputs of
 // views_linears.0 are constant along a ray, so their contribution is a per-ray bias (fp32, exact)
-__global__ void __launch_bounds__(128) viewbias_kernel(int64_t B, const float *__restrict__ P, const float *__restrict__ dirpe,
+__global__ void __launch_bounds__(256) viewbias_kernel(int64_t B, const float *__restrict__ P, const float *__restrict__ dirpe,
                                                        float *__restrict__ vb, int W_VIEWS, int B_VIEWS) {
-  // thread = output channel c: its 27 view-direction weights stay in registers for kRays rays (the strided weight reads
-  // are paid once per block); the ray's PE values are warp-uniform loads, the stores are coalesced
-  constexpr int kRays = 16;
-  const int c = threadIdx.x;
-  float w[27];
+  // block = 32 rays x 128 output channels.  The 128 x 27 view-direction weights (+ bias) and the block's 32 x 27 PE values are
+  // staged in shared memory once; thread = (channel c, ray group): 16 rays each, weights in registers, PE values as warp-uniform
+  // shared-memory broadcasts, coalesced 128-float stores.  (The first version looped 16 rays per thread over __ldg loads with
+  // 256 blocks of 128 threads: latency-bound at 21 us for 4096 rays -- as long as the whole positional encoding.)
+  __shared__ float s_w[128 * 28];
+  __shared__ float s_pe[32 * 28];
+  const int c = threadIdx.x & 127, half = threadIdx.x >> 7;
+  const int64_t r0 = (int64_t)blockIdx.x * 32;
+  for (int i = threadIdx.x; i < 128 * 28; i += 256) {
+    const int cc = i / 28, j = i % 28;
+    s_w[i] = j < 27 ? P[W_VIEWS + cc * 283 + 256 + j] : P[B_VIEWS + cc];
+  }
+  for (int i = threadIdx.x; i < 32 * 28; i += 256) {
+    const int rr = i / 28, j = i % 28;
+    s_pe[i] = (j < 27 && r0 + rr < B) ? dirpe[(r0 + rr) * 32 + j] : 0.f;
+  }
+  __syncthreads();
+  float w[28];
 #pragma unroll
-  for (int j = 0; j < 27; ++j) w[j] = P[W_VIEWS + c * 283 + 256 + j];
-  const float b = P[B_VIEWS + c];
-  const int64_t r0 = (int64_t)blockIdx.x * kRays;
-  for (int64_t ray = r0; ray < r0 + kRays && ray < B; ++ray) {
-    const float *pe = dirpe + ray * 32;
-    float s = b;
+  for (int j = 0; j < 28; ++j) w[j] = s_w[c * 28 + j];
+#pragma unroll 4
+  for (int k = 0; k < 16; ++k) {
+    const int rr = half * 16 + k;
+    if (r0 + rr >= B) break;
+    float acc = w[27];
 #pragma unroll
-    for (int j = 0; j < 27; ++j) s = fmaf(w[j], __ldg(pe + j), s);
-    vb[ray * 128 + c] = s;
+    for (int j = 0; j < 27; ++j) acc = fmaf(w[j], s_pe[rr * 28 + j], acc);
+    vb[(r0 + rr) * 128 + c] = acc;
   }
 }
 
@@ -1432,26 +1445,28 @@ static size_t tc_vb_bytes(int64_t n, int S) {
   int64_t B = (n + S - 1) / S;
   return (size_t)((B * 128 * 4 + 1023) / 1024) * 1024;
 }
-// How many of the three terms dYhi^T Xhi + dYhi^T Xlo + dYlo^T Xhi the split-precision weight gradient carries.  Measured at
-// 2048 rays x (64+128) against the oracle (tools/x3_wgrad_passes.py, profiles/r02g_wgrad_passes.log): gradient rel-L2 3.3e-5 /
-// 3.2e-5 / 3.0e-5 for 1 / 2 / 3 terms -- a sum over 10^5..10^6 rows averages the bf16 rounding of its operands away -- so the
-// default is ONE term, and then the stash keeps only the hi images (half the bytes).  $FLNERF_X3_WGRAD_PASSES=3 restores all.
-static int x3_wgrad_passes() {
-  static int passes = -1;
-  if (passes < 0) {
+// How many of the three terms dYhi^T Xhi + dYhi^T Xlo + dYlo^T Xhi the split-precision weight gradient carries.  The sum over
+// the rows averages the bf16 rounding of its operands away: measured against the oracle (tools/x3_wgrad_passes.py,
+// profiles/r02g_wgrad_passes.log) the gradient's rel-L2 at 393 216 rows (2048 rays x 192) is 3.3e-5 / 3.2e-5 / 3.0e-5 for
+// 1 / 2 / 3 terms, while 16..24-ray batches (3..5 k rows) need all three to stay under 2e-3.  Default: ONE term from 65 536
+// rows on (any training batch), three below; with one term the stash keeps only the hi images (half the bytes).
+// $FLNERF_X3_WGRAD_PASSES = 1 | 2 | 3 forces a count.
+static int x3_wgrad_passes(int64_t n) {
+  static int forced = -1;
+  if (forced < 0) {
     const char *e = getenv("FLNERF_X3_WGRAD_PASSES");
-    passes = e ? atoi(e) : 1;
-    if (passes < 1 || passes > 3) passes = 1;
+    forced = e ? atoi(e) : 0;
+    if (forced < 0 || forced > 3) forced = 0;
   }
-  return passes;
+  return forced ? forced : (n >= 65536 ? 1 : 3);
 }
-static bool x3_stash_lo(bool x3) { return x3 && x3_wgrad_passes() > 1; }
-static size_t tc_tile_act_bytes(bool x3) { return x3_stash_lo(x3) ? tc::TILE_ACT_BYTES_X3 : tc::TILE_ACT_BYTES; }
+static bool x3_stash_lo(bool x3, int64_t n) { return x3 && x3_wgrad_passes(n) > 1; }
+static size_t tc_tile_act_bytes(bool x3, int64_t n) { return x3_stash_lo(x3, n) ? tc::TILE_ACT_BYTES_X3 : tc::TILE_ACT_BYTES; }
 size_t mlp_tc_stash_bytes(int64_t n, int S, int training, bool x3) {
   size_t tiles = (size_t)(flnerf_padded_rows(n) / 128);
-  return tc_vb_bytes(n, S) + (training ? tiles * (tc_tile_act_bytes(x3) + tc::TILE_MASK_BYTES) : 0);
+  return tc_vb_bytes(n, S) + (training ? tiles * (tc_tile_act_bytes(x3, n) + tc::TILE_MASK_BYTES) : 0);
 }
-size_t mlp_tc_bwd_workspace_bytes(int64_t n, bool x3) { return (size_t)(flnerf_padded_rows(n) / 128) * tc_tile_act_bytes(x3); }
+size_t mlp_tc_bwd_workspace_bytes(int64_t n, bool x3) { return (size_t)(flnerf_padded_rows(n) / 128) * tc_tile_act_bytes(x3, n); }
 
 int mlp_tc_pack_weights(flnerf_ctx *ctx, int kind, const float *params, void *packed, cudaStream_t st) {
   FL_REQUIRE(tc::setup_tables(ctx->sm_count) == 0, "mlp_tc: table setup failed: %s", cudaGetErrorString(cudaGetLastError()));
@@ -1468,15 +1483,15 @@ int mlp_tc_forward(flnerf_ctx *ctx, bool x3, int kind, const float *params, cons
   const tc::NetDesc &nd = tc::g_desc[kind];
   int64_t B = n / S;
   float *vb = (float *)stash;
-  FL_LAUNCH(tc::viewbias_kernel, (unsigned)ceil_div64(B, 16), 128, 0, st, B, params, dirpe, vb, nd.w_views, nd.b_views);
+  FL_LAUNCH(tc::viewbias_kernel, (unsigned)ceil_div64(B, 32), 256, 0, st, B, params, dirpe, vb, nd.w_views, nd.b_views);
   tc::FwdParams p{};
   p.P = params; p.packed = (const uint8_t *)packed; p.pe_tiles = (const uint8_t *)pe_tiles; p.viewbias = vb;
-  p.raw = raw; p.n = n; p.S = S; p.kind = kind; p.stash_lo = x3_stash_lo(x3) ? 1 : 0;
+  p.raw = raw; p.n = n; p.S = S; p.kind = kind; p.stash_lo = x3_stash_lo(x3, n) ? 1 : 0;
   int64_t n_pad = flnerf_padded_rows(n);
   p.n_pairs = (int)(n_pad / 256);
   if (training) {
     p.stash_act = (uint8_t *)stash + tc_vb_bytes(n, S);
-    p.stash_mask = (uint32_t *)(p.stash_act + (size_t)(n_pad / 128) * tc_tile_act_bytes(x3));
+    p.stash_mask = (uint32_t *)(p.stash_act + (size_t)(n_pad / 128) * tc_tile_act_bytes(x3, n));
   }
   FL_CHECK_CUDA(cudaMemsetAsync(raw, 0, (size_t)n * 4 * sizeof(float), st));  // column-half warps accumulate into it
   if (x3 || kind != 0) {
@@ -1506,10 +1521,10 @@ int mlp_tc_backward(flnerf_ctx *ctx, bool x3, int kind, const float *params, con
   const tc::NetDesc &nd = tc::g_desc[kind];
   int64_t n_pad = flnerf_padded_rows(n);
   const uint8_t *stash_act = (const uint8_t *)stash + tc_vb_bytes(n, S);
-  const uint32_t *stash_mask = (const uint32_t *)(stash_act + (size_t)(n_pad / 128) * tc_tile_act_bytes(x3));
+  const uint32_t *stash_mask = (const uint32_t *)(stash_act + (size_t)(n_pad / 128) * tc_tile_act_bytes(x3, n));
   tc::DgradParams d{};
   d.P = params; d.packed_dg = (const uint8_t *)packed + nd.fwd_bytes; d.draw = draw; d.stash_mask = stash_mask;
-  d.dy = (uint8_t *)ws; d.n = n; d.n_pairs = (int)(n_pad / 256); d.kind = kind; d.stash_lo = x3_stash_lo(x3) ? 1 : 0;
+  d.dy = (uint8_t *)ws; d.n = n; d.n_pairs = (int)(n_pad / 256); d.kind = kind; d.stash_lo = x3_stash_lo(x3, n) ? 1 : 0;
   if ((stages & 1) && x3) {
     const int grid = tc::pair_grid(d.n_pairs * 2, ctx->sm_count);
     FL_LAUNCH(tc::mlp_dgrad_x3, grid, tc::kThreads, tc::LayD::SMEM, st, d);
@@ -1526,7 +1541,7 @@ int mlp_tc_backward(flnerf_ctx *ctx, bool x3, int kind, const float *params, con
   tc::WgradParams w{};
   w.dy = (const uint8_t *)ws; w.stash_act = stash_act; w.pe_tiles = (const uint8_t *)pe_tiles; w.draw = draw;
   w.G = grads; w.n = n; w.n_tiles = (int)(n_pad / 128); w.dirpe = dirpe; w.S = S; w.kind = kind;
-  w.tile_stride = tc_tile_act_bytes(x3); w.slot_stride = x3_stash_lo(x3) ? tc::SLOT_BYTES_X3 : 65536;
+  w.tile_stride = tc_tile_act_bytes(x3, n); w.slot_stride = x3_stash_lo(x3, n) ? tc::SLOT_BYTES_X3 : 65536;
   w.helper_flags = 7;
   static long long *dbg = nullptr;
   const bool want_dbg = getenv("FLNERF_WG_DEBUG") != nullptr;
@@ -1536,7 +1551,7 @@ int mlp_tc_backward(flnerf_ctx *ctx, bool x3, int kind, const float *params, con
     // dW = (dYhi + dYlo)^T (Xhi + Xlo) ~= dYhi^T Xhi [+ dYhi^T Xlo [+ dYlo^T Xhi]]: up to three passes of the same kernel over
     // the hi / lo images, each with the CUDA-core reductions that belong to its operands (see x3_wgrad_passes)
     const size_t pe_lo = (size_t)w.n_tiles * nd.pe_slabs * tc::PE_BYTES;
-    const int passes = x3_wgrad_passes();
+    const int passes = x3_wgrad_passes(n);
     FL_LAUNCH(tc::mlp_wgrad_tc, tc::g_wgrad_grid, tc::kWgThreads, tc::SMEM_WG, st, w);
     if (passes >= 2) {
       w.b_part = 65536; w.pe_part = pe_lo; w.helper_flags = 2;

@@ -6,6 +6,7 @@
 // intrinsics wherever the reference performs separate tensor ops, so that no FMA contraction
 // changes the rounding relative to torch (x*freq is exact; sinf/cosf are the accurate versions).
 #include "common.cuh"
+#include "tc_ptx.cuh"
 
 namespace {
 
@@ -177,8 +178,11 @@ template <bool kX3, bool kFrame>
 __global__ void __launch_bounds__(128) encode_tc_kernel(int64_t n, int64_t n_pad, int S, const float *__restrict__ rays11,
                                                         const float *__restrict__ z, uint8_t *__restrict__ tiles, size_t lo_off,
                                                         FrameArgs fa) {
+  // block = one 128-row tile (n_pad is a multiple of 128: no partial blocks).  The tile is assembled in shared memory in the
+  // very image the MLP kernels consume, then leaves as ONE 16 KB bulk store per tile set (cp.async.bulk: full 128-byte lines
+  // instead of 32 scattered 16-byte pieces per store instruction).
+  __shared__ __align__(1024) uint8_t s_tile[kX3 ? 2 : 1][16384];
   const int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (row >= n_pad) return;
   uint32_t pk[32], pl[32];
 #pragma unroll
   for (int i = 0; i < 32; ++i) { pk[i] = 0u; pl[i] = 0u; }
@@ -202,7 +206,12 @@ __global__ void __launch_bounds__(128) encode_tc_kernel(int64_t n, int64_t n_pad
       }
       sample_point(q, zj, p);
     } else {
-      sample_point(rays11 + (row / S) * 11, z[row], p);
+      const int64_t ray = row / S;
+      sample_point(rays11 + ray * 11, z[row], p);
+      if (fa.dirpe && row == ray * S) {       // the ray's first sample also writes its view-direction PE (saves a launch)
+        const float vd[3] = {rays11[ray * 11 + 8], rays11[ray * 11 + 9], rays11[ray * 11 + 10]};
+        for (int ch = 0; ch < 32; ++ch) fa.dirpe[ray * 32 + ch] = ch < 27 ? pe_channel(vd, ch) : 0.0f;
+      }
     }
     v[0] = p[0]; v[1] = p[1]; v[2] = p[2];
     v[63] = 0.f;
@@ -232,12 +241,22 @@ __global__ void __launch_bounds__(128) encode_tc_kernel(int64_t n, int64_t n_pad
     }
   }
   const uint32_t r = (uint32_t)(row & 127);
-  uint8_t *dst = tiles + (row >> 7) * 16384 + (r >> 3) * 1024u + (r & 7u) * 128u;
+  const uint32_t roff = (r >> 3) * 1024u + (r & 7u) * 128u;
 #pragma unroll
   for (uint32_t q = 0; q < 8; ++q) {
-    *reinterpret_cast<uint4 *>(dst + ((q ^ (r & 7u)) << 4)) = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+    *reinterpret_cast<uint4 *>(s_tile[0] + roff + ((q ^ (r & 7u)) << 4)) = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
     if (kX3)
-      *reinterpret_cast<uint4 *>(dst + lo_off + ((q ^ (r & 7u)) << 4)) = make_uint4(pl[4 * q], pl[4 * q + 1], pl[4 * q + 2], pl[4 * q + 3]);
+      *reinterpret_cast<uint4 *>(s_tile[kX3 ? 1 : 0] + roff + ((q ^ (r & 7u)) << 4)) =
+          make_uint4(pl[4 * q], pl[4 * q + 1], pl[4 * q + 2], pl[4 * q + 3]);
+  }
+  tc::fence_async_smem();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint8_t *dst = tiles + (row >> 7) * 16384;
+    tc::bulk_s2g(dst, tc::smem_u32(s_tile[0]), 16384u);
+    if (kX3) tc::bulk_s2g(dst + lo_off, tc::smem_u32(s_tile[kX3 ? 1 : 0]), 16384u);
+    tc::bulk_commit();
+    tc::bulk_wait_all0();        // the source is this block's shared memory: it must outlive the copy
   }
 }
 
@@ -311,15 +330,6 @@ __global__ void pack_xrows_kernel(int64_t n, int64_t n_pad, int in_pts, int n_sl
   const size_t off = ((size_t)tile * n_slabs + sl) * 16384 + sw128_offset(r, (uint32_t)q * 8);
   *reinterpret_cast<uint4 *>(tiles + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
   if (lo_off) *reinterpret_cast<uint4 *>(tiles + lo_off + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-}
-
-__global__ void dirpe_kernel(int64_t B, const float *__restrict__ rays11, float *__restrict__ dirpe) {
-  int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= B * 32) return;
-  int64_t ray = idx >> 5;
-  int ch = (int)(idx & 31);
-  float v[3] = {rays11[ray * 11 + 8], rays11[ray * 11 + 9], rays11[ray * 11 + 10]};
-  dirpe[idx] = ch < 27 ? pe_channel(v, ch) : 0.0f;
 }
 
 // images: fp32 [n,H,W,3], or -- lut != nullptr -- uint8 [n,H,W,3] decoded through lut[256] (the loaders' float32(u / 255.)
@@ -457,9 +467,10 @@ int flnerf_encode_tc(flnerf_ctx *ctx, int64_t B, int S, const float *rays11, con
   FL_REQUIRE(ctx && rays11 && z && pe_tiles && dirpe && S > 0 && B >= 0, "flnerf_encode_tc: bad arguments");
   if (B == 0) return 0;
   int64_t n = B * S, n_pad = flnerf_padded_rows(n);
+  FrameArgs fa{};
+  fa.dirpe = dirpe;
   FL_LAUNCH((encode_tc_kernel<false, false>), (unsigned)ceil_div64(n_pad, 128), 128, 0, stream, n, n_pad, S, rays11, z,
-            (uint8_t *)pe_tiles, (size_t)0, FrameArgs{});
-  FL_LAUNCH(dirpe_kernel, (unsigned)ceil_div64(B * 32, 256), 256, 0, stream, B, rays11, dirpe);
+            (uint8_t *)pe_tiles, (size_t)0, fa);
   return 0;
 }
 
@@ -468,9 +479,10 @@ int flnerf_encode_tc_x3(flnerf_ctx *ctx, int64_t B, int S, const float *rays11, 
   FL_REQUIRE(ctx && rays11 && z && pe_tiles && dirpe && S > 0 && B >= 0, "flnerf_encode_tc_x3: bad arguments");
   if (B == 0) return 0;
   int64_t n = B * S, n_pad = flnerf_padded_rows(n);
+  FrameArgs fa{};
+  fa.dirpe = dirpe;
   FL_LAUNCH((encode_tc_kernel<true, false>), (unsigned)ceil_div64(n_pad, 128), 128, 0, stream, n, n_pad, S, rays11, z,
-            (uint8_t *)pe_tiles, (size_t)(n_pad / 128) * 16384, FrameArgs{});
-  FL_LAUNCH(dirpe_kernel, (unsigned)ceil_div64(B * 32, 256), 256, 0, stream, B, rays11, dirpe);
+            (uint8_t *)pe_tiles, (size_t)(n_pad / 128) * 16384, fa);
   return 0;
 }
 

@@ -31,7 +31,7 @@ __device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity)
   return ok;
 }
 // Bounded wait: a protocol bug must surface as a trapped kernel (error code to the host), never as a hung GPU.
-__device__ __noinline__ void mbar_timeout(uint32_t bar, uint32_t parity) {
+static __device__ __noinline__ void mbar_timeout(uint32_t bar, uint32_t parity) {
   printf("flnerf: mbarrier timeout block %d thread %d bar %u parity %u\n", blockIdx.x, threadIdx.x, bar, parity);
   __trap();
 }
