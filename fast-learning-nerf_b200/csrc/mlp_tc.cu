@@ -1427,6 +1427,10 @@ static int setup_tables(int sm_count) {
   if (cudaFuncSetAttribute(mlp_fwd_gen<3, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, LayF::SMEM) != cudaSuccess) return 1;
   if (cudaFuncSetAttribute(mlp_fwd_gen<3, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, LayF::SMEM) != cudaSuccess) return 1;
   if (cudaFuncSetAttribute(mlp_fwd_gen<1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, LayF::SMEM) != cudaSuccess) return 1;
+  if (cudaFuncSetAttribute(mlp_fwd_gen<3, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, LayF::SMEM) != cudaSuccess) return 1;
+  if (cudaFuncSetAttribute(mlp_fwd_gen<3, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, LayF::SMEM) != cudaSuccess) return 1;
+  if (cudaFuncSetAttribute(mlp_fwd_gen<3, 1, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, LayF::SMEM) != cudaSuccess) return 1;
+  if (cudaFuncSetAttribute(mlp_fwd_gen<3, 1, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, LayF::SMEM) != cudaSuccess) return 1;
   if (cudaFuncSetAttribute(mlp_dgrad_x3, cudaFuncAttributeMaxDynamicSharedMemorySize, LayD::SMEM) != cudaSuccess) return 1;
   g_tables_ready = true;
   return 0;
@@ -1497,7 +1501,21 @@ int mlp_tc_forward(flnerf_ctx *ctx, bool x3, int kind, const float *params, cons
   if (x3 || kind != 0) {
     // one 128-row tile per CTA, ring items consumed in order: any number of positional slabs, one or three MMA passes
     const int grid = tc::pair_grid(p.n_pairs * 2, ctx->sm_count);
-    if (x3 && kind == 0) FL_LAUNCH((tc::mlp_fwd_gen<3, 1>), grid, tc::kThreads, tc::LayF::SMEM, st, p);
+    // split mode: activations travel to the next layer's MMA through TENSOR MEMORY (A-in-TMEM) unless the stash must keep
+    // the lo images too (they are staged in shared memory then); $FLNERF_X3_ATMEM=0 selects the shared-memory variant
+    static int atmem = -1;
+    if (atmem < 0) { const char *e = getenv("FLNERF_X3_ATMEM"); atmem = e ? atoi(e) : 1; }
+    const bool at = x3 && atmem && !(training && p.stash_lo);
+    p.prof = (x3 && kind == 0) ? tc::prof_buffer() : nullptr;
+    if (p.prof) {      // FLNERF_TC_PROF=1: per-role cycle accounting of the split forward kernel
+      if (at) FL_LAUNCH((tc::mlp_fwd_gen<3, 1, true, true>), grid, tc::kThreads, tc::LayF::SMEM, st, p);
+      else FL_LAUNCH((tc::mlp_fwd_gen<3, 1, false, true>), grid, tc::kThreads, tc::LayF::SMEM, st, p);
+      tc::prof_report(at ? "fwd_x3_atmem" : "fwd_x3", grid, p.n_pairs, st);
+      return 0;
+    }
+    if (at && kind == 0) FL_LAUNCH((tc::mlp_fwd_gen<3, 1, true>), grid, tc::kThreads, tc::LayF::SMEM, st, p);
+    else if (at) FL_LAUNCH((tc::mlp_fwd_gen<3, 2, true>), grid, tc::kThreads, tc::LayF::SMEM, st, p);
+    else if (x3 && kind == 0) FL_LAUNCH((tc::mlp_fwd_gen<3, 1>), grid, tc::kThreads, tc::LayF::SMEM, st, p);
     else if (x3) FL_LAUNCH((tc::mlp_fwd_gen<3, 2>), grid, tc::kThreads, tc::LayF::SMEM, st, p);
     else FL_LAUNCH((tc::mlp_fwd_gen<1, 2>), grid, tc::kThreads, tc::LayF::SMEM, st, p);
     return 0;

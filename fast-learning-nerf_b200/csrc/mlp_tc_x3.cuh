@@ -20,23 +20,37 @@ constexpr int X3_DG_ITEMS = 2 * DG_CHUNKS;
 constexpr size_t TILE_ACT_BYTES_X3 = 2 * TILE_ACT_BYTES;  // per slot: [hi 64 KB][lo 64 KB]
 constexpr size_t SLOT_BYTES_X3 = 2 * 65536;
 
-// 8 consecutive columns of row r, split into hi / lo bf16 and written to the two images (lo = hi + ACT_BYTES)
-__device__ __forceinline__ void store_split8(uint8_t *row_hi, uint32_t pos, const float x[8]) {
+// TMEM map of the A-in-TMEM variants (kAT): fp32 accumulator in columns [0, 256), the NEXT layer's A operand as packed bf16
+// pairs behind it -- hi image in [256, 384), lo image in [384, 512) (column 256 + k/2 holds features k, k+1): all 512 columns.
+constexpr uint32_t TM_A_HI = 256, TM_A_LO = 384;
+
+// 8 consecutive columns [c, c+8) of row r, split into hi / lo bf16.
+//   kAT = false: both go to the shared-memory images (lo image = hi + ACT_BYTES) the next layer's MMA reads;
+//   kAT = true : both go to TENSOR MEMORY (tcgen05.st; taddr = this thread's lane + TM_A_HI + c/2); the hi chunk is ALSO written
+//                to shared memory when `smem_hi` (training: the stash bulk stores ship it from there).
+template <bool kAT>
+__device__ __forceinline__ void store_split8(uint8_t *row_hi, uint32_t pos, const float x[8], uint32_t taddr = 0, bool smem_hi = true) {
   uint32_t h[4], l[4];
 #pragma unroll
   for (int e = 0; e < 4; ++e) {
     h[e] = pack_bf16_fast(x[2 * e], x[2 * e + 1]);
     l[e] = pack_bf16_fast(x[2 * e] - bf16_lo(h[e]), x[2 * e + 1] - bf16_hi(h[e]));
   }
-  *reinterpret_cast<uint4 *>(row_hi + pos) = make_uint4(h[0], h[1], h[2], h[3]);
-  *reinterpret_cast<uint4 *>(row_hi + ACT_BYTES + pos) = make_uint4(l[0], l[1], l[2], l[3]);
+  if (kAT) {
+    tmem_st4(taddr, h[0], h[1], h[2], h[3]);
+    tmem_st4(taddr + (TM_A_LO - TM_A_HI), l[0], l[1], l[2], l[3]);
+    if (smem_hi) *reinterpret_cast<uint4 *>(row_hi + pos) = make_uint4(h[0], h[1], h[2], h[3]);
+  } else {
+    *reinterpret_cast<uint4 *>(row_hi + pos) = make_uint4(h[0], h[1], h[2], h[3]);
+    *reinterpret_cast<uint4 *>(row_hi + ACT_BYTES + pos) = make_uint4(l[0], l[1], l[2], l[3]);
+  }
 }
 
 // forward: 32 accumulator columns [c0, c0+32) of row r -> +bias -> (relu) -> hi/lo -> act images.
 // kType 0 relu, 1 relu + alpha head (fp32 activations), 2 linear.  Returns the ReLU mask word (see fwd_block).
-template <int kType, bool kMask>
+template <int kType, bool kMask, bool kAT>
 __device__ __forceinline__ uint32_t fwd_block_x3(const uint32_t v[32], const float *s_b, uint8_t *act_hi, uint32_t r,
-                                                 uint32_t c0, const float *s_wa, float &alpha) {
+                                                 uint32_t c0, const float *s_wa, float &alpha, uint32_t t_row, bool smem_hi) {
   uint32_t m = 0;
   uint8_t *row_hi = act_hi + (c0 >> 6) * SLAB_BYTES + (r >> 3) * 1024u + (r & 7u) * 128u;
   const uint32_t q0 = (c0 & 63u) >> 3;
@@ -69,30 +83,31 @@ __device__ __forceinline__ uint32_t fwd_block_x3(const uint32_t v[32], const flo
         alpha = fmaf(x[4 * e + 3], a.w, alpha);
       }
     }
-    store_split8(row_hi, ((q0 + g) ^ (r & 7u)) << 4, x);
+    store_split8<kAT>(row_hi, ((q0 + g) ^ (r & 7u)) << 4, x, t_row + TM_A_HI + (c0 + 8 * g) / 2, smem_hi);
   }
   return m;
 }
 
-template <int kType, bool kMask>
+// t_row = TMEM address of this thread's lane at column 0 (kAT: where the next layer's A operand goes)
+template <int kType, bool kMask, bool kAT>
 __device__ __forceinline__ uint2 fwd_epilogue_x3(uint32_t tmem_rc, uint32_t cq, const float *s_bias, uint8_t *act_hi,
-                                                 uint32_t r, const float *s_wa, float &alpha) {
+                                                 uint32_t r, const float *s_wa, float &alpha, uint32_t t_row, bool smem_hi) {
   uint32_t va[32];
   const uint32_t c0 = cq * 64;
   uint2 mk;
   tmem_ld32(tmem_rc, va);
   tmem_ld_wait(va);
-  mk.x = fwd_block_x3<kType, kMask>(va, s_bias, act_hi, r, c0, s_wa, alpha);
+  mk.x = fwd_block_x3<kType, kMask, kAT>(va, s_bias, act_hi, r, c0, s_wa, alpha, t_row, smem_hi);
   tmem_ld32(tmem_rc + 32, va);
   tmem_ld_wait(va);
-  mk.y = fwd_block_x3<kType, kMask>(va, s_bias, act_hi, r, c0 + 32, s_wa, alpha);
+  mk.y = fwd_block_x3<kType, kMask, kAT>(va, s_bias, act_hi, r, c0 + 32, s_wa, alpha, t_row, smem_hi);
   return mk;
 }
 
 // views_linears.0 (N=128: 64 columns per warp) + rgb_linear on CUDA cores from the fp32 activations
-template <class Params>
+template <bool kAT, class Params>
 __device__ __forceinline__ uint2 fwd_views_rgb_x3(const Params &p, uint32_t tmem_row, uint32_t ch, uint8_t *act_hi, uint32_t r,
-                                                  int64_t row, bool live, const float *s_head) {
+                                                  int64_t row, bool live, const float *s_head, bool smem_hi) {
   const int64_t ray = (row < p.n ? row : p.n - 1) / p.S;
   const float4 *vb4 = reinterpret_cast<const float4 *>(p.viewbias + ray * 128);
   float c0 = 0.f, c1 = 0.f, c2 = 0.f;
@@ -125,7 +140,16 @@ __device__ __forceinline__ uint2 fwd_views_rgb_x3(const Params &p, uint32_t tmem
         c1 = fmaf(x[j], s_head[128 + k], c1);
         c2 = fmaf(x[j], s_head[256 + k], c2);
       }
-      store_split8(row_hi, ((q0 + g) ^ (r & 7u)) << 4, x);
+      if (kAT) {   // h9 feeds no MMA: only its hi image is needed, in shared memory, for the stash
+        if (smem_hi) {
+          uint32_t h[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) h[e] = pack_bf16_fast(x[2 * e], x[2 * e + 1]);
+          *reinterpret_cast<uint4 *>(row_hi + (((q0 + g) ^ (r & 7u)) << 4)) = make_uint4(h[0], h[1], h[2], h[3]);
+        }
+      } else {
+        store_split8<false>(row_hi, ((q0 + g) ^ (r & 7u)) << 4, x);
+      }
     }
     mk2[i] = m;
   }
@@ -147,6 +171,13 @@ __device__ __forceinline__ void warp_store_slab_x3(uint8_t *dst_slot, const uint
 }
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 
+// pair MMA over one 64-wide K chunk with A in tensor memory: 4 k-steps of 16 features = 8 packed columns each
+__device__ __forceinline__ void issue_chunk_ts(uint32_t tmem_d, uint32_t tmem_a, uint32_t b_smem, uint32_t idesc, bool first) {
+  const uint64_t db = make_smem_desc(b_smem, 0, 1024);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) umma2_bf16_ts(tmem_d, tmem_a + 8 * k, db + 2 * k, idesc, (first && k == 0) ? 0u : 1u);
+}
+
 // =================================================================================================
 // forward, one tile per CTA.  kPasses = 3: split precision (hi and lo images, three MMA groups per chunk); kPasses = 1: plain
 // bf16 (hi image only) -- used for networks whose positional input does not fit the ping-pong kernel's ring program
@@ -157,9 +188,11 @@ __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.
 //   L5     : 4 x W (activation slabs), then for every positional slab s: Wpe_s, PE_s
 //   L6..L9 : 4 x W
 // =================================================================================================
-template <int kPasses, int kPeSlabs>
+template <int kPasses, int kPeSlabs, bool kAT = false, bool kProf = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) mlp_fwd_gen(FwdParams p) {
   constexpr bool kX3 = kPasses == 3;
+  const bool prof_on = kProf && p.prof != nullptr;      // per-role cycle accounting (FLNERF_TC_PROF), compiled out otherwise
+  static_assert(!kAT || kX3, "A-in-TMEM is the split-precision kernel's variant (one tile per CTA leaves 256 TMEM columns free)");
   constexpr int kPer = kX3 ? 2 : 1;                                    // ring items per operand
   constexpr int kItems = kPer * (2 * kPeSlabs + 16 + 4 + 2 * kPeSlabs + 16);
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -178,8 +211,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) mlp_fwd
     // ---------------------------------------------------------------- producer (both CTAs): local halves
     if (lane == 0) {
       LayF::Ring ring;
+      long long pw = 0;
+      const long long pt0 = prof_on ? clock64() : 0;
       auto push = [&](const uint8_t *src, uint32_t bytes) {
+        const long long c0 = prof_on ? clock64() : 0;
         mbar_wait(LayF::w_empty(bar, ring.stage), ring.phase ^ 1);
+        if (prof_on) pw += clock64() - c0;
         mbar_arrive_expect_tx(LayF::w_full(bar, ring.stage), bytes);
         bulk_g2s(s_w + ring.stage * WSTAGE, src, bytes, LayF::w_full(bar, ring.stage));
         ring.next();
@@ -211,6 +248,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) mlp_fwd
           }
         }
       }
+      if (prof_on) { p.prof[blockIdx.x * PROF_SLOTS + 4] = pw; p.prof[blockIdx.x * PROF_SLOTS + 5] = clock64() - pt0; }
     }
   } else if (warp == 1) {
     if (lane == 0 && cr != 0) {
@@ -227,7 +265,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) mlp_fwd
       // -------------------------------------------------------------- pair MMA issuer (leader)
       const uint32_t idesc256 = make_idesc(256, 256, 0, 0), idesc128 = make_idesc(256, 128, 0, 0);
       uint32_t q = 0, n_act = 0;
-      auto wait_full = [&](uint32_t i) { mbar_wait(LayF::w_full(bar, LayF::item_stage(i)), LayF::item_phase(i)); };
+      long long wa = 0, ww = 0;
+      const long long mt0 = prof_on ? clock64() : 0;
+      auto wait_full = [&](uint32_t i) {
+        const long long c0 = prof_on ? clock64() : 0;
+        mbar_wait(LayF::w_full(bar, LayF::item_stage(i)), LayF::item_phase(i));
+        if (prof_on) ww += clock64() - c0;
+      };
       auto release = [&](uint32_t i) { umma2_commit_multicast(LayF::w_empty(bar, LayF::item_stage(i)), (uint16_t)3); };
       auto st = [&](uint32_t i) { return s_w + LayF::item_stage(i) * WSTAGE; };
       const uint32_t a_hi = s_act, a_lo = s_act + ACT_BYTES;
@@ -246,7 +290,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) mlp_fwd
       for (int it = 0; it < iters; ++it) {
         for (int L = 0; L < 10; ++L) {
           if (!(it == 0 && L == 0)) {  // both CTAs' epilogue warps: inputs written, accumulator drained
+            const long long c0 = prof_on ? clock64() : 0;
             mbar_wait(LayF::act_ready(bar, 0), n_act & 1);
+            if (prof_on) wa += clock64() - c0;
             ++n_act;
           }
           tc_fence_after();
@@ -257,16 +303,26 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) mlp_fwd
             for (uint32_t c = 0; c < 4; ++c) {
               wait_full(q);
               tc_fence_after();
-              issue_chunk(tmem_base, a_hi + c * SLAB_BYTES, st(q), idesc, c == 0);
-              if (kX3) {
-                issue_chunk(tmem_base, a_lo + c * SLAB_BYTES, st(q), idesc, false);
+              if (kAT) {   // A (hi, then lo) from tensor memory, B = the hi weight chunk; then A hi x the lo chunk
+                issue_chunk_ts(tmem_base, tmem_base + TM_A_HI + c * 32, st(q), idesc, c == 0);
+                issue_chunk_ts(tmem_base, tmem_base + TM_A_LO + c * 32, st(q), idesc, false);
                 release(q);
                 wait_full(q + 1);
                 tc_fence_after();
-                issue_chunk(tmem_base, a_hi + c * SLAB_BYTES, st(q + 1), idesc, false);
+                issue_chunk_ts(tmem_base, tmem_base + TM_A_HI + c * 32, st(q + 1), idesc, false);
                 release(q + 1);
               } else {
-                release(q);
+                issue_chunk(tmem_base, a_hi + c * SLAB_BYTES, st(q), idesc, c == 0);
+                if (kX3) {
+                  issue_chunk(tmem_base, a_lo + c * SLAB_BYTES, st(q), idesc, false);
+                  release(q);
+                  wait_full(q + 1);
+                  tc_fence_after();
+                  issue_chunk(tmem_base, a_hi + c * SLAB_BYTES, st(q + 1), idesc, false);
+                  release(q + 1);
+                } else {
+                  release(q);
+                }
               }
               q += kPer;
             }
@@ -275,6 +331,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) mlp_fwd
           }
           umma2_commit_multicast(LayF::acc_full(bar, 0), (uint16_t)3);
         }
+      }
+      if (prof_on) {
+        long long *o = p.prof + blockIdx.x * PROF_SLOTS;
+        o[0] = clock64() - mt0; o[1] = wa; o[2] = 0; o[3] = ww; o[16] = 0; o[17] = 0;
       }
     }
   } else {
@@ -289,6 +349,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) mlp_fwd
     float *s_alpha = reinterpret_cast<float *>(smem + LayF::OFF_ALPHA);
     uint8_t *act_hi = smem + OFF_ACT;
     const uint32_t tmem_rc = tmem_base + ((quarter * 32) << 16) + cq * 64;
+    const bool prof = prof_on && e == 0 && lane == 0;
+    long long e_acc = 0, e_st = 0, e_body = 0, e_tail = 0;
+    const long long et0 = prof ? clock64() : 0;
     const bool stash_lo = kX3 && p.stash_lo;
     const size_t tile_bytes = stash_lo ? TILE_ACT_BYTES_X3 : TILE_ACT_BYTES, slot_bytes = stash_lo ? SLOT_BYTES_X3 : 65536;
     uint32_t n_layer = 0;
@@ -302,24 +365,29 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) mlp_fwd
       uint32_t *stash_mask = live ? p.stash_mask : nullptr;
       for (int L = 0; L < 10; ++L, ++n_layer) {
         const bool has_cols = L < 9 || cq < 2;   // the views layer has 128 outputs: column quarters 0,1 only
+        const long long c0 = prof ? clock64() : 0;
         mbar_wait(LayF::acc_full(bar, 0), n_layer & 1);
         tc_fence_after();
+        const long long c1 = prof ? clock64() : 0;
         if (p.stash_act) {  // my store of the previous layer reads the piece this layer overwrites
           if (lane == 0 && store_pending) bulk_wait_read0();
           __syncwarp();
         }
+        const long long c2 = prof ? clock64() : 0;
         float alpha = 0.f;
         uint2 mk = make_uint2(0u, 0u);
         const bool want_mask = stash_mask != nullptr;
+        const uint32_t t_row = tmem_base + ((quarter * 32) << 16);
+        const bool smem_hi = p.stash_act != nullptr;      // kAT: shared memory only stages the stash stores
         if (L <= 7) {
           const float *sb = s_bias + L * 256;
           if (kX3) {
             if (L < 7) {
-              if (want_mask) mk = fwd_epilogue_x3<0, true>(tmem_rc, cq, sb, act_hi, r, s_wa, alpha);
-              else fwd_epilogue_x3<0, false>(tmem_rc, cq, sb, act_hi, r, s_wa, alpha);
+              if (want_mask) mk = fwd_epilogue_x3<0, true, kAT>(tmem_rc, cq, sb, act_hi, r, s_wa, alpha, t_row, smem_hi);
+              else fwd_epilogue_x3<0, false, kAT>(tmem_rc, cq, sb, act_hi, r, s_wa, alpha, t_row, smem_hi);
             } else {
-              if (want_mask) mk = fwd_epilogue_x3<1, true>(tmem_rc, cq, sb, act_hi, r, s_wa, alpha);
-              else fwd_epilogue_x3<1, false>(tmem_rc, cq, sb, act_hi, r, s_wa, alpha);
+              if (want_mask) mk = fwd_epilogue_x3<1, true, kAT>(tmem_rc, cq, sb, act_hi, r, s_wa, alpha, t_row, smem_hi);
+              else fwd_epilogue_x3<1, false, kAT>(tmem_rc, cq, sb, act_hi, r, s_wa, alpha, t_row, smem_hi);
             }
           } else {
             if (L < 7) {
@@ -340,15 +408,17 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) mlp_fwd
             }
           }
         } else if (L == 8) {
-          if (kX3) fwd_epilogue_x3<2, false>(tmem_rc, cq, s_bias + 8 * 256, act_hi, r, s_wa, alpha);
+          if (kX3) fwd_epilogue_x3<2, false, kAT>(tmem_rc, cq, s_bias + 8 * 256, act_hi, r, s_wa, alpha, t_row, smem_hi);
           else fwd_epilogue_q<2, false>(tmem_rc, cq, s_bias + 8 * 256, act_hi, r, s_wa, alpha);
         } else if (has_cols) {
-          if (kX3) mk = fwd_views_rgb_x3(p, tmem_rc - cq * 64, cq, act_hi, r, row, live, s_head);
+          if (kX3) mk = fwd_views_rgb_x3<kAT>(p, tmem_rc - cq * 64, cq, act_hi, r, row, live, s_head, smem_hi);
           else mk = fwd_views_rgb(p, tmem_rc - cq * 64, cq, act_hi, r, row, live, s_head);
         }
+        if (kAT) tmem_st_wait();       // the A operand is in tensor memory before the issuer hears of it
         tc_fence_before();
         fence_async_smem();
         __syncwarp();
+        const long long c3 = prof ? clock64() : 0;
         if (lane == 0) {
           mbar_arrive_cluster(mapa_cluster(LayF::act_ready(bar, 0), 0));  // the leader's barrier
           if (stash_act && has_cols) {
@@ -360,7 +430,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) mlp_fwd
         }
         if (want_mask && L != 8 && has_cols)
           *reinterpret_cast<uint2 *>(stash_mask + mask_word_offset(tile, L < 9 ? L : 8, cq, r)) = mk;
+        if (prof) { e_acc += c1 - c0; e_st += c2 - c1; e_body += c3 - c2; e_tail += clock64() - c3; }
       }
+    }
+    if (prof) {
+      long long *o = p.prof + blockIdx.x * PROF_SLOTS + 6;
+      o[0] = clock64() - et0; o[1] = e_acc; o[2] = e_st; o[3] = e_body; o[4] = e_tail;
+      for (int k = 5; k < 10; ++k) o[k] = 0;
     }
     if (lane == 0 && store_pending) bulk_wait_all0();
   }
@@ -389,7 +465,7 @@ __device__ __forceinline__ void dgrad_block_x3(const uint32_t v[32], uint32_t m,
       if (kUseMask) gv = (m & (0x80000000u >> i)) ? 0.f : gv;  // mask bit 31 - i set = output i was inactive
       x[j] = gv;
     }
-    store_split8(row_hi, ((q0 + g) ^ (r & 7u)) << 4, x);
+    store_split8<false>(row_hi, ((q0 + g) ^ (r & 7u)) << 4, x);
   }
 }
 
@@ -424,7 +500,7 @@ __device__ __forceinline__ void dgrad_g9_x3(const float4 dr, const uint2 mk, uin
         const float gv = dr.x * s_head[k] + dr.y * s_head[128 + k] + dr.z * s_head[256 + k];
         x[j] = (mw[j2] & (0x80000000u >> i)) ? 0.f : gv;
       }
-      store_split8(row_hi, ((q0 + g) ^ (r & 7u)) << 4, x);
+      store_split8<false>(row_hi, ((q0 + g) ^ (r & 7u)) << 4, x);
     }
   }
 }

@@ -119,6 +119,25 @@ __device__ __forceinline__ void umma2_bf16(uint32_t tmem_d, uint64_t desc_a, uin
       ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// the same with the A operand in TENSOR MEMORY (tcgen05 "TS" form): A[m][k] of this CTA's 128 rows sits at TMEM lane m, 32-bit
+// column tmem_a + k/2 (two bf16 per column, k even in the low half) -- written there by the epilogue with tcgen05.st, so the
+// activations never touch shared memory on their way into the next layer's MMA.  K-major only; the 8-word vector is the
+// (unused) disable-output-lane mask of the cta_group::2 form.
+__device__ __forceinline__ void umma2_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc,
+                                              uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, {%5, %5, %5, %5, %5, %5, %5, %5}, p;\n\t}"
+      ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate), "r"(0u)
+      : "memory");
+}
+// 32 lanes x 4 consecutive 32-bit columns <- 4 registers per thread (thread i <-> TMEM lane base+i); SASS STTM
+__device__ __forceinline__ void tmem_st4(uint32_t taddr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(taddr), "r"(a), "r"(b), "r"(c), "r"(d)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 // arrives on the mbarrier at this offset in every CTA of cta_mask once all earlier pair-MMAs of this thread completed
 __device__ __forceinline__ void umma2_commit_multicast(uint32_t bar, uint16_t cta_mask) {
   asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
