@@ -623,6 +623,7 @@ def run_nerfpp(args):
 
     def timed(precision, first, warmup, steps, host=False):
         nets, optims = build(precision)
+        step = D.CascadeStep(nets, optims, [64, 128], 7, world, graph=not args.no_graph)
         pinned = None
         if host:
             pinned = []
@@ -635,7 +636,7 @@ def run_nerfpp(args):
                 o, d, t = (x.to(dev, non_blocking=True) for x in pinned[i % 3])
             else:
                 o, d, t, gid = mgr.batch(first + rank, n_rand, world)
-            losses, ret = D.cascade_batch(nets, optims, [64, 128], o, d, t, gb, 7, i * n_rand * 192, world)
+            losses, ret = step(o, d, t, gb, i * n_rand * 192)
             if host:
                 return torch.cat(losses).cpu()
             mgr.accumulate(ret["rgb"], t, gid)
@@ -687,6 +688,7 @@ def run_nerfpp(args):
                        "l2": "per-step activation stash (~%.1f GB) exceeds the 126 MB L2" % (n_rand * 512 * 5.1e3 / 1e9)},
             "e2e": {"value": gb * args.steps / (ms_e * 1e-3), "unit": "rays/s", "h2d_bytes_per_step": n_rand * 36, "d2h_bytes_per_step": 8},
             "gpu_launches": int(launches), "clocks": clk,
+            "launch_mode": "kernel by kernel" if (args.no_graph or world > 1) else "one CUDA graph per batch (both cascade levels)",
             "roofline": {"bound": "tensor", "kernel": "whole step", "achieved": tf, "peak": peaks["tf_sust"], "unit": "TFLOP/s",
                          "frac": tf / peaks["tf_sust"], "traffic": None,
                          "peak_source": peaks["src"] + " bf16 sustained; algorithmic FLOPs: 256 fg + 256 bg MLP evaluations per ray"},

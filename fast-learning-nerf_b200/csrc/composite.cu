@@ -379,7 +379,7 @@ int flnerf_pp_sample_pdf_merge(flnerf_ctx *ctx, int64_t B, int Nc, int Nf, const
   size_t smem = (size_t)kRaysPerBlock * (Nc - 1 + P2) * sizeof(float);
   FL_REQUIRE(smem <= 48 * 1024, "flnerf_pp_sample_pdf_merge: Nc+Nf=%d too large", Nc + Nf);
   FL_LAUNCH(k_merge_pp, (unsigned)ceil_div64(B, kRaysPerBlock), kRaysPerBlock * 32, smem, stream, B,
-            Nc, Nf, P2, z, weights, u, det, seed, offset, z_merged, z_samples, nullptr, (const flnerf_step_record *)nullptr);
+            Nc, Nf, P2, z, weights, u, det, seed, offset, z_merged, z_samples, nullptr, ctx->step_rec);
   return 0;
 }
 

@@ -54,10 +54,11 @@ __device__ __forceinline__ float sphere_exit(const float *o, const float *d, flo
 // jittered inside their mid-point intervals (perturb_samples, :72-81).  One thread per (ray, sample).
 __global__ void pp_depths0_kernel(int64_t B, int N, const float *__restrict__ ro, const float *__restrict__ rd,
                                   const float *__restrict__ t_fg, const float *__restrict__ t_bg, int perturb, uint64_t seed,
-                                  uint64_t offset, float *__restrict__ fg_far, float *__restrict__ fg_z,
-                                  float *__restrict__ bg_z) {
+                                  uint64_t offset, const flnerf_step_record *__restrict__ rec, float *__restrict__ fg_far,
+                                  float *__restrict__ fg_z, float *__restrict__ bg_z) {
   int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= B * N) return;
+  if (rec) offset += rec->rng_offset;
   int64_t ray = idx / N;
   int i = (int)(idx % N);
   float far = sphere_exit(ro + ray * 3, rd + ray * 3, nullptr, nullptr);
@@ -299,7 +300,7 @@ int flnerf_pp_depths0(flnerf_ctx *ctx, int64_t B, int N, const float *rays_o, co
              "flnerf_pp_depths0: bad arguments");
   if (B == 0) return 0;
   FL_LAUNCH(pp_depths0_kernel, (unsigned)ceil_div64(B * N, 256), 256, 0, stream, B, N, rays_o, rays_d, t_fg, t_bg, perturb, seed,
-            offset, fg_far, fg_z, bg_z);
+            offset, ctx->step_rec, fg_far, fg_z, bg_z);
   return 0;
 }
 

@@ -278,7 +278,8 @@ int flnerf_ssim_psnr(flnerf_ctx *, int H, int W, const float *img0, const float 
 
 /* ---- one CUDA graph per training step (run_nerf.py:470-516 is a fixed kernel sequence; only four scalars change from
  * one iteration to the next).  While a device-side step record is attached to the context, flnerf_gather_batch ADDS
- * rec->first to its `first`, flnerf_coarse_depths / flnerf_sample_pdf_merge ADD rec->rng_offset to their `offset`, and
+ * rec->first to its `first`, flnerf_coarse_depths / flnerf_sample_pdf_merge (and the nerf++ pair flnerf_pp_depths0 /
+ * flnerf_pp_sample_pdf_merge) ADD rec->rng_offset to their `offset`, and
  * flnerf_adam_step takes its step size and bias correction from the record instead of (lr, t): the captured launches carry
  * no per-step host value, and the host updates the record with ONE tiny kernel before each replay. */
 typedef struct flnerf_step_record {

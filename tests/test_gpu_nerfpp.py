@@ -272,3 +272,44 @@ def test_nerfpp_driver_trains_checkpoints_and_interchanges(tmp_path, monkeypatch
     start, third = D.create_nerf(0, D.config_parser().parse_args(argv))
     assert start == 9 and third["optim_1"].adam.t == models["optim_1"].adam.t + 1
     np.testing.assert_allclose(third["net_1"].flat.cpu().numpy(), mod.flat.cpu().numpy(), rtol=3e-6, atol=2e-7)
+
+
+@pytest.mark.parametrize("precision", ["bf16", "bf16x3"])
+def test_cascade_step_graph_replay_equals_eager(precision, tmp_path):
+    """ddp_train_nerf.CascadeStep: batches 3.. of a shape run as ONE replayed CUDA graph (rays through static buffers, Philox
+    offset and Adam scalars from the device-side step record) -- losses, predictions and both levels' weights must equal the
+    kernel-by-kernel run up to the summation order of the weight-gradient atomics (the tolerances of tests/test_gpu_graph.py),
+    and the launch accounting must count the replayed kernels."""
+    import ddp_train_nerf as D
+    from flnerf_b200 import lib
+    B, n_steps = 256, 5
+    o, d = _rays(B * n_steps, 5)
+    gt = torch.rand(B * n_steps, 3, generator=torch.Generator().manual_seed(6))
+    o, d, gt = (o * 0.7).cuda(), d.cuda(), gt.cuda()           # every origin inside the unit sphere (intersect_sphere)
+    assert float(o.norm(dim=-1).max()) < 0.95
+    out = {}
+    for graph in (False, True):
+        args = D.config_parser().parse_args(["--basedir", str(tmp_path / str(graph)), "--precision", precision, "--no_reload",
+                                             "--cascade_samples", "16,24"])
+        _, models = D.create_nerf(0, args)
+        nets, optims = [models["net_0"], models["net_1"]], [models["optim_0"], models["optim_1"]]
+        step = D.CascadeStep(nets, optims, [16, 24], seed=11, world=1, graph=graph)
+        lib.launch_count(reset=True)
+        losses, preds = [], []
+        for i in range(n_steps):
+            sl = slice(i * B, (i + 1) * B)
+            l, ret = step(o[sl], d[sl], gt[sl], B, i * B * 40)
+            losses.append(torch.cat(l).clone()); preds.append(ret["rgb"].clone())
+        torch.cuda.synchronize()
+        out[graph] = (torch.stack(losses), torch.cat(preds), nets[0].flat.clone(), nets[1].flat.clone(), lib.launch_count(),
+                      optims[0].adam.t)
+        assert (step._graph is not None) == graph
+    rtol = 2e-3 if precision == "bf16" else 1e-4
+    np.testing.assert_allclose(out[True][0].cpu().numpy(), out[False][0].cpu().numpy(), rtol=rtol)
+    np.testing.assert_allclose(out[True][1].cpu().numpy(), out[False][1].cpu().numpy(), atol=2e-3 if precision == "bf16" else 2e-5)
+    for k in (2, 3):
+        dw = (out[True][k] - out[False][k]).abs()
+        assert float(dw.mean()) < 2e-5 and float(dw.max()) <= n_steps * 2.1 * 5e-4     # Adam: sign flips of ~zero gradients only
+    assert out[True][5] == out[False][5] == n_steps
+    assert out[True][4] >= out[False][4]            # replays are counted kernel by kernel (+ the record writes)
+    assert float(out[True][0][-1, 1]) < float(out[True][0][0, 1])
