@@ -118,14 +118,20 @@ class Trainer:
         # one CUDA graph per full batch of step_from_tree: opt-in, because a replayed step returns
         # the SAME loss / output tensors every time (the graph's static outputs)
         self.use_graph = bool(int(os.environ.get("FLNERF_GRAPH", "0"))) if graph is None else bool(graph)
-        # Single process only: a CUDA graph that captured NCCL kernels keeps the communicator alive -- on 2 x B200 the step
-        # itself replayed correctly (1.78 M vs 1.76 M rays/s) but destroy_process_group() never returned at exit
-        # (profiles/r02g_*), so under data parallelism the step is launched kernel by kernel (costs ~1 %).
-        if self.world > 1:
+        # Single process by default: a CUDA graph that captured NCCL kernels keeps the communicator alive -- on 2 x B200 the
+        # step replayed correctly (1.77 M vs 1.75 M rays/s, profiles/r02o_*) but destroy_process_group() never returned
+        # unless every captured step had been dropped first (release_graph()).  Under data parallelism the step is therefore
+        # launched kernel by kernel (costs ~1.5 %) unless $FLNERF_GRAPH_DP=1 opts in.
+        if self.world > 1 and not int(os.environ.get("FLNERF_GRAPH_DP", "0")):
             self.use_graph = False
         self._graph = self._graph_key = self._graph_out = self._rec = None
         self._graph_seen, self._graph_launches = {}, 0
         self.sync_replicas()
+
+    def release_graph(self):
+        """Drop the captured step (and its private memory pool); the next full batch is captured again."""
+        self._graph = self._graph_key = self._graph_out = None
+        self._graph_seen = {}
 
     def sync_replicas(self):
         """nn.DataParallel held ONE copy of the weights (run_nerf.py:82,90).  Replicas built from unseeded RNGs or resumed
