@@ -390,6 +390,9 @@ def run_ours(args):
     K = synthetic.intrinsics(H, W, focal)
     n_img = args.images
     n_rand = args.n_rand                      # rays per rank per step
+    if args.scaling == "strong":
+        assert args.n_rand % world == 0
+        n_rand = args.n_rand // world         # fixed global batch (run_nerf.py's N_rand), split over the ranks
     poses = synthetic.lego_like_poses(n_img)
     torch.manual_seed(0)
     images = synthetic.render_scene(H, W, K, poses, n_samples=48, device=dev)
@@ -585,7 +588,7 @@ def run_ours(args):
     print(json.dumps({
         "metric": "training rays/sec (64+128 samples)", "value": value, "unit": "rays/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
+        "scaling": args.scaling, "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
         "config": {"workload": "lego 800x800 (synthetic cameras/images, %d train views), 64+128 samples, N_rand=%d per GPU "
                                "(global %d), quadtree on (init_level 2)" % (n_img, n_rand, gb),
                    "parallelism": "ray-sharded data parallel x%d, one gradient all-reduce per step" % world,
@@ -724,6 +727,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--precision", default=os.environ.get("FLNERF_PRECISION", "bf16"), choices=["bf16", "bf16x3", "fp32"])
     ap.add_argument("--n_rand", type=int, default=4096)
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak (default, BASELINE configs[3]): n_rand rays PER GPU; strong: n_rand rays in total, split over the ranks")
     ap.add_argument("--images", type=int, default=100)
     ap.add_argument("--no_cpu_baseline", action="store_true")
     ap.add_argument("--no_parity_leg", action="store_true")
