@@ -147,7 +147,7 @@ __device__ __forceinline__ uint2 fwd_views_rgb_x3(const Params &p, uint32_t tmem
           for (int e = 0; e < 4; ++e) h[e] = pack_bf16_fast(x[2 * e], x[2 * e + 1]);
           *reinterpret_cast<uint4 *>(row_hi + (((q0 + g) ^ (r & 7u)) << 4)) = make_uint4(h[0], h[1], h[2], h[3]);
         }
-      } else {
+      } else if (smem_hi) {   // h9 feeds no MMA: its images are only staged for the stash
         store_split8<false>(row_hi, ((q0 + g) ^ (r & 7u)) << 4, x);
       }
     }

@@ -7,27 +7,28 @@ import model
 from flnerf_b200 import ops, lib
 
 B, S = int(os.environ.get("KB_RAYS", 4096)), 192
+MODE = int(os.environ.get("KB_MODE", 1))          # 1 = bf16, 2 = bf16x3
 dev = torch.device("cuda")
 torch.manual_seed(0)
-net = model.NeRF(D=8, W=256, input_ch=63, input_ch_views=27, output_ch=5, skips=[4], use_viewdirs=True, precision="bf16").to(dev)
+net = model.NeRF(D=8, W=256, input_ch=63, input_ch_views=27, output_ch=5, skips=[4], use_viewdirs=True, precision="bf16" if MODE == 1 else "bf16x3").to(dev)
 rays = torch.cat([torch.randn(B, 3) * 0.3, torch.nn.functional.normalize(torch.randn(B, 3), dim=-1), 2 * torch.ones(B, 1),
                   6 * torch.ones(B, 1), torch.nn.functional.normalize(torch.randn(B, 3), dim=-1)], -1).to(dev)
 z = ops.coarse_depths(rays, S, True, False, None, 3, 0)
 n = B * S
-tiles, dirpe = ops.encode_tc(rays, z)
+tiles, dirpe = ops.encode_tc(rays, z, MODE)
 flat, packed = net._weights()
-raw, stash = ops.mlp_forward(1, flat, packed, tiles, dirpe, n, S, True)
+raw, stash = ops.mlp_forward(MODE, flat, packed, tiles, dirpe, n, S, True)
 draw = torch.randn(n, 4, device=dev) * 1e-3
 g = torch.zeros_like(flat)
-ws = ops.mlp_backward(1, flat, packed, tiles, dirpe, stash, draw, g, n, S)
-stash2 = ops._alloc_bytes(lib.load().flnerf_mlp_stash_bytes(1, n, S, 1), dev)
+ws = ops.mlp_backward(MODE, flat, packed, tiles, dirpe, stash, draw, g, n, S)
+stash2 = ops._alloc_bytes(lib.load().flnerf_mlp_stash_bytes(MODE, n, S, 1), dev)
 def fwd(train=1):
-    lib.check(lib.load().flnerf_mlp_forward(ops._ctx(raw), 1, ops._ptr(flat), ops._ptr(packed), n, S, ops._ptr(tiles),
+    lib.check(lib.load().flnerf_mlp_forward(ops._ctx(raw), MODE, ops._ptr(flat), ops._ptr(packed), n, S, ops._ptr(tiles),
                                             ops._ptr(dirpe), ops._ptr(raw), ops._ptr(stash2), train, ops._stream()), "fwd")
 cases = {"fwd": (lambda: fwd(1), 1186816.0), "fwd_infer": (lambda: fwd(0), 1186816.0),
-         "dgrad": (lambda: ops.mlp_backward(1, flat, packed, tiles, dirpe, stash, draw, g, n, S, 1, ws), 2.0 * 557696),
-         "wgrad": (lambda: ops.mlp_backward(1, flat, packed, tiles, dirpe, stash, draw, g, n, S, 2, ws), 2.0 * 593408),
-         "heads": (lambda: ops.mlp_backward(1, flat, packed, tiles, dirpe, stash, draw, g, n, S, 4, ws), 0.0)}
+         "dgrad": (lambda: ops.mlp_backward(MODE, flat, packed, tiles, dirpe, stash, draw, g, n, S, 1, ws), 2.0 * 557696),
+         "wgrad": (lambda: ops.mlp_backward(MODE, flat, packed, tiles, dirpe, stash, draw, g, n, S, 2, ws), 2.0 * 593408),
+         "heads": (lambda: ops.mlp_backward(MODE, flat, packed, tiles, dirpe, stash, draw, g, n, S, 4, ws), 0.0)}
 out = {}
 for k, (fn, flop) in cases.items():
     for _ in range(3): fn()
