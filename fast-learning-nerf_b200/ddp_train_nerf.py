@@ -290,9 +290,9 @@ def train_step(models, rays_o, rays_d, target_rgb, args, tree_mgr=None, seed=0):
     if L != 2:
         raise FlnerfError("train_step implements cascade_level = 2 (coarse + fine), like every config of the fork")
     epoch_size, bs = rays_o.shape[0], args.batch_size
-    step = models.get("_cascade_step")
-    if step is None or step.nets != nets:
-        step = models["_cascade_step"] = CascadeStep(nets, optims, samples, seed, world, graph=not getattr(args, "no_graph", False))
+    step = getattr(nets[0], "_cascade_step", None)       # kept on the first level's module: `models` stays the reference's dict
+    if step is None or step.nets != nets or step.optims != optims:
+        step = nets[0]._cascade_step = CascadeStep(nets, optims, samples, seed, world, graph=not getattr(args, "no_graph", False))
     step.seed = seed
     preds, it, offset = [], 0, 0
     for b0 in range(0, epoch_size, bs):
