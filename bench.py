@@ -579,7 +579,7 @@ def run_ours(args):
         r = reference_subprocess("cpu", 2, 1, 1024)
         if "value" in r:
             cpu = dict(r["cpu_baseline"])
-            cpu["sample"] = "2 steps (1 warm-up) of a 1024-ray batch of the same 64+128 step; " + cpu["sample"]
+            cpu["sample"] = "bounded sample of the same 64+128 step (a quarter batch, 1 warm-up step): " + cpu["sample"]
         else:       # the untracked reference copy is missing: time the oracle port instead
             cpu = {"unavailable": r.get("unavailable")}
         r = reference_subprocess("cuda", 5, 2, n_rand, gpu_index=local)
