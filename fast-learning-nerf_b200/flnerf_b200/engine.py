@@ -179,6 +179,7 @@ class Trainer:
         x, dirpe, stash = saved
         flat, packed = net._weights()
         ops.mlp_backward(net.mode, flat, packed, x, dirpe, stash, draw, net._flat_grad, n, S)
+        net._mask_grads()       # (a use_viewdirs=False model's frozen adapter; no-op otherwise)
 
     @torch.no_grad()
     def step(self, rays_o, rays_d, target, leaf_gid=None, leaf_max=None, global_batch: Optional[int] = None):

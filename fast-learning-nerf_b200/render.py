@@ -44,8 +44,8 @@ def render(H, W, K, chunk=1024 * 32, rays=None, c2w=None, ndc=True, near=0., far
         rays_o, rays_d = get_rays(H, W, K, c2w)
     else:
         rays_o, rays_d = rays
-    if not use_viewdirs:
-        raise FlnerfError("flnerf render implements use_viewdirs=True (lego/fern configs)")
+    # use_viewdirs=False (render.py:59-66 skipped): the packed rays still carry d/|d|, a model built without view
+    # directions multiplies it by zero weights (model.NeRF)
     view_src = rays_d
     if c2w_staticcam is not None:
         rays_o, rays_d = get_rays(H, W, K, c2w_staticcam)
@@ -125,8 +125,10 @@ def render_rays(ray_batch, network_fn, network_query_fn, N_samples, retraw=False
                 N_importance=0, network_fine=None, white_bkgd=False, raw_noise_std=0., verbose=False, pytest=False,
                 _coarse=None):
     """Volumetric rendering of a ray batch (render.py:195-305); same keys in the returned dict."""
+    if ray_batch.shape[-1] == 8:          # [o, d, near, far] (use_viewdirs=False, render.py:74-80): no view direction
+        ray_batch = torch.cat([ray_batch, ray_batch.new_zeros(ray_batch.shape[0], 3)], -1)
     if ray_batch.shape[-1] < 11:
-        raise FlnerfError("flnerf render_rays needs [o,d,near,far,viewdir] rays (use_viewdirs=True)")
+        raise FlnerfError("flnerf render_rays needs [o,d,near,far(,viewdir)] rays")
     rays11 = ray_batch.float().contiguous()
     B = rays11.shape[0]
     rays_d = rays11[:, 3:6]

@@ -101,8 +101,11 @@ def create_nerf(args):
         model_fine = make(args.netdepth_fine, args.netwidth_fine)
         grad_vars += list(model_fine.parameters())
     network_query_fn = NetworkQuery(embed_fn, embeddirs_fn, args.netchunk)
-    nets = [_unwrap(m) for m in (model, model_fine) if m is not None]
-    optimizer = FusedAdam(grad_vars, nets, lr=args.lrate, betas=(0.9, 0.999))
+    # the nets whose flat buffers the kernels and the fused optimiser work on (use_viewdirs=False: the inner net behind the
+    # reference-shaped module, model.NeRF.kernel_net; its Adam state is then NOT the reference's 20-tensor layout)
+    nets = [_unwrap(m).kernel_net for m in (model, model_fine) if m is not None]
+    optimizer = FusedAdam(grad_vars if args.use_viewdirs else [p for n in nets for p in n.parameters()], nets,
+                          lr=args.lrate, betas=(0.9, 0.999))
 
     start_epoch, start_iter = 0, 0
     basedir, expname = args.basedir, args.expname
@@ -238,7 +241,7 @@ def train(argv=None):
             treeManager.cur_level = global_epoch
             print("load '" + tree_pkl + "'")
 
-    nc, nf = _unwrap(render_kwargs_train['network_fn']), _unwrap(render_kwargs_train['network_fine'])
+    nc, nf = _unwrap(render_kwargs_train['network_fn']).kernel_net, _unwrap(render_kwargs_train['network_fine']).kernel_net
     trainer = Trainer(nc, nf, optimizer, H, W, K, near, far, args.N_samples, args.N_importance, args.white_bkgd,
                       args.perturb, args.lindisp, render_kwargs_train.get('ndc', True), args.raw_noise_std,
                       world_size=world, rank=rank, graph=not getattr(args, "no_graph", False))

@@ -331,3 +331,70 @@ def test_full_size_properties():
     net16.zero_grad(); (raw * (2 * gout)).sum().backward(); g2 = net16._flat_grad.clone()
     assert rel_l2(g2, 2 * g1) < 1e-4
     assert float(g1.abs().max()) > 0 and bool(torch.isfinite(g1).all())
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16x3"])
+def test_no_viewdirs_model_forward_backward_step_render(precision):
+    """use_viewdirs=False (nerf-ours/model.py:55-63: output_linear instead of the alpha / feature / views / rgb heads) on the
+    kernels of the use_viewdirs=True network through the frozen adapter of model.NeRF: forward, gradients and one fused Adam
+    step against a torch restatement of the reference formula (tests/test_host.py checks the mapping itself on the CPU),
+    the reference-shaped checkpoint, and render(use_viewdirs=False)."""
+    import model
+    import render as R, run_nerf, run_nerf_helpers as Hh
+    from flnerf_b200.engine import FusedAdam
+    from test_host import _no_viewdirs_reference
+    torch.manual_seed(0)
+    m = model.NeRF(D=8, W=256, input_ch=63, input_ch_views=0, output_ch=5, skips=[4], use_viewdirs=False, precision=precision).cuda()
+    sd0 = {k: v.detach().cpu().clone() for k, v in m.state_dict().items()}
+    x = torch.randn(300, 63, generator=torch.Generator().manual_seed(1))
+    pub = {k: v.clone().requires_grad_(True) for k, v in sd0.items()}
+    y_ref = _no_viewdirs_reference(pub, x)
+    inner = m.kernel_net
+    opt = FusedAdam(list(inner.parameters()), [inner], lr=1e-3)
+    opt.zero_grad()
+    y = m(x.cuda())
+    assert y.shape == (300, 5) and float(y[:, 4].abs().max()) == 0.0
+    scale = float(y_ref.detach().abs().max())
+    assert float((y[:, :4].detach().cpu() - y_ref[:, :4].detach()).abs().max()) <= 1e-4 * scale
+    g = torch.randn(300, 4, generator=torch.Generator().manual_seed(2))
+    (y[:, :4] * g.cuda()).sum().backward()
+    (y_ref[:, :4] * g).sum().backward()
+    grads = {n: p.grad.detach().cpu().clone() for n, p in inner.named_parameters()}
+    rel = lambda a, b: float((a.double() - b.double()).norm() / b.double().norm())
+    # 300 rows: nothing averages the split mode's operand rounding away (tests/test_gpu_x3.py holds it to 2e-3 at 4096 rays)
+    gtol = 2e-3 if precision == "fp32" else 6e-3
+    assert rel(grads["feature_linear.weight"][0:3], pub["output_linear.weight"].grad[0:3]) <= gtol
+    assert rel(grads["feature_linear.bias"][0:3], pub["output_linear.bias"].grad[0:3]) <= gtol
+    assert rel(grads["alpha_linear.weight"], pub["output_linear.weight"].grad[3:4]) <= gtol
+    for i in (0, 5, 7):
+        assert rel(grads["pts_linears.%d.weight" % i], pub["pts_linears.%d.weight" % i].grad) <= gtol, i
+    for k in ("views_linears.0.weight", "views_linears.0.bias", "rgb_linear.weight", "rgb_linear.bias"):
+        assert float(grads[k].abs().max()) == 0.0                     # the adapter is frozen
+    assert float(grads["feature_linear.weight"][3:].abs().max()) == 0.0
+    opt.step()
+    live = [k for k in sd0 if k.startswith(("pts_linears", "output_linear"))]
+    torch.optim.Adam([pub[k] for k in live], lr=1e-3).step()           # the reference's optimiser on the reference's tensors
+    new = {k: v.detach().cpu() for k, v in m.state_dict().items()}
+    for k in live:
+        d = (new[k] - pub[k].detach()).abs()
+        assert float(d.mean()) <= 2e-5 and float(d.max()) <= 2.1e-3, k  # Adam: sign flips of ~zero gradients only
+    assert torch.equal(new["views_linears.0.weight"], sd0["views_linears.0.weight"])
+    assert float((new["output_linear.weight"][0] - sd0["output_linear.weight"][0]).abs().max()) > 0
+    # render(use_viewdirs=False): rays without view directions; the fused ray path equals the explicit-points path
+    H = W = 12
+    K = np.array([[20.0, 0, 6.0], [0, 20.0, 6.0], [0, 0, 1]])
+    gq = torch.Generator().manual_seed(3)
+    ro = torch.tensor([0.0, 0.0, 4.0]).expand(64, 3).contiguous()
+    rd = torch.nn.functional.normalize(torch.cat([torch.randn(64, 2, generator=gq) * 0.2, -torch.ones(64, 1)], -1), dim=-1)
+    q = run_nerf.NetworkQuery(Hh.get_embedder(10)[0], None, 65536)
+    with torch.no_grad():
+        rgb, disp, acc, ex = R.render(H, W, K, rays=torch.stack([ro, rd], 0).cuda(), ndc=False, near=2.0, far=6.0, use_viewdirs=False,
+                                      network_query_fn=q, network_fn=m, network_fine=m, N_samples=16, N_importance=16,
+                                      white_bkgd=True, perturb=0.0, retraw=True)
+        assert rgb.shape == (64, 3) and bool(torch.isfinite(rgb).all()) and ex["raw"].shape == (64, 32, 4)
+        z = torch.linspace(2.0, 6.0, 16).expand(64, 16).contiguous().cuda()
+        pts = ro.cuda()[:, None] + rd.cuda()[:, None] * z[..., None]
+        raw_pts = q(pts, None, m)[..., :4]
+        rays11 = torch.cat([ro, rd, torch.full((64, 1), 2.0), torch.full((64, 1), 6.0), torch.zeros(64, 3)], -1).cuda()
+        raw_rays = m.query_rays(rays11, z)
+        assert float((raw_pts - raw_rays).abs().max()) <= 1e-5 * max(1.0, float(raw_rays.abs().max()))

@@ -111,3 +111,58 @@ def test_bench_clock_sampler_window():
     assert w["samples"] == 4 and "no sample fell inside" in w["window"]
     none = bench.ClockSampler(0)
     assert none.window(0, 1)["reasons"] == ["nvidia-smi unavailable"]
+
+
+def _no_viewdirs_reference(sd, x):
+    """nerf-ours/model.py:38-63 with use_viewdirs=False, restated on a reference-named state dict: eight relu(Linear) layers with
+    the skip concatenation after layer 4, then output_linear (W -> output_ch)."""
+    h = x
+    for i in range(8):
+        h = torch.relu(torch.nn.functional.linear(h, sd["pts_linears.%d.weight" % i], sd["pts_linears.%d.bias" % i]))
+        if i == 4:
+            h = torch.cat([x, h], -1)
+    return torch.nn.functional.linear(h, sd["output_linear.weight"], sd["output_linear.bias"])
+
+
+def test_no_viewdirs_model_maps_exactly_onto_the_viewdirs_kernels():
+    """use_viewdirs=False (model.py:55-63) runs on an inner use_viewdirs=True net through a frozen +-1 adapter (model.NeRF.
+    _build_inner).  CPU check of the mapping, with the ORACLE's use_viewdirs=True forward standing in for the kernels: same
+    parameter names / shapes / initial values as the reference's constructor, forward equal to the reference formula, and the
+    gradients of the inner net's live entries equal to the reference's output_linear / pts_linears gradients."""
+    import model
+    torch.manual_seed(0)
+    m = model.NeRF(D=8, W=256, input_ch=63, input_ch_views=0, output_ch=5, skips=[4], use_viewdirs=False, precision="fp32")
+    sd = m.state_dict()
+    assert list(sd)[-4:] == ["views_linears.0.weight", "views_linears.0.bias", "output_linear.weight", "output_linear.bias"]
+    assert sd["views_linears.0.weight"].shape == (128, 256) and sd["output_linear.weight"].shape == (5, 256) and len(sd) == 20
+    import ref_shim
+    if ref_shim.available():                                 # the unmodified constructor, same seed: same tensors
+        torch.manual_seed(0)
+        ref = ref_shim.load().model.NeRF(D=8, W=256, input_ch=63, input_ch_views=0, output_ch=5, skips=[4], use_viewdirs=False)
+        assert list(ref.state_dict()) == list(sd) and all(torch.equal(sd[k], v) for k, v in ref.state_dict().items())
+    x = torch.randn(48, 63, generator=torch.Generator().manual_seed(1))
+    pub = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    y_ref = _no_viewdirs_reference(pub, x)
+    inner = {k: v.detach().clone().requires_grad_(True) for k, v in m.kernel_net.state_dict().items()}
+    y_in = O.mlp_forward(inner, torch.cat([x, torch.zeros(48, 27)], -1))
+    assert float((y_in - y_ref[:, :4]).abs().max()) <= 1e-6
+    g = torch.randn(48, 4, generator=torch.Generator().manual_seed(2))
+    (y_in * g).sum().backward()
+    (y_ref[:, :4] * g).sum().backward()
+    tol = dict(rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(inner["feature_linear.weight"].grad[0:3], pub["output_linear.weight"].grad[0:3], **tol)
+    np.testing.assert_allclose(inner["feature_linear.bias"].grad[0:3], pub["output_linear.bias"].grad[0:3], **tol)
+    np.testing.assert_allclose(inner["alpha_linear.weight"].grad, pub["output_linear.weight"].grad[3:4], **tol)
+    for i in range(8):
+        np.testing.assert_allclose(inner["pts_linears.%d.weight" % i].grad, pub["pts_linears.%d.weight" % i].grad, **tol)
+    assert float(inner["feature_linear.weight"].grad[3:].abs().max()) == 0.0
+    # checkpoint round trip through the "module." holder: the inner net follows a load, state_dict() follows the inner net
+    import run_nerf
+    h = run_nerf.ModuleHolder(m)
+    shifted = {k: v + 0.5 for k, v in h.state_dict().items()}
+    h.load_state_dict(shifted)
+    assert torch.equal(m._inner.alpha_linear.weight, shifted["module.output_linear.weight"][3:4])
+    with torch.no_grad():
+        m._inner.feature_linear.weight[1].fill_(7.0)          # what the fused optimiser does: update the inner net only
+    assert torch.equal(h.state_dict()["module.output_linear.weight"][1], torch.full((256,), 7.0))
+    assert torch.equal(h.state_dict()["module.output_linear.weight"][4], shifted["module.output_linear.weight"][4])
